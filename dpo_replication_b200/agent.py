@@ -1,0 +1,148 @@
+"""GACAgent (reference GAC/agent.py) on the B200 engine: same constructor signature and
+defaults, same public methods, `train_one_step()` mutates in place and returns None."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import dist as gdist
+from .engine import Arena, Engine, f32, keras_default_init
+from .helpers import ActionSampler, ReplayBuffer, normalize, update
+from .networks import AutoRegressiveStochasticActor, Critic, Value
+
+
+class GACAgent:
+    """GAC agent; actions live in [-1, 1]^A (agent.py:18-119)."""
+
+    def __init__(self, action_dim, state_dim, buffer_size=1000000, action_samples=10, mode='linear', beta=1, tau=5e-3,
+                 q_normalization=0.01, gamma=0.99, normalize_obs=False, normalize_rewards=False, batch_size=64,
+                 actor='AIQN', *args, device=None, chunk_rows=0, engine=0, **kwargs):
+        self.action_dim, self.state_dim, self.buffer_size = action_dim, state_dim, buffer_size
+        self.gamma, self.action_samples, self.mode, self.beta, self.tau = gamma, action_samples, mode, beta, tau
+        self.batch_size = batch_size
+        self.normalize_observations, self.q_normalization, self.normalize_rewards = normalize_obs, q_normalization, normalize_rewards
+        if actor != 'AIQN':
+            # StochasticActor (IQN, networks.py:271-323) is row 1 of SURVEY.md §8f ("next")
+            raise NotImplementedError("only the AIQN actor is on the accelerated path")
+        if normalize_obs or normalize_rewards:
+            raise NotImplementedError("RunningMeanStd normalisation is out of scope (off by default, agent.py:25)")
+        self.obs_rms = None
+        self.ret_rms = None
+        if not torch.cuda.is_available():
+            raise RuntimeError("dpo_replication_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        S, A = state_dim, action_dim
+        self.arena = Arena(S, A, self.device)
+        self.engine = Engine(S, A, batch_size, action_samples, self.device, chunk_rows=chunk_rows, engine=engine)
+        mk = dict(arena=self.arena, init=False)
+        self.actor = AutoRegressiveStochasticActor(S, A, role="online", **mk)
+        self.target_actor = AutoRegressiveStochasticActor(S, A, role="target", **mk)
+        self.critics = Critic(S, A, role="online", **mk)
+        self.target_critics = Critic(S, A, role="target", **mk)
+        self.value = Value(S, role="online", **mk)
+        self.target_value = Value(S, role="target", **mk)
+        for net in ("actor", "fnn1", "fnn2", "value"):
+            self.arena.load(self.arena.online, net, keras_default_init(S, A, net))
+        # agent.py:114-116: hard copies.  target_value has no variables yet when update() runs in
+        # the reference, so it keeps its own independent initialisation.
+        update(self.target_actor, self.actor, 1.0)
+        update(self.target_critics, self.critics, 1.0)
+        self.arena.load(self.arena.target, "value", keras_default_init(S, A, "value"))
+        self.replay = ReplayBuffer(S, A, buffer_size)
+        self.action_sampler = ActionSampler(self.actor.action_dim)
+        self._hp = self.engine.hparams(gamma, tau, q_normalization, beta, mode)
+
+    # ---- weights in / out (parity harness) ------------------------------------------------
+    def load_state(self, nets: Dict[str, Dict[str, np.ndarray]]):
+        """Load {actor,fnn1,fnn2,value,target_*,m_*,v_*,t_*} as produced by the oracle."""
+        ar = self.arena
+        for name in ("actor", "fnn1", "fnn2", "value"):
+            ar.load(ar.online, name, nets[name])
+            ar.load(ar.target, name, nets["target_" + name])
+            if "m_" + name in nets:
+                ar.load(ar.adam_m, name, nets["m_" + name])
+                ar.load(ar.adam_v, name, nets["v_" + name])
+        ts = [int(nets.get("t_" + n, 0)) for n in ("actor", "fnn1", "fnn2", "value")]
+        ar.adam_t.copy_(torch.tensor(ts, dtype=torch.int32))
+
+    def dump_state(self):
+        ar = self.arena
+        out = {}
+        for name in ("actor", "fnn1", "fnn2", "value"):
+            out[name] = ar.dump(ar.online, name)
+            out["target_" + name] = ar.dump(ar.target, name)
+            out["m_" + name] = ar.dump(ar.adam_m, name)
+            out["v_" + name] = ar.dump(ar.adam_v, name)
+        t = ar.adam_t.cpu().tolist()
+        for i, name in enumerate(("actor", "fnn1", "fnn2", "value")):
+            out["t_" + name] = t[i]
+        return out
+
+    # ---- the hot path ---------------------------------------------------------------------
+    def draw_noise(self) -> Dict[str, torch.Tensor]:
+        """The reference's seven tf.random sites for one step, drawn on device."""
+        B, K, A, dev = self.batch_size, self.action_samples, self.action_dim, self.device
+        P = B * K
+        return dict(critic_u=torch.rand(B, A, device=dev), value_tau=torch.rand(P, A, device=dev),
+                    filter_tau=torch.rand(P, A, device=dev), filter_normal=torch.randn(P, A, device=dev),
+                    filter_rand=torch.rand(P, A, device=dev) * 2 - 1, actor_tau=torch.rand(2 * P, A, device=dev))
+
+    def train_on_batch(self, batch: Dict, noise: Optional[Dict] = None, taps: Optional[Dict[str, torch.Tensor]] = None):
+        """One train step on an explicit replay batch {s,a,r,sp,it} (+ injected randomness).
+        Everything runs on the engine's stream with no host synchronisation; with an initialised
+        torch.distributed group the gradient arena is all-reduced (SUM) between the two phases."""
+        b = {k: f32(batch[k], self.device) for k in ("s", "a", "r", "sp", "it")}
+        n = self.draw_noise() if noise is None else {k: f32(v, self.device) for k, v in noise.items()}
+        io = self.engine.step_io(self.arena, b, n, taps)
+        self._keep = (b, n, io)                 # keep the inputs alive until the stream is done with them
+        self.engine.step_grads(io, self._hp)
+        gdist.allreduce_grads(self.arena.grad)
+        self.engine.step_apply(io, self._hp)
+
+    def train_one_step(self):
+        """agent.py:121-168."""
+        t = self.replay.sample_batch(self.batch_size, device=self.device)
+        batch = dict(s=normalize(t.s, self.obs_rms), a=t.a, r=normalize(t.r, self.ret_rms), sp=normalize(t.sp, self.obs_rms), it=t.it)
+        self.train_on_batch(batch)
+
+    def _sample_positive_advantage_actions(self, states, *, noise: Optional[Dict] = None):
+        """agent.py:170-216 -> (good_states, good_actions, advantages).  This API-compatible
+        form returns dynamically shaped tensors and therefore synchronises on M; the fused
+        train step keeps M on the device."""
+        s = f32(states, self.device)
+        B, K, A = s.shape[0], self.action_samples, self.action_dim
+        P = B * K
+        eng = self.engine if B == self.batch_size else Engine(self.state_dim, A, B, K, self.device)
+        n = noise or {}
+        g = lambda k, f: f32(n[k], self.device) if k in n else f()
+        sidx = torch.arange(B, dtype=torch.int32, device=self.device).repeat(K)            # row = k*B + b
+        ar = self.arena
+        ta = eng.aiqn_sample(ar.net_slice(ar.target, "actor"), s, sidx, g("filter_tau", lambda: torch.rand(P, A, device=self.device)))
+        ta = torch.clamp(ta + g("filter_normal", lambda: torch.randn(P, A, device=self.device)) * 0.01, -1, 1)
+        ra = g("filter_rand", lambda: torch.rand(P, A, device=self.device) * 2 - 1)
+        acts = torch.cat([ta, ra], 0).contiguous()
+        sidx2 = torch.cat([sidx, sidx]).contiguous()
+        q = eng.critic_eval(ar.net_slice(ar.target, "fnn1"), ar.net_slice(ar.target, "fnn2"), s, sidx2, acts)
+        v = eng.value_eval(ar.net_slice(ar.target, "value"), s)[sidx2.long()].contiguous()
+        r = eng.advantage_compact(q.reshape(-1), v.reshape(-1), acts, sidx2)
+        M = int(r["m"].item())
+        self._last_filter = dict(q=q, v=v, idx=r["idx"][:M].reshape(-1, 1), actions=acts)
+        return s[r["state_idx"][:M].long()], r["actions"][:M], r["adv"][:M].reshape(-1, 1)
+
+    def get_action(self, states):
+        """agent.py:218-228."""
+        return self.action_sampler.get_actions(self.actor, states)
+
+    def select_perturbed_action(self, state, action_noise=None):
+        """agent.py:230-248."""
+        state = normalize(f32(state, self.device), self.obs_rms)
+        action = self.action_sampler.get_actions(self.actor, state)
+        if action_noise is not None:
+            action = action + f32(action_noise(), self.device)
+        return torch.clamp(action, -1, 1)
+
+    def store_transition(self, state, action, reward, next_state, is_done):
+        """agent.py:250-268 (normalisation statistics are out of scope, see __init__)."""
+        self.replay.store(state, action, reward, next_state, is_done)

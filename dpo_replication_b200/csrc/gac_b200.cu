@@ -1,0 +1,729 @@
+// libgac_b200.so -- C ABI + orchestration of the GAC train step on B200 (sm_100a).
+// See include/gac_b200.h for the contract and the reference file:line each entry replaces.
+#include <math.h>
+#include <new>
+
+#include "gac_common.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "kernels_elem.cuh"
+
+namespace gac {
+thread_local char g_err[512] = {0};
+}
+using namespace gac;
+
+// ------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------
+static const int kAlign = 32;  // floats (128 B)
+static int64_t align_up64(int64_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+static void fnn_shapes(int n_in, int rows[6], int cols[6]) {
+  const int r[6] = {n_in, GAC_H1, GAC_H1, GAC_H2, GAC_H2, 1};
+  const int c[6] = {GAC_H1, 1, GAC_H2, 1, 1, 1};
+  for (int i = 0; i < 6; ++i) { rows[i] = r[i]; cols[i] = c[i]; }
+}
+// offsets of the six FNN variables relative to the FNN's first float
+static void fnn_offsets(int n_in, int64_t off[7]) {
+  int rows[6], cols[6];
+  fnn_shapes(n_in, rows, cols);
+  int64_t o = 0;
+  for (int i = 0; i < 6; ++i) { off[i] = o; o = align_up64(o + (int64_t)rows[i] * cols[i]); }
+  off[6] = o;
+}
+
+extern "C" int gac_layout(int32_t S, int32_t A, gac_layout_t* out) {
+  if (!out || S <= 0 || A <= 0) return fail(GAC_ERR_INVALID, "gac_layout: bad arguments");
+  const int ar[13] = {GAC_NB, GAC_E, GAC_E, GAC_E, GAC_E, 1, GAC_NB, GAC_E, 2 * GAC_E, GAC_E, 2, S, GAC_E};
+  const int ac[13] = {GAC_E, 1, GAC_E, 1, 1, 1, GAC_E, 1, GAC_G, GAC_G, GAC_G, GAC_E, 1};
+  int64_t o = 0;
+  int v = 0;
+  out->net_begin[GAC_NET_ACTOR] = 0;
+  for (int i = 0; i < 13; ++i, ++v) {
+    out->offsets[v] = o; out->rows[v] = ar[i]; out->cols[v] = ac[i];
+    o = align_up64(o + (int64_t)ar[i] * ac[i]);
+  }
+  const int nin[3] = {S + A, S + A, S};
+  for (int f = 0; f < 3; ++f) {
+    out->net_begin[GAC_NET_FNN1 + f] = o;
+    int rows[6], cols[6];
+    fnn_shapes(nin[f], rows, cols);
+    for (int i = 0; i < 6; ++i, ++v) {
+      out->offsets[v] = o; out->rows[v] = rows[i]; out->cols[v] = cols[i];
+      o = align_up64(o + (int64_t)rows[i] * cols[i]);
+    }
+  }
+  out->offsets[GAC_NVARS] = o;
+  out->net_begin[GAC_NNETS] = o;
+  return GAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// context = partition of the caller's workspace
+// ------------------------------------------------------------------------------------------
+struct gac_ctx {
+  gac_config_t cfg;
+  gac_layout_t lay;
+  cudaStream_t stream;
+  int64_t launches;
+  int P, Mc, nchunks, Rs, NUs, NUa, max_splits;
+  // sampler / critic scratch (Rs rows per pass)
+  float *se_u, *sx_u, *cosb, *ae, *mxa, *mh, *hA, *hB, *u, *y1;
+  float *cx, *ch0a, *ch0b, *ch1a, *ch1b;
+  // TD scratch (B rows)
+  float *td_x, *td_h0, *td_h1, *td_pred, *td_dout, *td_da1, *td_da0, *td_y, *td_vnext, *td_vcrit;
+  // step scratch
+  float *taus2, *acts2, *cand, *q3, *vt, *v2, *adv_sel, *act_sel, *sum_adv, *blk_adv, *loss_part, *alpha, *gscale;
+  int *sidx3, *pos, *sidx_sel, *blk_count, *m_dev, *rows_c, *skip;
+  int64_t* idx_sel;
+  // actor-train chunk (step-major [A][Mc][w])
+  float *a_se_u, *a_sx_u, *a_dsx_u, *a_dse_u;
+  float *ca, *cn, *a_ae, *mx, *dmh, *zs, *rs, *cs, *mhh, *hall, *ne, *au, *ay1, *dy1p, *du, *dne, *dhu, *dhc0, *dhc1, *dop;
+  float *pred_c, *dpred_c;
+  const int* bwd_sidx; const float* bwd_states; int bwd_nstates; const int* bwd_drows;  // saved by supervised_fwd
+  float *spart, *cpart;
+};
+
+namespace {
+
+struct Bump {
+  char* base; size_t off;
+  template <typename T> T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+int derive(gac_ctx* c) {
+  const gac_config_t& f = c->cfg;
+  if (f.S <= 0 || f.A <= 0 || f.B <= 0 || f.K <= 0) return fail(GAC_ERR_INVALID, "gac_config: S, A, B, K must be positive");
+  const int64_t P = (int64_t)f.B * f.K;
+  if (3 * P > (int64_t)1 << 30) return fail(GAC_ERR_INVALID, "gac_config: B*K too large");
+  c->P = (int)P;
+  int mc = f.chunk_rows > 0 ? f.chunk_rows : (int)(2 * P < 65536 ? 2 * P : 65536);
+  c->Mc = round_up(mc, 128);
+  c->nchunks = cdiv(2 * c->P, c->Mc);
+  c->Rs = round_up((int)(2 * P < 131072 ? 2 * P : 131072), 128);
+  c->NUs = c->Rs > f.B ? c->Rs : f.B;
+  c->NUa = f.B > 1024 ? f.B : 1024;
+  if (c->NUa > c->Mc && c->Mc >= f.B) c->NUa = c->Mc > f.B ? c->Mc : f.B;
+  c->max_splits = 32;
+  return gac_layout(f.S, f.A, &c->lay);
+}
+
+size_t partition(gac_ctx* c, void* ws) {
+  Bump b{reinterpret_cast<char*>(ws), 0};
+  const gac_config_t& f = c->cfg;
+  const size_t Rs = c->Rs, B = f.B, P = c->P, A = f.A, S = f.S, Mc = c->Mc, AM = A * Mc;
+  c->se_u = b.take<float>(c->NUs * GAC_E); c->sx_u = b.take<float>((size_t)c->NUs * GAC_G);
+  c->cosb = b.take<float>(Rs * GAC_NB); c->ae = b.take<float>(Rs * GAC_E);
+  c->mxa = b.take<float>(Rs * GAC_G); c->mh = b.take<float>(Rs * GAC_G);
+  c->hA = b.take<float>(Rs * GAC_E); c->hB = b.take<float>(Rs * GAC_E);
+  c->u = b.take<float>(Rs * GAC_E); c->y1 = b.take<float>(Rs * GAC_E);
+  c->cx = b.take<float>(Rs * (S + A));
+  c->ch0a = b.take<float>(Rs * GAC_H1); c->ch0b = b.take<float>(Rs * GAC_H1);
+  c->ch1a = b.take<float>(Rs * GAC_H2); c->ch1b = b.take<float>(Rs * GAC_H2);
+  c->td_x = b.take<float>(B * (S + A)); c->td_h0 = b.take<float>(B * GAC_H1); c->td_h1 = b.take<float>(B * GAC_H2);
+  c->td_pred = b.take<float>(B); c->td_dout = b.take<float>(B); c->td_da1 = b.take<float>(B * GAC_H2);
+  c->td_da0 = b.take<float>(B * GAC_H1); c->td_y = b.take<float>(B); c->td_vnext = b.take<float>(B);
+  c->td_vcrit = b.take<float>(B);
+  c->taus2 = b.take<float>(2 * P * A); c->acts2 = b.take<float>(2 * P * A); c->cand = b.take<float>(3 * P * A);
+  c->q3 = b.take<float>(3 * P); c->vt = b.take<float>(B); c->v2 = b.take<float>(2 * P);
+  c->adv_sel = b.take<float>(2 * P); c->act_sel = b.take<float>(2 * P * A); c->sum_adv = b.take<float>(1);
+  const size_t nblk = (2 * P + CMP_BLOCK - 1) / CMP_BLOCK;
+  c->blk_adv = b.take<float>(nblk); c->loss_part = b.take<float>((2 * P * A + 255) / 256 + 1);
+  c->alpha = b.take<float>(GAC_NNETS); c->gscale = b.take<float>(GAC_NNETS);
+  c->sidx3 = b.take<int>(3 * P); c->pos = b.take<int>(2 * P); c->sidx_sel = b.take<int>(2 * P);
+  c->blk_count = b.take<int>(nblk); c->m_dev = b.take<int>(1); c->rows_c = b.take<int>(c->nchunks + 1);
+  c->skip = b.take<int>(GAC_NNETS); c->idx_sel = b.take<int64_t>(2 * P);
+  c->a_se_u = b.take<float>((size_t)c->NUa * GAC_E); c->a_sx_u = b.take<float>((size_t)c->NUa * GAC_G);
+  c->a_dsx_u = b.take<float>((size_t)c->NUa * GAC_G); c->a_dse_u = b.take<float>((size_t)c->NUa * GAC_E);
+  c->ca = b.take<float>(AM * GAC_NB); c->cn = b.take<float>(AM * GAC_NB);
+  c->a_ae = b.take<float>(AM * GAC_E); c->mx = b.take<float>(AM * GAC_G); c->dmh = b.take<float>(AM * GAC_G);
+  c->zs = b.take<float>(AM * GAC_E); c->rs = b.take<float>(AM * GAC_E); c->cs = b.take<float>(AM * GAC_E);
+  c->mhh = b.take<float>(AM * GAC_E); c->hall = b.take<float>((AM + Mc) * GAC_E);
+  c->ne = b.take<float>(AM * GAC_E); c->au = b.take<float>(AM * GAC_E); c->ay1 = b.take<float>(AM * GAC_E);
+  c->dy1p = b.take<float>(AM * GAC_E); c->du = b.take<float>(AM * GAC_E); c->dne = b.take<float>(AM * GAC_E);
+  c->dhu = b.take<float>(AM * GAC_E); c->dhc0 = b.take<float>(Mc * GAC_E); c->dhc1 = b.take<float>(Mc * GAC_E);
+  c->dop = b.take<float>(AM); c->pred_c = b.take<float>(Mc * A); c->dpred_c = b.take<float>(Mc * A);
+  c->spart = b.take<float>((size_t)c->max_splits * GAC_E * GAC_G);
+  const size_t maxrows = AM > Rs ? AM : Rs;
+  c->cpart = b.take<float>(((maxrows + COLSUM_ROWS - 1) / COLSUM_ROWS + 1) * GAC_G);
+  return (b.off + 255) & ~(size_t)255;
+}
+
+#define LAUNCHED(ctx, name) do { (ctx)->launches++; GAC_LAUNCH_CHECK(name); } while (0)
+
+inline const float* var(const gac_ctx* c, const float* net_base, int net, int v) {
+  return net_base + (c->lay.offsets[v] - c->lay.net_begin[net]);
+}
+inline float* var(const gac_ctx* c, float* net_base, int net, int v) {
+  return net_base + (c->lay.offsets[v] - c->lay.net_begin[net]);
+}
+
+// GEMM dispatch: tcgen05 3xTF32 engine where the shape qualifies, else SIMT; split-K for the
+// weight-gradient contractions (reduction over activation rows), reduced deterministically.
+int run_gemm(gac_ctx* c, GemmArgs g) {
+  cudaStream_t st = c->stream;
+  if (g.M <= 0 || g.N <= 0) return GAC_OK;
+  const bool tc = c->cfg.engine == 0 && tc_gemm_supported(g);
+  if (g.valid_on_k || g.K >= 8192) {
+    const int tiles = cdiv(g.M, 128) * cdiv(g.N, 128);
+    int splits = (4 * 148) / tiles;
+    if (splits > c->max_splits) splits = c->max_splits;
+    if (splits > g.K / 512) splits = g.K / 512;
+    if ((size_t)g.M * g.N > (size_t)GAC_E * GAC_G) splits = 1;
+    if (splits > 1) {
+      if (g.ldc != g.N) return fail(GAC_ERR_INVALID, "split-K destination must be dense");
+      GemmArgs p = g;
+      p.C = c->spart; p.ldc = g.N; p.splitk = splits; p.split_stride = (long long)g.M * g.N;
+      p.bias = nullptr; p.add = nullptr; p.mul = nullptr; p.gate = nullptr; p.act = ACT_NONE; p.accumulate = 0;
+      if (tc) GAC_CUDA(launch_gemm_tc(p, st)); else GAC_CUDA(launch_gemm_simt(p, st));
+      c->launches++;
+      const long long n = (long long)g.M * g.N;
+      reduce_splits_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(c->spart, n, splits, g.C, n, g.accumulate);
+      LAUNCHED(c, "reduce_splits");
+      return GAC_OK;
+    }
+  }
+  if (tc) GAC_CUDA(launch_gemm_tc(g, st)); else GAC_CUDA(launch_gemm_simt(g, st));
+  c->launches++;
+  return GAC_OK;
+}
+
+// dst[n] (+)= sum_r w[r] * X[r][n] over live rows
+int run_colsum(gac_ctx* c, const float* X, int ldx, const float* w, int N, long long rows, RowValid rv, float* dst, int accumulate) {
+  const int nblk = (int)cdiv64(rows, COLSUM_ROWS);
+  colsum_kernel<<<dim3(cdiv(N, 128), nblk), 128, 0, c->stream>>>(X, ldx, w, N, rows, rv, c->cpart);
+  LAUNCHED(c, "colsum");
+  reduce_splits_kernel<<<cdiv(N, 256), 256, 0, c->stream>>>(c->cpart, N, nblk, dst, N, accumulate);
+  LAUNCHED(c, "colsum_reduce");
+  return GAC_OK;
+}
+
+// FNN forward on `rows` rows of x (rows, n_in): h0, h1 saved, out (rows) = linear head
+int fnn_forward(gac_ctx* c, const float* fnn, int n_in, const float* x, int rows, float* h0, float* h1) {
+  int64_t off[7];
+  fnn_offsets(n_in, off);
+  GemmArgs g = gemm_args(rows, GAC_H1, n_in, x, n_in, fnn + off[0], GAC_H1, h0, GAC_H1);
+  g.bias = fnn + off[1]; g.act = ACT_LRELU; g.alpha = 0.01f;
+  GAC_TRY(run_gemm(c, g));
+  g = gemm_args(rows, GAC_H2, GAC_H1, h0, GAC_H1, fnn + off[2], GAC_H2, h1, GAC_H2);
+  g.bias = fnn + off[3]; g.act = ACT_LRELU; g.alpha = 0.01f;
+  GAC_TRY(run_gemm(c, g));
+  return GAC_OK;
+}
+
+int value_eval(gac_ctx* c, const float* value, const float* states, int rows, float* v) {
+  const int S = c->cfg.S;
+  int64_t off[7];
+  fnn_offsets(S, off);
+  for (int r0 = 0; r0 < rows; r0 += c->Rs) {
+    const int n = rows - r0 < c->Rs ? rows - r0 : c->Rs;
+    GAC_TRY(fnn_forward(c, value, S, states + (size_t)r0 * S, n, c->ch0a, c->ch1a));
+    rowdot_kernel<<<cdiv(n * 32, 256), 256, 0, c->stream>>>(c->ch1a, GAC_H2, value + off[4], value + off[5], nullptr, nullptr,
+                                                           nullptr, GAC_H2, n, 0, v + r0, 1, nullptr, 0, RowValid{nullptr, 1});
+    LAUNCHED(c, "rowdot");
+  }
+  return GAC_OK;
+}
+
+int critic_eval(gac_ctx* c, const float* f1, const float* f2, const float* states_u, const int* sidx, const float* actions,
+                int rows, float* q) {
+  const int S = c->cfg.S, A = c->cfg.A, W = S + A;
+  int64_t off[7];
+  fnn_offsets(W, off);
+  for (int r0 = 0; r0 < rows; r0 += c->Rs) {
+    const int n = rows - r0 < c->Rs ? rows - r0 : c->Rs;
+    concat_gather_kernel<<<(unsigned)cdiv64((long long)n * W, 256), 256, 0, c->stream>>>(
+        states_u, sidx ? sidx + r0 : nullptr, actions + (size_t)r0 * A, S, A, n, c->cx);
+    LAUNCHED(c, "concat_gather");
+    GAC_TRY(fnn_forward(c, f1, W, c->cx, n, c->ch0a, c->ch1a));
+    GAC_TRY(fnn_forward(c, f2, W, c->cx, n, c->ch0b, c->ch1b));
+    rowdot_kernel<<<cdiv(n * 32, 256), 256, 0, c->stream>>>(c->ch1a, GAC_H2, f1 + off[4], f1 + off[5], c->ch1b, f2 + off[4],
+                                                           f2 + off[5], GAC_H2, n, 0, q + r0, 1, nullptr, 0, RowValid{nullptr, 1});
+    LAUNCHED(c, "rowdot_min");
+  }
+  return GAC_OK;
+}
+
+// per-unique-state prep: se = lrelu_.2(lrelu_.01(s Ws + bs)); sx = se Kx[0:400] + b_in
+int state_prep(gac_ctx* c, const float* actor, const float* states_u, int n_states, float* se_u, float* sx_u) {
+  const int S = c->cfg.S;
+  GemmArgs g = gemm_args(n_states, GAC_E, S, states_u, S, var(c, actor, 0, GAC_A_WS), GAC_E, se_u, GAC_E);
+  g.bias = var(c, actor, 0, GAC_A_BS); g.act = ACT_LRELU2;
+  GAC_TRY(run_gemm(c, g));
+  g = gemm_args(n_states, GAC_G, GAC_E, se_u, GAC_E, var(c, actor, 0, GAC_A_KX), GAC_G, sx_u, GAC_G);
+  g.bias = var(c, actor, 0, GAC_A_GB);
+  GAC_TRY(run_gemm(c, g));
+  return GAC_OK;
+}
+
+int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const float* taus, int rows, float* actions) {
+  const int A = c->cfg.A;
+  cudaStream_t st = c->stream;
+  const RowValid all{nullptr, 1};
+  float* hprev = c->hA; float* hcur = c->hB;
+  const float* kxa = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
+  for (int d = 0; d < A; ++d) {
+    cos_basis_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(d ? actions + d - 1 : nullptr, A, c->cosb, rows, all);
+    LAUNCHED(c, "cos_basis");
+    GemmArgs g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->ae, GAC_E);
+    g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f;
+    GAC_TRY(run_gemm(c, g));
+    g = gemm_args(rows, GAC_G, GAC_E, c->ae, GAC_E, kxa, GAC_G, c->mxa, GAC_G);
+    GAC_TRY(run_gemm(c, g));
+    if (d) {
+      g = gemm_args(rows, GAC_G, GAC_E, hprev, GAC_E, var(c, actor, 0, GAC_A_U), GAC_G, c->mh, GAC_G);
+      GAC_TRY(run_gemm(c, g));
+    }
+    gru_gates_fwd_kernel<<<(unsigned)cdiv64((long long)rows * GAC_E, 256), 256, 0, st>>>(
+        c->sx_u, sidx, c->mxa, d ? c->mh : nullptr, var(c, actor, 0, GAC_A_GB) + GAC_G, hprev, hcur, nullptr, nullptr, nullptr,
+        nullptr, rows, all);
+    LAUNCHED(c, "gru_gates_fwd");
+    cos_basis_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(taus + d, A, c->cosb, rows, all);
+    LAUNCHED(c, "cos_basis");
+    g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->u, GAC_E);
+    g.bias = var(c, actor, 0, GAC_A_BN); g.mul = hcur; g.ldmul = GAC_E;
+    GAC_TRY(run_gemm(c, g));
+    g = gemm_args(rows, GAC_E, GAC_E, c->u, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->y1, GAC_E);
+    g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f;
+    GAC_TRY(run_gemm(c, g));
+    rowdot_kernel<<<cdiv(rows * 32, 256), 256, 0, st>>>(c->y1, GAC_E, var(c, actor, 0, GAC_A_W2), var(c, actor, 0, GAC_A_B2),
+                                                       nullptr, nullptr, nullptr, GAC_E, rows, 1, actions + d, A, nullptr, 0, all);
+    LAUNCHED(c, "rowdot_tanh");
+    float* t = hprev; hprev = hcur; hcur = t;
+  }
+  return GAC_OK;
+}
+
+int aiqn_sample(gac_ctx* c, const float* actor, const float* states_u, int n_states, const int* sidx, const float* taus,
+                int rows, float* actions) {
+  if (n_states > c->NUs) return fail(GAC_ERR_WORKSPACE, "gac_aiqn_sample: n_states exceeds the workspace capacity");
+  GAC_TRY(state_prep(c, actor, states_u, n_states, c->se_u, c->sx_u));
+  const int A = c->cfg.A;
+  for (int r0 = 0; r0 < rows; r0 += c->Rs) {
+    const int n = rows - r0 < c->Rs ? rows - r0 : c->Rs;
+    GAC_TRY(aiqn_sample_rows(c, actor, sidx + r0, taus + (size_t)r0 * A, n, actions + (size_t)r0 * A));
+  }
+  return GAC_OK;
+}
+
+int td_fwd_bwd(gac_ctx* c, const float* fnn, int n_in, const float* x, const float* y, int rows, float* grad, float* loss_out) {
+  if (rows > c->cfg.B) return fail(GAC_ERR_WORKSPACE, "gac_td_fwd_bwd: rows exceeds B");
+  cudaStream_t st = c->stream;
+  const RowValid all{nullptr, 1};
+  int64_t off[7];
+  fnn_offsets(n_in, off);
+  GAC_TRY(fnn_forward(c, fnn, n_in, x, rows, c->td_h0, c->td_h1));
+  rowdot_kernel<<<cdiv(rows * 32, 256), 256, 0, st>>>(c->td_h1, GAC_H2, fnn + off[4], fnn + off[5], nullptr, nullptr, nullptr,
+                                                     GAC_H2, rows, 0, c->td_pred, 1, nullptr, 0, all);
+  LAUNCHED(c, "rowdot");
+  td_dout_kernel<<<1, 1024, 0, st>>>(c->td_pred, y, rows, c->td_dout, loss_out);
+  LAUNCHED(c, "td_dout");
+  // layer 3
+  GAC_TRY(run_colsum(c, c->td_h1, GAC_H2, c->td_dout, GAC_H2, rows, all, grad + off[4], 0));
+  GAC_TRY(run_colsum(c, c->td_dout, 1, nullptr, 1, rows, all, grad + off[5], 0));
+  outer_gate_kernel<<<(unsigned)cdiv64((long long)rows * GAC_H2, 256), 256, 0, st>>>(c->td_dout, fnn + off[4], c->td_h1, GAC_H2,
+                                                                                  rows, 0.01f, c->td_da1, all);
+  LAUNCHED(c, "outer_gate");
+  // layer 2
+  GemmArgs g = gemm_args(GAC_H1, GAC_H2, rows, c->td_h0, GAC_H1, c->td_da1, GAC_H2, grad + off[2], GAC_H2);
+  g.transA = 1;
+  GAC_TRY(run_gemm(c, g));
+  GAC_TRY(run_colsum(c, c->td_da1, GAC_H2, nullptr, GAC_H2, rows, all, grad + off[3], 0));
+  g = gemm_args(rows, GAC_H1, GAC_H2, c->td_da1, GAC_H2, fnn + off[2], GAC_H2, c->td_da0, GAC_H1);
+  g.transB = 1; g.gate = c->td_h0; g.ldgate = GAC_H1; g.gate_alpha = 0.01f;
+  GAC_TRY(run_gemm(c, g));
+  // layer 1
+  g = gemm_args(n_in, GAC_H1, rows, x, n_in, c->td_da0, GAC_H1, grad + off[0], GAC_H1);
+  g.transA = 1;
+  GAC_TRY(run_gemm(c, g));
+  GAC_TRY(run_colsum(c, c->td_da0, GAC_H1, nullptr, GAC_H1, rows, all, grad + off[1], 0));
+  return GAC_OK;
+}
+
+int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_states, const int* sidx, const float* taus,
+                   const float* teacher, int max_rows, const int* d_rows, float* pred) {
+  const int A = c->cfg.A, Mc = c->Mc;
+  if (max_rows > Mc) return fail(GAC_ERR_WORKSPACE, "gac_aiqn_supervised_fwd: max_rows exceeds chunk_rows");
+  if (n_states > c->NUa) return fail(GAC_ERR_WORKSPACE, "gac_aiqn_supervised_fwd: n_states exceeds the workspace capacity");
+  cudaStream_t st = c->stream;
+  // rows beyond max_rows inside the chunk are dead too: clamp through a device counter
+  int* live = c->rows_c + c->nchunks;  // scratch slot
+  if (d_rows) GAC_CUDA(cudaMemcpyAsync(live, d_rows, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  else GAC_CUDA(cudaMemcpyAsync(live, &max_rows, sizeof(int), cudaMemcpyHostToDevice, st));
+  const RowValid rv{live, Mc};
+  const long long AM = (long long)A * Mc;
+  c->bwd_sidx = sidx; c->bwd_states = states_u; c->bwd_nstates = n_states; c->bwd_drows = live;
+  GAC_TRY(state_prep(c, actor, states_u, n_states, c->a_se_u, c->a_sx_u));
+  cos_basis_seq_kernel<<<(unsigned)cdiv64(AM * GAC_NB, 256), 256, 0, st>>>(teacher, taus, A, Mc, c->ca, c->cn, live);
+  LAUNCHED(c, "cos_basis_seq");
+  GemmArgs g = gemm_args((int)AM, GAC_E, GAC_NB, c->ca, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->a_ae, GAC_E);
+  g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc;
+  GAC_TRY(run_gemm(c, g));
+  g = gemm_args((int)AM, GAC_G, GAC_E, c->a_ae, GAC_E, var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, GAC_G, c->mx, GAC_G);
+  g.dyn_rows = live; g.seg_rows = Mc;
+  GAC_TRY(run_gemm(c, g));
+  for (int d = 0; d < A; ++d) {
+    const size_t o4 = (size_t)d * Mc * GAC_E, o12 = (size_t)d * Mc * GAC_G;
+    if (d) {
+      g = gemm_args(Mc, GAC_G, GAC_E, c->hall + o4, GAC_E, var(c, actor, 0, GAC_A_U), GAC_G, c->dmh + o12, GAC_G);
+      g.dyn_rows = live; g.seg_rows = Mc;
+      GAC_TRY(run_gemm(c, g));
+    }
+    gru_gates_fwd_kernel<<<(unsigned)cdiv64((long long)Mc * GAC_E, 256), 256, 0, st>>>(
+        c->a_sx_u, sidx, c->mx + o12, d ? c->dmh + o12 : nullptr, var(c, actor, 0, GAC_A_GB) + GAC_G, c->hall + o4,
+        c->hall + o4 + (size_t)Mc * GAC_E, c->zs + o4, c->rs + o4, c->cs + o4, c->mhh + o4, Mc, rv);
+    LAUNCHED(c, "gru_gates_fwd");
+  }
+  g = gemm_args((int)AM, GAC_E, GAC_NB, c->cn, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->ne, GAC_E);
+  g.bias = var(c, actor, 0, GAC_A_BN); g.dyn_rows = live; g.seg_rows = Mc;
+  GAC_TRY(run_gemm(c, g));
+  mul_kernel<<<(unsigned)cdiv64(AM * GAC_E, 256), 256, 0, st>>>(c->ne, c->hall + (size_t)Mc * GAC_E, AM * GAC_E, Mc, live, c->au);
+  LAUNCHED(c, "hadamard");
+  g = gemm_args((int)AM, GAC_E, GAC_E, c->au, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->ay1, GAC_E);
+  g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f; g.dyn_rows = live; g.seg_rows = Mc;
+  GAC_TRY(run_gemm(c, g));
+  for (int d = 0; d < A; ++d) {
+    rowdot_kernel<<<cdiv(Mc * 32, 256), 256, 0, st>>>(c->ay1 + (size_t)d * Mc * GAC_E, GAC_E, var(c, actor, 0, GAC_A_W2),
+                                                     var(c, actor, 0, GAC_A_B2), nullptr, nullptr, nullptr, GAC_E, Mc, 1,
+                                                     c->pred_c + d, A, pred ? pred + d : nullptr, A, rv);
+    LAUNCHED(c, "rowdot_tanh");
+  }
+  return GAC_OK;
+}
+
+int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, int acc) {
+  const int A = c->cfg.A, Mc = c->Mc, S = c->cfg.S;
+  if (!c->bwd_drows) return fail(GAC_ERR_INVALID, "gac_aiqn_bwd: no saved forward");
+  cudaStream_t st = c->stream;
+  const int* live = c->bwd_drows;
+  const RowValid rv{live, Mc};
+  const long long AM = (long long)A * Mc;
+  const float* kxa = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
+  auto G = [&](int v) { return var(c, grad, 0, v); };
+  auto wgrad = [&](int M, int N, const float* X, int ldx, const float* dY, int ldy, long long rows, float* dst, bool dyn) {
+    GemmArgs g = gemm_args(M, N, (int)rows, X, ldx, dY, ldy, dst, N);
+    g.transA = 1; g.accumulate = acc;
+    if (dyn) { g.dyn_rows = live; g.seg_rows = Mc; g.valid_on_k = 1; }
+    return run_gemm(c, g);
+  };
+  // head
+  head_dop_kernel<<<(unsigned)cdiv64(AM, 256), 256, 0, st>>>(dpred, c->pred_c, A, Mc, live, c->dop);
+  LAUNCHED(c, "head_dop");
+  GAC_TRY(run_colsum(c, c->ay1, GAC_E, c->dop, GAC_E, AM, rv, G(GAC_A_W2), acc));
+  GAC_TRY(run_colsum(c, c->dop, 1, nullptr, 1, AM, rv, G(GAC_A_B2), acc));
+  outer_gate_kernel<<<(unsigned)cdiv64(AM * GAC_E, 256), 256, 0, st>>>(c->dop, var(c, actor, 0, GAC_A_W2), c->ay1, GAC_E, AM, 0.01f,
+                                                                      c->dy1p, rv);
+  LAUNCHED(c, "outer_gate");
+  GAC_TRY(wgrad(GAC_E, GAC_E, c->au, GAC_E, c->dy1p, GAC_E, AM, G(GAC_A_W1), true));
+  GAC_TRY(run_colsum(c, c->dy1p, GAC_E, nullptr, GAC_E, AM, rv, G(GAC_A_B1), acc));
+  GemmArgs g = gemm_args((int)AM, GAC_E, GAC_E, c->dy1p, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->du, GAC_E);
+  g.transB = 1; g.dyn_rows = live; g.seg_rows = Mc;
+  GAC_TRY(run_gemm(c, g));
+  hadamard_bwd_kernel<<<(unsigned)cdiv64(AM * GAC_E, 256), 256, 0, st>>>(c->du, c->hall + (size_t)Mc * GAC_E, c->ne, AM * GAC_E, Mc, live,
+                                                                        c->dne, c->dhu);
+  LAUNCHED(c, "hadamard_bwd");
+  GAC_TRY(wgrad(GAC_NB, GAC_E, c->cn, GAC_NB, c->dne, GAC_E, AM, G(GAC_A_WN), true));
+  GAC_TRY(run_colsum(c, c->dne, GAC_E, nullptr, GAC_E, AM, rv, G(GAC_A_BN), acc));
+  // recurrence, reverse time.  mx is overwritten with dmx step by step (it is dead after the forward gates)
+  float* dh_next = nullptr; float* carry = c->dhc0;
+  for (int d = A - 1; d >= 0; --d) {
+    const size_t o4 = (size_t)d * Mc * GAC_E, o12 = (size_t)d * Mc * GAC_G;
+    gru_gates_bwd_kernel<<<(unsigned)cdiv64((long long)Mc * GAC_E, 256), 256, 0, st>>>(
+        dh_next, c->dhu + o4, c->zs + o4, c->rs + o4, c->cs + o4, c->mhh + o4, d ? c->hall + o4 : nullptr, c->mx + o12, c->dmh + o12,
+        carry, Mc, rv);
+    LAUNCHED(c, "gru_gates_bwd");
+    if (d) {
+      g = gemm_args(Mc, GAC_E, GAC_G, c->dmh + o12, GAC_G, var(c, actor, 0, GAC_A_U), GAC_G, carry, GAC_E);
+      g.transB = 1; g.accumulate = 1; g.dyn_rows = live; g.seg_rows = Mc;
+      GAC_TRY(run_gemm(c, g));
+    }
+    dh_next = carry;
+    carry = carry == c->dhc0 ? c->dhc1 : c->dhc0;
+  }
+  // time-parallel weight gradients of the GRU
+  GAC_TRY(wgrad(GAC_E, GAC_G, c->hall, GAC_E, c->dmh, GAC_G, AM, G(GAC_A_U), true));
+  GAC_TRY(run_colsum(c, c->dmh, GAC_G, nullptr, GAC_G, AM, rv, G(GAC_A_GB) + GAC_G, acc));
+  GAC_TRY(run_colsum(c, c->mx, GAC_G, nullptr, GAC_G, AM, rv, G(GAC_A_GB), acc));
+  GAC_TRY(wgrad(GAC_E, GAC_G, c->a_ae, GAC_E, c->mx, GAC_G, AM, G(GAC_A_KX) + (size_t)GAC_E * GAC_G, true));
+  g = gemm_args((int)AM, GAC_E, GAC_G, c->mx, GAC_G, kxa, GAC_G, c->du, GAC_E);
+  g.transB = 1; g.gate = c->a_ae; g.ldgate = GAC_E; g.gate_alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc;
+  GAC_TRY(run_gemm(c, g));
+  GAC_TRY(wgrad(GAC_NB, GAC_E, c->ca, GAC_NB, c->du, GAC_E, AM, G(GAC_A_WA), true));
+  GAC_TRY(run_colsum(c, c->du, GAC_E, nullptr, GAC_E, AM, rv, G(GAC_A_BA), acc));
+  // state half: reduce d(sx) per unique state, then B-row GEMMs
+  const int NU = c->bwd_nstates;
+  segment_sum_kernel<<<dim3(NU, cdiv(GAC_G, 256)), 256, 0, st>>>(c->mx, c->bwd_sidx, A, Mc, live, 0, c->a_dsx_u);
+  LAUNCHED(c, "segment_sum");
+  GAC_TRY(wgrad(GAC_E, GAC_G, c->a_se_u, GAC_E, c->a_dsx_u, GAC_G, NU, G(GAC_A_KX), false));
+  g = gemm_args(NU, GAC_E, GAC_G, c->a_dsx_u, GAC_G, var(c, actor, 0, GAC_A_KX), GAC_G, c->a_dse_u, GAC_E);
+  g.transB = 1; g.gate = c->a_se_u; g.ldgate = GAC_E; g.gate_alpha = 0.01f * 0.2f;
+  GAC_TRY(run_gemm(c, g));
+  GAC_TRY(wgrad(S, GAC_E, c->bwd_states, S, c->a_dse_u, GAC_E, NU, G(GAC_A_WS), false));
+  GAC_TRY(run_colsum(c, c->a_dse_u, GAC_E, nullptr, GAC_E, NU, RowValid{nullptr, 1}, G(GAC_A_BS), acc));
+  return GAC_OK;
+}
+
+int compact(gac_ctx* c, const float* q, const float* v, int n, int64_t* idx_out, int* pos_out, int* m_out, float* sum_adv_out,
+            float* adv_out, const float* actions, int A, float* actions_out, const int* sidx, int* sidx_out) {
+  if (n > 2 * c->P) return fail(GAC_ERR_WORKSPACE, "gac_advantage_compact: n exceeds 2*B*K");
+  cudaStream_t st = c->stream;
+  const int nblk = cdiv(n, CMP_BLOCK);
+  compact_count_kernel<<<nblk, CMP_BLOCK, 0, st>>>(q, v, n, c->blk_count);
+  LAUNCHED(c, "compact_count");
+  compact_scan_kernel<<<1, 1024, 0, st>>>(c->blk_count, nblk, m_out);
+  LAUNCHED(c, "compact_scan");
+  compact_scatter_kernel<<<nblk, CMP_BLOCK, 0, st>>>(q, v, n, c->blk_count, idx_out, pos_out, adv_out, actions, A, actions_out, sidx,
+                                                     sidx_out, c->blk_adv);
+  LAUNCHED(c, "compact_scatter");
+  final_sum_kernel<<<1, 1024, 0, st>>>(c->blk_adv, nblk, sum_adv_out, 0);
+  LAUNCHED(c, "final_sum");
+  return GAC_OK;
+}
+
+int qhuber(gac_ctx* c, const float* pred, const float* target, const float* taus, const float* w, int max_rows, const int* d_rows,
+           int A, float inv_norm, float* dpred, float* loss_out, int accumulate) {
+  const long long n = (long long)max_rows * A;
+  const int nblk = (int)cdiv64(n, 256);
+  if (nblk > (2 * c->P * A + 255) / 256 + 1) return fail(GAC_ERR_WORKSPACE, "gac_qhuber_loss_bwd: rows exceed 2*B*K");
+  qhuber_kernel<<<nblk, 256, 0, c->stream>>>(pred, target, taus, w, A, max_rows, d_rows, inv_norm, dpred, c->loss_part);
+  LAUNCHED(c, "qhuber");
+  final_sum_kernel<<<1, 1024, 0, c->stream>>>(c->loss_part, nblk, loss_out, accumulate);
+  LAUNCHED(c, "final_sum");
+  return GAC_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* gac_last_error(void) { return g_err; }
+int gac_abi_version(void) { return GAC_B200_ABI_VERSION; }
+
+size_t gac_workspace_bytes(const gac_config_t* cfg) {
+  if (!cfg) return 0;
+  gac_ctx tmp;
+  memset(&tmp, 0, sizeof(tmp));
+  tmp.cfg = *cfg;
+  if (derive(&tmp) != 0) return 0;
+  return partition(&tmp, nullptr);
+}
+
+int gac_create(const gac_config_t* cfg, void* workspace, size_t workspace_bytes, void* stream, gac_ctx_t** out) {
+  if (!cfg || !workspace || !out) return fail(GAC_ERR_INVALID, "gac_create: null argument");
+  gac_ctx* c = new (std::nothrow) gac_ctx;
+  if (!c) return fail(GAC_ERR_INVALID, "gac_create: out of host memory");
+  memset(c, 0, sizeof(*c));
+  c->cfg = *cfg;
+  c->stream = reinterpret_cast<cudaStream_t>(stream);
+  int rc = derive(c);
+  if (rc) { delete c; return rc; }
+  const size_t need = partition(c, nullptr);
+  if (workspace_bytes < need) { delete c; return fail(GAC_ERR_WORKSPACE, "gac_create: workspace too small"); }
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) { delete c; return fail(GAC_ERR_INVALID, "gac_create: workspace must be 256-byte aligned"); }
+  partition(c, workspace);
+  // constants
+  float ipi[GAC_NB];
+  const float pif = 3.14159274101257324f;  // fl32(pi)
+  for (int i = 0; i < GAC_NB; ++i) ipi[i] = (float)(i + 1) * pif;
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_ipi, ipi, sizeof(ipi), 0, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->hall, 0, (size_t)c->Mc * GAC_E * sizeof(float), c->stream);  // h_{-1} = 0
+  if (e == cudaSuccess) e = tc_gemm_init();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) { delete c; return fail(GAC_ERR_CUDA, "gac_create: %s", cudaGetErrorString(e)); }
+  *out = c;
+  return GAC_OK;
+}
+
+void gac_destroy(gac_ctx_t* ctx) { delete ctx; }
+int64_t gac_launch_count(const gac_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+
+int gac_polyak(float* target, const float* source, int64_t n, float rho, void* stream) {
+  if (!target || !source || n < 0) return fail(GAC_ERR_INVALID, "gac_polyak: bad arguments");
+  if (n == 0) return GAC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float omr = (float)(1.0 - (double)rho);  // helpers.py:86: (1.0 - rate) in Python float, then fp32
+  const bool aligned = ((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(source)) & 15) == 0;
+  if (aligned) polyak_kernel<<<(unsigned)cdiv64(cdiv64(n, 4), 256), 256, 0, st>>>(target, source, n, omr, rho);
+  else polyak_scalar_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(target, source, n, omr, rho);
+  GAC_LAUNCH_CHECK("polyak");
+  return GAC_OK;
+}
+
+int gac_adam_polyak(gac_ctx_t* c, float* online, float* target, float* adam_m, float* adam_v, const float* grad,
+                    const gac_hparams_t* hp, int32_t* adam_t, const float* grad_scale, const int32_t* skip) {
+  if (!c || !online || !target || !adam_m || !adam_v || !grad || !hp || !adam_t) return fail(GAC_ERR_INVALID, "gac_adam_polyak: null argument");
+  cudaStream_t st = c->stream;
+  adam_prep_kernel<<<1, 32, 0, st>>>(adam_t, skip, hp->lr, hp->beta1, hp->beta2, c->alpha);
+  LAUNCHED(c, "adam_prep");
+  AdamNets nets;
+  for (int i = 0; i <= GAC_NNETS; ++i) nets.begin[i] = c->lay.net_begin[i];
+  const int64_t n4 = c->lay.net_begin[GAC_NNETS] / 4;
+  const float omr = (float)(1.0 - (double)hp->rho);
+  adam_polyak_kernel<<<(unsigned)cdiv64(n4, 256), 256, 0, st>>>(
+      reinterpret_cast<float4*>(online), reinterpret_cast<float4*>(target), reinterpret_cast<float4*>(adam_m),
+      reinterpret_cast<float4*>(adam_v), reinterpret_cast<const float4*>(grad), nets, c->alpha, grad_scale, skip, 1.f - hp->beta1,
+      1.f - hp->beta2, hp->eps, omr, hp->rho);
+  LAUNCHED(c, "adam_polyak");
+  return GAC_OK;
+}
+
+int gac_aiqn_sample(gac_ctx_t* c, const float* actor, const float* states_u, int32_t n_states, const int32_t* state_idx,
+                    const float* taus, int32_t rows, float* actions) {
+  if (!c || !actor || !states_u || !state_idx || !taus || !actions || rows < 0) return fail(GAC_ERR_INVALID, "gac_aiqn_sample: bad arguments");
+  return aiqn_sample(c, actor, states_u, n_states, state_idx, taus, rows, actions);
+}
+
+int gac_critic_eval(gac_ctx_t* c, const float* fnn1, const float* fnn2, const float* states_u, const int32_t* state_idx,
+                    const float* actions, int32_t rows, float* q) {
+  if (!c || !fnn1 || !fnn2 || !states_u || !actions || !q) return fail(GAC_ERR_INVALID, "gac_critic_eval: bad arguments");
+  return critic_eval(c, fnn1, fnn2, states_u, state_idx, actions, rows, q);
+}
+
+int gac_value_eval(gac_ctx_t* c, const float* value, const float* states, int32_t rows, float* v) {
+  if (!c || !value || !states || !v) return fail(GAC_ERR_INVALID, "gac_value_eval: bad arguments");
+  return value_eval(c, value, states, rows, v);
+}
+
+int gac_advantage_compact(gac_ctx_t* c, const float* q, const float* v, int32_t n, int64_t* idx_out, int32_t* pos_out, int32_t* m_out,
+                          float* sum_adv_out, float* adv_out, const float* actions, int32_t A, float* actions_out,
+                          const int32_t* state_idx, int32_t* sidx_out) {
+  if (!c || !q || !v || !idx_out || !m_out || !sum_adv_out || n <= 0) return fail(GAC_ERR_INVALID, "gac_advantage_compact: bad arguments");
+  return compact(c, q, v, n, idx_out, pos_out, m_out, sum_adv_out, adv_out, actions, A, actions_out, state_idx, sidx_out);
+}
+
+int gac_aiqn_supervised_fwd(gac_ctx_t* c, const float* actor, const float* states_u, int32_t n_states, const int32_t* state_idx,
+                            const float* taus, const float* teacher, int32_t max_rows, const int32_t* d_rows, float* pred) {
+  if (!c || !actor || !states_u || !state_idx || !taus || !teacher) return fail(GAC_ERR_INVALID, "gac_aiqn_supervised_fwd: bad arguments");
+  return supervised_fwd(c, actor, states_u, n_states, state_idx, taus, teacher, max_rows, d_rows, pred);
+}
+
+int gac_qhuber_loss_bwd(gac_ctx_t* c, const float* pred, const float* target, const float* taus, const float* weights,
+                        int32_t max_rows, const int32_t* d_rows, int32_t A, float inv_norm, float* dpred, float* loss_out) {
+  if (!c || !pred || !target || !taus || !dpred || !loss_out) return fail(GAC_ERR_INVALID, "gac_qhuber_loss_bwd: bad arguments");
+  return qhuber(c, pred, target, taus, weights, max_rows, d_rows, A, inv_norm, dpred, loss_out, 1);
+}
+
+int gac_aiqn_bwd(gac_ctx_t* c, const float* actor, const float* dpred, float* grad_actor, int32_t accumulate) {
+  if (!c || !actor || !dpred || !grad_actor) return fail(GAC_ERR_INVALID, "gac_aiqn_bwd: bad arguments");
+  return aiqn_bwd(c, actor, dpred, grad_actor, accumulate);
+}
+
+int gac_td_fwd_bwd(gac_ctx_t* c, const float* fnn, int32_t n_in, const float* x, const float* y, int32_t rows, float* grad_fnn,
+                   float* loss_out) {
+  if (!c || !fnn || !x || !y || !grad_fnn || !loss_out) return fail(GAC_ERR_INVALID, "gac_td_fwd_bwd: bad arguments");
+  return td_fwd_bwd(c, fnn, n_in, x, y, rows, grad_fnn, loss_out);
+}
+
+int gac_gemm(gac_ctx_t* c, int32_t engine, const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t transA,
+             int32_t transB) {
+  if (!c || !A || !B || !C) return fail(GAC_ERR_INVALID, "gac_gemm: bad arguments");
+  GemmArgs g = gemm_args(M, N, K, A, transA ? M : K, B, transB ? K : N, C, N);
+  g.transA = transA; g.transB = transB;
+  if (engine == 0) {
+    if (!tc_gemm_supported(g)) return fail(GAC_ERR_UNSUPPORTED, "gac_gemm: shape not supported by the tcgen05 engine");
+    GAC_CUDA(launch_gemm_tc(g, c->stream));
+  } else {
+    GAC_CUDA(launch_gemm_simt(g, c->stream));
+  }
+  c->launches++;
+  return GAC_OK;
+}
+
+// ---- the train step -------------------------------------------------------------------------
+int gac_step_grads(gac_ctx_t* c, const gac_step_io_t* io, const gac_hparams_t* hp) {
+  if (!c || !io || !hp) return fail(GAC_ERR_INVALID, "gac_step_grads: null argument");
+  if (hp->mode != 0 && hp->mode != 1) return fail(GAC_ERR_UNSUPPORTED, "target density mode must be linear or boltzmann (networks.py:94-95)");
+  const int S = c->cfg.S, A = c->cfg.A, B = c->cfg.B, K = c->cfg.K, P = c->P, Mc = c->Mc;
+  cudaStream_t st = c->stream;
+  const gac_layout_t& L = c->lay;
+  const float* t_actor = io->target + L.net_begin[GAC_NET_ACTOR];
+  const float* t_f1 = io->target + L.net_begin[GAC_NET_FNN1];
+  const float* t_f2 = io->target + L.net_begin[GAC_NET_FNN2];
+  const float* t_v = io->target + L.net_begin[GAC_NET_VALUE];
+  float* stats = io->grad + L.net_begin[GAC_NNETS];
+
+  // row -> state maps: [0,P) state-major (networks.py:464-467), [P,3P) sample-major (agent.py:186)
+  // (static per (B,K); rebuilt each step: 3P ints)
+  sidx3_kernel<<<cdiv(3 * P, 256), 256, 0, st>>>(c->sidx3, P, B, K);
+  LAUNCHED(c, "sidx3");
+
+  // ---- Critic.train (networks.py:410-426) ----
+  critic_train_x_kernel<<<cdiv(B * (S + A), 256), 256, 0, st>>>(io->s, io->a, io->critic_u, hp->q_normalization, S, A, B, c->td_x);
+  LAUNCHED(c, "critic_train_x");
+  GAC_TRY(value_eval(c, t_v, io->sp, B, c->td_vnext));
+  td_target_kernel<<<cdiv(B, 256), 256, 0, st>>>(io->r, c->td_vnext, io->done, hp->gamma, B, c->td_y);
+  LAUNCHED(c, "td_target");
+  GAC_TRY(td_fwd_bwd(c, io->online + L.net_begin[GAC_NET_FNN1], S + A, c->td_x, c->td_y, B, io->grad + L.net_begin[GAC_NET_FNN1], stats + 0));
+  GAC_TRY(td_fwd_bwd(c, io->online + L.net_begin[GAC_NET_FNN2], S + A, c->td_x, c->td_y, B, io->grad + L.net_begin[GAC_NET_FNN2], stats + 1));
+
+  // ---- both target-actor sampling passes in one 2P-row batch (F9) ----
+  GAC_CUDA(cudaMemcpyAsync(c->taus2, io->value_tau, (size_t)P * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  GAC_CUDA(cudaMemcpyAsync(c->taus2 + (size_t)P * A, io->filter_tau, (size_t)P * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  GAC_TRY(aiqn_sample(c, t_actor, io->s, B, c->sidx3, c->taus2, 2 * P, c->acts2));
+  // candidates: [value-pass actions ; clip(target actions + 0.01 N) ; uniform random actions]
+  GAC_CUDA(cudaMemcpyAsync(c->cand, c->acts2, (size_t)P * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  noise_clip_kernel<<<(unsigned)cdiv64((long long)P * A, 256), 256, 0, st>>>(c->acts2 + (size_t)P * A, io->filter_normal, 0.01f,
+                                                                           (long long)P * A, c->cand + (size_t)P * A);
+  LAUNCHED(c, "noise_clip");
+  GAC_CUDA(cudaMemcpyAsync(c->cand + (size_t)2 * P * A, io->filter_rand, (size_t)P * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  GAC_TRY(critic_eval(c, t_f1, t_f2, io->s, c->sidx3, c->cand, 3 * P, c->q3));
+
+  // ---- Value.train (networks.py:483-496) ----
+  mean_k_kernel<<<cdiv(B * 32, 256), 256, 0, st>>>(c->q3, K, B, c->td_vcrit);
+  LAUNCHED(c, "mean_k");
+  GAC_TRY(td_fwd_bwd(c, io->online + L.net_begin[GAC_NET_VALUE], S, io->s, c->td_vcrit, B, io->grad + L.net_begin[GAC_NET_VALUE], stats + 2));
+
+  // ---- advantage filter (agent.py:198-215) ----
+  GAC_TRY(value_eval(c, t_v, io->s, B, c->vt));
+  gather_kernel<<<cdiv(2 * P, 256), 256, 0, st>>>(c->vt, c->sidx3 + P, 2 * P, c->v2);
+  LAUNCHED(c, "gather_v");
+  GAC_TRY(compact(c, c->q3 + P, c->v2, 2 * P, c->idx_sel, c->pos, c->m_dev, c->sum_adv, c->adv_sel, c->cand + (size_t)P * A, A,
+                  c->act_sel, c->sidx3 + P, c->sidx_sel));
+  chunk_rows_kernel<<<1, 1024, 0, st>>>(c->m_dev, Mc, c->nchunks, c->rows_c);
+  LAUNCHED(c, "chunk_rows");
+  stats_m_kernel<<<1, 32, 0, st>>>(c->m_dev, stats);
+  LAUNCHED(c, "stats_m");
+  GAC_CUDA(cudaMemcpyAsync(stats + 4, c->sum_adv, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  GAC_CUDA(cudaMemsetAsync(stats + 3, 0, sizeof(float), st));
+
+  // ---- IQNActor.train (networks.py:122-141) in row chunks; un-normalised weights ----
+  float* g_actor = io->grad + L.net_begin[GAC_NET_ACTOR];
+  const float* o_actor = io->online + L.net_begin[GAC_NET_ACTOR];
+  for (int ch = 0; ch < c->nchunks; ++ch) {
+    const size_t r0 = (size_t)ch * Mc;
+    const int maxr = (int)((size_t)2 * P - r0 < (size_t)Mc ? (size_t)2 * P - r0 : (size_t)Mc);
+    GAC_TRY(supervised_fwd(c, o_actor, io->s, B, c->sidx_sel + r0, io->actor_tau + r0 * A, c->act_sel + r0 * A, maxr, c->rows_c + ch, nullptr));
+    GAC_TRY(qhuber(c, c->pred_c, c->act_sel + r0 * A, io->actor_tau + r0 * A, hp->mode == 0 ? c->adv_sel + r0 : nullptr, maxr,
+                   c->rows_c + ch, A, 1.f, c->dpred_c, stats + 3, 1));
+    GAC_TRY(aiqn_bwd(c, o_actor, c->dpred_c, g_actor, ch > 0));
+  }
+
+  // optional taps for the parity tests
+  if (io->sel_idx) GAC_CUDA(cudaMemcpyAsync(io->sel_idx, c->idx_sel, (size_t)2 * P * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  if (io->q_out) GAC_CUDA(cudaMemcpyAsync(io->q_out, c->q3 + P, (size_t)2 * P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (io->v_out) GAC_CUDA(cudaMemcpyAsync(io->v_out, c->v2, (size_t)2 * P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (io->cand_actions) GAC_CUDA(cudaMemcpyAsync(io->cand_actions, c->cand + (size_t)P * A, (size_t)2 * P * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (io->value_actions) GAC_CUDA(cudaMemcpyAsync(io->value_actions, c->cand, (size_t)P * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return GAC_OK;
+}
+
+int gac_step_apply(gac_ctx_t* c, const gac_step_io_t* io, const gac_hparams_t* hp) {
+  if (!c || !io || !hp) return fail(GAC_ERR_INVALID, "gac_step_apply: null argument");
+  cudaStream_t st = c->stream;
+  const gac_layout_t& L = c->lay;
+  const float* stats = io->grad + L.net_begin[GAC_NNETS];
+  apply_prep_kernel<<<1, 32, 0, st>>>(stats, c->cfg.A, hp->mode, c->gscale, c->skip);
+  LAUNCHED(c, "apply_prep");
+  return gac_adam_polyak(c, io->online, io->target, io->adam_m, io->adam_v, io->grad, hp, io->adam_t, c->gscale, c->skip);
+}
+
+}  // extern "C"

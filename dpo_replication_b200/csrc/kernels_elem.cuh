@@ -1,0 +1,497 @@
+// Elementwise / reduction / compaction kernels of the GAC step (all HBM- or L2-bound).
+#pragma once
+#include "gac_common.cuh"
+
+namespace gac {
+
+// i_pi[i] = fl32(fl32(i+1) * fl32(pi)): the reference builds the constant as
+// np.arange(1,65,float32) * np.pi (GAC/networks.py:45) -- SURVEY.md F4.
+__constant__ float c_ipi[GAC_NB];
+
+struct RowValid {          // row r live iff (r % seg) < *dyn  (dyn == nullptr: always live)
+  const int* dyn; int seg;
+  __device__ __forceinline__ bool operator()(int r) const { return !dyn || (r % seg) < *dyn; }
+};
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// fixed-order block sum (deterministic); result valid on thread 0
+__device__ __forceinline__ float block_sum(float v, float* sh /* >= 32 floats */) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x == 0) for (int i = 0; i < (int)(blockDim.x + 31) / 32; ++i) t += sh[i];
+  return t;
+}
+
+// ---- cosine basis: out[r][i] = cos(fl32(x[r*incx] * i_pi[i]))   networks.py:44-47 ----
+__global__ void cos_basis_kernel(const float* __restrict__ x, int incx, float* __restrict__ out, int rows, RowValid rv) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = idx >> 6, i = idx & 63;
+  if (r >= rows || !rv(r)) return;
+  const float xv = x ? x[(size_t)r * incx] : 0.f;
+  out[idx] = cosf(__fmul_rn(xv, c_ipi[i]));
+}
+
+// teacher-forced "shifted action": step d reads action d-1 (0 for d == 0)   networks.py:253-255
+// out[(d*seg + r)][i] = cos(shift * i_pi[i]); second output for the noise embedding of tau[r][d].
+__global__ void cos_basis_seq_kernel(const float* __restrict__ teacher, const float* __restrict__ taus, int A, int seg,
+                                     float* __restrict__ ca, float* __restrict__ cn, const int* dyn) {
+  const int nvalid = dyn ? *dyn : seg;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = idx & 63;
+  const long long rs = idx >> 6;
+  if (rs >= (long long)A * seg) return;
+  const int d = rs / seg, r = rs % seg;
+  if (r >= nvalid) return;
+  const float prev = d == 0 ? 0.f : teacher[(size_t)r * A + d - 1];
+  ca[idx] = cosf(__fmul_rn(prev, c_ipi[i]));
+  cn[idx] = cosf(__fmul_rn(taus[(size_t)r * A + d], c_ipi[i]));
+}
+
+// ---- x = concat(states[sidx[r]], actions[r])   networks.py:385 ----
+__global__ void concat_gather_kernel(const float* __restrict__ states, const int* __restrict__ sidx,
+                                     const float* __restrict__ actions, int S, int A, int rows, float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = S + A;
+  if (idx >= (long long)rows * W) return;
+  const int r = idx / W, c = idx % W;
+  out[idx] = c < S ? states[(size_t)(sidx ? sidx[r] : r) * S + c] : actions[(size_t)r * A + (c - S)];
+}
+
+// ---- Critic.train input: concat(s, clip(a + (2u-1)*qn, -1, 1))   networks.py:411-417 ----
+__global__ void critic_train_x_kernel(const float* __restrict__ s, const float* __restrict__ a, const float* __restrict__ u,
+                                      float qn, int S, int A, int B, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = S + A;
+  if (idx >= B * W) return;
+  const int r = idx / W, c = idx % W;
+  if (c < S) { out[idx] = s[r * S + c]; return; }
+  const float nz = (u[r * A + c - S] * 2.f - 1.f) * qn;
+  out[idx] = fminf(fmaxf(a[r * A + c - S] + nz, -1.f), 1.f);
+}
+
+// ---- GRU gates (Keras GRU, reset_after=True, gate order [z|r|h]) ----
+// mx = sx_u[sidx[row]] (state half of the input projection + input bias, hoisted per unique
+// state) + mxa[row] (action half); mh = mhr[row] + b1 (recurrent bias).  mhr == nullptr means
+// h_prev == 0 (first step: 0*U is skipped, the bias is still added).
+__global__ void gru_gates_fwd_kernel(const float* __restrict__ sx_u, const int* __restrict__ sidx,
+                                     const float* __restrict__ mxa, const float* __restrict__ mhr,
+                                     const float* __restrict__ b1, const float* __restrict__ hprev,
+                                     float* __restrict__ hout, float* __restrict__ zs, float* __restrict__ rs_,
+                                     float* __restrict__ cs, float* __restrict__ mhhs, int rows, RowValid rv) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * GAC_E) return;
+  const int row = idx / GAC_E, j = idx % GAC_E;
+  if (!rv(row)) return;
+  const float* sx = sx_u + (size_t)sidx[row] * GAC_G;
+  const float* mx = mxa + (size_t)row * GAC_G;
+  const float xz = sx[j] + mx[j], xr = sx[GAC_E + j] + mx[GAC_E + j], xh = sx[2 * GAC_E + j] + mx[2 * GAC_E + j];
+  float hz = b1[j], hr = b1[GAC_E + j], hh = b1[2 * GAC_E + j];
+  float hp = 0.f;
+  if (mhr) {
+    const float* mh = mhr + (size_t)row * GAC_G;
+    hz += mh[j]; hr += mh[GAC_E + j]; hh += mh[2 * GAC_E + j];
+    hp = hprev[idx];
+  }
+  const float z = sigmoid_f(xz + hz), r = sigmoid_f(xr + hr);
+  const float c = tanhf(xh + r * hh);
+  hout[idx] = z * hp + (1.f - z) * c;
+  if (zs) { zs[idx] = z; rs_[idx] = r; cs[idx] = c; mhhs[idx] = hh; }
+}
+
+// backward of the gates for one step; dh = dh_next + dhu.  Writes dmx, dmh (rows,1200) and
+// dh_carry = dh*z (the GEMM dmh*U^T is accumulated on top of it afterwards).
+__global__ void gru_gates_bwd_kernel(const float* __restrict__ dh_next, const float* __restrict__ dhu,
+                                     const float* __restrict__ zs, const float* __restrict__ rs_,
+                                     const float* __restrict__ cs, const float* __restrict__ mhhs,
+                                     const float* __restrict__ hprev, float* __restrict__ dmx, float* __restrict__ dmh,
+                                     float* __restrict__ dh_carry, int rows, RowValid rv) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * GAC_E) return;
+  const int row = idx / GAC_E, j = idx % GAC_E;
+  if (!rv(row)) return;
+  const float dh = (dh_next ? dh_next[idx] : 0.f) + dhu[idx];
+  const float z = zs[idx], r = rs_[idx], c = cs[idx], hp = hprev ? hprev[idx] : 0.f;
+  const float dz = dh * (hp - c), dc = dh * (1.f - z);
+  const float dcp = dc * (1.f - c * c);
+  const float dzp = dz * z * (1.f - z);
+  const float drp = dcp * mhhs[idx] * r * (1.f - r);
+  const size_t o = (size_t)row * GAC_G + j;
+  dmx[o] = dzp; dmx[o + GAC_E] = drp; dmx[o + 2 * GAC_E] = dcp;
+  dmh[o] = dzp; dmh[o + GAC_E] = drp; dmh[o + 2 * GAC_E] = dcp * r;
+  dh_carry[idx] = dh * z;
+}
+
+// ---- out[r] = f(dot(x[r,:n], w) + b): one warp per row.  mode 0: identity, 1: tanh. ----
+// Twin variant takes a second (x2, w2, b2) and writes min (Critic.__call__, networks.py:388).
+__global__ void rowdot_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b,
+                              const float* __restrict__ x2, const float* __restrict__ w2, const float* __restrict__ b2,
+                              int n, int rows, int mode, float* __restrict__ out, int inc_out, float* __restrict__ out2,
+                              int inc_out2, RowValid rv) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows || !rv(row)) return;
+  float s = 0.f;
+  for (int j = lane; j < n; j += 32) s = fmaf(x[(size_t)row * ldx + j], w[j], s);
+  s = warp_sum(s) + b[0];
+  if (x2) {
+    float t = 0.f;
+    for (int j = lane; j < n; j += 32) t = fmaf(x2[(size_t)row * ldx + j], w2[j], t);
+    t = warp_sum(t) + b2[0];
+    s = fminf(s, t);
+  }
+  if (mode == 1) s = tanhf(s);
+  if (lane == 0) {
+    out[(size_t)row * inc_out] = s;
+    if (out2) out2[(size_t)row * inc_out2] = s;
+  }
+}
+
+// ---- agent.py:189-190: a = clip(a + 0.01*n, -1, 1) ----
+__global__ void noise_clip_kernel(const float* __restrict__ a, const float* __restrict__ nrm, float scale, long long n,
+                                  float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fminf(fmaxf(a[i] + nrm[i] * scale, -1.f), 1.f);
+}
+
+// ---- networks.py:484-485: v_critic[b] = mean_k q[b*K + k] (state-major rows) ----
+__global__ void mean_k_kernel(const float* __restrict__ q, int K, int B, float* __restrict__ out) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s += q[(size_t)b * K + k];
+  s = warp_sum(s);
+  if (lane == 0) out[b] = s / (float)K;
+}
+
+__global__ void gather_kernel(const float* __restrict__ src, const int* __restrict__ idx, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+
+// ---- networks.py:415: yQ = r + gamma * V_tgt(s') * (1 - done) ----
+__global__ void td_target_kernel(const float* __restrict__ r, const float* __restrict__ vnext, const float* __restrict__ done,
+                                 float gamma, int B, float* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) y[i] = r[i] + gamma * vnext[i] * (1.f - done[i]);
+}
+
+// ---- mse over a size-1 axis, gradient of the SUM (F5): dout = 2(pred-y); loss = sum (pred-y)^2.
+// single block (B is small); deterministic ----
+__global__ void td_dout_kernel(const float* __restrict__ pred, const float* __restrict__ y, int B, float* __restrict__ dout,
+                               float* __restrict__ loss) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float d = pred[i] - y[i];
+    dout[i] = 2.f * d;
+    acc += d * d;
+  }
+  const float t = block_sum(acc, sh);
+  if (threadIdx.x == 0) *loss = t;
+}
+
+// ---- dx[r][j] = dout[r] * w[j] * (y[r][j] > 0 ? 1 : alpha): backward of a width-1 Dense
+// through the LeakyReLU of the layer below (FNN layer 3, AIQN dense_layer_2). ----
+__global__ void outer_gate_kernel(const float* __restrict__ dout, const float* __restrict__ w, const float* __restrict__ y,
+                                  int n, long long rows, float alpha, float* __restrict__ dx, RowValid rv) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * n) return;
+  const long long r = idx / n;
+  const int j = idx % n;
+  if (!rv((int)r)) return;
+  dx[idx] = dout[r] * w[j] * (y[idx] > 0.f ? 1.f : alpha);
+}
+
+// ---- AIQN head backward, step-major: dop[d*seg+r] = dpred[r][d] * (1 - pred[r][d]^2) ----
+__global__ void head_dop_kernel(const float* __restrict__ dpred, const float* __restrict__ pred, int A, int seg,
+                                const int* dyn, float* __restrict__ dop) {
+  const int nvalid = dyn ? *dyn : seg;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)A * seg) return;
+  const int d = idx / seg, r = idx % seg;
+  if (r >= nvalid) return;
+  const float p = pred[(size_t)r * A + d];
+  dop[idx] = dpred[(size_t)r * A + d] * (1.f - p * p);
+}
+
+// ---- dne = du * h ; dhu = du * ne ----
+__global__ void hadamard_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h, const float* __restrict__ ne,
+                                    long long n, int seg, const int* dyn, float* __restrict__ dne, float* __restrict__ dhu) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  if (dyn && (int)((idx / GAC_E) % seg) >= *dyn) return;
+  const float d = du[idx];
+  dne[idx] = d * h[idx];
+  dhu[idx] = d * ne[idx];
+}
+
+// ---- out = a * b on live rows (u = ne * h, networks.py:220/:265) ----
+__global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, int seg, const int* dyn,
+                           float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  if (dyn && (int)((idx / GAC_E) % seg) >= *dyn) return;
+  out[idx] = a[idx] * b[idx];
+}
+
+// row -> state index of the 3P candidate rows of one step: [0,P) state-major
+// (networks.py:464-467), [P,3P) sample-major (agent.py:186)
+__global__ void sidx3_kernel(int* __restrict__ s, int P, int B, int K) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= 3 * P) return;
+  s[r] = r < P ? r / K : (r % P) % B;
+}
+
+// ---- column sums with optional row weights: part[blk][n] = sum_{r in blk} w[r] * X[r][n] ----
+// (bias gradients, the width-1 layer's weight gradient).  Deterministic two-stage reduction.
+constexpr int COLSUM_ROWS = 256;
+__global__ void colsum_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ w, int N, long long rows,
+                              RowValid rv, float* __restrict__ part) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long long r0 = (long long)blockIdx.y * COLSUM_ROWS;
+  const long long r1 = min(rows, r0 + COLSUM_ROWS);
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    if (!rv((int)r)) continue;
+    const float x = X[(size_t)r * ldx + n];
+    s += w ? w[r] * x : x;
+  }
+  part[(size_t)blockIdx.y * N + n] = s;
+}
+
+// ---- quantile Huber loss + gradient (networks.py:113-120; App. A.6), elementwise Huber ----
+// dpred = |tau - 1[u>0]| * w[r] * clip(u,-1,1) * inv_norm ; loss partials per block.
+__global__ void qhuber_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ taus,
+                              const float* __restrict__ w, int A, int max_rows, const int* dyn, float inv_norm,
+                              float* __restrict__ dpred, float* __restrict__ part) {
+  __shared__ float sh[32];
+  const int nvalid = dyn ? min(*dyn, max_rows) : max_rows;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.f;
+  if (idx < (long long)nvalid * A) {
+    const int r = idx / A;
+    const float u = pred[idx] - target[idx];
+    const float ind = u > 0.f ? 1.f : 0.f;
+    const float au = fabsf(u), qq = fminf(au, 1.f);
+    const float hub = 0.5f * qq * qq + (au - qq);
+    const float coef = fabsf(taus[idx] - ind) * (w ? w[r] : 1.f);
+    l = coef * hub * inv_norm;
+    dpred[idx] = coef * fminf(fmaxf(u, -1.f), 1.f) * inv_norm;
+  }
+  const float t = block_sum(l, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+// single-block ordered sum of partials: out = (accumulate ? out : 0) + sum part[0..n)
+__global__ void final_sum_kernel(const float* __restrict__ part, int n, float* __restrict__ out, int accumulate) {
+  __shared__ float sh[32];
+  // fixed assignment: thread t sums part[t], part[t+blockDim], ... then fixed-order block sum
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+  const float t = block_sum(s, sh);
+  if (threadIdx.x == 0) *out = (accumulate ? *out : 0.f) + t;
+}
+
+// ------------------------------------------------------------------------------------------
+// Advantage filter: stable compaction of {i : q[i] > v[i]} (agent.py:207-215).
+// 1024 candidates per block; ballot + popc inside a warp, smem scan across the 32 warps,
+// a single-block scan across blocks.  NaN compares false, ties are excluded (strict >).
+// ------------------------------------------------------------------------------------------
+constexpr int CMP_BLOCK = 1024;
+__global__ void compact_count_kernel(const float* __restrict__ q, const float* __restrict__ v, int n, int* __restrict__ blk_count) {
+  __shared__ int sh[32];
+  const int i = blockIdx.x * CMP_BLOCK + threadIdx.x;
+  const bool f = i < n && q[i] > v[i];
+  const unsigned b = __ballot_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 32; ++w) t += sh[w];
+    blk_count[blockIdx.x] = t;
+  }
+}
+// exclusive scan of block counts (in place) and total -> *m_out
+__global__ void compact_scan_kernel(int* __restrict__ blk_count, int nblk, int* __restrict__ m_out) {
+  __shared__ int sh[1024];
+  const int per = (nblk + 1023) / 1024;
+  const int b0 = threadIdx.x * per, b1 = min(nblk, b0 + per);
+  int s = 0;
+  for (int b = b0; b < b1; ++b) s += blk_count[b];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int t = 0; t < 1024; ++t) { const int c = sh[t]; sh[t] = run; run += c; }
+    *m_out = run;
+  }
+  __syncthreads();
+  int run = sh[threadIdx.x];
+  for (int b = b0; b < b1; ++b) { const int c = blk_count[b]; blk_count[b] = run; run += c; }
+}
+__global__ void compact_scatter_kernel(const float* __restrict__ q, const float* __restrict__ v, int n,
+                                       const int* __restrict__ blk_off, int64_t* __restrict__ idx_out,
+                                       int* __restrict__ pos_out, float* __restrict__ adv_out,
+                                       const float* __restrict__ actions, int A, float* __restrict__ actions_out,
+                                       const int* __restrict__ sidx, int* __restrict__ sidx_out,
+                                       float* __restrict__ blk_adv) {
+  __shared__ int shc[32];
+  __shared__ float shf[32];
+  const int i = blockIdx.x * CMP_BLOCK + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float adv = 0.f;
+  bool f = false;
+  if (i < n) { const float qq = q[i], vv = v[i]; f = qq > vv; adv = qq - vv; }
+  const unsigned b = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) shc[w] = __popc(b);
+  __syncthreads();
+  int woff = 0;
+  for (int k = 0; k < w; ++k) woff += shc[k];
+  const int pos = blk_off[blockIdx.x] + woff + __popc(b & ((1u << lane) - 1u));
+  if (i < n && pos_out) pos_out[i] = pos;
+  if (f) {
+    idx_out[pos] = (int64_t)i;
+    if (adv_out) adv_out[pos] = adv;
+    if (sidx_out) sidx_out[pos] = sidx[i];
+    if (actions_out) for (int d = 0; d < A; ++d) actions_out[(size_t)pos * A + d] = actions[(size_t)i * A + d];
+  }
+  const float t = block_sum(f ? adv : 0.f, shf);
+  if (threadIdx.x == 0) blk_adv[blockIdx.x] = t;
+}
+
+// ---- per-unique-state reduction of d(sx): dsx_u[b][n] (+)= sum over live rows j of this
+// chunk with sidx[j] == b of sum_d dmx[(d*seg + j)][n].  One block per (state, column slab);
+// the block scans the chunk's sidx in order, so the summation order is fixed. ----
+__global__ void segment_sum_kernel(const float* __restrict__ dmx, const int* __restrict__ sidx, int A, int seg,
+                                   const int* dyn, int accumulate, float* __restrict__ dsx_u) {
+  __shared__ int list[256];
+  __shared__ int wcnt[8];
+  __shared__ int nlist;
+  const int b = blockIdx.x;
+  const int n = blockIdx.y * 256 + threadIdx.x;   // 256 threads, 5 slabs cover 1200 (tail masked)
+  const int nvalid = dyn ? min(*dyn, seg) : seg;
+  float s = (accumulate && n < GAC_G) ? dsx_u[(size_t)b * GAC_G + n] : 0.f;
+  for (int base = 0; base < nvalid; base += 256) {
+    const int j = base + threadIdx.x;
+    const bool hit = j < nvalid && sidx[j] == b;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wcnt[w] = __popc(bal);
+    __syncthreads();
+    int off = 0;
+    for (int k = 0; k < w; ++k) off += wcnt[k];
+    if (hit) list[off + __popc(bal & ((1u << lane) - 1u))] = j;
+    if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < 8; ++k) t += wcnt[k]; nlist = t; }
+    __syncthreads();
+    if (n < GAC_G)
+      for (int e = 0; e < nlist; ++e) {
+        const int jj = list[e];
+        for (int d = 0; d < A; ++d) s += dmx[((size_t)d * seg + jj) * GAC_G + n];
+      }
+    __syncthreads();
+  }
+  if (n < GAC_G) dsx_u[(size_t)b * GAC_G + n] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam (Keras OptimizerV2 formula) fused with the Polyak target update
+// (helpers.py:86) over the flat arenas; 128-bit accesses, 36 B/param of HBM traffic.
+// ------------------------------------------------------------------------------------------
+struct AdamNets {
+  long long begin[GAC_NNETS + 1];
+};
+// one thread: advances step counters and derives alpha_t per net in fp32 like Keras does
+__global__ void adam_prep_kernel(int* __restrict__ adam_t, const int* __restrict__ skip, float lr, float b1, float b2,
+                                 float* __restrict__ alpha) {
+  const int n = threadIdx.x;
+  if (n >= GAC_NNETS) return;
+  if (skip && skip[n]) { alpha[n] = 0.f; return; }
+  const int t = adam_t[n] + 1;
+  adam_t[n] = t;
+  const float b1p = powf(b1, (float)t), b2p = powf(b2, (float)t);
+  alpha[n] = lr * sqrtf(1.f - b2p) / (1.f - b1p);
+}
+__global__ void adam_polyak_kernel(float4* __restrict__ p, float4* __restrict__ tg, float4* __restrict__ m, float4* __restrict__ v,
+                                   const float4* __restrict__ g, AdamNets nets, const float* __restrict__ alpha,
+                                   const float* __restrict__ gscale, const int* __restrict__ skip, float omb1, float omb2,
+                                   float eps, float one_minus_rho, float rho) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = i4 * 4;
+  if (i >= nets.begin[GAC_NNETS]) return;
+  int net = 0;
+#pragma unroll
+  for (int k = 1; k < GAC_NNETS; ++k) net += (i >= nets.begin[k]);
+  float4 pp = p[i4];
+  if (!(skip && skip[net])) {
+    const float a = alpha[net], sc = gscale ? gscale[net] : 1.f;
+    float4 gg = g[i4], mm = m[i4], vv = v[i4];
+    float* pf = &pp.x; float* gf = &gg.x; float* mf = &mm.x; float* vf = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = gf[k] * sc;
+      mf[k] = mf[k] + (gk - mf[k]) * omb1;
+      vf[k] = vf[k] + (gk * gk - vf[k]) * omb2;
+      pf[k] = pf[k] - a * mf[k] / (sqrtf(vf[k]) + eps);
+    }
+    m[i4] = mm; v[i4] = vv; p[i4] = pp;
+  }
+  float4 tt = tg[i4];
+  tt.x = __fadd_rn(__fmul_rn(tt.x, one_minus_rho), __fmul_rn(pp.x, rho));
+  tt.y = __fadd_rn(__fmul_rn(tt.y, one_minus_rho), __fmul_rn(pp.y, rho));
+  tt.z = __fadd_rn(__fmul_rn(tt.z, one_minus_rho), __fmul_rn(pp.z, rho));
+  tt.w = __fadd_rn(__fmul_rn(tt.w, one_minus_rho), __fmul_rn(pp.w, rho));
+  tg[i4] = tt;
+}
+
+// helpers.update alone: t <- fl(fl(t*(1-rho)) + fl(s*rho)); vector body + scalar tail
+__global__ void polyak_kernel(float* __restrict__ t, const float* __restrict__ s, long long n, float one_minus_rho, float rho) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = i4 * 4;
+  if (i + 3 < n) {
+    float4 tt = reinterpret_cast<float4*>(t)[i4];
+    const float4 ss = reinterpret_cast<const float4*>(s)[i4];
+    tt.x = __fadd_rn(__fmul_rn(tt.x, one_minus_rho), __fmul_rn(ss.x, rho));
+    tt.y = __fadd_rn(__fmul_rn(tt.y, one_minus_rho), __fmul_rn(ss.y, rho));
+    tt.z = __fadd_rn(__fmul_rn(tt.z, one_minus_rho), __fmul_rn(ss.z, rho));
+    tt.w = __fadd_rn(__fmul_rn(tt.w, one_minus_rho), __fmul_rn(ss.w, rho));
+    reinterpret_cast<float4*>(t)[i4] = tt;
+  } else {
+    for (long long k = i; k < n; ++k) t[k] = __fadd_rn(__fmul_rn(t[k], one_minus_rho), __fmul_rn(s[k], rho));
+  }
+}
+__global__ void polyak_scalar_kernel(float* __restrict__ t, const float* __restrict__ s, long long n, float one_minus_rho, float rho) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) t[i] = __fadd_rn(__fmul_rn(t[i], one_minus_rho), __fmul_rn(s[i], rho));
+}
+
+// ---- step glue: chunk row counts and the actor gradient normalisation ----
+// rows_c[c] = clamp(M - c*chunk, 0, chunk)
+__global__ void chunk_rows_kernel(const int* __restrict__ m, int chunk, int nchunks, int* __restrict__ rows_c) {
+  const int c = threadIdx.x;
+  if (c < nchunks) rows_c[c] = max(0, min(chunk, *m - c * chunk));
+}
+// stats (after the cross-rank SUM) -> gscale[4], skip[4].  IQNActor.train: weights = adv/sum(adv)
+// (linear) or 1 (boltzmann, F6); loss = mean over M*A (networks.py:91,93,120); agent.py:158 skip.
+__global__ void apply_prep_kernel(const float* __restrict__ stats, int A, int mode, float* __restrict__ gscale, int* __restrict__ skip) {
+  if (threadIdx.x != 0) return;
+  const float M = stats[5], sadv = stats[4];
+  for (int n = 0; n < GAC_NNETS; ++n) { gscale[n] = 1.f; skip[n] = 0; }
+  if (M < 0.5f) { skip[GAC_NET_ACTOR] = 1; gscale[GAC_NET_ACTOR] = 0.f; return; }
+  const float denom = M * (float)A;
+  gscale[GAC_NET_ACTOR] = mode == 0 ? 1.f / (denom * sadv) : 1.f / denom;
+}
+__global__ void stats_m_kernel(const int* __restrict__ m, float* __restrict__ stats) {
+  if (threadIdx.x == 0) { stats[5] = (float)*m; stats[6] = 0.f; stats[7] = 0.f; }
+}
+
+}  // namespace gac
