@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the GAC train step (BASELINE.json): sampled (s,a) pairs/s and train steps/s
+at HalfCheetah dims (S=17, A=6, B=256 states per GPU, K=64 samples) on 1/2/4/8 B200.
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+  python bench.py --impl reference ...                   # reference-equivalent CPU path
+
+A "step" is one full GACAgent.train_one_step (agent.py:121-168): Critic.train, Value.train
+(P sampler rows), the advantage filter (P sampler rows + 2P critic rows), IQNActor.train on the
+M selected rows (supervised forward + BPTT), Adam x4, Polyak x3.  Data is synthetic
+(SURVEY.md §8d); data-parallel ranks each own B states (weak scaling) and exchange one SUM
+all-reduce of the gradient arena per step.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (S, A, B per rank, K)
+    "halfcheetah": (17, 6, 256, 64),      # BASELINE.json configs[1] -- the metric's config
+    "pendulum": (3, 1, 64, 32),           # configs[0]
+    "humanoid": (376, 17, 256, 128),      # configs[2]
+    "ant": (111, 8, 16384, 256),          # configs[3]: B is the GLOBAL batch, split over ranks (strong scaling)
+}
+METRIC = "GAC sampled (s,a) pairs/s through full train steps (HalfCheetah dims; steps/s in steps_per_s)"
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic work: F_min counts the exact hoists, F_ref the reference as written
+# ---------------------------------------------------------------------------------------------
+def step_flops(S, A, B, K, M):
+    P = B * K
+    samp_ref = 2 * (400 * S + 1651600 * A)
+    samp_min = 2 * ((400 * S + 480000) / K + 1171600 * A - 480000)
+    critic = 2 * 2 * ((S + A) * 400 + 120300)
+    sup_fwd = 2 * (400 * S + A * (2 * 25600 + 1440000 + 160400))
+    f_ref = 2 * P * samp_ref + 3 * P * critic + 3 * M * sup_fwd
+    f_min = 2 * P * samp_min + 3 * P * critic + 3 * M * sup_fwd
+    return f_ref, f_min
+
+
+def peaks():
+    """Measured roofline denominators (driver-written MEASURED_PEAKS.json) or the stated fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (profiling recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [ln.split(",") for ln in open(self.f.name).read().strip().splitlines() if ln.count(",") >= 6]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = [float(r[0]) for r in rows]
+        out["sm_mhz"] = float(np.median(sm))
+        out["sm_max_mhz"] = float(rows[0][1])
+        out["power_w_max"] = max(float(r[2]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out["reasons"] = [n for i, n in enumerate(names) if any("Active" in r[3 + i] and "Not" not in r[3 + i] for r in rows)]
+        out["samples"] = len(rows)
+        return out
+
+
+def synth(S, A, B, K, seed):
+    from oracle import gac_oracle as O   # bench: synthetic-input recipe shared with the tests (not on the timed path)
+    rng = np.random.default_rng(seed)
+    return O.make_batch(rng, S, A, B), O.make_noise(rng, A, B, K)
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference-equivalent CPU path (TensorFlow is not installable -- DESIGN.md)
+# ---------------------------------------------------------------------------------------------
+def time_cpu_reference(S, A, B, K, steps, warmup, budget_s=None):
+    import torch
+    from oracle import gac_oracle as O
+    from oracle import torch_ref as T
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(1)
+    nets = O.make_agent(rng, S, A)
+    nets["target_value"]["b2"] = nets["target_value"]["b2"] - np.float32(0.0)
+    agent = T.TorchGAC(nets, A, K)
+    batch, noise = O.make_batch(rng, S, A, B), O.make_noise(rng, A, B, K)
+    for _ in range(warmup):
+        agent.train_one_step(batch, noise)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        agent.train_one_step(batch, noise)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return dt / done, done, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    S, A, B, K = CONFIGS[args.config]
+    Bs = min(B, 32)                       # bounded sample: 32 of the 256 states per step, same K
+    sec, done, cores = time_cpu_reference(S, A, Bs, K, args.steps, args.warmup)
+    pairs = 2 * Bs * K / sec
+    line = {"impl": "reference", "metric": METRIC, "value": pairs, "unit": "pairs/s", "n_gpus": args.gpus, "steps": done,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3 * (B / Bs), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: S={S} A={A} B={B} K={K} full GAC train step",
+                       "note": "reference-equivalent CPU path (torch-CPU eager op-for-op mirror; TensorFlow not installable)"},
+            "steps_per_s": 1.0 / (sec * (B / Bs)),
+            "cpu_baseline": {"value": pairs, "unit": "pairs/s", "cores": cores, "kind": "port",
+                             "sample": f"{done} full train steps on {Bs} of the {B} states (K={K}); ms_per_step scaled x{B // Bs} to the full batch"},
+            "e2e": {"value": pairs, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    import __graft_entry__ as ge
+    ge.build()
+    from dpo_replication_b200 import GACAgent
+
+    S, A, B, K = CONFIGS[args.config]
+    scaling = "weak"
+    if args.config == "ant":              # strong scaling on the fixed global batch
+        B, scaling = B // world, "strong"
+    P = B * K
+    torch.manual_seed(1234)               # identical replicas
+    agent = GACAgent(A, S, action_samples=K, batch_size=B, device=dev, engine=args.engine, chunk_rows=args.chunk_rows)
+    batch_np, noise_np = synth(S, A, B, K, 1000 * 2 + rank)
+    to_dev = lambda d: {k: torch.from_numpy(v).to(dev) for k, v in d.items()}
+    batch, noise = to_dev(batch_np), to_dev(noise_np)
+
+    # centre V_target so that about half of the 2P candidates have positive advantage
+    taps = dict(q_out=torch.zeros(2 * P, device=dev), v_out=torch.zeros(2 * P, device=dev))
+    agent.train_on_batch(batch, noise, taps)
+    shift = (taps["q_out"] - taps["v_out"]).median()
+    if world > 1:
+        dist.all_reduce(shift)
+        shift /= world
+    for buf in (agent.arena.target, agent.arena.online):
+        agent.arena.view(buf, "value.b2").add_(shift)
+
+    m_log = torch.zeros(args.steps + args.warmup + 1, device=dev)
+
+    def step(i):
+        agent.train_on_batch(batch, noise)
+        m_log[i].copy_(agent.arena.stats[5])
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    launches0 = agent.engine.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    launches = agent.engine.launch_count() - launches0
+    clk = clocks.stop() if clocks else None
+    m_mean = float(m_log[args.warmup:args.warmup + args.steps].mean().item())
+
+    # ---- end to end: host (pinned) replay batch -> H2D -> public API step -> D2H stats, every step ----
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in batch_np.items()}
+    stats_host = torch.zeros(8).pin_memory()
+    h2d = sum(v.numel() * 4 for v in pinned.values())
+
+    def e2e_step():
+        b = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        agent.train_on_batch(b)                              # RNG drawn on device, as the reference's tf.random does
+        stats_host.copy_(agent.arena.stats, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2.item()) / args.steps
+
+    # ---- roofline of the dominant kernel: the tcgen05 3xTF32 GEMM at the step's dominant shape
+    # (rows x 400) * (400 x 1200) with rows = 2P, timed live with CUDA events on the same stream ----
+    roof = None
+    if rank == 0:
+        eng = agent.engine
+        rows = 2 * P
+        a = torch.randn(rows, 400, device=dev)
+        w = torch.randn(400, 1200, device=dev)
+        n_rep = 20
+        for _ in range(3):
+            eng.gemm(a, w, engine=args.engine)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n_rep):
+            eng.gemm(a, w, engine=args.engine)
+        e1.record()
+        torch.cuda.synchronize()
+        kms = e0.elapsed_time(e1) / n_rep
+        pk = peaks()
+        tf32_peak = pk["bf16_burst"] / 2.0
+        peak = tf32_peak / 3.0 if args.engine == 0 else 74.0
+        ach = 2.0 * rows * 400 * 1200 / (kms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<3xTF32>" if args.engine == 0 else "gemm_simt_kernel",
+                "shape": f"({rows}x400)*(400x1200)", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": None, "ms_per_launch": kms,
+                "peak_source": (f"{pk['source']} bf16 burst {pk['bf16_burst']} TF/s / 2 (TF32) / 3 (3xTF32 passes)" if args.engine == 0
+                                else "fp32 SIMT: 148 SM x 128 FMA x 2 x 1.965 GHz")}
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        pairs_per_step = 2 * P * world
+        value = pairs_per_step / (ms_per_step * 1e-3)
+        f_ref, f_min = step_flops(S, A, B, K, m_mean)
+        pk = peaks()
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            Bs = min(B, 32)
+            sec, done, cores = time_cpu_reference(S, A, Bs, K, steps=20, warmup=1, budget_s=15.0)
+            cpu = {"value": 2 * Bs * K / sec, "unit": "pairs/s", "cores": cores, "kind": "port",
+                   "sample": f"{done} full train steps of the reference-equivalent torch-CPU path on {Bs} of the {B} states (K={K})"}
+        line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{args.config}: S={S} A={A} B={B}/GPU K={K} full GAC train step (AIQN actor, twin critic, value)",
+                           "global_batch": B * world, "action_samples": K, "parallelism": f"dp{world}",
+                           "selected_rows_mean": m_mean, "candidate_rows": 2 * P,
+                           "l2": "per-step working set (activations saved for BPTT) is GBs >> 126 MB L2; no flush needed",
+                           "engine": "tcgen05 3xTF32" if args.engine == 0 else "SIMT fp32"},
+                "steps_per_s": 1e3 / ms_per_step,
+                "step_flops": {"algorithmic_gflop_min": f_min / 1e9, "as_written_gflop": f_ref / 1e9,
+                               "achieved_tflops_min": f_min * world / (ms_per_step * 1e-3) / 1e12,
+                               "frac_of_3xtf32_peak": f_min / (ms_per_step * 1e-3) / 1e12 / (pk["bf16_sustained"] / 6.0)},
+                "clocks": clk, "gpu_launches": int(launches),
+                "e2e": {"value": pairs_per_step / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms},
+                "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="halfcheetah", choices=sorted(CONFIGS))
+    ap.add_argument("--engine", type=int, default=0, help="0 = tcgen05 3xTF32 GEMMs, 1 = SIMT fp32")
+    ap.add_argument("--chunk-rows", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

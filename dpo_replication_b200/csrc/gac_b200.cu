@@ -78,7 +78,7 @@ struct gac_ctx {
   int *sidx3, *pos, *sidx_sel, *blk_count, *m_dev, *rows_c, *skip;
   int64_t* idx_sel;
   // actor-train chunk (step-major [A][Mc][w])
-  float *a_se_u, *a_sx_u, *a_dsx_u, *a_dse_u;
+  float *a_se_u, *a_sx_u, *a_dsx_u, *a_dse_u, *a_states; int* a_sidx;
   float *ca, *cn, *a_ae, *mx, *dmh, *zs, *rs, *cs, *mhh, *hall, *ne, *au, *ay1, *dy1p, *du, *dne, *dhu, *dhc0, *dhc1, *dop;
   float *pred_c, *dpred_c;
   const int* bwd_sidx; const float* bwd_states; int bwd_nstates; const int* bwd_drows;  // saved by supervised_fwd
@@ -141,6 +141,7 @@ size_t partition(gac_ctx* c, void* ws) {
   c->skip = b.take<int>(GAC_NNETS); c->idx_sel = b.take<int64_t>(2 * P);
   c->a_se_u = b.take<float>((size_t)c->NUa * GAC_E); c->a_sx_u = b.take<float>((size_t)c->NUa * GAC_G);
   c->a_dsx_u = b.take<float>((size_t)c->NUa * GAC_G); c->a_dse_u = b.take<float>((size_t)c->NUa * GAC_E);
+  c->a_states = b.take<float>((size_t)c->NUa * S); c->a_sidx = b.take<int>(Mc);
   c->ca = b.take<float>(AM * GAC_NB); c->cn = b.take<float>(AM * GAC_NB);
   c->a_ae = b.take<float>(AM * GAC_E); c->mx = b.take<float>(AM * GAC_G); c->dmh = b.take<float>(AM * GAC_G);
   c->zs = b.take<float>(AM * GAC_E); c->rs = b.take<float>(AM * GAC_E); c->cs = b.take<float>(AM * GAC_E);
@@ -358,7 +359,11 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
   else GAC_CUDA(cudaMemcpyAsync(live, &max_rows, sizeof(int), cudaMemcpyHostToDevice, st));
   const RowValid rv{live, Mc};
   const long long AM = (long long)A * Mc;
-  c->bwd_sidx = sidx; c->bwd_states = states_u; c->bwd_nstates = n_states; c->bwd_drows = live;
+  // the backward needs the row->state map and the unique states: keep private copies (the
+  // caller's buffers may be gone by then)
+  GAC_CUDA(cudaMemcpyAsync(c->a_sidx, sidx, (size_t)max_rows * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  GAC_CUDA(cudaMemcpyAsync(c->a_states, states_u, (size_t)n_states * c->cfg.S * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  c->bwd_sidx = c->a_sidx; c->bwd_states = c->a_states; c->bwd_nstates = n_states; c->bwd_drows = live;
   GAC_TRY(state_prep(c, actor, states_u, n_states, c->a_se_u, c->a_sx_u));
   cos_basis_seq_kernel<<<(unsigned)cdiv64(AM * GAC_NB, 256), 256, 0, st>>>(teacher, taus, A, Mc, c->ca, c->cn, live);
   LAUNCHED(c, "cos_basis_seq");
