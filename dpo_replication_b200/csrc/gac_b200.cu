@@ -172,15 +172,27 @@ int run_gemm(gac_ctx* c, GemmArgs g) {
   if (g.M <= 0 || g.N <= 0) return GAC_OK;
   const bool tc = c->cfg.engine == 0 && tc_gemm_supported(g);
   if (g.valid_on_k || g.K >= 8192) {
-    const int tiles = cdiv(g.M, 128) * cdiv(g.N, 128);
-    int splits = (4 * 148) / tiles;
+    // weight-gradient shape: small output, long reduction over activation rows => split-K.
+    // On the tensor-core engine compute the transposed product (dY^T X) so that the LONG weight
+    // dimension fills the 128-row MMA tile and the TMEM-lane-per-thread epilogue stores coalesce.
+    if (tc && g.transA && !g.transB && !g.transC && g.ldc == g.N && g.N >= g.M) {
+      GemmArgs w = g;
+      w.M = g.N; w.N = g.M;
+      w.A = g.B; w.lda = g.ldb; w.transA = 1;      // A'(m', k) = dY[k][m']
+      w.B = g.A; w.ldb = g.lda; w.transB = 0;      // B'(k, n') = X[k][n']
+      w.transC = 1;                                // C'(m', n') -> dW[n'][m'],  ldc = original N
+      g = w;
+    }
+    const int tiles = tc ? cdiv(g.M, tc::BM) * cdiv(g.N, tc::plan_for(g.N).bn) : cdiv(g.M, 128) * cdiv(g.N, 128);
+    int splits = (2 * 148) / tiles;
     if (splits > c->max_splits) splits = c->max_splits;
     if (splits > g.K / 512) splits = g.K / 512;
     if ((size_t)g.M * g.N > (size_t)GAC_E * GAC_G) splits = 1;
     if (splits > 1) {
-      if (g.ldc != g.N) return fail(GAC_ERR_INVALID, "split-K destination must be dense");
+      const bool dense = g.transC ? (g.ldc == g.M) : (g.ldc == g.N);
+      if (!dense) return fail(GAC_ERR_INVALID, "split-K destination must be dense");
       GemmArgs p = g;
-      p.C = c->spart; p.ldc = g.N; p.splitk = splits; p.split_stride = (long long)g.M * g.N;
+      p.C = c->spart; p.splitk = splits; p.split_stride = (long long)g.M * g.N;
       p.bias = nullptr; p.add = nullptr; p.mul = nullptr; p.gate = nullptr; p.act = ACT_NONE; p.accumulate = 0;
       if (tc) GAC_CUDA(launch_gemm_tc(p, st)); else GAC_CUDA(launch_gemm_simt(p, st));
       c->launches++;

@@ -55,7 +55,7 @@ struct GemmArgs {
   int M, N, K;
   const float* A; int lda; int transA;  // transA: A(m,k) = A[k*lda + m]
   const float* B; int ldb; int transB;  // transB: B(k,n) = B[n*ldb + k]
-  float* C; int ldc;
+  float* C; int ldc; int transC;        // transC: C(m,n) stored at C[n*ldc + m]
   const float* bias;
   const float* add; int ldadd; const int* addidx;
   const float* mul; int ldmul;
@@ -87,7 +87,7 @@ __device__ __forceinline__ float gemm_epilogue(const GemmArgs& g, float acc, int
   else if (g.act == ACT_LRELU2) v = lrelu_f(lrelu_f(v, 0.01f), 0.2f);
   if (g.mul) v *= g.mul[(size_t)m * g.ldmul + n];
   if (g.gate) v *= (g.gate[(size_t)m * g.ldgate + n] > 0.f ? 1.f : g.gate_alpha);
-  if (g.accumulate) v += g.C[(size_t)m * g.ldc + n];
+  if (g.accumulate) v += g.transC ? g.C[(size_t)n * g.ldc + m] : g.C[(size_t)m * g.ldc + n];
   return v;
 }
 

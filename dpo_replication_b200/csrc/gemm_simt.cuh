@@ -106,8 +106,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs g) {
     for (int j = 0; j < 8; ++j) {
       const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
       if (n >= g.N) continue;
-      if (g.splitk > 1) Cout[(size_t)m * g.ldc + n] = acc[i][j];
-      else g.C[(size_t)m * g.ldc + n] = gemm_epilogue(g, acc[i][j], m, n);
+      const size_t ci = g.transC ? (size_t)n * g.ldc + m : (size_t)m * g.ldc + n;
+      if (g.splitk > 1) Cout[ci] = acc[i][j];
+      else g.C[ci] = gemm_epilogue(g, acc[i][j], m, n);
     }
   }
 }

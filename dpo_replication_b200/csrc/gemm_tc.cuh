@@ -11,7 +11,9 @@
 // cannot meet.  Roofline for this engine = measured TF32 dense peak / 3.
 //
 // Structure (one 128 x bn output tile per CTA, bn a multiple of 16 <= 256):
-//   warps 0-7  loaders, then epilogue.  They read the fp32 operands straight from their natural
+//   warps 0-7  loaders (two groups of 4 warps alternate K blocks so one group's global-load
+//              latency overlaps the other's smem stores), then epilogue.  They read the fp32
+//              operands straight from their natural
 //              row-major arena / activation layouts (either orientation: the transposition
 //              needed by weight-gradient contractions happens here, in registers), split every
 //              value into hi/lo and store both into K-major, 128B-swizzled smem tiles that
@@ -102,47 +104,106 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
-// Stage `rows` x 32 fp32 values (hi and lo tiles) for one operand.
-//   TRANS = false: element (r, k) = src[(row0 + r) * ld + k0 + k]   (k contiguous in memory)
-//   TRANS = true : element (r, k) = src[(k0 + k) * ld + row0 + r]   (r contiguous in memory)
-// Out-of-range / dead entries are zero.  Each thread owns 16-byte chunks (4 consecutive k of one
-// row); chunk c of row r lands at r*128 + ((c ^ (r & 7)) << 4): the 128B swizzle UMMA expects.
-template <bool TRANS, bool VEC>
-__device__ __forceinline__ void stage_operand(const float* __restrict__ src, int ld, int row0, int row_end, int rows, int k0,
-                                              int kend, uint32_t s_hi, uint32_t s_lo, int tid, bool k_dyn, bool r_dyn, int seg,
-                                              int nvalid) {
-  const int nchunks = rows * 8;
-  for (int q = tid; q < nchunks; q += LOADER_WARPS * 32) {
-    int r, c;
-    if (!TRANS) { r = q >> 3; c = q & 7; } else { r = q % rows; c = q / rows; }
-    const int gr = row0 + r, gk = k0 + 4 * c;
-    float x[4] = {0.f, 0.f, 0.f, 0.f};
-    bool row_ok = gr < row_end;
-    if (row_ok && r_dyn) row_ok = (gr % seg) < nvalid;
-    if (row_ok) {
-      if (!TRANS && VEC && gk + 3 < kend && !k_dyn) {
-        const float4 t = *reinterpret_cast<const float4*>(src + (size_t)gr * ld + gk);
-        x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int kk = gk + j;
-          bool ok = kk < kend;
-          if (ok && k_dyn) ok = (kk % seg) < nvalid;
-          if (ok) x[j] = TRANS ? src[(size_t)kk * ld + gr] : src[(size_t)gr * ld + kk];
-        }
-      }
+// ---- K-block schedule ---------------------------------------------------------------------
+// Non-dynamic GEMMs walk [kbeg, kend) in 32-wide blocks.  Weight-gradient GEMMs reduce over
+// activation rows laid out step-major as nseg segments of seg rows of which only the first
+// `nvalid` are live (M is data dependent and stays on the device): only LIVE blocks are
+// enumerated and split-K partitions the live blocks, so dead rows cost neither loads nor MMAs.
+struct KMap {
+  int dyn, kbeg, kend, seg, bps, nvalid, ibeg, nkb;
+};
+__device__ __forceinline__ KMap make_kmap(const GemmArgs& g, int nvalid, int split) {
+  KMap km;
+  km.dyn = (g.dyn_rows && g.valid_on_k) ? 1 : 0;
+  km.seg = g.seg_rows; km.nvalid = nvalid; km.kbeg = 0; km.kend = g.K; km.bps = 0; km.ibeg = 0;
+  if (km.dyn) {
+    const int nv = min(nvalid, g.seg_rows);
+    km.nvalid = nv;
+    km.bps = (nv + BK - 1) / BK;
+    const int total = (g.K / g.seg_rows) * km.bps;
+    const int per = g.splitk > 1 ? (total + g.splitk - 1) / g.splitk : total;
+    km.ibeg = min(total, split * per);
+    km.nkb = min(total, km.ibeg + per) - km.ibeg;
+  } else {
+    if (g.splitk > 1) {
+      const int per = ((g.K + g.splitk - 1) / g.splitk + BK - 1) / BK * BK;
+      km.kbeg = min(g.K, split * per);
+      km.kend = min(g.K, km.kbeg + per);
     }
-    float h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) split_tf32(x[j], h[j], l[j]);
-    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(s_hi + off), "f"(h[0]), "f"(h[1]), "f"(h[2]), "f"(h[3]) : "memory");
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "f"(l[0]), "f"(l[1]), "f"(l[2]), "f"(l[3]) : "memory");
+    km.nkb = (km.kend - km.kbeg + BK - 1) / BK;
+  }
+  return km;
+}
+__device__ __forceinline__ void kmap_get(const KMap& km, int kb, int& k0, int& live) {
+  if (km.dyn) {
+    const int i = km.ibeg + kb;
+    const int sgm = i / km.bps, blk = i - sgm * km.bps;
+    k0 = sgm * km.seg + blk * BK;
+    live = min(BK, km.nvalid - blk * BK);
+  } else {
+    k0 = km.kbeg + kb * BK;
+    live = min(BK, km.kend - k0);
   }
 }
 
-// TB here means "B is stored (N, K) row-major" (g.transB); !TB is the natural Keras (K, N).
+// ---- operand staging ------------------------------------------------------------------------
+// One loader group (128 threads) stages a rows x 32 fp32 tile: global -> registers (all loads
+// issued back to back so their latencies overlap), then registers -> hi/lo split -> smem.
+//   TRANS = false: element (r, k) = src[(row0 + r) * ld + k0 + k]   (k contiguous in memory)
+//   TRANS = true : element (r, k) = src[(k0 + k) * ld + row0 + r]   (r contiguous in memory)
+// Thread t owns 16-byte chunks q = t + 128 i (4 consecutive k of one row); chunk c of row r
+// lands at r*128 + ((c ^ (r & 7)) << 4): the 128-byte swizzle the UMMA descriptor declares.
+constexpr int GROUP = 128;
+template <bool TRANS>
+__device__ __forceinline__ void chunk_rc(int q, int rows, int& r, int& c) {
+  if (!TRANS) { r = q >> 3; c = q & 7; } else { c = q / rows; r = q - c * rows; }
+}
+template <bool TRANS, bool VEC, int NCH>
+__device__ __forceinline__ void load_operand(float (&x)[NCH][4], const float* __restrict__ src, int ld, int row0, int row_end,
+                                             int rows, int k0, int live, int t) {
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    x[i][0] = x[i][1] = x[i][2] = x[i][3] = 0.f;
+    const int q = t + GROUP * i;
+    if (q >= rows * 8) continue;
+    int r, c;
+    chunk_rc<TRANS>(q, rows, r, c);
+    const int gr = row0 + r, kc = 4 * c;
+    if (gr >= row_end || kc >= live) continue;
+    if (!TRANS) {
+      const float* p = src + (size_t)gr * ld + k0 + kc;
+      if (VEC && kc + 3 < live) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        x[i][0] = v.x; x[i][1] = v.y; x[i][2] = v.z; x[i][3] = v.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (kc + j < live) x[i][j] = p[j];
+      }
+    } else {
+      const float* p = src + (size_t)(k0 + kc) * ld + gr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (kc + j < live) x[i][j] = p[(size_t)j * ld];
+    }
+  }
+}
+template <bool TRANS, int NCH>
+__device__ __forceinline__ void store_operand(const float (&x)[NCH][4], uint32_t s_hi, uint32_t s_lo, int rows, int t) {
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int q = t + GROUP * i;
+    if (q >= rows * 8) continue;
+    int r, c;
+    chunk_rc<TRANS>(q, rows, r, c);
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_tf32(x[i][j], h[j], l[j]);
+    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(s_hi + off), "f"(h[0]), "f"(h[1]), "f"(h[2]), "f"(h[3]));
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "f"(l[0]), "f"(l[1]), "f"(l[2]), "f"(l[3]));
+  }
+}
+
+// TB means "B is stored (N, K) row-major" (g.transB); !TB is the natural Keras (K, N).
 template <bool TA, bool TB, bool VEC>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, int bn, int stages, int tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
@@ -152,21 +213,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * bn;
   const int nvalid = g.dyn_rows ? *g.dyn_rows : 0x7fffffff;
-  if (!g.valid_on_k && g.dyn_rows && (m0 % g.seg_rows) >= nvalid) return;   // dead tile (uniform per CTA)
+  const bool r_dyn = g.dyn_rows && !g.valid_on_k;
+  if (r_dyn && (m0 % g.seg_rows) >= nvalid) return;   // dead tile (uniform per CTA)
+  // rows of this tile that are live (forward / dgrad with a device-side row count)
+  const int m_end = r_dyn ? min(g.M, m0 - (m0 % g.seg_rows) + nvalid) : g.M;
 
-  int kbeg = 0, kend = g.K;
-  if (g.splitk > 1) {
-    const int per = ((g.K + g.splitk - 1) / g.splitk + BK - 1) / BK * BK;
-    kbeg = min(g.K, (int)blockIdx.z * per);
-    kend = min(g.K, kbeg + per);
-  }
-  const int nkb = (kend - kbeg + BK - 1) / BK;
+  const KMap km = make_kmap(g, nvalid, blockIdx.z);
+  const int nkb = km.nkb;
 
   const uint32_t stage_bytes = 2 * A_TILE_BYTES + 2 * (uint32_t)bn * 128u;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
   if (tid == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&bar_full[s]), LOADER_WARPS); mbar_init(smem_u32(&bar_empty[s]), 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&bar_full[s]), LOADER_WARPS / 2); mbar_init(smem_u32(&bar_empty[s]), 1); }
     mbar_init(smem_u32(&bar_accum), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -180,18 +239,21 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
   const uint32_t tmem_d = tmem_slot;
 
   if (warp < LOADER_WARPS) {
-    // ------------------------------ loaders ------------------------------
-    const bool k_dyn = g.dyn_rows && g.valid_on_k, r_dyn = g.dyn_rows && !g.valid_on_k;
-    for (int kb = 0; kb < nkb; ++kb) {
+    // ------------------------------ loaders: two groups alternate K blocks ------------------------------
+    const int grp = warp >> 2, t = tid & (GROUP - 1);
+    for (int kb = grp; kb < nkb; kb += 2) {
+      int k0, live;
+      kmap_get(km, kb, k0, live);
+      float xa[8][4], xb[16][4];
+      load_operand<TA, VEC, 8>(xa, g.A, g.lda, m0, m_end, BM, k0, live, t);
+      // B tile rows are output columns n; element (n, k) = B(k, n)
+      load_operand<!TB, VEC, 16>(xb, g.B, g.ldb, n0, g.N, bn, k0, live, t);
       const int s = kb % stages;
       const uint32_t ph = (uint32_t)(kb / stages) & 1u;
       mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
       const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
-      const int k0 = kbeg + kb * BK;
-      stage_operand<TA, VEC>(g.A, g.lda, m0, g.M, BM, k0, kend, sa, sa + A_TILE_BYTES, tid, k_dyn, r_dyn, g.seg_rows, nvalid);
-      // B tile rows are output columns n; element (n, k) = B(k, n)
-      stage_operand<!TB, VEC>(g.B, g.ldb, n0, g.N, bn, k0, kend, sa + 2 * A_TILE_BYTES, sa + 2 * A_TILE_BYTES + (uint32_t)bn * 128u, tid,
-                              k_dyn, false, g.seg_rows, nvalid);
+      store_operand<TA, 8>(xa, sa, sa + A_TILE_BYTES, BM, t);
+      store_operand<!TB, 16>(xb, sa + 2 * A_TILE_BYTES, sa + 2 * A_TILE_BYTES + (uint32_t)bn * 128u, bn, t);
       fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
@@ -203,10 +265,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
     }
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
     const int m = m0 + quarter * 32 + lane;
-    bool m_ok = m < g.M;
-    if (m_ok && g.dyn_rows && !g.valid_on_k) m_ok = (m % g.seg_rows) < nvalid;
+    const bool m_ok = m < m_end;
     float* Cout = g.C + (g.splitk > 1 ? (size_t)blockIdx.z * g.split_stride : 0);
-    const bool vec_st = VEC && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0) && (n0 % 4 == 0);
+    const bool vec_st = VEC && !g.transC && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0) && (n0 % 4 == 0);
     for (int ci = warp >> 2; ci < bn / 16; ci += 2) {
       float v[16];
       if (nkb > 0) {
@@ -227,14 +288,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
         for (int j = 0; j < 16; ++j)
           if (nb + j < g.N) v[j] = gemm_epilogue(g, v[j], m, nb + j);
       }
-      float* crow = Cout + (size_t)m * g.ldc + nb;
-      if (vec_st && nb + 15 < g.N) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
+      if (g.transC) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (nb + j < g.N) crow[j] = v[j];
+          if (nb + j < g.N) Cout[(size_t)(nb + j) * g.ldc + m] = v[j];     // lanes = consecutive m: coalesced
+      } else {
+        float* crow = Cout + (size_t)m * g.ldc + nb;
+        if (vec_st && nb + 15 < g.N) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < g.N) crow[j] = v[j];
+        }
       }
     }
   } else {
@@ -244,13 +311,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % stages;
         const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+        int k0, live;
+        kmap_get(km, kb, k0, live);
         mbar_wait(smem_u32(&bar_full[s]), ph);
         tc_fence_after();
         const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
         const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
         const uint64_t b_hi = make_desc(sa + 2 * A_TILE_BYTES), b_lo = make_desc(sa + 2 * A_TILE_BYTES + (uint32_t)bn * 128u);
-        const int k0 = kbeg + kb * BK;
-        const int ksteps = min(4, (kend - k0 + 7) / 8);
+        const int ksteps = (live + 7) / 8;
         for (int j = 0; j < ksteps; ++j) {
           const uint64_t adv = (uint64_t)(j * 2);            // +32 bytes (8 tf32) in the >>4 address field
           const uint32_t acc = (kb | j) ? 1u : 0u;
