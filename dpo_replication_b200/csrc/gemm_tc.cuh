@@ -154,35 +154,49 @@ __device__ __forceinline__ void kmap_get(const KMap& km, int kb, int& k0, int& l
 // Thread t owns 16-byte chunks q = t + 128 i (4 consecutive k of one row); chunk c of row r
 // lands at r*128 + ((c ^ (r & 7)) << 4): the 128-byte swizzle the UMMA descriptor declares.
 constexpr int GROUP = 128;
+// Chunk ownership of thread t (t in [0,128)), chosen so that no per-chunk division is needed and
+// both global loads and swizzled smem stores are conflict-free / coalesced:
+//   !TRANS: chunk i -> row (t >> 3) + 16 i, 16-byte column c = t & 7     (8 lanes = one 128-B row)
+//    TRANS: chunk i -> row t + 128 (i >> 3), column c = i & 7            (32 lanes = 32 consecutive rows)
 template <bool TRANS>
-__device__ __forceinline__ void chunk_rc(int q, int rows, int& r, int& c) {
-  if (!TRANS) { r = q >> 3; c = q & 7; } else { c = q / rows; r = q - c * rows; }
+__device__ __forceinline__ void chunk_rc(int i, int t, int& r, int& c) {
+  if (!TRANS) { r = (t >> 3) + 16 * i; c = t & 7; } else { r = t + GROUP * (i >> 3); c = i & 7; }
 }
 template <bool TRANS, bool VEC, int NCH>
 __device__ __forceinline__ void load_operand(float (&x)[NCH][4], const float* __restrict__ src, int ld, int row0, int row_end,
                                              int rows, int k0, int live, int t) {
+  if (!TRANS) {
+    const int c = t & 7, kc = 4 * c;
+    const float* p0 = src + (size_t)(row0 + (t >> 3)) * ld + k0 + kc;
+    const bool full = VEC && (kc + 3 < live);
 #pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-    x[i][0] = x[i][1] = x[i][2] = x[i][3] = 0.f;
-    const int q = t + GROUP * i;
-    if (q >= rows * 8) continue;
-    int r, c;
-    chunk_rc<TRANS>(q, rows, r, c);
-    const int gr = row0 + r, kc = 4 * c;
-    if (gr >= row_end || kc >= live) continue;
-    if (!TRANS) {
-      const float* p = src + (size_t)gr * ld + k0 + kc;
-      if (VEC && kc + 3 < live) {
-        const float4 v = *reinterpret_cast<const float4*>(p);
-        x[i][0] = v.x; x[i][1] = v.y; x[i][2] = v.z; x[i][3] = v.w;
+    for (int i = 0; i < NCH; ++i) {
+      const int r = (t >> 3) + 16 * i;
+      const float* p = p0 + (size_t)(16 * i) * ld;
+      x[i][0] = x[i][1] = x[i][2] = x[i][3] = 0.f;
+      if (r < rows && row0 + r < row_end) {
+        if (full) {
+          const float4 v = *reinterpret_cast<const float4*>(p);
+          x[i][0] = v.x; x[i][1] = v.y; x[i][2] = v.z; x[i][3] = v.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (kc + j < live) x[i][j] = p[j];
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int ii = 0; ii < NCH / 8; ++ii) {
+      const int r = t + GROUP * ii;
+      const bool ok = r < rows && row0 + r < row_end;
+      const float* p = src + (size_t)k0 * ld + row0 + r;
+      if (ok && live == BK) {
+#pragma unroll
+        for (int k = 0; k < BK; ++k) x[ii * 8 + (k >> 2)][k & 3] = p[(size_t)k * ld];
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (kc + j < live) x[i][j] = p[j];
+        for (int k = 0; k < BK; ++k) x[ii * 8 + (k >> 2)][k & 3] = (ok && k < live) ? p[(size_t)k * ld] : 0.f;
       }
-    } else {
-      const float* p = src + (size_t)(k0 + kc) * ld + gr;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (kc + j < live) x[i][j] = p[(size_t)j * ld];
     }
   }
 }
@@ -190,10 +204,9 @@ template <bool TRANS, int NCH>
 __device__ __forceinline__ void store_operand(const float (&x)[NCH][4], uint32_t s_hi, uint32_t s_lo, int rows, int t) {
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
-    const int q = t + GROUP * i;
-    if (q >= rows * 8) continue;
     int r, c;
-    chunk_rc<TRANS>(q, rows, r, c);
+    chunk_rc<TRANS>(i, t, r, c);
+    if (r >= rows) continue;
     float h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) split_tf32(x[i][j], h[j], l[j]);
