@@ -68,6 +68,7 @@ struct gac_ctx {
   cudaStream_t stream;
   int64_t launches;
   int P, Mc, nchunks, Rs, NUs, NUa, max_splits;
+  const unsigned char* pk[16];   // packed pointer per slot (valid for the current call)
   // sampler / critic scratch (Rs rows per pass)
   float *se_u, *sx_u, *cosb, *ae, *mxa, *mh, *hA, *hB, *u, *y1;
   float *cx, *ch0a, *ch0b, *ch1a, *ch1b;
@@ -83,6 +84,7 @@ struct gac_ctx {
   float *pred_c, *dpred_c;
   const int* bwd_sidx; const float* bwd_states; int bwd_nstates; const int* bwd_drows;  // saved by supervised_fwd
   float *spart, *cpart;
+  unsigned char* pack[16]; size_t pack_bytes;   // pre-split / pre-swizzled weight tiles (tc::pack_b_kernel)
 };
 
 namespace {
@@ -153,6 +155,10 @@ size_t partition(gac_ctx* c, void* ws) {
   c->spart = b.take<float>((size_t)c->max_splits * GAC_E * GAC_G);
   const size_t maxrows = AM > Rs ? AM : Rs;
   c->cpart = b.take<float>(((maxrows + COLSUM_ROWS - 1) / COLSUM_ROWS + 1) * GAC_G);
+  c->pack_bytes = tc_packed_bytes(GAC_E, GAC_G);
+  if (tc_packed_bytes(GAC_G, GAC_E) > c->pack_bytes) c->pack_bytes = tc_packed_bytes(GAC_G, GAC_E);
+  c->pack_bytes = (c->pack_bytes + 1023) & ~(size_t)1023;
+  for (int i = 0; i < 16; ++i) c->pack[i] = b.take<unsigned char>(c->pack_bytes);
   return (b.off + 255) & ~(size_t)255;
 }
 
@@ -163,6 +169,16 @@ inline const float* var(const gac_ctx* c, const float* net_base, int net, int v)
 }
 inline float* var(const gac_ctx* c, float* net_base, int net, int v) {
   return net_base + (c->lay.offsets[v] - c->lay.net_begin[net]);
+}
+
+// Pre-split + pre-swizzle a weight matrix for the tensor-core engine (nullptr on the SIMT engine).
+enum { PK_T_WA = 0, PK_T_KXA, PK_T_U, PK_T_WN, PK_T_W1, PK_O_WA, PK_O_KXA, PK_O_U, PK_O_WN, PK_O_W1, PK_O_W1T, PK_O_UT, PK_O_KXAT,
+       PK_C_F1, PK_C_F2 };
+const unsigned char* pack_w(gac_ctx* c, int slot, const float* W, int ld, int K, int N, int transB) {
+  if (c->cfg.engine != 0 || K < 32 || N < 32 || tc_packed_bytes(K, N) > c->pack_bytes) return nullptr;
+  if (tc_pack_b(W, ld, transB, K, N, c->pack[slot], c->stream) != cudaSuccess) return nullptr;
+  c->launches++;
+  return c->pack[slot];
 }
 
 // GEMM dispatch: tcgen05 3xTF32 engine where the shape qualifies, else SIMT; split-K for the
@@ -218,14 +234,14 @@ int run_colsum(gac_ctx* c, const float* X, int ldx, const float* w, int N, long 
 }
 
 // FNN forward on `rows` rows of x (rows, n_in): h0, h1 saved, out (rows) = linear head
-int fnn_forward(gac_ctx* c, const float* fnn, int n_in, const float* x, int rows, float* h0, float* h1) {
+int fnn_forward(gac_ctx* c, const float* fnn, int n_in, const float* x, int rows, float* h0, float* h1, const unsigned char* w1_packed = nullptr) {
   int64_t off[7];
   fnn_offsets(n_in, off);
   GemmArgs g = gemm_args(rows, GAC_H1, n_in, x, n_in, fnn + off[0], GAC_H1, h0, GAC_H1);
   g.bias = fnn + off[1]; g.act = ACT_LRELU; g.alpha = 0.01f;
   GAC_TRY(run_gemm(c, g));
   g = gemm_args(rows, GAC_H2, GAC_H1, h0, GAC_H1, fnn + off[2], GAC_H2, h1, GAC_H2);
-  g.bias = fnn + off[3]; g.act = ACT_LRELU; g.alpha = 0.01f;
+  g.bias = fnn + off[3]; g.act = ACT_LRELU; g.alpha = 0.01f; g.Bpacked = w1_packed;
   GAC_TRY(run_gemm(c, g));
   return GAC_OK;
 }
@@ -249,13 +265,15 @@ int critic_eval(gac_ctx* c, const float* f1, const float* f2, const float* state
   const int S = c->cfg.S, A = c->cfg.A, W = S + A;
   int64_t off[7];
   fnn_offsets(W, off);
+  const unsigned char* pk1 = rows >= 1024 ? pack_w(c, PK_C_F1, f1 + off[2], GAC_H2, GAC_H1, GAC_H2, 0) : nullptr;
+  const unsigned char* pk2 = rows >= 1024 ? pack_w(c, PK_C_F2, f2 + off[2], GAC_H2, GAC_H1, GAC_H2, 0) : nullptr;
   for (int r0 = 0; r0 < rows; r0 += c->Rs) {
     const int n = rows - r0 < c->Rs ? rows - r0 : c->Rs;
     concat_gather_kernel<<<(unsigned)cdiv64((long long)n * W, 256), 256, 0, c->stream>>>(
         states_u, sidx ? sidx + r0 : nullptr, actions + (size_t)r0 * A, S, A, n, c->cx);
     LAUNCHED(c, "concat_gather");
-    GAC_TRY(fnn_forward(c, f1, W, c->cx, n, c->ch0a, c->ch1a));
-    GAC_TRY(fnn_forward(c, f2, W, c->cx, n, c->ch0b, c->ch1b));
+    GAC_TRY(fnn_forward(c, f1, W, c->cx, n, c->ch0a, c->ch1a, pk1));
+    GAC_TRY(fnn_forward(c, f2, W, c->cx, n, c->ch0b, c->ch1b, pk2));
     rowdot_kernel<<<cdiv(n * 32, 256), 256, 0, c->stream>>>(c->ch1a, GAC_H2, f1 + off[4], f1 + off[5], c->ch1b, f2 + off[4],
                                                            f2 + off[5], GAC_H2, n, 0, q + r0, 1, nullptr, 0, RowValid{nullptr, 1});
     LAUNCHED(c, "rowdot_min");
@@ -285,12 +303,14 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
     cos_basis_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(d ? actions + d - 1 : nullptr, A, c->cosb, rows, all);
     LAUNCHED(c, "cos_basis");
     GemmArgs g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->ae, GAC_E);
-    g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f;
+    g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.Bpacked = c->pk[PK_T_WA];
     GAC_TRY(run_gemm(c, g));
     g = gemm_args(rows, GAC_G, GAC_E, c->ae, GAC_E, kxa, GAC_G, c->mxa, GAC_G);
+    g.Bpacked = c->pk[PK_T_KXA];
     GAC_TRY(run_gemm(c, g));
     if (d) {
       g = gemm_args(rows, GAC_G, GAC_E, hprev, GAC_E, var(c, actor, 0, GAC_A_U), GAC_G, c->mh, GAC_G);
+      g.Bpacked = c->pk[PK_T_U];
       GAC_TRY(run_gemm(c, g));
     }
     gru_gates_fwd_kernel<<<(unsigned)cdiv64((long long)rows * GAC_E, 256), 256, 0, st>>>(
@@ -300,10 +320,10 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
     cos_basis_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(taus + d, A, c->cosb, rows, all);
     LAUNCHED(c, "cos_basis");
     g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->u, GAC_E);
-    g.bias = var(c, actor, 0, GAC_A_BN); g.mul = hcur; g.ldmul = GAC_E;
+    g.bias = var(c, actor, 0, GAC_A_BN); g.mul = hcur; g.ldmul = GAC_E; g.Bpacked = c->pk[PK_T_WN];
     GAC_TRY(run_gemm(c, g));
     g = gemm_args(rows, GAC_E, GAC_E, c->u, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->y1, GAC_E);
-    g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f;
+    g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f; g.Bpacked = c->pk[PK_T_W1];
     GAC_TRY(run_gemm(c, g));
     rowdot_kernel<<<cdiv(rows * 32, 256), 256, 0, st>>>(c->y1, GAC_E, var(c, actor, 0, GAC_A_W2), var(c, actor, 0, GAC_A_B2),
                                                        nullptr, nullptr, nullptr, GAC_E, rows, 1, actions + d, A, nullptr, 0, all);
@@ -318,6 +338,11 @@ int aiqn_sample(gac_ctx* c, const float* actor, const float* states_u, int n_sta
   if (n_states > c->NUs) return fail(GAC_ERR_WORKSPACE, "gac_aiqn_sample: n_states exceeds the workspace capacity");
   GAC_TRY(state_prep(c, actor, states_u, n_states, c->se_u, c->sx_u));
   const int A = c->cfg.A;
+  c->pk[PK_T_WA] = pack_w(c, PK_T_WA, var(c, actor, 0, GAC_A_WA), GAC_E, GAC_NB, GAC_E, 0);
+  c->pk[PK_T_KXA] = pack_w(c, PK_T_KXA, var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, GAC_G, GAC_E, GAC_G, 0);
+  c->pk[PK_T_U] = pack_w(c, PK_T_U, var(c, actor, 0, GAC_A_U), GAC_G, GAC_E, GAC_G, 0);
+  c->pk[PK_T_WN] = pack_w(c, PK_T_WN, var(c, actor, 0, GAC_A_WN), GAC_E, GAC_NB, GAC_E, 0);
+  c->pk[PK_T_W1] = pack_w(c, PK_T_W1, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 0);
   for (int r0 = 0; r0 < rows; r0 += c->Rs) {
     const int n = rows - r0 < c->Rs ? rows - r0 : c->Rs;
     GAC_TRY(aiqn_sample_rows(c, actor, sidx + r0, taus + (size_t)r0 * A, n, actions + (size_t)r0 * A));
@@ -377,19 +402,28 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
   GAC_CUDA(cudaMemcpyAsync(c->a_states, states_u, (size_t)n_states * c->cfg.S * sizeof(float), cudaMemcpyDeviceToDevice, st));
   c->bwd_sidx = c->a_sidx; c->bwd_states = c->a_states; c->bwd_nstates = n_states; c->bwd_drows = live;
   GAC_TRY(state_prep(c, actor, states_u, n_states, c->a_se_u, c->a_sx_u));
+  const float* kxa_w = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
+  c->pk[PK_O_WA] = pack_w(c, PK_O_WA, var(c, actor, 0, GAC_A_WA), GAC_E, GAC_NB, GAC_E, 0);
+  c->pk[PK_O_KXA] = pack_w(c, PK_O_KXA, kxa_w, GAC_G, GAC_E, GAC_G, 0);
+  c->pk[PK_O_U] = pack_w(c, PK_O_U, var(c, actor, 0, GAC_A_U), GAC_G, GAC_E, GAC_G, 0);
+  c->pk[PK_O_WN] = pack_w(c, PK_O_WN, var(c, actor, 0, GAC_A_WN), GAC_E, GAC_NB, GAC_E, 0);
+  c->pk[PK_O_W1] = pack_w(c, PK_O_W1, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 0);
+  c->pk[PK_O_W1T] = pack_w(c, PK_O_W1T, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 1);
+  c->pk[PK_O_UT] = pack_w(c, PK_O_UT, var(c, actor, 0, GAC_A_U), GAC_G, GAC_G, GAC_E, 1);
+  c->pk[PK_O_KXAT] = pack_w(c, PK_O_KXAT, kxa_w, GAC_G, GAC_G, GAC_E, 1);
   cos_basis_seq_kernel<<<(unsigned)cdiv64(AM * GAC_NB, 256), 256, 0, st>>>(teacher, taus, A, Mc, c->ca, c->cn, live);
   LAUNCHED(c, "cos_basis_seq");
   GemmArgs g = gemm_args((int)AM, GAC_E, GAC_NB, c->ca, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->a_ae, GAC_E);
-  g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc;
+  g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_WA];
   GAC_TRY(run_gemm(c, g));
-  g = gemm_args((int)AM, GAC_G, GAC_E, c->a_ae, GAC_E, var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, GAC_G, c->mx, GAC_G);
-  g.dyn_rows = live; g.seg_rows = Mc;
+  g = gemm_args((int)AM, GAC_G, GAC_E, c->a_ae, GAC_E, kxa_w, GAC_G, c->mx, GAC_G);
+  g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_KXA];
   GAC_TRY(run_gemm(c, g));
   for (int d = 0; d < A; ++d) {
     const size_t o4 = (size_t)d * Mc * GAC_E, o12 = (size_t)d * Mc * GAC_G;
     if (d) {
       g = gemm_args(Mc, GAC_G, GAC_E, c->hall + o4, GAC_E, var(c, actor, 0, GAC_A_U), GAC_G, c->dmh + o12, GAC_G);
-      g.dyn_rows = live; g.seg_rows = Mc;
+      g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_U];
       GAC_TRY(run_gemm(c, g));
     }
     gru_gates_fwd_kernel<<<(unsigned)cdiv64((long long)Mc * GAC_E, 256), 256, 0, st>>>(
@@ -398,12 +432,12 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
     LAUNCHED(c, "gru_gates_fwd");
   }
   g = gemm_args((int)AM, GAC_E, GAC_NB, c->cn, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->ne, GAC_E);
-  g.bias = var(c, actor, 0, GAC_A_BN); g.dyn_rows = live; g.seg_rows = Mc;
+  g.bias = var(c, actor, 0, GAC_A_BN); g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_WN];
   GAC_TRY(run_gemm(c, g));
   mul_kernel<<<(unsigned)cdiv64(AM * GAC_E, 256), 256, 0, st>>>(c->ne, c->hall + (size_t)Mc * GAC_E, AM * GAC_E, Mc, live, c->au);
   LAUNCHED(c, "hadamard");
   g = gemm_args((int)AM, GAC_E, GAC_E, c->au, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->ay1, GAC_E);
-  g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f; g.dyn_rows = live; g.seg_rows = Mc;
+  g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_W1];
   GAC_TRY(run_gemm(c, g));
   for (int d = 0; d < A; ++d) {
     rowdot_kernel<<<cdiv(Mc * 32, 256), 256, 0, st>>>(c->ay1 + (size_t)d * Mc * GAC_E, GAC_E, var(c, actor, 0, GAC_A_W2),
@@ -440,7 +474,7 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   GAC_TRY(wgrad(GAC_E, GAC_E, c->au, GAC_E, c->dy1p, GAC_E, AM, G(GAC_A_W1), true));
   GAC_TRY(run_colsum(c, c->dy1p, GAC_E, nullptr, GAC_E, AM, rv, G(GAC_A_B1), acc));
   GemmArgs g = gemm_args((int)AM, GAC_E, GAC_E, c->dy1p, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->du, GAC_E);
-  g.transB = 1; g.dyn_rows = live; g.seg_rows = Mc;
+  g.transB = 1; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_W1T];
   GAC_TRY(run_gemm(c, g));
   hadamard_bwd_kernel<<<(unsigned)cdiv64(AM * GAC_E, 256), 256, 0, st>>>(c->du, c->hall + (size_t)Mc * GAC_E, c->ne, AM * GAC_E, Mc, live,
                                                                         c->dne, c->dhu);
@@ -457,7 +491,7 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
     LAUNCHED(c, "gru_gates_bwd");
     if (d) {
       g = gemm_args(Mc, GAC_E, GAC_G, c->dmh + o12, GAC_G, var(c, actor, 0, GAC_A_U), GAC_G, carry, GAC_E);
-      g.transB = 1; g.accumulate = 1; g.dyn_rows = live; g.seg_rows = Mc;
+      g.transB = 1; g.accumulate = 1; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_UT];
       GAC_TRY(run_gemm(c, g));
     }
     dh_next = carry;
@@ -469,7 +503,7 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   GAC_TRY(run_colsum(c, c->mx, GAC_G, nullptr, GAC_G, AM, rv, G(GAC_A_GB), acc));
   GAC_TRY(wgrad(GAC_E, GAC_G, c->a_ae, GAC_E, c->mx, GAC_G, AM, G(GAC_A_KX) + (size_t)GAC_E * GAC_G, true));
   g = gemm_args((int)AM, GAC_E, GAC_G, c->mx, GAC_G, kxa, GAC_G, c->du, GAC_E);
-  g.transB = 1; g.gate = c->a_ae; g.ldgate = GAC_E; g.gate_alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc;
+  g.transB = 1; g.gate = c->a_ae; g.ldgate = GAC_E; g.gate_alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_KXAT];
   GAC_TRY(run_gemm(c, g));
   GAC_TRY(wgrad(GAC_NB, GAC_E, c->ca, GAC_NB, c->du, GAC_E, AM, G(GAC_A_WA), true));
   GAC_TRY(run_colsum(c, c->du, GAC_E, nullptr, GAC_E, AM, rv, G(GAC_A_BA), acc));
@@ -645,8 +679,14 @@ int gac_gemm(gac_ctx_t* c, int32_t engine, const float* A, const float* B, float
   if (!c || !A || !B || !C) return fail(GAC_ERR_INVALID, "gac_gemm: bad arguments");
   GemmArgs g = gemm_args(M, N, K, A, transA ? M : K, B, transB ? K : N, C, N);
   g.transA = transA; g.transB = transB;
-  if (engine == 0) {
+  if (engine == 0 || engine == 2) {
     if (!tc_gemm_supported(g)) return fail(GAC_ERR_UNSUPPORTED, "gac_gemm: shape not supported by the tcgen05 engine");
+    if (engine == 2) {   // B treated as a weight matrix: pre-split / pre-swizzled once, fetched by bulk copies
+      if (transA || tc_packed_bytes(K, N) > c->pack_bytes) return fail(GAC_ERR_UNSUPPORTED, "gac_gemm: packed-B needs !transA and a weight-sized B");
+      GAC_CUDA(tc_pack_b(B, g.ldb, transB, K, N, c->pack[15], c->stream));
+      c->launches++;
+      g.Bpacked = c->pack[15];
+    }
     GAC_CUDA(launch_gemm_tc(g, c->stream));
   } else {
     GAC_CUDA(launch_gemm_simt(g, c->stream));

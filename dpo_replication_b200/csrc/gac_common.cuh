@@ -55,6 +55,7 @@ struct GemmArgs {
   int M, N, K;
   const float* A; int lda; int transA;  // transA: A(m,k) = A[k*lda + m]
   const float* B; int ldb; int transB;  // transB: B(k,n) = B[n*ldb + k]
+  const unsigned char* Bpacked;        // optional: B pre-split/pre-swizzled by tc::pack_b_kernel (weights)
   float* C; int ldc; int transC;        // transC: C(m,n) stored at C[n*ldc + m]
   const float* bias;
   const float* add; int ldadd; const int* addidx;

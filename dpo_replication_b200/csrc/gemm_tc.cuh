@@ -217,7 +217,7 @@ __device__ __forceinline__ void store_operand(const float (&x)[NCH][4], uint32_t
 }
 
 // TB means "B is stored (N, K) row-major" (g.transB); !TB is the natural Keras (K, N).
-template <bool TA, bool TB, bool VEC>
+template <bool TA, bool TB, bool VEC, bool PACKED>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, int bn, int stages, int tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_accum;
@@ -257,16 +257,30 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
     for (int kb = grp; kb < nkb; kb += 2) {
       int k0, live;
       kmap_get(km, kb, k0, live);
-      float xa[8][4], xb[16][4];
+      constexpr int NB_CH = PACKED ? 8 : 16;
+      float xa[8][4], xb[NB_CH][4];
       load_operand<TA, VEC, 8>(xa, g.A, g.lda, m0, m_end, BM, k0, live, t);
       // B tile rows are output columns n; element (n, k) = B(k, n)
-      load_operand<!TB, VEC, 16>(xb, g.B, g.ldb, n0, g.N, bn, k0, live, t);
+      if constexpr (!PACKED) load_operand<!TB, VEC, NB_CH>(xb, g.B, g.ldb, n0, g.N, bn, k0, live, t);
       const int s = kb % stages;
       const uint32_t ph = (uint32_t)(kb / stages) & 1u;
       mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
       const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
+      if constexpr (PACKED) {
+        // weights: one elected thread pulls the pre-split, pre-swizzled hi|lo tile pair with a
+        // single bulk async copy (UBLKCP) that completes on the stage's full barrier
+        if (t == 0) {
+          const uint32_t bytes = 2u * (uint32_t)bn * 128u;
+          const unsigned char* srcp = g.Bpacked + ((size_t)blockIdx.x * (size_t)((g.K + BK - 1) / BK) + (size_t)(k0 / BK)) * bytes;
+          const uint32_t bar = smem_u32(&bar_full[s]);
+          asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa + 2 * A_TILE_BYTES),
+                       "l"(srcp), "r"(bytes), "r"(bar)
+                       : "memory");
+        }
+      }
       store_operand<TA, 8>(xa, sa, sa + A_TILE_BYTES, BM, t);
-      store_operand<!TB, 16>(xb, sa + 2 * A_TILE_BYTES, sa + 2 * A_TILE_BYTES + (uint32_t)bn * 128u, bn, t);
+      if constexpr (!PACKED) store_operand<!TB, NB_CH>(xb, sa + 2 * A_TILE_BYTES, sa + 2 * A_TILE_BYTES + (uint32_t)bn * 128u, bn, t);
       fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
@@ -280,7 +294,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
     const int m = m0 + quarter * 32 + lane;
     const bool m_ok = m < m_end;
     float* Cout = g.C + (g.splitk > 1 ? (size_t)blockIdx.z * g.split_stride : 0);
-    const bool vec_st = VEC && !g.transC && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0) && (n0 % 4 == 0);
+    const bool vec_st = !g.transC && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0) && (n0 % 4 == 0);
+    // every epilogue operand that is present is 16-byte addressable per 16-column chunk?
+    auto al16 = [](const void* p, int ld) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0)); };
+    const bool fast_epi = al16(g.bias, 4) && al16(g.add, g.ldadd) && al16(g.mul, g.ldmul) && al16(g.gate, g.ldgate) &&
+                          (!g.accumulate || g.transC || vec_st);
     for (int ci = warp >> 2; ci < bn / 16; ci += 2) {
       float v[16];
       if (nkb > 0) {
@@ -296,10 +314,57 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
       }
       if (!m_ok) continue;
       const int nb = n0 + ci * 16;
+      const bool full = nb + 15 < g.N;
       if (g.splitk <= 1) {
+        if (full && fast_epi) {
+          // chunk-level epilogue: every option is one uniform branch + 128-bit loads
+          if (g.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(g.bias + nb);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (nb + j < g.N) v[j] = gemm_epilogue(g, v[j], m, nb + j);
+            for (int q = 0; q < 4; ++q) { const float4 b = b4[q]; v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w; }
+          }
+          if (g.add) {
+            const float4* a4 = reinterpret_cast<const float4*>(g.add + (size_t)(g.addidx ? g.addidx[m] : m) * g.ldadd + nb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float4 b = a4[q]; v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w; }
+          }
+          if (g.act == ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = lrelu_f(v[j], g.alpha);
+          } else if (g.act == ACT_LRELU2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = lrelu_f(lrelu_f(v[j], 0.01f), 0.2f);
+          }
+          if (g.mul) {
+            const float4* m4 = reinterpret_cast<const float4*>(g.mul + (size_t)m * g.ldmul + nb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float4 b = m4[q]; v[4 * q] *= b.x; v[4 * q + 1] *= b.y; v[4 * q + 2] *= b.z; v[4 * q + 3] *= b.w; }
+          }
+          if (g.gate) {
+            const float4* g4 = reinterpret_cast<const float4*>(g.gate + (size_t)m * g.ldgate + nb);
+            const float ga = g.gate_alpha;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b = g4[q];
+              v[4 * q] *= b.x > 0.f ? 1.f : ga; v[4 * q + 1] *= b.y > 0.f ? 1.f : ga;
+              v[4 * q + 2] *= b.z > 0.f ? 1.f : ga; v[4 * q + 3] *= b.w > 0.f ? 1.f : ga;
+            }
+          }
+          if (g.accumulate) {
+            if (g.transC) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += Cout[(size_t)(nb + j) * g.ldc + m];
+            } else {
+              const float4* c4 = reinterpret_cast<const float4*>(Cout + (size_t)m * g.ldc + nb);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { const float4 b = c4[q]; v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w; }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < g.N) v[j] = gemm_epilogue(g, v[j], m, nb + j);
+        }
       }
       if (g.transC) {
 #pragma unroll
@@ -307,7 +372,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
           if (nb + j < g.N) Cout[(size_t)(nb + j) * g.ldc + m] = v[j];     // lanes = consecutive m: coalesced
       } else {
         float* crow = Cout + (size_t)m * g.ldc + nb;
-        if (vec_st && nb + 15 < g.N) {
+        if (vec_st && full) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         } else {
@@ -353,6 +418,35 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
   }
 }
 
+// Pack a weight matrix B (K x N; element (k,n) = transB ? W[n*ld + k] : W[k*ld + n]) into the
+// exact shared-memory image the MMA wants: for every (n tile j, K block kb) a contiguous
+// [hi tile | lo tile] pair, each bn rows x 128 bytes, K-major, 128-byte swizzled, zero padded.
+// Runs once per weight update (the weights change once per train step); every CTA of every GEMM
+// that uses the matrix then fetches its B tiles with one bulk copy instead of staging them
+// through registers.
+__global__ void pack_b_kernel(const float* __restrict__ W, int ld, int transB, int K, int N, int bn, unsigned char* __restrict__ out) {
+  const int nkb = (K + BK - 1) / BK, ntile = (N + bn - 1) / bn;
+  const long long total = (long long)ntile * nkb * bn * 8;
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  const int r = (int)(q % bn);
+  const int c = (int)((q / bn) % 8);
+  const int kb = (int)((q / ((long long)bn * 8)) % nkb);
+  const int j = (int)(q / ((long long)bn * 8 * nkb));
+  const int n = j * bn + r;
+  float h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int k = kb * BK + 4 * c + e;
+    const float x = (n < N && k < K) ? (transB ? W[(size_t)n * ld + k] : W[(size_t)k * ld + n]) : 0.f;
+    split_tf32(x, h[e], l[e]);
+  }
+  unsigned char* tile = out + ((size_t)j * nkb + kb) * (2u * (size_t)bn * 128u);
+  const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+  *reinterpret_cast<float4*>(tile + off) = make_float4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<float4*>(tile + (size_t)bn * 128u + off) = make_float4(l[0], l[1], l[2], l[3]);
+}
+
 struct Plan { int bn, stages, tmem_cols; size_t smem; };
 inline Plan plan_for(int N) {
   Plan p;
@@ -372,32 +466,47 @@ inline Plan plan_for(int N) {
 
 inline bool tc_gemm_supported(const GemmArgs& g) { return g.K >= 32 && g.N >= 32 && g.M >= 1; }
 
-template <bool TA, bool TB, bool VEC>
+template <bool TA, bool TB, bool VEC, bool PACKED>
 inline cudaError_t tc_set_attr() {
-  return cudaFuncSetAttribute(tc::gemm_tc_kernel<TA, TB, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT);
+  return cudaFuncSetAttribute(tc::gemm_tc_kernel<TA, TB, VEC, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT);
 }
 inline cudaError_t tc_gemm_init() {
   cudaError_t e;
-#define GAC_TC_ATTR(a, b, c) if ((e = tc_set_attr<a, b, c>()) != cudaSuccess) return e;
-  GAC_TC_ATTR(false, false, false) GAC_TC_ATTR(false, false, true) GAC_TC_ATTR(false, true, false) GAC_TC_ATTR(false, true, true)
-  GAC_TC_ATTR(true, false, false) GAC_TC_ATTR(true, false, true) GAC_TC_ATTR(true, true, false) GAC_TC_ATTR(true, true, true)
+#define GAC_TC_ATTR(a, b, c, d) if ((e = tc_set_attr<a, b, c, d>()) != cudaSuccess) return e;
+  GAC_TC_ATTR(false, false, false, false) GAC_TC_ATTR(false, false, true, false) GAC_TC_ATTR(false, true, false, false)
+  GAC_TC_ATTR(false, true, true, false) GAC_TC_ATTR(true, false, false, false) GAC_TC_ATTR(true, false, true, false)
+  GAC_TC_ATTR(true, true, false, false) GAC_TC_ATTR(true, true, true, false)
+  GAC_TC_ATTR(false, false, false, true) GAC_TC_ATTR(false, false, true, true)
 #undef GAC_TC_ATTR
   return cudaSuccess;
+}
+
+inline size_t tc_packed_bytes(int K, int N) {
+  const tc::Plan p = tc::plan_for(N);
+  return (size_t)cdiv(N, p.bn) * cdiv(K, tc::BK) * 2 * p.bn * 128;
+}
+inline cudaError_t tc_pack_b(const float* W, int ld, int transB, int K, int N, unsigned char* out, cudaStream_t st) {
+  const tc::Plan p = tc::plan_for(N);
+  const long long total = (long long)cdiv(N, p.bn) * cdiv(K, tc::BK) * p.bn * 8;
+  tc::pack_b_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(W, ld, transB, K, N, p.bn, out);
+  return cudaGetLastError();
 }
 
 inline cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   const tc::Plan p = tc::plan_for(g.N);
   dim3 grid(cdiv(g.N, p.bn), cdiv(g.M, tc::BM), g.splitk > 1 ? g.splitk : 1);
   // 16-byte vector accesses need aligned bases and leading dimensions
-  const bool vec = (g.lda % 4 == 0) && (g.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
-#define GAC_TC_LAUNCH(a, b, c) tc::gemm_tc_kernel<a, b, c><<<grid, tc::THREADS, p.smem, st>>>(g, p.bn, p.stages, p.tmem_cols)
-  if (g.transA) {
-    if (g.transB) { if (vec) GAC_TC_LAUNCH(true, true, true); else GAC_TC_LAUNCH(true, true, false); }
-    else { if (vec) GAC_TC_LAUNCH(true, false, true); else GAC_TC_LAUNCH(true, false, false); }
+  const bool veca = (g.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
+  const bool vec = veca && (g.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
+#define GAC_TC_LAUNCH(a, b, c, d) tc::gemm_tc_kernel<a, b, c, d><<<grid, tc::THREADS, p.smem, st>>>(g, p.bn, p.stages, p.tmem_cols)
+  if (g.Bpacked && !g.transA && g.splitk <= 1) {
+    if (veca) GAC_TC_LAUNCH(false, false, true, true); else GAC_TC_LAUNCH(false, false, false, true);
+  } else if (g.transA) {
+    if (g.transB) { if (vec) GAC_TC_LAUNCH(true, true, true, false); else GAC_TC_LAUNCH(true, true, false, false); }
+    else { if (vec) GAC_TC_LAUNCH(true, false, true, false); else GAC_TC_LAUNCH(true, false, false, false); }
   } else {
-    if (g.transB) { if (vec) GAC_TC_LAUNCH(false, true, true); else GAC_TC_LAUNCH(false, true, false); }
-    else { if (vec) GAC_TC_LAUNCH(false, false, true); else GAC_TC_LAUNCH(false, false, false); }
+    if (g.transB) { if (vec) GAC_TC_LAUNCH(false, true, true, false); else GAC_TC_LAUNCH(false, true, false, false); }
+    else { if (vec) GAC_TC_LAUNCH(false, false, true, false); else GAC_TC_LAUNCH(false, false, false, false); }
   }
 #undef GAC_TC_LAUNCH
   return cudaGetLastError();

@@ -180,7 +180,8 @@ int gac_step_grads(gac_ctx_t* ctx, const gac_step_io_t* io /* host */, const gac
 int gac_step_apply(gac_ctx_t* ctx, const gac_step_io_t* io /* host */, const gac_hparams_t* hp /* host */);
 
 /* ---- plain GEMM entry used by the tests and the micro-benchmarks:
- * C(M,N) = A(M,K) * B(K,N), engine 0 = tcgen05 3xTF32, 1 = SIMT fp32. ---- */
+ * C(M,N) = A(M,K) * B(K,N), engine 0 = tcgen05 3xTF32, 1 = SIMT fp32,
+ * 2 = tcgen05 3xTF32 with B pre-packed as a weight matrix (bulk-copy path). ---- */
 int gac_gemm(gac_ctx_t* ctx, int32_t engine, const float* A, const float* B, float* C, int32_t M, int32_t N,
              int32_t K, int32_t transA, int32_t transB);
 
