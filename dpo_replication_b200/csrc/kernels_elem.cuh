@@ -259,14 +259,33 @@ __global__ void colsum_kernel(const float* __restrict__ X, int ldx, const float*
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const long long r0 = (long long)blockIdx.y * COLSUM_ROWS;
-  const long long r1 = min(rows, r0 + COLSUM_ROWS);
-  float s = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    if (!rv((int)r)) continue;
-    const float x = X[(size_t)r * ldx + n];
-    s += w ? w[r] * x : x;
+  long long r1 = min(rows, r0 + COLSUM_ROWS);
+  // a block of 256 rows never straddles a segment (seg is a multiple of 128 and of 256 or the
+  // block is clipped below): live rows of this block are a prefix [r0, r_live)
+  if (rv.dyn) {
+    const long long seg0 = (r0 / rv.seg) * rv.seg;
+    const long long seg_end = seg0 + rv.seg;
+    const long long live_end = seg0 + min(*rv.dyn, rv.seg);
+    if (r1 > seg_end) {           // straddling block (seg not a multiple of 256): fall back to per-row checks
+      float s = 0.f;
+      for (long long r = r0; r < r1; ++r)
+        if (rv((int)r)) { const float x = X[(size_t)r * ldx + n]; s += w ? w[r] * x : x; }
+      part[(size_t)blockIdx.y * N + n] = s;
+      return;
+    }
+    r1 = min(r1, live_end);
   }
-  part[(size_t)blockIdx.y * N + n] = s;
+  // 4 independent accumulators: 4 loads in flight per thread (the serial version was latency bound)
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  long long r = r0;
+  for (; r + 3 < r1; r += 4) {
+    const float x0 = X[(size_t)r * ldx + n], x1 = X[(size_t)(r + 1) * ldx + n];
+    const float x2 = X[(size_t)(r + 2) * ldx + n], x3 = X[(size_t)(r + 3) * ldx + n];
+    if (w) { s0 += w[r] * x0; s1 += w[r + 1] * x1; s2 += w[r + 2] * x2; s3 += w[r + 3] * x3; }
+    else { s0 += x0; s1 += x1; s2 += x2; s3 += x3; }
+  }
+  for (; r < r1; ++r) { const float x = X[(size_t)r * ldx + n]; s0 += w ? w[r] * x : x; }
+  part[(size_t)blockIdx.y * N + n] = (s0 + s1) + (s2 + s3);
 }
 
 // ---- quantile Huber loss + gradient (networks.py:113-120; App. A.6), elementwise Huber ----
@@ -396,7 +415,14 @@ __global__ void segment_sum_kernel(const float* __restrict__ dmx, const int* __r
     if (n < GAC_G)
       for (int e = 0; e < nlist; ++e) {
         const int jj = list[e];
-        for (int d = 0; d < A; ++d) s += dmx[((size_t)d * seg + jj) * GAC_G + n];
+        float t0 = 0.f, t1 = 0.f;
+        int d = 0;
+        for (; d + 1 < A; d += 2) {
+          t0 += dmx[((size_t)d * seg + jj) * GAC_G + n];
+          t1 += dmx[((size_t)(d + 1) * seg + jj) * GAC_G + n];
+        }
+        if (d < A) t0 += dmx[((size_t)d * seg + jj) * GAC_G + n];
+        s += t0 + t1;
       }
     __syncthreads();
   }
