@@ -83,7 +83,7 @@ struct gac_ctx {
   float *ca, *cn, *a_ae, *mx, *dmh, *zs, *rs, *cs, *mhh, *hall, *ne, *au, *ay1, *dy1p, *du, *dne, *dhu, *dhc0, *dhc1, *dop;
   float *pred_c, *dpred_c;
   const int* bwd_sidx; const float* bwd_states; int bwd_nstates; const int* bwd_drows;  // saved by supervised_fwd
-  float *spart, *cpart;
+  float *spart, *cpart, *fpart0, *fpart1;
   unsigned char* pack[16]; size_t pack_bytes;   // pre-split / pre-swizzled weight tiles (tc::pack_b_kernel)
 };
 
@@ -155,6 +155,8 @@ size_t partition(gac_ctx* c, void* ws) {
   c->spart = b.take<float>((size_t)c->max_splits * GAC_E * GAC_G);
   const size_t maxrows = AM > Rs ? AM : Rs;
   c->cpart = b.take<float>(((maxrows + COLSUM_ROWS - 1) / COLSUM_ROWS + 1) * GAC_G);
+  const size_t nrb = (AM + FB_ROWS - 1) / FB_ROWS + 1;
+  c->fpart0 = b.take<float>(nrb * GAC_G); c->fpart1 = b.take<float>(nrb * GAC_G);
   c->pack_bytes = tc_packed_bytes(GAC_E, GAC_G);
   if (tc_packed_bytes(GAC_G, GAC_E) > c->pack_bytes) c->pack_bytes = tc_packed_bytes(GAC_G, GAC_E);
   c->pack_bytes = (c->pack_bytes + 1023) & ~(size_t)1023;
@@ -228,7 +230,7 @@ int run_colsum(gac_ctx* c, const float* X, int ldx, const float* w, int N, long 
   const int nblk = (int)cdiv64(rows, COLSUM_ROWS);
   colsum_kernel<<<dim3(cdiv(N, 128), nblk), 128, 0, c->stream>>>(X, ldx, w, N, rows, rv, c->cpart);
   LAUNCHED(c, "colsum");
-  reduce_splits_kernel<<<cdiv(N, 256), 256, 0, c->stream>>>(c->cpart, N, nblk, dst, N, accumulate);
+  reduce_cols_kernel<<<cdiv(N, 32), dim3(32, 8), 0, c->stream>>>(c->cpart, nblk, N, dst, accumulate);
   LAUNCHED(c, "colsum_reduce");
   return GAC_OK;
 }
@@ -466,28 +468,33 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   // head
   head_dop_kernel<<<(unsigned)cdiv64(AM, 256), 256, 0, st>>>(dpred, c->pred_c, A, Mc, live, c->dop);
   LAUNCHED(c, "head_dop");
-  GAC_TRY(run_colsum(c, c->ay1, GAC_E, c->dop, GAC_E, AM, rv, G(GAC_A_W2), acc));
   GAC_TRY(run_colsum(c, c->dop, 1, nullptr, 1, AM, rv, G(GAC_A_B2), acc));
-  outer_gate_kernel<<<(unsigned)cdiv64(AM * GAC_E, 256), 256, 0, st>>>(c->dop, var(c, actor, 0, GAC_A_W2), c->ay1, GAC_E, AM, 0.01f,
-                                                                      c->dy1p, rv);
-  LAUNCHED(c, "outer_gate");
+  const int nrb_all = (int)cdiv64(AM, FB_ROWS);
+  head_bwd_kernel<<<dim3(GAC_E / FB_COLS, nrb_all), FB_COLS, 0, st>>>(c->dop, var(c, actor, 0, GAC_A_W2), c->ay1, AM, rv, c->dy1p,
+                                                                      c->fpart0, c->fpart1);
+  LAUNCHED(c, "head_bwd");
+  reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, 8), 0, st>>>(c->fpart0, nrb_all, GAC_E, G(GAC_A_B1), acc);
+  LAUNCHED(c, "reduce_cols");
+  reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, 8), 0, st>>>(c->fpart1, nrb_all, GAC_E, G(GAC_A_W2), acc);
+  LAUNCHED(c, "reduce_cols");
   GAC_TRY(wgrad(GAC_E, GAC_E, c->au, GAC_E, c->dy1p, GAC_E, AM, G(GAC_A_W1), true));
-  GAC_TRY(run_colsum(c, c->dy1p, GAC_E, nullptr, GAC_E, AM, rv, G(GAC_A_B1), acc));
   GemmArgs g = gemm_args((int)AM, GAC_E, GAC_E, c->dy1p, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->du, GAC_E);
   g.transB = 1; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_W1T];
   GAC_TRY(run_gemm(c, g));
-  hadamard_bwd_kernel<<<(unsigned)cdiv64(AM * GAC_E, 256), 256, 0, st>>>(c->du, c->hall + (size_t)Mc * GAC_E, c->ne, AM * GAC_E, Mc, live,
-                                                                        c->dne, c->dhu);
+  hadamard_bwd_kernel<<<dim3(GAC_E / FB_COLS, nrb_all), FB_COLS, 0, st>>>(c->du, c->hall + (size_t)Mc * GAC_E, c->ne, AM, rv, c->dne,
+                                                                          c->dhu, c->fpart0);
   LAUNCHED(c, "hadamard_bwd");
+  reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, 8), 0, st>>>(c->fpart0, nrb_all, GAC_E, G(GAC_A_BN), acc);
+  LAUNCHED(c, "reduce_cols");
   GAC_TRY(wgrad(GAC_NB, GAC_E, c->cn, GAC_NB, c->dne, GAC_E, AM, G(GAC_A_WN), true));
-  GAC_TRY(run_colsum(c, c->dne, GAC_E, nullptr, GAC_E, AM, rv, G(GAC_A_BN), acc));
   // recurrence, reverse time.  mx is overwritten with dmx step by step (it is dead after the forward gates)
   float* dh_next = nullptr; float* carry = c->dhc0;
+  const int nrb_step = Mc / FB_ROWS;
   for (int d = A - 1; d >= 0; --d) {
     const size_t o4 = (size_t)d * Mc * GAC_E, o12 = (size_t)d * Mc * GAC_G;
-    gru_gates_bwd_kernel<<<(unsigned)cdiv64((long long)Mc * GAC_E, 256), 256, 0, st>>>(
+    gru_gates_bwd_kernel<<<dim3(GAC_E / FB_COLS, nrb_step), FB_COLS, 0, st>>>(
         dh_next, c->dhu + o4, c->zs + o4, c->rs + o4, c->cs + o4, c->mhh + o4, d ? c->hall + o4 : nullptr, c->mx + o12, c->dmh + o12,
-        carry, Mc, rv);
+        carry, Mc, rv, c->fpart0 + (size_t)d * nrb_step * GAC_G, c->fpart1 + (size_t)d * nrb_step * GAC_G);
     LAUNCHED(c, "gru_gates_bwd");
     if (d) {
       g = gemm_args(Mc, GAC_E, GAC_G, c->dmh + o12, GAC_G, var(c, actor, 0, GAC_A_U), GAC_G, carry, GAC_E);
@@ -499,8 +506,10 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   }
   // time-parallel weight gradients of the GRU
   GAC_TRY(wgrad(GAC_E, GAC_G, c->hall, GAC_E, c->dmh, GAC_G, AM, G(GAC_A_U), true));
-  GAC_TRY(run_colsum(c, c->dmh, GAC_G, nullptr, GAC_G, AM, rv, G(GAC_A_GB) + GAC_G, acc));
-  GAC_TRY(run_colsum(c, c->mx, GAC_G, nullptr, GAC_G, AM, rv, G(GAC_A_GB), acc));
+  reduce_cols_kernel<<<cdiv(GAC_G, 32), dim3(32, 8), 0, st>>>(c->fpart1, A * nrb_step, GAC_G, G(GAC_A_GB) + GAC_G, acc);
+  LAUNCHED(c, "reduce_cols");
+  reduce_cols_kernel<<<cdiv(GAC_G, 32), dim3(32, 8), 0, st>>>(c->fpart0, A * nrb_step, GAC_G, G(GAC_A_GB), acc);
+  LAUNCHED(c, "reduce_cols");
   GAC_TRY(wgrad(GAC_E, GAC_G, c->a_ae, GAC_E, c->mx, GAC_G, AM, G(GAC_A_KX) + (size_t)GAC_E * GAC_G, true));
   g = gemm_args((int)AM, GAC_E, GAC_G, c->mx, GAC_G, kxa, GAC_G, c->du, GAC_E);
   g.transB = 1; g.gate = c->a_ae; g.ldgate = GAC_E; g.gate_alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_KXAT];

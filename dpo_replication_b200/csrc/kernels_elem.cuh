@@ -108,27 +108,116 @@ __global__ void gru_gates_fwd_kernel(const float* __restrict__ sx_u, const int* 
   if (zs) { zs[idx] = z; rs_[idx] = r; cs[idx] = c; mhhs[idx] = hh; }
 }
 
+// Producer kernels below also emit per-row-block column sums (bias gradients) so that no second
+// pass over the activations is needed.  Layout: block = FB_COLS threads (one column each) x
+// FB_ROWS rows; thread loops over the rows with 4-way ILP; partial sums go to
+// part[(row_block) * ncols + col] and are reduced in fixed order by reduce_cols_kernel.
+constexpr int FB_COLS = 100;   // 400 = 4 x 100 columns
+constexpr int FB_ROWS = 64;
+
 // backward of the gates for one step; dh = dh_next + dhu.  Writes dmx, dmh (rows,1200) and
-// dh_carry = dh*z (the GEMM dmh*U^T is accumulated on top of it afterwards).
-__global__ void gru_gates_bwd_kernel(const float* __restrict__ dh_next, const float* __restrict__ dhu,
+// dh_carry = dh*z (the GEMM dmh*U^T is accumulated on top of it afterwards), plus the column
+// sums of dmx / dmh of this row block (gradients of the GRU input / recurrent bias).
+__global__ void __launch_bounds__(FB_COLS) gru_gates_bwd_kernel(const float* __restrict__ dh_next, const float* __restrict__ dhu,
                                      const float* __restrict__ zs, const float* __restrict__ rs_,
                                      const float* __restrict__ cs, const float* __restrict__ mhhs,
                                      const float* __restrict__ hprev, float* __restrict__ dmx, float* __restrict__ dmh,
-                                     float* __restrict__ dh_carry, int rows, RowValid rv) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)rows * GAC_E) return;
-  const int row = idx / GAC_E, j = idx % GAC_E;
-  if (!rv(row)) return;
-  const float dh = (dh_next ? dh_next[idx] : 0.f) + dhu[idx];
-  const float z = zs[idx], r = rs_[idx], c = cs[idx], hp = hprev ? hprev[idx] : 0.f;
-  const float dz = dh * (hp - c), dc = dh * (1.f - z);
-  const float dcp = dc * (1.f - c * c);
-  const float dzp = dz * z * (1.f - z);
-  const float drp = dcp * mhhs[idx] * r * (1.f - r);
-  const size_t o = (size_t)row * GAC_G + j;
-  dmx[o] = dzp; dmx[o + GAC_E] = drp; dmx[o + 2 * GAC_E] = dcp;
-  dmh[o] = dzp; dmh[o + GAC_E] = drp; dmh[o + 2 * GAC_E] = dcp * r;
-  dh_carry[idx] = dh * z;
+                                     float* __restrict__ dh_carry, int rows, RowValid rv, float* __restrict__ part_mx,
+                                     float* __restrict__ part_mh) {
+  const int j = blockIdx.x * FB_COLS + threadIdx.x;
+  const int r0 = blockIdx.y * FB_ROWS;
+  const int nvalid = rv.dyn ? min(*rv.dyn, rows) : rows;
+  const int r1 = min(r0 + FB_ROWS, nvalid);
+  float sz = 0.f, sr = 0.f, sc = 0.f, scr = 0.f;
+#pragma unroll 4
+  for (int row = r0; row < r1; ++row) {
+    const size_t idx = (size_t)row * GAC_E + j;
+    const float dh = (dh_next ? dh_next[idx] : 0.f) + dhu[idx];
+    const float z = zs[idx], r = rs_[idx], c = cs[idx], hp = hprev ? hprev[idx] : 0.f;
+    const float dz = dh * (hp - c), dc = dh * (1.f - z);
+    const float dcp = dc * (1.f - c * c);
+    const float dzp = dz * z * (1.f - z);
+    const float drp = dcp * mhhs[idx] * r * (1.f - r);
+    const size_t o = (size_t)row * GAC_G + j;
+    dmx[o] = dzp; dmx[o + GAC_E] = drp; dmx[o + 2 * GAC_E] = dcp;
+    dmh[o] = dzp; dmh[o + GAC_E] = drp; dmh[o + 2 * GAC_E] = dcp * r;
+    dh_carry[idx] = dh * z;
+    sz += dzp; sr += drp; sc += dcp; scr += dcp * r;
+  }
+  float* pm = part_mx + (size_t)blockIdx.y * GAC_G + j;
+  float* ph = part_mh + (size_t)blockIdx.y * GAC_G + j;
+  pm[0] = sz; pm[GAC_E] = sr; pm[2 * GAC_E] = sc;
+  ph[0] = sz; ph[GAC_E] = sr; ph[2 * GAC_E] = scr;
+}
+
+// dy1p[r][j] = dop[r] * w2[j] * lrelu'(y1[r][j]); partial sums: sum_r dy1p (d b1) and
+// sum_r y1*dop (d w2).  Rows are step-major with segment length seg.
+__global__ void __launch_bounds__(FB_COLS) head_bwd_kernel(const float* __restrict__ dop, const float* __restrict__ w2,
+                                                           const float* __restrict__ y1, long long rows, RowValid rv,
+                                                           float* __restrict__ dy1p, float* __restrict__ part_b1,
+                                                           float* __restrict__ part_w2) {
+  const int j = blockIdx.x * FB_COLS + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * FB_ROWS;
+  long long r1 = min(rows, r0 + FB_ROWS);
+  if (rv.dyn) { const long long seg0 = (r0 / rv.seg) * rv.seg; r1 = min(r1, seg0 + min(*rv.dyn, rv.seg)); }
+  const float w = w2[j];
+  float sb = 0.f, sw = 0.f;
+#pragma unroll 4
+  for (long long row = r0; row < r1; ++row) {
+    const size_t idx = (size_t)row * GAC_E + j;
+    const float y = y1[idx], d = dop[row];
+    const float g = d * w * (y > 0.f ? 1.f : 0.01f);
+    dy1p[idx] = g;
+    sb += g; sw += y * d;
+  }
+  part_b1[(size_t)blockIdx.y * GAC_E + j] = sb;
+  part_w2[(size_t)blockIdx.y * GAC_E + j] = sw;
+}
+
+// dne = du * h ; dhu = du * ne ; partial column sums of dne (gradient of the noise-embedding bias)
+__global__ void __launch_bounds__(FB_COLS) hadamard_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h,
+                                                               const float* __restrict__ ne, long long rows, RowValid rv,
+                                                               float* __restrict__ dne, float* __restrict__ dhu,
+                                                               float* __restrict__ part_bn) {
+  const int j = blockIdx.x * FB_COLS + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * FB_ROWS;
+  long long r1 = min(rows, r0 + FB_ROWS);
+  if (rv.dyn) { const long long seg0 = (r0 / rv.seg) * rv.seg; r1 = min(r1, seg0 + min(*rv.dyn, rv.seg)); }
+  float sb = 0.f;
+#pragma unroll 4
+  for (long long row = r0; row < r1; ++row) {
+    const size_t idx = (size_t)row * GAC_E + j;
+    const float d = du[idx];
+    const float a = d * h[idx];
+    dne[idx] = a;
+    dhu[idx] = d * ne[idx];
+    sb += a;
+  }
+  part_bn[(size_t)blockIdx.y * GAC_E + j] = sb;
+}
+
+// dst[n] = (accumulate ? dst[n] : 0) + sum_{s < nsplit} part[s*N + n], fixed order.
+// block (32, 8): 8 row lanes each sum every 8th partial with 4-way ILP, then a fixed-order smem fold.
+__global__ void reduce_cols_kernel(const float* __restrict__ part, int nsplit, int N, float* __restrict__ dst, int accumulate) {
+  __shared__ float sh[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x, ly = threadIdx.y;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (n < N) {
+    int s = ly;
+    for (; s + 24 < nsplit; s += 32) {
+      s0 += part[(size_t)s * N + n]; s1 += part[(size_t)(s + 8) * N + n];
+      s2 += part[(size_t)(s + 16) * N + n]; s3 += part[(size_t)(s + 24) * N + n];
+    }
+    for (; s < nsplit; s += 8) s0 += part[(size_t)s * N + n];
+  }
+  sh[ly][threadIdx.x] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ly == 0 && n < N) {
+    float t = accumulate ? dst[n] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
+    dst[n] = t;
+  }
 }
 
 // ---- out[r] = f(dot(x[r,:n], w) + b): one warp per row.  mode 0: identity, 1: tanh. ----
@@ -221,17 +310,6 @@ __global__ void head_dop_kernel(const float* __restrict__ dpred, const float* __
   if (r >= nvalid) return;
   const float p = pred[(size_t)r * A + d];
   dop[idx] = dpred[(size_t)r * A + d] * (1.f - p * p);
-}
-
-// ---- dne = du * h ; dhu = du * ne ----
-__global__ void hadamard_bwd_kernel(const float* __restrict__ du, const float* __restrict__ h, const float* __restrict__ ne,
-                                    long long n, int seg, const int* dyn, float* __restrict__ dne, float* __restrict__ dhu) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  if (dyn && (int)((idx / GAC_E) % seg) >= *dyn) return;
-  const float d = du[idx];
-  dne[idx] = d * h[idx];
-  dhu[idx] = d * ne[idx];
 }
 
 // ---- out = a * b on live rows (u = ne * h, networks.py:220/:265) ----
