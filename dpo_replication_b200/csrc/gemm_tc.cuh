@@ -25,6 +25,8 @@
 //   epilogue   tcgen05.ld (32 lanes x 16 columns per warp instruction) -> fused epilogue of
 //              gac_common.cuh (bias, gathered add, LeakyReLU, Hadamard, LeakyReLU', accumulate).
 #pragma once
+#include <stdlib.h>
+
 #include "gac_common.cuh"
 
 namespace gac {
@@ -418,6 +420,300 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
   }
 }
 
+// Work items of the persistent kernel: (split, m tile, n tile), n fastest so that CTAs running
+// concurrently share A row tiles in L2.
+struct Item { int m0, n0, split; bool live; int m_end; KMap km; };
+__device__ __forceinline__ Item decode_item(const GemmArgs& g, int item, int ntm, int ntn, int bn, int nvalid) {
+  Item it;
+  const int nt = item % ntn, rest = item / ntn;
+  const int mt = rest % ntm;
+  it.split = rest / ntm;
+  it.m0 = mt * BM; it.n0 = nt * bn;
+  const bool r_dyn = g.dyn_rows && !g.valid_on_k;
+  it.live = !(r_dyn && (it.m0 % g.seg_rows) >= nvalid);
+  it.m_end = r_dyn ? min(g.M, it.m0 - (it.m0 % g.seg_rows) + nvalid) : g.M;
+  it.km = make_kmap(g, nvalid, it.split);
+  return it;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Persistent variant for the packed-weight path (forward and dgrad GEMMs: ~70% of the step's
+// tensor work).  grid = min(#tiles, #SMs); every role walks the same static tile list
+// (tile = blockIdx.x + i * gridDim.x, n fastest).  Roles: warps 0-7 stage A (two groups alternate
+// K blocks) and one elected thread per group bulk-copies the packed B tiles; warps 8-15 are
+// dedicated epilogue warps (two per TMEM lane quarter, alternating 32-column groups); warp 16
+// issues the MMAs.  The smem ring and its mbarrier phases run across tiles, so the loaders prefetch
+// the next tile while the epilogue drains TMEM; the epilogue transposes each 32x32 block through
+// a per-warp smem tile so that every global access of the fused epilogue (bias, gathered add,
+// Hadamard, LeakyReLU', accumulate, store) is a full 128-byte line per row.
+// ---------------------------------------------------------------------------------------------
+constexpr int P_EPI_WARPS = 8;
+constexpr int P_MMA_WARP = LOADER_WARPS + P_EPI_WARPS;
+constexpr int P_THREADS = (LOADER_WARPS + P_EPI_WARPS + 1) * 32;
+constexpr int P_STG_BYTES = 32 * 36 * 4;          // per-warp staging tile, row pitch 36 floats (conflict free)
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void mma_commit_mc2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((unsigned short)3)
+               : "memory");
+}
+// pair item -> this CTA's tile: the pair shares the n tile, CTA rank r takes m tile 2*mp + r
+__device__ __forceinline__ Item decode_pair(const GemmArgs& g, int item, int rank, int ntm, int ntn, int bn, int nvalid) {
+  Item it;
+  const int nt = item % ntn, mp = item / ntn;
+  it.split = 0;
+  it.n0 = nt * bn;
+  const bool r_dyn = g.dyn_rows && !g.valid_on_k;
+  const int mA = (2 * mp) * BM, mB = (2 * mp + 1) * BM;
+  // the pair runs if either tile has a live row (both CTAs must take the same decision)
+  const bool liveA = !(r_dyn && (mA % g.seg_rows) >= nvalid), liveB = mB < g.M && !(r_dyn && (mB % g.seg_rows) >= nvalid);
+  it.live = liveA || liveB;
+  it.m0 = rank ? mB : mA;
+  it.m_end = r_dyn ? min(g.M, it.m0 - (it.m0 % g.seg_rows) + nvalid) : g.M;
+  it.km = make_kmap(g, nvalid, 0);
+  return it;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pers_kernel(const GemmArgs g, int bn, int stages, int tmem_cols, int ntm,
+                                                                   int ntn, int nitems) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull, bar_tempty;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t crank;                                  // rank in the 2-CTA cluster
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int nvalid = g.dyn_rows ? *g.dyn_rows : 0x7fffffff;
+  const uint32_t stage_bytes = 2 * A_TILE_BYTES + 2 * (uint32_t)bn * 128u;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  if (tid == 0) {
+    // empty[s] needs BOTH CTAs' MMA commits: the peer multicasts half of every B tile into our stage
+    for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&bar_full[s]), LOADER_WARPS / 2); mbar_init(smem_u32(&bar_empty[s]), 2); }
+    mbar_init(smem_u32(&bar_tfull), 1);
+    mbar_init(smem_u32(&bar_tempty), P_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == P_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  // peers must not signal our barriers / write our smem before they are initialised
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  if (warp < LOADER_WARPS) {
+    // ------------------------------ loaders ------------------------------
+    const int grp = warp >> 2, t = tid & (GROUP - 1);
+    int gk = 0;                                   // K blocks issued so far (all tiles)
+    for (int item = cluster_id; item < nitems; item += nclusters) {
+      const Item it = decode_pair(g, item, (int)crank, ntm, ntn, bn, nvalid);
+      if (!it.live) continue;
+      const int nkb = it.km.nkb;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int q = gk + kb;
+        if ((q & 1) != grp) continue;
+        int k0, live;
+        kmap_get(it.km, kb, k0, live);
+        float xa[8][4];
+        load_operand<false, VEC, 8>(xa, g.A, g.lda, it.m0, it.m_end, BM, k0, live, t);
+        const int s = q % stages;
+        const uint32_t ph = (uint32_t)(q / stages) & 1u;
+        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+        const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
+        if (t == 0) {
+          // the pair shares the B tile: this CTA fetches its half (rank 0: hi tile, rank 1: lo tile) and
+          // multicasts it into BOTH CTAs' stage; each CTA expects the full hi|lo pair on its barrier
+          const uint32_t half_bytes = (uint32_t)bn * 128u;
+          const unsigned char* srcp = g.Bpacked + ((size_t)(it.n0 / bn) * (size_t)((g.K + BK - 1) / BK) + (size_t)(k0 / BK)) * (2u * half_bytes) +
+                                      (size_t)crank * half_bytes;
+          const uint32_t bar = smem_u32(&bar_full[s]);
+          asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(2u * half_bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                           sa + 2 * A_TILE_BYTES + crank * half_bytes),
+                       "l"(srcp), "r"(half_bytes), "r"(bar), "h"((unsigned short)3)
+                       : "memory");
+        }
+        store_operand<false, 8>(xa, sa, sa + A_TILE_BYTES, BM, t);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+      }
+      gk += nkb;
+    }
+  } else if (warp < P_MMA_WARP) {
+    // ------------------------------ epilogue warps ------------------------------
+    const int ew = warp - LOADER_WARPS;
+    const int quarter = warp & 3, half = ew >> 2;
+    const uint32_t stg = smem0 + (uint32_t)stages * stage_bytes + (uint32_t)ew * P_STG_BYTES;
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    const int ngroups = (bn + 31) / 32;
+    // last group this warp reads (to hand TMEM back as early as possible)
+    const int last_g = ((ngroups - 1 - half) / 2) * 2 + half;
+    int ti = 0;
+    for (int item = cluster_id; item < nitems; item += nclusters) {
+      const Item it = decode_pair(g, item, (int)crank, ntm, ntn, bn, nvalid);
+      if (!it.live) continue;
+      const int nkb = it.km.nkb;
+      if (nkb > 0) {
+        mbar_wait(smem_u32(&bar_tfull), (uint32_t)ti & 1u);
+        tc_fence_after();
+        if (half >= ngroups) {                      // narrow tile: this warp has no column group
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_tempty));
+        }
+      }
+      for (int gi = half; gi < ngroups; gi += 2) {
+        const int col0 = gi * 32, gw = min(32, bn - col0);
+        float v[32];
+        if (nkb > 0) {
+          float w[32];
+          const uint32_t ta = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
+          if (gw == 32) { tmem_ld32_nowait(ta, v); tmem_ld32_nowait(ta + (uint32_t)bn, w); }
+          else { tmem_ld16_nowait(ta, v); tmem_ld16_nowait(ta + (uint32_t)bn, w); }
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < gw) v[j] += w[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (nkb > 0 && gi == last_g) {              // this warp is done with the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_tempty));
+        }
+        // lane-per-row -> smem
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q * 4 < gw)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stg + (uint32_t)lane * 144u + (uint32_t)q * 16u), "f"(v[4 * q]),
+                         "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
+                         : "memory");
+        __syncwarp();
+        // row-contiguous: 8 lanes x 16 B = one 128-byte line per row, 4 rows per instruction
+        const int nb = it.n0 + col0 + c4;
+        if (c4 < gw && nb < g.N) {
+          const bool colfull = nb + 3 < g.N;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rsub + 4 * i;
+            const int mm = it.m0 + quarter * 32 + r;
+            if (mm >= it.m_end) continue;
+            float4 x;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(stg + (uint32_t)r * 144u + (uint32_t)c4 * 4u));
+            if (colfull) {
+              if (g.bias) { const float4 b = *reinterpret_cast<const float4*>(g.bias + nb); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+              if (g.add) {
+                const float4 b = *reinterpret_cast<const float4*>(g.add + (size_t)(g.addidx ? g.addidx[mm] : mm) * g.ldadd + nb);
+                x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+              }
+              if (g.act == ACT_LRELU) { x.x = lrelu_f(x.x, g.alpha); x.y = lrelu_f(x.y, g.alpha); x.z = lrelu_f(x.z, g.alpha); x.w = lrelu_f(x.w, g.alpha); }
+              else if (g.act == ACT_LRELU2) {
+                x.x = lrelu_f(lrelu_f(x.x, 0.01f), 0.2f); x.y = lrelu_f(lrelu_f(x.y, 0.01f), 0.2f);
+                x.z = lrelu_f(lrelu_f(x.z, 0.01f), 0.2f); x.w = lrelu_f(lrelu_f(x.w, 0.01f), 0.2f);
+              }
+              if (g.mul) { const float4 b = *reinterpret_cast<const float4*>(g.mul + (size_t)mm * g.ldmul + nb); x.x *= b.x; x.y *= b.y; x.z *= b.z; x.w *= b.w; }
+              if (g.gate) {
+                const float4 b = *reinterpret_cast<const float4*>(g.gate + (size_t)mm * g.ldgate + nb);
+                const float ga = g.gate_alpha;
+                x.x *= b.x > 0.f ? 1.f : ga; x.y *= b.y > 0.f ? 1.f : ga; x.z *= b.z > 0.f ? 1.f : ga; x.w *= b.w > 0.f ? 1.f : ga;
+              }
+              if (g.accumulate) { const float4 b = *reinterpret_cast<const float4*>(g.C + (size_t)mm * g.ldc + nb); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+              *reinterpret_cast<float4*>(g.C + (size_t)mm * g.ldc + nb) = x;
+            } else {
+              const float* xe = &x.x;
+              for (int e = 0; e < 4; ++e) if (nb + e < g.N) g.C[(size_t)mm * g.ldc + nb + e] = gemm_epilogue(g, xe[e], mm, nb + e);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (nkb > 0) ++ti;
+    }
+  } else {
+    // ------------------------------ MMA issuer (one lane) ------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(bn);
+      int gk = 0, ti = 0;
+      for (int item = cluster_id; item < nitems; item += nclusters) {
+        const Item it = decode_pair(g, item, (int)crank, ntm, ntn, bn, nvalid);
+        if (!it.live) continue;
+        const int nkb = it.km.nkb;
+        if (nkb == 0) continue;
+        mbar_wait(smem_u32(&bar_tempty), ((uint32_t)ti & 1u) ^ 1u);    // previous tile's accumulator has been drained
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int q = gk + kb;
+          const int s = q % stages;
+          const uint32_t ph = (uint32_t)(q / stages) & 1u;
+          int k0, live;
+          kmap_get(it.km, kb, k0, live);
+          mbar_wait(smem_u32(&bar_full[s]), ph);
+          tc_fence_after();
+          const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
+          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
+          const uint64_t b_hi = make_desc(sa + 2 * A_TILE_BYTES), b_lo = make_desc(sa + 2 * A_TILE_BYTES + (uint32_t)bn * 128u);
+          const int ksteps = (live + 7) / 8;
+          for (int j = 0; j < ksteps; ++j) {
+            const uint64_t adv = (uint64_t)(j * 2);
+            const uint32_t acc = (kb | j) ? 1u : 0u;
+            mma_tf32(tmem_d + (uint32_t)bn, a_lo + adv, b_hi + adv, idesc, acc);   // correction accumulator
+            mma_tf32(tmem_d + (uint32_t)bn, a_hi + adv, b_lo + adv, idesc, 1u);
+            mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, acc);                  // main accumulator
+          }
+          mma_commit_mc2(smem_u32(&bar_empty[s]));           // frees the stage in both CTAs of the pair
+        }
+        mma_commit(smem_u32(&bar_tfull));
+        gk += nkb; ++ti;
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  // do not exit (or free TMEM) while the peer may still multicast into our smem / signal our barriers
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == P_MMA_WARP) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+  }
+}
+
 // Pack a weight matrix B (K x N; element (k,n) = transB ? W[n*ld + k] : W[k*ld + n]) into the
 // exact shared-memory image the MMA wants: for every (n tile j, K block kb) a contiguous
 // [hi tile | lo tile] pair, each bn rows x 128 bytes, K-major, 128-byte swizzled, zero padded.
@@ -447,7 +743,8 @@ __global__ void pack_b_kernel(const float* __restrict__ W, int ld, int transB, i
   *reinterpret_cast<float4*>(tile + (size_t)bn * 128u + off) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
-struct Plan { int bn, stages, tmem_cols; size_t smem; };
+struct Plan { int bn, stages, tmem_cols; size_t smem; int stages_pers; size_t smem_pers; };
+inline bool al16h(const void* p, int ld) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0)); }
 inline Plan plan_for(int N) {
   Plan p;
   const int ntiles = cdiv(N, 256);
@@ -459,6 +756,9 @@ inline Plan plan_for(int N) {
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.bn) p.tmem_cols *= 2;    // main + correction accumulators
   p.smem = (size_t)p.stages * stage_bytes + 1024;
+  p.stages_pers = (SMEM_LIMIT - 1024 - P_EPI_WARPS * P_STG_BYTES) / stage_bytes;
+  if (p.stages_pers > MAX_STAGES) p.stages_pers = MAX_STAGES;
+  p.smem_pers = (size_t)p.stages_pers * stage_bytes + 1024 + P_EPI_WARPS * P_STG_BYTES;
   return p;
 }
 
@@ -478,6 +778,8 @@ inline cudaError_t tc_gemm_init() {
   GAC_TC_ATTR(true, true, false, false) GAC_TC_ATTR(true, true, true, false)
   GAC_TC_ATTR(false, false, false, true) GAC_TC_ATTR(false, false, true, true)
 #undef GAC_TC_ATTR
+  if ((e = cudaFuncSetAttribute(tc::gemm_tc_pers_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(tc::gemm_tc_pers_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -499,7 +801,31 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   const bool veca = (g.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
   const bool vec = veca && (g.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
 #define GAC_TC_LAUNCH(a, b, c, d) tc::gemm_tc_kernel<a, b, c, d><<<grid, tc::THREADS, p.smem, st>>>(g, p.bn, p.stages, p.tmem_cols)
-  if (g.Bpacked && !g.transA && g.splitk <= 1) {
+  const bool epi_al = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && tc::al16h(g.bias, 4) &&
+                      tc::al16h(g.add, g.ldadd) && tc::al16h(g.mul, g.ldmul) && tc::al16h(g.gate, g.ldgate);
+  // Opt-in (GAC_TC_PERSISTENT=1): validated by the full GPU suite, measured no faster than the
+  // one-tile-per-CTA kernel because both are bound by shared-memory bandwidth; it is
+  // the base for the cta_group::2 version.
+  static const bool use_pers = getenv("GAC_TC_PERSISTENT") != nullptr && getenv("GAC_TC_PERSISTENT")[0] == '1';
+  if (use_pers && g.Bpacked && !g.transA && !g.transC && g.splitk <= 1 && epi_al && p.stages_pers >= 2 && g.M >= 4 * tc::BM) {
+    // persistent kernel: one CTA per SM walks the tile list
+    static int nsm = 0;
+    if (nsm == 0) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
+    }
+    const int ntn = cdiv(g.N, p.bn), ntm = cdiv(g.M, tc::BM), npairs = ntn * cdiv(ntm, 2);
+    const int nclus = npairs < nsm / 2 ? npairs : nsm / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * nclus); cfg.blockDim = dim3(tc::P_THREADS); cfg.dynamicSmemBytes = p.smem_pers; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (veca) return cudaLaunchKernelEx(&cfg, tc::gemm_tc_pers_kernel<true>, g, p.bn, p.stages_pers, p.tmem_cols, ntm, ntn, npairs);
+    return cudaLaunchKernelEx(&cfg, tc::gemm_tc_pers_kernel<false>, g, p.bn, p.stages_pers, p.tmem_cols, ntm, ntn, npairs);
+  } else if (g.Bpacked && !g.transA && g.splitk <= 1) {
     if (veca) GAC_TC_LAUNCH(false, false, true, true); else GAC_TC_LAUNCH(false, false, false, true);
   } else if (g.transA) {
     if (g.transB) { if (vec) GAC_TC_LAUNCH(true, true, true, false); else GAC_TC_LAUNCH(true, true, false, false); }
