@@ -32,6 +32,7 @@ CONFIGS = {
     "pendulum": (3, 1, 64, 32),           # configs[0]
     "humanoid": (376, 17, 256, 128),      # configs[2]
     "ant": (111, 8, 16384, 256),          # configs[3]: B is the GLOBAL batch, split over ranks (strong scaling)
+    "walker2d": (17, 6, 1000000, 32),     # configs[4]: forward-only sampler sweep over 1M states x 32 + Polyak bandwidth
 }
 METRIC = "GAC sampled (s,a) pairs/s through full train steps (HalfCheetah dims; steps/s in steps_per_s)"
 
@@ -280,6 +281,7 @@ def run_gpu(args):
                 "peak_source": (f"{pk['source']} bf16 burst {pk['bf16_burst']} TF/s / 2 (TF32) / 3 (3xTF32 passes)" if args.engine == 0
                                 else "fp32 SIMT: 148 SM x 128 FMA x 2 x 1.965 GHz")}
 
+    hbm = hbm_kernels(agent, dev) if (rank == 0 and world == 1) else None
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -308,10 +310,87 @@ def run_gpu(args):
                 "clocks": clk, "gpu_launches": int(launches),
                 "e2e": {"value": pairs_per_step / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms},
-                "roofline": roof, "cpu_baseline": cpu}
+                "roofline": roof, "cpu_baseline": cpu, "hbm_kernels": hbm}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return 0
+
+
+def hbm_kernels(agent, dev, reps=10):
+    """Achieved HBM GB/s of the streaming optimiser kernels on a stacked arena >= 1 GiB (a population
+    of parameter sets): at the real 8 MB model size they are L2 resident and launch bound."""
+    import torch
+    eng = agent.engine
+    n = 1 << 28                                  # 2^28 floats = 1 GiB per array
+    t = torch.zeros(n, device=dev); s_ = torch.ones(n, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        eng.polyak(t, s_, 5e-3)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        eng.polyak(t, s_, 5e-3)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    pk = peaks()
+    gbs = 12.0 * n / (ms * 1e-3) / 1e9            # read t, read s, write t
+    out = {"polyak": {"bytes_per_param": 12, "params": n, "ms": ms, "achieved_gbs": gbs, "peak_gbs": pk["hbm"], "frac": gbs / pk["hbm"]}}
+    del t, s_
+    # the model-sized fused Adam+Polyak sweep (L2 resident): report time and effective bandwidth
+    ar = agent.arena
+    hp = eng.hparams()
+    for _ in range(2):
+        eng.adam_polyak(ar.online, ar.target, ar.adam_m, ar.adam_v, ar.grad, hp, ar.adam_t)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        eng.adam_polyak(ar.online, ar.target, ar.adam_m, ar.adam_v, ar.grad, hp, ar.adam_t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out["adam_polyak_model_size"] = {"bytes_per_param": 36, "params": ar.n, "ms": ms, "effective_gbs": 36.0 * ar.n / (ms * 1e-3) / 1e9,
+                                     "note": "8 MB working set: L2 resident, launch-latency bound (2 launches)"}
+    return out
+
+
+def run_sweep(args):
+    """configs[4]: forward-only AIQN sampling over 1,000,000 states x 32 samples (Walker2d dims), streamed
+    in state chunks, + the Polyak / delayed-actor update bandwidth."""
+    import torch
+    import __graft_entry__ as ge
+    ge.build()
+    from dpo_replication_b200 import GACAgent
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda:0")
+    S, A, NS, K = CONFIGS["walker2d"]
+    chunk_states = 4096
+    agent = GACAgent(A, S, action_samples=K, batch_size=chunk_states, device=dev, engine=args.engine, chunk_rows=128)
+    eng, ar = agent.engine, agent.arena
+    rows = chunk_states * K
+    sidx = torch.arange(chunk_states, dtype=torch.int32, device=dev).repeat_interleave(K)
+    n_chunks = NS // chunk_states if not args.sweep_chunks else args.sweep_chunks
+    states = torch.randn(chunk_states, S, device=dev)
+    taus = torch.rand(rows, A, device=dev)
+    base = ar.net_slice(ar.target, "actor")
+    for _ in range(2):
+        eng.aiqn_sample(base, states, sidx, taus)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_chunks):
+        out = eng.aiqn_sample(base, states, sidx, taus)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    pairs = n_chunks * rows
+    f_min = 2 * ((400 * S + 480000) / K + 1171600 * A - 480000)
+    line = {"metric": "AIQN forward-only sampled (s,a) pairs/s (Walker2d dims, 1M states x 32, streamed)", "value": pairs / (ms * 1e-3),
+            "unit": "pairs/s", "n_gpus": 1, "ms_total": ms, "pairs": pairs, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"walker2d sweep: S={S} A={A} states={n_chunks * chunk_states} K={K} chunk={chunk_states} states"},
+            "achieved_tflops_min": pairs * f_min / (ms * 1e-3) / 1e12, "hbm_kernels": hbm_kernels(agent, dev)}
+    print(json.dumps(line))
     return 0
 
 
@@ -325,10 +404,13 @@ def main():
     ap.add_argument("--engine", type=int, default=0, help="0 = tcgen05 3xTF32 GEMMs, 1 = SIMT fp32")
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep-chunks", type=int, default=0, help="walker2d sweep: number of 4096-state chunks (0 = all 1M states)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "walker2d":
+        return run_sweep(args)
     return run_gpu(args)
 
 
