@@ -1,6 +1,7 @@
 // libgac_b200.so -- C ABI + orchestration of the GAC train step on B200 (sm_100a).
 // See include/gac_b200.h for the contract and the reference file:line each entry replaces.
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 
 #include "gac_common.cuh"
@@ -69,6 +70,7 @@ struct gac_ctx {
   int64_t launches;
   int P, Mc, nchunks, Rs, NUs, NUa, max_splits;
   const unsigned char* pk[16];   // packed pointer per slot (valid for the current call)
+  int pk_bn[16];                 // tile width each slot was packed for (0 = one-tile-per-CTA kernel)
   // sampler / critic scratch (Rs rows per pass)
   float *se_u, *sx_u, *cosb, *ae, *mxa, *mh, *hA, *hB, *u, *y1;
   float *cx, *ch0a, *ch0b, *ch1a, *ch1b;
@@ -154,7 +156,7 @@ size_t partition(gac_ctx* c, void* ws) {
   c->dop = b.take<float>(AM); c->pred_c = b.take<float>(Mc * A); c->dpred_c = b.take<float>(Mc * A);
   c->spart = b.take<float>((size_t)c->max_splits * GAC_E * GAC_G);
   const size_t maxrows = AM > Rs ? AM : Rs;
-  c->cpart = b.take<float>(((maxrows + COLSUM_ROWS - 1) / COLSUM_ROWS + 1) * GAC_G);
+  c->cpart = b.take<float>(((maxrows + COLSUM_ROWS - 1) / COLSUM_ROWS + 8192 / 16 + 1) * GAC_G);
   const size_t nrb = (AM + FB_ROWS - 1) / FB_ROWS + 1;
   c->fpart0 = b.take<float>(nrb * GAC_G); c->fpart1 = b.take<float>(nrb * GAC_G);
   c->pack_bytes = tc_packed_bytes(GAC_E, GAC_G);
@@ -176,10 +178,15 @@ inline float* var(const gac_ctx* c, float* net_base, int net, int v) {
 // Pre-split + pre-swizzle a weight matrix for the tensor-core engine (nullptr on the SIMT engine).
 enum { PK_T_WA = 0, PK_T_KXA, PK_T_U, PK_T_WN, PK_T_W1, PK_O_WA, PK_O_KXA, PK_O_U, PK_O_WN, PK_O_W1, PK_O_W1T, PK_O_UT, PK_O_KXAT,
        PK_C_F1, PK_C_F2 };
-const unsigned char* pack_w(gac_ctx* c, int slot, const float* W, int ld, int K, int N, int transB) {
+// rows = the smallest row count of the GEMMs that will use this image: large problems use the
+// cta_group::2 persistent kernel (128-wide tiles), small ones the one-tile-per-CTA kernel.
+const unsigned char* pack_w(gac_ctx* c, int slot, const float* W, int ld, int K, int N, int transB, int rows) {
+  c->pk_bn[slot] = 0;
   if (c->cfg.engine != 0 || K < 32 || N < 32 || tc_packed_bytes(K, N) > c->pack_bytes) return nullptr;
-  if (tc_pack_b(W, ld, transB, K, N, c->pack[slot], c->stream) != cudaSuccess) return nullptr;
+  const int bn = (tc_pair_enabled() && rows >= 1024) ? tc::pair_bn(N) : 0;
+  if (tc_pack_b(W, ld, transB, K, N, c->pack[slot], c->stream, bn) != cudaSuccess) return nullptr;
   c->launches++;
+  c->pk_bn[slot] = bn;
   return c->pack[slot];
 }
 
@@ -205,8 +212,8 @@ int run_gemm(gac_ctx* c, GemmArgs g) {
     int splits = (2 * 148) / tiles;
     // tcgen05 truncates toward zero when it adds into the fp32 accumulator (measured: relative
     // shrink ~2.0e-9 per reduction element, tools/gemm_accuracy.py), so bound the chain that one
-    // TMEM accumulator sees to 2048 reduction rows; the partials are summed in fp32 (round to nearest)
-    if (tc && splits < cdiv(g.K, 2048)) splits = cdiv(g.K, 2048);
+    // TMEM accumulator sees to 4096 reduction rows (<= 8e-6); the partials are summed in fp32 (round to nearest)
+    if (tc && splits < cdiv(g.K, 4096)) splits = cdiv(g.K, 4096);
     if (splits > c->max_splits) splits = c->max_splits;
     if (splits > g.K / 512) splits = g.K / 512;
     if ((size_t)g.M * g.N > (size_t)GAC_E * GAC_G) splits = 1;
@@ -231,8 +238,9 @@ int run_gemm(gac_ctx* c, GemmArgs g) {
 
 // dst[n] (+)= sum_r w[r] * X[r][n] over live rows
 int run_colsum(gac_ctx* c, const float* X, int ldx, const float* w, int N, long long rows, RowValid rv, float* dst, int accumulate) {
-  const int nblk = (int)cdiv64(rows, COLSUM_ROWS);
-  colsum_kernel<<<dim3(cdiv(N, 128), nblk), 128, 0, c->stream>>>(X, ldx, w, N, rows, rv, c->cpart);
+  const int rpb = rows <= 8192 ? 16 : COLSUM_ROWS;
+  const int nblk = (int)cdiv64(rows, rpb);
+  colsum_kernel<<<dim3(cdiv(N, 128), nblk), 128, 0, c->stream>>>(X, ldx, w, N, rows, rv, c->cpart, rpb);
   LAUNCHED(c, "colsum");
   reduce_cols_kernel<<<cdiv(N, 32), dim3(32, 8), 0, c->stream>>>(c->cpart, nblk, N, dst, accumulate);
   LAUNCHED(c, "colsum_reduce");
@@ -240,14 +248,14 @@ int run_colsum(gac_ctx* c, const float* X, int ldx, const float* w, int N, long 
 }
 
 // FNN forward on `rows` rows of x (rows, n_in): h0, h1 saved, out (rows) = linear head
-int fnn_forward(gac_ctx* c, const float* fnn, int n_in, const float* x, int rows, float* h0, float* h1, const unsigned char* w1_packed = nullptr) {
+int fnn_forward(gac_ctx* c, const float* fnn, int n_in, const float* x, int rows, float* h0, float* h1, const unsigned char* w1_packed = nullptr, int w1_bn = 0) {
   int64_t off[7];
   fnn_offsets(n_in, off);
   GemmArgs g = gemm_args(rows, GAC_H1, n_in, x, n_in, fnn + off[0], GAC_H1, h0, GAC_H1);
   g.bias = fnn + off[1]; g.act = ACT_LRELU; g.alpha = 0.01f;
   GAC_TRY(run_gemm(c, g));
   g = gemm_args(rows, GAC_H2, GAC_H1, h0, GAC_H1, fnn + off[2], GAC_H2, h1, GAC_H2);
-  g.bias = fnn + off[3]; g.act = ACT_LRELU; g.alpha = 0.01f; g.Bpacked = w1_packed;
+  g.bias = fnn + off[3]; g.act = ACT_LRELU; g.alpha = 0.01f; g.Bpacked = w1_packed; g.Bpacked_bn = w1_bn;
   GAC_TRY(run_gemm(c, g));
   return GAC_OK;
 }
@@ -271,15 +279,15 @@ int critic_eval(gac_ctx* c, const float* f1, const float* f2, const float* state
   const int S = c->cfg.S, A = c->cfg.A, W = S + A;
   int64_t off[7];
   fnn_offsets(W, off);
-  const unsigned char* pk1 = rows >= 1024 ? pack_w(c, PK_C_F1, f1 + off[2], GAC_H2, GAC_H1, GAC_H2, 0) : nullptr;
-  const unsigned char* pk2 = rows >= 1024 ? pack_w(c, PK_C_F2, f2 + off[2], GAC_H2, GAC_H1, GAC_H2, 0) : nullptr;
+  const unsigned char* pk1 = rows >= 1024 ? pack_w(c, PK_C_F1, f1 + off[2], GAC_H2, GAC_H1, GAC_H2, 0, rows < c->Rs ? rows : (rows % c->Rs ? rows % c->Rs : c->Rs)) : nullptr;
+  const unsigned char* pk2 = rows >= 1024 ? pack_w(c, PK_C_F2, f2 + off[2], GAC_H2, GAC_H1, GAC_H2, 0, rows < c->Rs ? rows : (rows % c->Rs ? rows % c->Rs : c->Rs)) : nullptr;
   for (int r0 = 0; r0 < rows; r0 += c->Rs) {
     const int n = rows - r0 < c->Rs ? rows - r0 : c->Rs;
     concat_gather_kernel<<<(unsigned)cdiv64((long long)n * W, 256), 256, 0, c->stream>>>(
         states_u, sidx ? sidx + r0 : nullptr, actions + (size_t)r0 * A, S, A, n, c->cx);
     LAUNCHED(c, "concat_gather");
-    GAC_TRY(fnn_forward(c, f1, W, c->cx, n, c->ch0a, c->ch1a, pk1));
-    GAC_TRY(fnn_forward(c, f2, W, c->cx, n, c->ch0b, c->ch1b, pk2));
+    GAC_TRY(fnn_forward(c, f1, W, c->cx, n, c->ch0a, c->ch1a, pk1, c->pk_bn[PK_C_F1]));
+    GAC_TRY(fnn_forward(c, f2, W, c->cx, n, c->ch0b, c->ch1b, pk2, c->pk_bn[PK_C_F2]));
     rowdot_kernel<<<cdiv(n * 32, 256), 256, 0, c->stream>>>(c->ch1a, GAC_H2, f1 + off[4], f1 + off[5], c->ch1b, f2 + off[4],
                                                            f2 + off[5], GAC_H2, n, 0, q + r0, 1, nullptr, 0, RowValid{nullptr, 1});
     LAUNCHED(c, "rowdot_min");
@@ -309,14 +317,14 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
     cos_basis_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(d ? actions + d - 1 : nullptr, A, c->cosb, rows, all);
     LAUNCHED(c, "cos_basis");
     GemmArgs g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->ae, GAC_E);
-    g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.Bpacked = c->pk[PK_T_WA];
+    g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.Bpacked = c->pk[PK_T_WA]; g.Bpacked_bn = c->pk_bn[PK_T_WA];
     GAC_TRY(run_gemm(c, g));
     g = gemm_args(rows, GAC_G, GAC_E, c->ae, GAC_E, kxa, GAC_G, c->mxa, GAC_G);
-    g.Bpacked = c->pk[PK_T_KXA];
+    g.Bpacked = c->pk[PK_T_KXA]; g.Bpacked_bn = c->pk_bn[PK_T_KXA];
     GAC_TRY(run_gemm(c, g));
     if (d) {
       g = gemm_args(rows, GAC_G, GAC_E, hprev, GAC_E, var(c, actor, 0, GAC_A_U), GAC_G, c->mh, GAC_G);
-      g.Bpacked = c->pk[PK_T_U];
+      g.Bpacked = c->pk[PK_T_U]; g.Bpacked_bn = c->pk_bn[PK_T_U];
       GAC_TRY(run_gemm(c, g));
     }
     gru_gates_fwd_kernel<<<(unsigned)cdiv64((long long)rows * GAC_E, 256), 256, 0, st>>>(
@@ -326,10 +334,10 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
     cos_basis_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(taus + d, A, c->cosb, rows, all);
     LAUNCHED(c, "cos_basis");
     g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->u, GAC_E);
-    g.bias = var(c, actor, 0, GAC_A_BN); g.mul = hcur; g.ldmul = GAC_E; g.Bpacked = c->pk[PK_T_WN];
+    g.bias = var(c, actor, 0, GAC_A_BN); g.mul = hcur; g.ldmul = GAC_E; g.Bpacked = c->pk[PK_T_WN]; g.Bpacked_bn = c->pk_bn[PK_T_WN];
     GAC_TRY(run_gemm(c, g));
     g = gemm_args(rows, GAC_E, GAC_E, c->u, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->y1, GAC_E);
-    g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f; g.Bpacked = c->pk[PK_T_W1];
+    g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f; g.Bpacked = c->pk[PK_T_W1]; g.Bpacked_bn = c->pk_bn[PK_T_W1];
     GAC_TRY(run_gemm(c, g));
     rowdot_kernel<<<cdiv(rows * 32, 256), 256, 0, st>>>(c->y1, GAC_E, var(c, actor, 0, GAC_A_W2), var(c, actor, 0, GAC_A_B2),
                                                        nullptr, nullptr, nullptr, GAC_E, rows, 1, actions + d, A, nullptr, 0, all);
@@ -344,11 +352,11 @@ int aiqn_sample(gac_ctx* c, const float* actor, const float* states_u, int n_sta
   if (n_states > c->NUs) return fail(GAC_ERR_WORKSPACE, "gac_aiqn_sample: n_states exceeds the workspace capacity");
   GAC_TRY(state_prep(c, actor, states_u, n_states, c->se_u, c->sx_u));
   const int A = c->cfg.A;
-  c->pk[PK_T_WA] = pack_w(c, PK_T_WA, var(c, actor, 0, GAC_A_WA), GAC_E, GAC_NB, GAC_E, 0);
-  c->pk[PK_T_KXA] = pack_w(c, PK_T_KXA, var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, GAC_G, GAC_E, GAC_G, 0);
-  c->pk[PK_T_U] = pack_w(c, PK_T_U, var(c, actor, 0, GAC_A_U), GAC_G, GAC_E, GAC_G, 0);
-  c->pk[PK_T_WN] = pack_w(c, PK_T_WN, var(c, actor, 0, GAC_A_WN), GAC_E, GAC_NB, GAC_E, 0);
-  c->pk[PK_T_W1] = pack_w(c, PK_T_W1, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 0);
+  c->pk[PK_T_WA] = pack_w(c, PK_T_WA, var(c, actor, 0, GAC_A_WA), GAC_E, GAC_NB, GAC_E, 0, rows);
+  c->pk[PK_T_KXA] = pack_w(c, PK_T_KXA, var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, GAC_G, GAC_E, GAC_G, 0, rows);
+  c->pk[PK_T_U] = pack_w(c, PK_T_U, var(c, actor, 0, GAC_A_U), GAC_G, GAC_E, GAC_G, 0, rows);
+  c->pk[PK_T_WN] = pack_w(c, PK_T_WN, var(c, actor, 0, GAC_A_WN), GAC_E, GAC_NB, GAC_E, 0, rows);
+  c->pk[PK_T_W1] = pack_w(c, PK_T_W1, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 0, rows);
   for (int r0 = 0; r0 < rows; r0 += c->Rs) {
     const int n = rows - r0 < c->Rs ? rows - r0 : c->Rs;
     GAC_TRY(aiqn_sample_rows(c, actor, sidx + r0, taus + (size_t)r0 * A, n, actions + (size_t)r0 * A));
@@ -409,27 +417,27 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
   c->bwd_sidx = c->a_sidx; c->bwd_states = c->a_states; c->bwd_nstates = n_states; c->bwd_drows = live;
   GAC_TRY(state_prep(c, actor, states_u, n_states, c->a_se_u, c->a_sx_u));
   const float* kxa_w = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
-  c->pk[PK_O_WA] = pack_w(c, PK_O_WA, var(c, actor, 0, GAC_A_WA), GAC_E, GAC_NB, GAC_E, 0);
-  c->pk[PK_O_KXA] = pack_w(c, PK_O_KXA, kxa_w, GAC_G, GAC_E, GAC_G, 0);
-  c->pk[PK_O_U] = pack_w(c, PK_O_U, var(c, actor, 0, GAC_A_U), GAC_G, GAC_E, GAC_G, 0);
-  c->pk[PK_O_WN] = pack_w(c, PK_O_WN, var(c, actor, 0, GAC_A_WN), GAC_E, GAC_NB, GAC_E, 0);
-  c->pk[PK_O_W1] = pack_w(c, PK_O_W1, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 0);
-  c->pk[PK_O_W1T] = pack_w(c, PK_O_W1T, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 1);
-  c->pk[PK_O_UT] = pack_w(c, PK_O_UT, var(c, actor, 0, GAC_A_U), GAC_G, GAC_G, GAC_E, 1);
-  c->pk[PK_O_KXAT] = pack_w(c, PK_O_KXAT, kxa_w, GAC_G, GAC_G, GAC_E, 1);
+  c->pk[PK_O_WA] = pack_w(c, PK_O_WA, var(c, actor, 0, GAC_A_WA), GAC_E, GAC_NB, GAC_E, 0, c->Mc);
+  c->pk[PK_O_KXA] = pack_w(c, PK_O_KXA, kxa_w, GAC_G, GAC_E, GAC_G, 0, c->Mc);
+  c->pk[PK_O_U] = pack_w(c, PK_O_U, var(c, actor, 0, GAC_A_U), GAC_G, GAC_E, GAC_G, 0, c->Mc);
+  c->pk[PK_O_WN] = pack_w(c, PK_O_WN, var(c, actor, 0, GAC_A_WN), GAC_E, GAC_NB, GAC_E, 0, c->Mc);
+  c->pk[PK_O_W1] = pack_w(c, PK_O_W1, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 0, c->Mc);
+  c->pk[PK_O_W1T] = pack_w(c, PK_O_W1T, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 1, c->Mc);
+  c->pk[PK_O_UT] = pack_w(c, PK_O_UT, var(c, actor, 0, GAC_A_U), GAC_G, GAC_G, GAC_E, 1, c->Mc);
+  c->pk[PK_O_KXAT] = pack_w(c, PK_O_KXAT, kxa_w, GAC_G, GAC_G, GAC_E, 1, c->Mc);
   cos_basis_seq_kernel<<<(unsigned)cdiv64(AM * GAC_NB, 256), 256, 0, st>>>(teacher, taus, A, Mc, c->ca, c->cn, live);
   LAUNCHED(c, "cos_basis_seq");
   GemmArgs g = gemm_args((int)AM, GAC_E, GAC_NB, c->ca, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->a_ae, GAC_E);
-  g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_WA];
+  g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_WA]; g.Bpacked_bn = c->pk_bn[PK_O_WA];
   GAC_TRY(run_gemm(c, g));
   g = gemm_args((int)AM, GAC_G, GAC_E, c->a_ae, GAC_E, kxa_w, GAC_G, c->mx, GAC_G);
-  g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_KXA];
+  g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_KXA]; g.Bpacked_bn = c->pk_bn[PK_O_KXA];
   GAC_TRY(run_gemm(c, g));
   for (int d = 0; d < A; ++d) {
     const size_t o4 = (size_t)d * Mc * GAC_E, o12 = (size_t)d * Mc * GAC_G;
     if (d) {
       g = gemm_args(Mc, GAC_G, GAC_E, c->hall + o4, GAC_E, var(c, actor, 0, GAC_A_U), GAC_G, c->dmh + o12, GAC_G);
-      g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_U];
+      g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_U]; g.Bpacked_bn = c->pk_bn[PK_O_U];
       GAC_TRY(run_gemm(c, g));
     }
     gru_gates_fwd_kernel<<<(unsigned)cdiv64((long long)Mc * GAC_E, 256), 256, 0, st>>>(
@@ -438,12 +446,12 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
     LAUNCHED(c, "gru_gates_fwd");
   }
   g = gemm_args((int)AM, GAC_E, GAC_NB, c->cn, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->ne, GAC_E);
-  g.bias = var(c, actor, 0, GAC_A_BN); g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_WN];
+  g.bias = var(c, actor, 0, GAC_A_BN); g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_WN]; g.Bpacked_bn = c->pk_bn[PK_O_WN];
   GAC_TRY(run_gemm(c, g));
   mul_kernel<<<(unsigned)cdiv64(AM * GAC_E, 256), 256, 0, st>>>(c->ne, c->hall + (size_t)Mc * GAC_E, AM * GAC_E, Mc, live, c->au);
   LAUNCHED(c, "hadamard");
   g = gemm_args((int)AM, GAC_E, GAC_E, c->au, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->ay1, GAC_E);
-  g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_W1];
+  g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_W1]; g.Bpacked_bn = c->pk_bn[PK_O_W1];
   GAC_TRY(run_gemm(c, g));
   for (int d = 0; d < A; ++d) {
     rowdot_kernel<<<cdiv(Mc * 32, 256), 256, 0, st>>>(c->ay1 + (size_t)d * Mc * GAC_E, GAC_E, var(c, actor, 0, GAC_A_W2),
@@ -483,7 +491,7 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   LAUNCHED(c, "reduce_cols");
   GAC_TRY(wgrad(GAC_E, GAC_E, c->au, GAC_E, c->dy1p, GAC_E, AM, G(GAC_A_W1), true));
   GemmArgs g = gemm_args((int)AM, GAC_E, GAC_E, c->dy1p, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->du, GAC_E);
-  g.transB = 1; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_W1T];
+  g.transB = 1; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_W1T]; g.Bpacked_bn = c->pk_bn[PK_O_W1T];
   GAC_TRY(run_gemm(c, g));
   hadamard_bwd_kernel<<<dim3(GAC_E / FB_COLS, nrb_all), FB_COLS, 0, st>>>(c->du, c->hall + (size_t)Mc * GAC_E, c->ne, AM, rv, c->dne,
                                                                           c->dhu, c->fpart0);
@@ -502,7 +510,7 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
     LAUNCHED(c, "gru_gates_bwd");
     if (d) {
       g = gemm_args(Mc, GAC_E, GAC_G, c->dmh + o12, GAC_G, var(c, actor, 0, GAC_A_U), GAC_G, carry, GAC_E);
-      g.transB = 1; g.accumulate = 1; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_UT];
+      g.transB = 1; g.accumulate = 1; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_UT]; g.Bpacked_bn = c->pk_bn[PK_O_UT];
       GAC_TRY(run_gemm(c, g));
     }
     dh_next = carry;
@@ -516,13 +524,13 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   LAUNCHED(c, "reduce_cols");
   GAC_TRY(wgrad(GAC_E, GAC_G, c->a_ae, GAC_E, c->mx, GAC_G, AM, G(GAC_A_KX) + (size_t)GAC_E * GAC_G, true));
   g = gemm_args((int)AM, GAC_E, GAC_G, c->mx, GAC_G, kxa, GAC_G, c->du, GAC_E);
-  g.transB = 1; g.gate = c->a_ae; g.ldgate = GAC_E; g.gate_alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_KXAT];
+  g.transB = 1; g.gate = c->a_ae; g.ldgate = GAC_E; g.gate_alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_KXAT]; g.Bpacked_bn = c->pk_bn[PK_O_KXAT];
   GAC_TRY(run_gemm(c, g));
   GAC_TRY(wgrad(GAC_NB, GAC_E, c->ca, GAC_NB, c->du, GAC_E, AM, G(GAC_A_WA), true));
   GAC_TRY(run_colsum(c, c->du, GAC_E, nullptr, GAC_E, AM, rv, G(GAC_A_BA), acc));
   // state half: reduce d(sx) per unique state, then B-row GEMMs
   const int NU = c->bwd_nstates;
-  segment_sum_kernel<<<dim3(NU, cdiv(GAC_G, 256)), 256, 0, st>>>(c->mx, c->bwd_sidx, A, Mc, live, 0, c->a_dsx_u);
+  segment_sum_kernel<<<NU, 256, 0, st>>>(c->mx, c->bwd_sidx, A, Mc, live, 0, c->a_dsx_u);
   LAUNCHED(c, "segment_sum");
   GAC_TRY(wgrad(GAC_E, GAC_G, c->a_se_u, GAC_E, c->a_dsx_u, GAC_G, NU, G(GAC_A_KX), false));
   g = gemm_args(NU, GAC_E, GAC_G, c->a_dsx_u, GAC_G, var(c, actor, 0, GAC_A_KX), GAC_G, c->a_dse_u, GAC_E);
@@ -696,9 +704,11 @@ int gac_gemm(gac_ctx_t* c, int32_t engine, const float* A, const float* B, float
     if (!tc_gemm_supported(g)) return fail(GAC_ERR_UNSUPPORTED, "gac_gemm: shape not supported by the tcgen05 engine");
     if (engine == 2) {   // B treated as a weight matrix: pre-split / pre-swizzled once, fetched by bulk copies
       if (transA || tc_packed_bytes(K, N) > c->pack_bytes) return fail(GAC_ERR_UNSUPPORTED, "gac_gemm: packed-B needs !transA and a weight-sized B");
-      GAC_CUDA(tc_pack_b(B, g.ldb, transB, K, N, c->pack[15], c->stream));
+      const int pbn = (tc_pair_enabled() && M >= 1024) ? tc::pair_bn(N) : 0;
+      GAC_CUDA(tc_pack_b(B, g.ldb, transB, K, N, c->pack[15], c->stream, pbn));
       c->launches++;
-      g.Bpacked = c->pack[15];
+      g.Bpacked = c->pack[15]; g.Bpacked_bn = pbn;
+      if (getenv("GAC_TC_TIMELINE")) g.dbg = reinterpret_cast<unsigned long long*>(c->spart);   // scratch: 16 x 8 stamps
     }
     GAC_CUDA(launch_gemm_tc(g, c->stream));
   } else {

@@ -56,6 +56,7 @@ struct GemmArgs {
   const float* A; int lda; int transA;  // transA: A(m,k) = A[k*lda + m]
   const float* B; int ldb; int transB;  // transB: B(k,n) = B[n*ldb + k]
   const unsigned char* Bpacked;        // optional: B pre-split/pre-swizzled by tc::pack_b_kernel (weights)
+  int Bpacked_bn;                      // tile width the packed image was built for (selects the kernel)
   float* C; int ldc; int transC;        // transC: C(m,n) stored at C[n*ldc + m]
   const float* bias;
   const float* add; int ldadd; const int* addidx;
@@ -68,6 +69,7 @@ struct GemmArgs {
   const int* dyn_rows; int seg_rows; int valid_on_k;
   // split-K: blockIdx.z = split, raw partial (no epilogue) stored at C + z*split_stride
   int splitk; long long split_stride;
+  unsigned long long* dbg;               // optional timeline probe (tools/gemm_probe.py --timeline)
 };
 
 inline GemmArgs gemm_args(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc) {

@@ -448,9 +448,10 @@ __device__ __forceinline__ Item decode_item(const GemmArgs& g, int item, int ntm
 // a per-warp smem tile so that every global access of the fused epilogue (bias, gathered add,
 // Hadamard, LeakyReLU', accumulate, store) is a full 128-byte line per row.
 // ---------------------------------------------------------------------------------------------
-constexpr int P_EPI_WARPS = 8;
-constexpr int P_MMA_WARP = LOADER_WARPS + P_EPI_WARPS;
-constexpr int P_THREADS = (LOADER_WARPS + P_EPI_WARPS + 1) * 32;
+constexpr int P_LOADER_WARPS = 16;               // 4 groups x 4 warps: 4 K blocks of global loads in flight per CTA
+constexpr int P_EPI_WARPS = 4;                   // one per TMEM lane quarter (overlapped with the next tile via TMEM double buffering)
+constexpr int P_MMA_WARP = P_LOADER_WARPS + P_EPI_WARPS;
+constexpr int P_THREADS = (P_LOADER_WARPS + P_EPI_WARPS + 1) * 32;
 constexpr int P_STG_BYTES = 32 * 36 * 4;          // per-warp staging tile, row pitch 36 floats (conflict free)
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
@@ -478,11 +479,6 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void mma_commit_mc2(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"((unsigned short)3)
-               : "memory");
-}
 // pair item -> this CTA's tile: the pair shares the n tile, CTA rank r takes m tile 2*mp + r
 __device__ __forceinline__ Item decode_pair(const GemmArgs& g, int item, int rank, int ntm, int ntn, int bn, int nvalid) {
   Item it;
@@ -500,11 +496,41 @@ __device__ __forceinline__ Item decode_pair(const GemmArgs& g, int item, int ran
   return it;
 }
 
+// ---------------------------------------------------------------------------------------------
+// cta_group::2 variant of the persistent kernel: the two CTAs of a cluster form one 256 x bn MMA.
+// Each SM stages its own 128 rows of A and only ITS half of the B tile, so per SM the MMA reads
+// (4 KB + bn*16 B) per instruction instead of (4 KB + bn*32 B): the kernel is shared-memory
+// bandwidth bound in cta_group::1 and this removes ~1/3 of that traffic.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t make_idesc2(int n) {   // M = 256 (m_dim = 16)
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32_2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit2_mc(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((unsigned short)3)
+               : "memory");
+}
+// arrive on the barrier at the same offset in cluster rank 0 (local for the leader itself)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(bar));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+}
+
 template <bool VEC>
-__global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pers_kernel(const GemmArgs g, int bn, int stages, int tmem_cols, int ntm,
+__global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pair_kernel(const GemmArgs g, int bn, int stages, int tmem_cols, int ntm,
                                                                    int ntn, int nitems) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull, bar_tempty;
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_pfull[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -512,19 +538,25 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pers_kernel(const GemmAr
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
   const int nvalid = g.dyn_rows ? *g.dyn_rows : 0x7fffffff;
-  const uint32_t stage_bytes = 2 * A_TILE_BYTES + 2 * (uint32_t)bn * 128u;
+  const uint32_t hb = (uint32_t)(bn / 2) * 128u;      // this CTA's half of a B tile (bytes)
+  const uint32_t stage_bytes = 2 * A_TILE_BYTES + 2 * hb;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
   if (tid == 0) {
-    // empty[s] needs BOTH CTAs' MMA commits: the peer multicasts half of every B tile into our stage
-    for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&bar_full[s]), LOADER_WARPS / 2); mbar_init(smem_u32(&bar_empty[s]), 2); }
-    mbar_init(smem_u32(&bar_tfull), 1);
-    mbar_init(smem_u32(&bar_tempty), P_EPI_WARPS);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), LOADER_WARPS / 2);    // this CTA's A stores (4 warps per group) + its B bytes
+      mbar_init(smem_u32(&bar_pfull[s]), 1);                  // leader only: "the peer's stage is full too"
+      mbar_init(smem_u32(&bar_empty[s]), 1);                  // the pair's MMAs retired (multicast commit)
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tfull[b]), 1);
+      mbar_init(smem_u32(&bar_tempty[b]), 2 * P_EPI_WARPS);   // leader: both CTAs' epilogue warps
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == P_MMA_WARP) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -534,74 +566,92 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pers_kernel(const GemmAr
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
 
-  if (warp < LOADER_WARPS) {
+  if (warp < P_LOADER_WARPS) {
     // ------------------------------ loaders ------------------------------
+    // up to four 4-warp groups take K blocks round-robin (measured per group and K block: ~1500 cycles of
+    // global-load latency + ~650 split/store + ~450 barrier traffic => one K block per ~800 cycles with 4
+    // groups, below the MMA time); parity waits cannot alias as long as #groups <= #stages
     const int grp = warp >> 2, t = tid & (GROUP - 1);
+    const int ngrp = stages < 4 ? stages : 4;
     int gk = 0;                                   // K blocks issued so far (all tiles)
-    for (int item = cluster_id; item < nitems; item += nclusters) {
+    int nstamp = 0;
+    for (int item = cluster_id; item < nitems && grp < ngrp; item += nclusters) {
       const Item it = decode_pair(g, item, (int)crank, ntm, ntn, bn, nvalid);
       if (!it.live) continue;
       const int nkb = it.km.nkb;
       for (int kb = 0; kb < nkb; ++kb) {
         const int q = gk + kb;
-        if ((q & 1) != grp) continue;
+        if ((q % ngrp) != grp) continue;
         int k0, live;
         kmap_get(it.km, kb, k0, live);
+        const bool stamp = g.dbg && blockIdx.x == 0 && tid == 0 && nstamp < 16;
+        unsigned long long s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+        if (stamp) s0 = clock64();
         float xa[8][4];
         load_operand<false, VEC, 8>(xa, g.A, g.lda, it.m0, it.m_end, BM, k0, live, t);
+        if (stamp) { float acc = 0.f; for (int i = 0; i < 8; ++i) acc += xa[i][0]; if (acc == 123.456f) s1 = 1; s1 += clock64(); }   // data has landed
         const int s = q % stages;
         const uint32_t ph = (uint32_t)(q / stages) & 1u;
         mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+        if (stamp) s2 = clock64();
         const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
         if (t == 0) {
-          // the pair shares the B tile: this CTA fetches its half (rank 0: hi tile, rank 1: lo tile) and
-          // multicasts it into BOTH CTAs' stage; each CTA expects the full hi|lo pair on its barrier
-          const uint32_t half_bytes = (uint32_t)bn * 128u;
-          const unsigned char* srcp = g.Bpacked + ((size_t)(it.n0 / bn) * (size_t)((g.K + BK - 1) / BK) + (size_t)(k0 / BK)) * (2u * half_bytes) +
-                                      (size_t)crank * half_bytes;
+          // cta_group::2: this CTA supplies rows [rank*bn/2, (rank+1)*bn/2) of the B tile (hi and lo)
+          const unsigned char* tile = g.Bpacked + ((size_t)(it.n0 / bn) * (size_t)((g.K + BK - 1) / BK) + (size_t)(k0 / BK)) * (size_t)(4u * hb);
           const uint32_t bar = smem_u32(&bar_full[s]);
-          asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(2u * half_bytes) : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-                           sa + 2 * A_TILE_BYTES + crank * half_bytes),
-                       "l"(srcp), "r"(half_bytes), "r"(bar), "h"((unsigned short)3)
+          asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(2u * hb) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa + 2 * A_TILE_BYTES),
+                       "l"(tile + (size_t)crank * hb), "r"(hb), "r"(bar)
+                       : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa + 2 * A_TILE_BYTES + hb),
+                       "l"(tile + 2u * (size_t)hb + (size_t)crank * hb), "r"(hb), "r"(bar)
                        : "memory");
         }
         store_operand<false, 8>(xa, sa, sa + A_TILE_BYTES, BM, t);
+        if (stamp) s3 = clock64();
         fence_proxy_async();
+        if (stamp) s4 = clock64();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+        if (stamp) {
+          unsigned long long* d = g.dbg + 256 + nstamp * 8;
+          d[0] = s0; d[1] = s1; d[2] = s2; d[3] = s3; d[4] = s4; d[5] = clock64(); d[6] = (unsigned long long)q;
+          ++nstamp;
+        }
       }
       gk += nkb;
     }
   } else if (warp < P_MMA_WARP) {
     // ------------------------------ epilogue warps ------------------------------
-    const int ew = warp - LOADER_WARPS;
-    const int quarter = warp & 3, half = ew >> 2;
+    const int ew = warp - P_LOADER_WARPS;
+    const int quarter = warp & 3, half = 0;
     const uint32_t stg = smem0 + (uint32_t)stages * stage_bytes + (uint32_t)ew * P_STG_BYTES;
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     const int ngroups = (bn + 31) / 32;
     // last group this warp reads (to hand TMEM back as early as possible)
-    const int last_g = ((ngroups - 1 - half) / 2) * 2 + half;
+    const int last_g = ngroups - 1;
     int ti = 0;
     for (int item = cluster_id; item < nitems; item += nclusters) {
       const Item it = decode_pair(g, item, (int)crank, ntm, ntn, bn, nvalid);
       if (!it.live) continue;
       const int nkb = it.km.nkb;
       if (nkb > 0) {
-        mbar_wait(smem_u32(&bar_tfull), (uint32_t)ti & 1u);
+        mbar_wait(smem_u32(&bar_tfull[ti & 1]), (uint32_t)(ti >> 1) & 1u);
         tc_fence_after();
+        if (g.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && ti < 16) g.dbg[ti * 8 + 4] = clock64();
         if (half >= ngroups) {                      // narrow tile: this warp has no column group
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bar_tempty));
+          if (lane == 0) mbar_arrive_leader(smem_u32(&bar_tempty[ti & 1]));
         }
       }
-      for (int gi = half; gi < ngroups; gi += 2) {
+      const uint32_t tbuf = tmem_d + (uint32_t)((ti & 1) * 2 * bn);   // this tile's accumulator buffer
+      for (int gi = 0; gi < ngroups; ++gi) {
         const int col0 = gi * 32, gw = min(32, bn - col0);
         float v[32];
         if (nkb > 0) {
           float w[32];
-          const uint32_t ta = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
+          const uint32_t ta = tbuf + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
           if (gw == 32) { tmem_ld32_nowait(ta, v); tmem_ld32_nowait(ta + (uint32_t)bn, w); }
           else { tmem_ld16_nowait(ta, v); tmem_ld16_nowait(ta + (uint32_t)bn, w); }
           tmem_wait_ld();
@@ -614,7 +664,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pers_kernel(const GemmAr
         if (nkb > 0 && gi == last_g) {              // this warp is done with the accumulator
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bar_tempty));
+          if (lane == 0) mbar_arrive_leader(smem_u32(&bar_tempty[ti & 1]));
         }
         // lane-per-row -> smem
 #pragma unroll
@@ -662,20 +712,27 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pers_kernel(const GemmAr
         }
         __syncwarp();
       }
+      if (g.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && ti < 16) g.dbg[ti * 8 + 5] = clock64();
       if (nkb > 0) ++ti;
     }
   } else {
-    // ------------------------------ MMA issuer (one lane) ------------------------------
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(bn);
+    // ------------------------------ MMA warp ------------------------------
+    if (lane == 0 && crank == 0) {
+      // leader: one lane issues the pair's MMAs (M = 256 across the two CTAs, each SM reads its own
+      // 128 rows of A and its own half of B from shared memory)
+      const uint32_t idesc = make_idesc2(bn);
       int gk = 0, ti = 0;
       for (int item = cluster_id; item < nitems; item += nclusters) {
-        const Item it = decode_pair(g, item, (int)crank, ntm, ntn, bn, nvalid);
+        const Item it = decode_pair(g, item, 0, ntm, ntn, bn, nvalid);
         if (!it.live) continue;
         const int nkb = it.km.nkb;
         if (nkb == 0) continue;
-        mbar_wait(smem_u32(&bar_tempty), ((uint32_t)ti & 1u) ^ 1u);    // previous tile's accumulator has been drained
+        unsigned long long t0 = 0, t1 = 0, t2 = 0;
+        if (g.dbg && blockIdx.x == 0) t0 = clock64();
+        mbar_wait(smem_u32(&bar_tempty[ti & 1]), ((uint32_t)(ti >> 1) & 1u) ^ 1u);   // both CTAs drained this buffer's previous tile
+        const uint32_t tbuf = tmem_d + (uint32_t)((ti & 1) * 2 * bn);
         tc_fence_after();
+        if (g.dbg && blockIdx.x == 0) t1 = clock64();
         for (int kb = 0; kb < nkb; ++kb) {
           const int q = gk + kb;
           const int s = q % stages;
@@ -683,22 +740,42 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pers_kernel(const GemmAr
           int k0, live;
           kmap_get(it.km, kb, k0, live);
           mbar_wait(smem_u32(&bar_full[s]), ph);
+          mbar_wait(smem_u32(&bar_pfull[s]), ph);
           tc_fence_after();
+          if (g.dbg && blockIdx.x == 0 && kb == 0) t2 = clock64();
           const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
           const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
-          const uint64_t b_hi = make_desc(sa + 2 * A_TILE_BYTES), b_lo = make_desc(sa + 2 * A_TILE_BYTES + (uint32_t)bn * 128u);
+          const uint64_t b_hi = make_desc(sa + 2 * A_TILE_BYTES), b_lo = make_desc(sa + 2 * A_TILE_BYTES + hb);
           const int ksteps = (live + 7) / 8;
           for (int j = 0; j < ksteps; ++j) {
             const uint64_t adv = (uint64_t)(j * 2);
             const uint32_t acc = (kb | j) ? 1u : 0u;
-            mma_tf32(tmem_d + (uint32_t)bn, a_lo + adv, b_hi + adv, idesc, acc);   // correction accumulator
-            mma_tf32(tmem_d + (uint32_t)bn, a_hi + adv, b_lo + adv, idesc, 1u);
-            mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, acc);                  // main accumulator
+            mma_tf32_2(tbuf + (uint32_t)bn, a_lo + adv, b_hi + adv, idesc, acc);   // correction accumulator
+            mma_tf32_2(tbuf + (uint32_t)bn, a_hi + adv, b_lo + adv, idesc, 1u);
+            mma_tf32_2(tbuf, a_hi + adv, b_hi + adv, idesc, acc);                  // main accumulator
           }
-          mma_commit_mc2(smem_u32(&bar_empty[s]));           // frees the stage in both CTAs of the pair
+          mma_commit2_mc(smem_u32(&bar_empty[s]));           // frees the stage in both CTAs
         }
-        mma_commit(smem_u32(&bar_tfull));
+        mma_commit2_mc(smem_u32(&bar_tfull[ti & 1]));        // accumulators complete in both CTAs
+        if (g.dbg && blockIdx.x == 0 && ti < 16) {
+          g.dbg[ti * 8 + 0] = t0; g.dbg[ti * 8 + 1] = t1; g.dbg[ti * 8 + 2] = t2; g.dbg[ti * 8 + 3] = clock64();
+        }
         gk += nkb; ++ti;
+      }
+    } else if (lane == 0) {
+      // peer: relay "my stage is full" to the leader's MMA thread
+      int gk = 0;
+      for (int item = cluster_id; item < nitems; item += nclusters) {
+        const Item it = decode_pair(g, item, 1, ntm, ntn, bn, nvalid);
+        if (!it.live) continue;
+        const int nkb = it.km.nkb;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int q = gk + kb;
+          const int s = q % stages;
+          mbar_wait(smem_u32(&bar_full[s]), (uint32_t)(q / stages) & 1u);
+          mbar_arrive_leader(smem_u32(&bar_pfull[s]));
+        }
+        gk += nkb;
       }
     }
     __syncwarp();
@@ -710,7 +787,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pers_kernel(const GemmAr
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (warp == P_MMA_WARP) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -744,6 +821,8 @@ __global__ void pack_b_kernel(const float* __restrict__ W, int ld, int transB, i
 }
 
 struct Plan { int bn, stages, tmem_cols; size_t smem; int stages_pers; size_t smem_pers; };
+// cta_group::2 kernel: tiles <= 128 wide so that two accumulator buffers (main + correction each) fit in 512 TMEM columns
+inline int pair_bn(int N) { const int nt = cdiv(N, 128); int bn = round_up(cdiv(N, nt), 16); return bn > 128 ? 128 : bn; }
 inline bool al16h(const void* p, int ld) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0)); }
 inline Plan plan_for(int N) {
   Plan p;
@@ -778,19 +857,30 @@ inline cudaError_t tc_gemm_init() {
   GAC_TC_ATTR(true, true, false, false) GAC_TC_ATTR(true, true, true, false)
   GAC_TC_ATTR(false, false, false, true) GAC_TC_ATTR(false, false, true, true)
 #undef GAC_TC_ATTR
-  if ((e = cudaFuncSetAttribute(tc::gemm_tc_pers_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(tc::gemm_tc_pers_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(tc::gemm_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(tc::gemm_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
+// The cta_group::2 persistent kernel (TMEM double buffered) passes the whole GPU suite but is, as of
+// round 1, slower than the one-tile-per-CTA kernel: its register-staged A operand is bound by global
+// load latency (profiles/r1_pair_kernel_timeline.txt).  Opt in with GAC_TC_PAIR=1.
+inline bool tc_pair_enabled() {
+  static const bool on = getenv("GAC_TC_PAIR") != nullptr && getenv("GAC_TC_PAIR")[0] == '1';
+  return on;
+}
 inline size_t tc_packed_bytes(int K, int N) {
   const tc::Plan p = tc::plan_for(N);
-  return (size_t)cdiv(N, p.bn) * cdiv(K, tc::BK) * 2 * p.bn * 128;
+  const size_t a = (size_t)cdiv(N, p.bn) * cdiv(K, tc::BK) * 2 * p.bn * 128;
+  const int pb = tc::pair_bn(N);
+  const size_t b = (size_t)cdiv(N, pb) * cdiv(K, tc::BK) * 2 * pb * 128;
+  return a > b ? a : b;
 }
-inline cudaError_t tc_pack_b(const float* W, int ld, int transB, int K, int N, unsigned char* out, cudaStream_t st) {
-  const tc::Plan p = tc::plan_for(N);
-  const long long total = (long long)cdiv(N, p.bn) * cdiv(K, tc::BK) * p.bn * 8;
-  tc::pack_b_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(W, ld, transB, K, N, p.bn, out);
+// bn = 0: the one-tile-per-CTA kernel's tile width; otherwise the given width (cta_group::2 kernel)
+inline cudaError_t tc_pack_b(const float* W, int ld, int transB, int K, int N, unsigned char* out, cudaStream_t st, int bn = 0) {
+  if (bn == 0) bn = tc::plan_for(N).bn;
+  const long long total = (long long)cdiv(N, bn) * cdiv(K, tc::BK) * bn * 8;
+  tc::pack_b_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(W, ld, transB, K, N, bn, out);
   return cudaGetLastError();
 }
 
@@ -806,25 +896,34 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   // Opt-in (GAC_TC_PERSISTENT=1): validated by the full GPU suite, measured no faster than the
   // one-tile-per-CTA kernel because both are bound by shared-memory bandwidth; it is
   // the base for the cta_group::2 version.
-  static const bool use_pers = getenv("GAC_TC_PERSISTENT") != nullptr && getenv("GAC_TC_PERSISTENT")[0] == '1';
-  if (use_pers && g.Bpacked && !g.transA && !g.transC && g.splitk <= 1 && epi_al && p.stages_pers >= 2 && g.M >= 4 * tc::BM) {
-    // persistent kernel: one CTA per SM walks the tile list
-    static int nsm = 0;
-    if (nsm == 0) {
+  if (g.Bpacked && g.Bpacked_bn > 0) {
+    // packed for the cta_group::2 persistent kernel
+    if (g.transA || g.transC || g.splitk > 1 || !epi_al) return cudaErrorInvalidValue;
+    static int nsm2 = 0;
+    if (nsm2 == 0) {
       int dev = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm2, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm2 <= 0) nsm2 = 148;
     }
-    const int ntn = cdiv(g.N, p.bn), ntm = cdiv(g.M, tc::BM), npairs = ntn * cdiv(ntm, 2);
-    const int nclus = npairs < nsm / 2 ? npairs : nsm / 2;
+    const int pbn = g.Bpacked_bn;
+    const int ntn = cdiv(g.N, pbn), ntm = cdiv(g.M, tc::BM), npairs = ntn * cdiv(ntm, 2);
+    const int nclus = npairs < nsm2 / 2 ? npairs : nsm2 / 2;
+    const int pstage = 2 * (int)tc::A_TILE_BYTES + 2 * (pbn / 2) * 128;
+    int pst = (tc::SMEM_LIMIT - 1024 - tc::P_EPI_WARPS * tc::P_STG_BYTES) / pstage;
+    if (pst > tc::MAX_STAGES) pst = tc::MAX_STAGES;
+    const size_t psmem = (size_t)pst * pstage + 1024 + tc::P_EPI_WARPS * tc::P_STG_BYTES;
+    int tcols = 32;
+    while (tcols < 4 * pbn) tcols *= 2;                       // 2 buffers x (main + correction)
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * nclus); cfg.blockDim = dim3(tc::P_THREADS); cfg.dynamicSmemBytes = p.smem_pers; cfg.stream = st;
+    cfg.gridDim = dim3(2 * nclus); cfg.blockDim = dim3(tc::P_THREADS); cfg.dynamicSmemBytes = psmem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (veca) return cudaLaunchKernelEx(&cfg, tc::gemm_tc_pers_kernel<true>, g, p.bn, p.stages_pers, p.tmem_cols, ntm, ntn, npairs);
-    return cudaLaunchKernelEx(&cfg, tc::gemm_tc_pers_kernel<false>, g, p.bn, p.stages_pers, p.tmem_cols, ntm, ntn, npairs);
+    if (veca) return cudaLaunchKernelEx(&cfg, tc::gemm_tc_pair_kernel<true>, g, pbn, pst, tcols, ntm, ntn, npairs);
+    return cudaLaunchKernelEx(&cfg, tc::gemm_tc_pair_kernel<false>, g, pbn, pst, tcols, ntm, ntn, npairs);
+  }
+  if (false) {
   } else if (g.Bpacked && !g.transA && g.splitk <= 1) {
     if (veca) GAC_TC_LAUNCH(false, false, true, true); else GAC_TC_LAUNCH(false, false, false, true);
   } else if (g.transA) {

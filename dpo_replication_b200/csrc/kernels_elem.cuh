@@ -332,12 +332,14 @@ __global__ void sidx3_kernel(int* __restrict__ s, int P, int B, int K) {
 // ---- column sums with optional row weights: part[blk][n] = sum_{r in blk} w[r] * X[r][n] ----
 // (bias gradients, the width-1 layer's weight gradient).  Deterministic two-stage reduction.
 constexpr int COLSUM_ROWS = 256;
+// rpb rows per block (256 for the long time-parallel arrays, 16 for the B-row TD tensors: a single block
+// walking 256 rows serially is latency bound at ~50 us)
 __global__ void colsum_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ w, int N, long long rows,
-                              RowValid rv, float* __restrict__ part) {
+                              RowValid rv, float* __restrict__ part, int rpb) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
-  const long long r0 = (long long)blockIdx.y * COLSUM_ROWS;
-  long long r1 = min(rows, r0 + COLSUM_ROWS);
+  const long long r0 = (long long)blockIdx.y * rpb;
+  long long r1 = min(rows, r0 + rpb);
   // a block of 256 rows never straddles a segment (seg is a multiple of 128 and of 256 or the
   // block is clipped below): live rows of this block are a prefix [r0, r_live)
   if (rv.dyn) {
@@ -475,9 +477,14 @@ __global__ void segment_sum_kernel(const float* __restrict__ dmx, const int* __r
   __shared__ int wcnt[8];
   __shared__ int nlist;
   const int b = blockIdx.x;
-  const int n = blockIdx.y * 256 + threadIdx.x;   // 256 threads, 5 slabs cover 1200 (tail masked)
   const int nvalid = dyn ? min(*dyn, seg) : seg;
-  float s = (accumulate && n < GAC_G) ? dsx_u[(size_t)b * GAC_G + n] : 0.f;
+  constexpr int NS = (GAC_G + 255) / 256;                  // 5 column slabs per thread, one scan of sidx per state
+  float s[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) {
+    const int n = k * 256 + threadIdx.x;
+    s[k] = (accumulate && n < GAC_G) ? dsx_u[(size_t)b * GAC_G + n] : 0.f;
+  }
   for (int base = 0; base < nvalid; base += 256) {
     const int j = base + threadIdx.x;
     const bool hit = j < nvalid && sidx[j] == b;
@@ -490,21 +497,24 @@ __global__ void segment_sum_kernel(const float* __restrict__ dmx, const int* __r
     if (hit) list[off + __popc(bal & ((1u << lane) - 1u))] = j;
     if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < 8; ++k) t += wcnt[k]; nlist = t; }
     __syncthreads();
-    if (n < GAC_G)
-      for (int e = 0; e < nlist; ++e) {
-        const int jj = list[e];
-        float t0 = 0.f, t1 = 0.f;
-        int d = 0;
-        for (; d + 1 < A; d += 2) {
-          t0 += dmx[((size_t)d * seg + jj) * GAC_G + n];
-          t1 += dmx[((size_t)(d + 1) * seg + jj) * GAC_G + n];
+    for (int e = 0; e < nlist; ++e) {
+      const int jj = list[e];
+      for (int d = 0; d < A; ++d) {
+        const float* row = dmx + ((size_t)d * seg + jj) * GAC_G;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+          const int n = k * 256 + threadIdx.x;
+          if (n < GAC_G) s[k] += row[n];
         }
-        if (d < A) t0 += dmx[((size_t)d * seg + jj) * GAC_G + n];
-        s += t0 + t1;
       }
+    }
     __syncthreads();
   }
-  if (n < GAC_G) dsx_u[(size_t)b * GAC_G + n] = s;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) {
+    const int n = k * 256 + threadIdx.x;
+    if (n < GAC_G) dsx_u[(size_t)b * GAC_G + n] = s[k];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
