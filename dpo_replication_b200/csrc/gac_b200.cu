@@ -530,7 +530,7 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   GAC_TRY(run_colsum(c, c->du, GAC_E, nullptr, GAC_E, AM, rv, G(GAC_A_BA), acc));
   // state half: reduce d(sx) per unique state, then B-row GEMMs
   const int NU = c->bwd_nstates;
-  segment_sum_kernel<<<NU, 256, 0, st>>>(c->mx, c->bwd_sidx, A, Mc, live, 0, c->a_dsx_u);
+  segment_sum_kernel<<<dim3(NU, cdiv(GAC_G, 256)), 256, 0, st>>>(c->mx, c->bwd_sidx, A, Mc, live, 0, c->a_dsx_u);
   LAUNCHED(c, "segment_sum");
   GAC_TRY(wgrad(GAC_E, GAC_G, c->a_se_u, GAC_E, c->a_dsx_u, GAC_G, NU, G(GAC_A_KX), false));
   g = gemm_args(NU, GAC_E, GAC_G, c->a_dsx_u, GAC_G, var(c, actor, 0, GAC_A_KX), GAC_G, c->a_dse_u, GAC_E);

@@ -477,14 +477,9 @@ __global__ void segment_sum_kernel(const float* __restrict__ dmx, const int* __r
   __shared__ int wcnt[8];
   __shared__ int nlist;
   const int b = blockIdx.x;
+  const int n = blockIdx.y * 256 + threadIdx.x;   // 256 threads, 5 slabs cover 1200 (tail masked)
   const int nvalid = dyn ? min(*dyn, seg) : seg;
-  constexpr int NS = (GAC_G + 255) / 256;                  // 5 column slabs per thread, one scan of sidx per state
-  float s[NS];
-#pragma unroll
-  for (int k = 0; k < NS; ++k) {
-    const int n = k * 256 + threadIdx.x;
-    s[k] = (accumulate && n < GAC_G) ? dsx_u[(size_t)b * GAC_G + n] : 0.f;
-  }
+  float s = (accumulate && n < GAC_G) ? dsx_u[(size_t)b * GAC_G + n] : 0.f;
   for (int base = 0; base < nvalid; base += 256) {
     const int j = base + threadIdx.x;
     const bool hit = j < nvalid && sidx[j] == b;
@@ -497,24 +492,21 @@ __global__ void segment_sum_kernel(const float* __restrict__ dmx, const int* __r
     if (hit) list[off + __popc(bal & ((1u << lane) - 1u))] = j;
     if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < 8; ++k) t += wcnt[k]; nlist = t; }
     __syncthreads();
-    for (int e = 0; e < nlist; ++e) {
-      const int jj = list[e];
-      for (int d = 0; d < A; ++d) {
-        const float* row = dmx + ((size_t)d * seg + jj) * GAC_G;
-#pragma unroll
-        for (int k = 0; k < NS; ++k) {
-          const int n = k * 256 + threadIdx.x;
-          if (n < GAC_G) s[k] += row[n];
+    if (n < GAC_G)
+      for (int e = 0; e < nlist; ++e) {
+        const int jj = list[e];
+        float t0 = 0.f, t1 = 0.f;
+        int d = 0;
+        for (; d + 1 < A; d += 2) {
+          t0 += dmx[((size_t)d * seg + jj) * GAC_G + n];
+          t1 += dmx[((size_t)(d + 1) * seg + jj) * GAC_G + n];
         }
+        if (d < A) t0 += dmx[((size_t)d * seg + jj) * GAC_G + n];
+        s += t0 + t1;
       }
-    }
     __syncthreads();
   }
-#pragma unroll
-  for (int k = 0; k < NS; ++k) {
-    const int n = k * 256 + threadIdx.x;
-    if (n < GAC_G) dsx_u[(size_t)b * GAC_G + n] = s[k];
-  }
+  if (n < GAC_G) dsx_u[(size_t)b * GAC_G + n] = s;
 }
 
 // ------------------------------------------------------------------------------------------
