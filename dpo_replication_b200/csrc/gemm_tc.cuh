@@ -25,6 +25,7 @@
 //   epilogue   tcgen05.ld (32 lanes x 16 columns per warp instruction) -> fused epilogue of
 //              gac_common.cuh (bias, gathered add, LeakyReLU, Hadamard, LeakyReLU', accumulate).
 #pragma once
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "gac_common.cuh"
@@ -448,11 +449,12 @@ __device__ __forceinline__ Item decode_item(const GemmArgs& g, int item, int ntm
 // a per-warp smem tile so that every global access of the fused epilogue (bias, gathered add,
 // Hadamard, LeakyReLU', accumulate, store) is a full 128-byte line per row.
 // ---------------------------------------------------------------------------------------------
-constexpr int P_LOADER_WARPS = 16;               // 4 groups x 4 warps: 4 K blocks of global loads in flight per CTA
-constexpr int P_EPI_WARPS = 4;                   // one per TMEM lane quarter (overlapped with the next tile via TMEM double buffering)
-constexpr int P_MMA_WARP = P_LOADER_WARPS + P_EPI_WARPS;
-constexpr int P_THREADS = (P_LOADER_WARPS + P_EPI_WARPS + 1) * 32;
-constexpr int P_STG_BYTES = 32 * 36 * 4;          // per-warp staging tile, row pitch 36 floats (conflict free)
+constexpr int P_SPLIT_WARPS = 8;                 // 2 groups x 4 warps: smem -> smem hi/lo split of the TMA-loaded A tiles
+constexpr int P_EPI_WARPS = 8;                   // two per TMEM lane quarter
+constexpr int P_MMA_WARP = P_SPLIT_WARPS + P_EPI_WARPS;     // leader: MMA issue; peer: "my stage is full" relay
+constexpr int P_TMA_WARP = P_MMA_WARP + 1;                  // one lane: A tiles by TMA, B halves by bulk copy
+constexpr int P_THREADS = (P_SPLIT_WARPS + P_EPI_WARPS + 2) * 32;
+constexpr int P_STG_BYTES = 32 * 36 * 4;          // per-warp epilogue staging tile, row pitch 36 floats (conflict free)
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
   uint32_t r[32];
@@ -497,10 +499,17 @@ __device__ __forceinline__ Item decode_pair(const GemmArgs& g, int item, int ran
 }
 
 // ---------------------------------------------------------------------------------------------
-// cta_group::2 variant of the persistent kernel: the two CTAs of a cluster form one 256 x bn MMA.
-// Each SM stages its own 128 rows of A and only ITS half of the B tile, so per SM the MMA reads
-// (4 KB + bn*16 B) per instruction instead of (4 KB + bn*32 B): the kernel is shared-memory
-// bandwidth bound in cta_group::1 and this removes ~1/3 of that traffic.
+// Persistent cta_group::2 GEMM for the packed-weight path (forward and dgrad GEMMs).
+//   * the two CTAs of a cluster form one 256 x bn MMA; each SM holds its own 128 rows of A and only
+//     its half of the B tile, which lifts the SS-operand-fetch bound of cta_group::1;
+//   * tiles are <= 128 wide so that TWO accumulator buffers (main + correction each) fit in the 512
+//     TMEM columns: the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * A is loaded by TMA (cp.async.bulk.tensor, 128B hardware swizzle = the UMMA layout) into a raw
+//     ring by one producer lane, so no global-load latency sits in a compute warp; two splitter groups
+//     turn each raw tile into the hi / lo tiles smem -> smem (pure 16-byte-chunk map, the swizzle is
+//     position preserving); B halves arrive by bulk copy from the packed image;
+//   * the epilogue transposes 32x32 blocks through per-warp smem tiles: every global access of the
+//     fused epilogue is a full 128-byte line per row.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t make_idesc2(int n) {   // M = 256 (m_dim = 16)
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -526,11 +535,10 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pair_kernel(const GemmArgs g, int bn, int stages, int tmem_cols, int ntm,
-                                                                   int ntn, int nitems) {
+__global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pair_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmapA, int bn,
+                                                                   int stages, int tmem_cols, int ntm, int ntn, int nitems) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_pfull[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_pfull[MAX_STAGES], bar_empty[MAX_STAGES], bar_afull[MAX_STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -541,12 +549,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pair_kernel(const GemmAr
   const uint32_t hb = (uint32_t)(bn / 2) * 128u;      // this CTA's half of a B tile (bytes)
   const uint32_t stage_bytes = 2 * A_TILE_BYTES + 2 * hb;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg0 = smem0 + (uint32_t)stages * stage_bytes;                 // epilogue staging tiles
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), LOADER_WARPS / 2);    // this CTA's A stores (4 warps per group) + its B bytes
+      mbar_init(smem_u32(&bar_full[s]), P_SPLIT_WARPS / 2);   // the splitter group's 4 warps (+ this CTA's B bytes)
       mbar_init(smem_u32(&bar_pfull[s]), 1);                  // leader only: "the peer's stage is full too"
       mbar_init(smem_u32(&bar_empty[s]), 1);                  // the pair's MMAs retired (multicast commit)
+      mbar_init(smem_u32(&bar_afull[s]), 1);                  // producer's arrive.expect_tx + the A tile's TMA bytes
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_tfull[b]), 1);
@@ -560,108 +570,85 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pair_kernel(const GemmAr
   }
   tc_fence_before();
   __syncthreads();
-  // peers must not signal our barriers / write our smem before they are initialised
+  // peers must not signal our barriers before they are initialised
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
 
-  if (warp < P_LOADER_WARPS) {
-    // ------------------------------ loaders ------------------------------
-    // up to four 4-warp groups take K blocks round-robin (measured per group and K block: ~1500 cycles of
-    // global-load latency + ~650 split/store + ~450 barrier traffic => one K block per ~800 cycles with 4
-    // groups, below the MMA time); parity waits cannot alias as long as #groups <= #stages
-    const int grp = warp >> 2, t = tid & (GROUP - 1);
-    const int ngrp = stages < 4 ? stages : 4;
-    int gk = 0;                                   // K blocks issued so far (all tiles)
-    int nstamp = 0;
-    for (int item = cluster_id; item < nitems && grp < ngrp; item += nclusters) {
+  if (warp < P_SPLIT_WARPS) {
+    // ------------------------------ splitters: A_lo = x - trunc_tf32(x) ------------------------------
+    // TMA lands the raw fp32 tile directly in the stage's A_hi slot: kind::tf32 ignores the low 13 mantissa
+    // bits of its operands, so the raw tile IS the hi operand; only the lo tile is computed here
+    // (smem -> smem, a pure 16-byte-chunk map because the 128B swizzle is position preserving).
+    const int grp = warp >> 2, t = tid & (GROUP - 1);          // group g owns the K blocks q = g (mod 2)
+    int gk = 0;
+    for (int item = cluster_id; item < nitems; item += nclusters) {
       const Item it = decode_pair(g, item, (int)crank, ntm, ntn, bn, nvalid);
       if (!it.live) continue;
       const int nkb = it.km.nkb;
       for (int kb = 0; kb < nkb; ++kb) {
         const int q = gk + kb;
-        if ((q % ngrp) != grp) continue;
-        int k0, live;
-        kmap_get(it.km, kb, k0, live);
-        const bool stamp = g.dbg && blockIdx.x == 0 && tid == 0 && nstamp < 16;
-        unsigned long long s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
-        if (stamp) s0 = clock64();
-        float xa[8][4];
-        load_operand<false, VEC, 8>(xa, g.A, g.lda, it.m0, it.m_end, BM, k0, live, t);
-        if (stamp) { float acc = 0.f; for (int i = 0; i < 8; ++i) acc += xa[i][0]; if (acc == 123.456f) s1 = 1; s1 += clock64(); }   // data has landed
+        if ((q & 1) != grp) continue;
         const int s = q % stages;
-        const uint32_t ph = (uint32_t)(q / stages) & 1u;
-        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-        if (stamp) s2 = clock64();
+        mbar_wait(smem_u32(&bar_afull[s]), (uint32_t)(q / stages) & 1u);           // TMA landed the A tile of this stage
         const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
-        if (t == 0) {
-          // cta_group::2: this CTA supplies rows [rank*bn/2, (rank+1)*bn/2) of the B tile (hi and lo)
-          const unsigned char* tile = g.Bpacked + ((size_t)(it.n0 / bn) * (size_t)((g.K + BK - 1) / BK) + (size_t)(k0 / BK)) * (size_t)(4u * hb);
-          const uint32_t bar = smem_u32(&bar_full[s]);
-          asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(2u * hb) : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa + 2 * A_TILE_BYTES),
-                       "l"(tile + (size_t)crank * hb), "r"(hb), "r"(bar)
-                       : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa + 2 * A_TILE_BYTES + hb),
-                       "l"(tile + 2u * (size_t)hb + (size_t)crank * hb), "r"(hb), "r"(bar)
-                       : "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t off = (uint32_t)(t + GROUP * i) * 16u;
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(sa + off));
+          const float l0 = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u), l1 = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          const float l2 = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u), l3 = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sa + A_TILE_BYTES + off), "f"(l0), "f"(l1), "f"(l2), "f"(l3));
         }
-        store_operand<false, 8>(xa, sa, sa + A_TILE_BYTES, BM, t);
-        if (stamp) s3 = clock64();
         fence_proxy_async();
-        if (stamp) s4 = clock64();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
-        if (stamp) {
-          unsigned long long* d = g.dbg + 256 + nstamp * 8;
-          d[0] = s0; d[1] = s1; d[2] = s2; d[3] = s3; d[4] = s4; d[5] = clock64(); d[6] = (unsigned long long)q;
-          ++nstamp;
-        }
       }
       gk += nkb;
     }
   } else if (warp < P_MMA_WARP) {
     // ------------------------------ epilogue warps ------------------------------
-    const int ew = warp - P_LOADER_WARPS;
-    const int quarter = warp & 3, half = 0;
-    const uint32_t stg = smem0 + (uint32_t)stages * stage_bytes + (uint32_t)ew * P_STG_BYTES;
+    const int ew = warp - P_SPLIT_WARPS;
+    const int quarter = warp & 3, half = ew >> 2;
+    const uint32_t stg = stg0 + (uint32_t)ew * P_STG_BYTES;
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     const int ngroups = (bn + 31) / 32;
-    // last group this warp reads (to hand TMEM back as early as possible)
-    const int last_g = ngroups - 1;
+    const int last_g = ngroups - 1 - half >= 0 ? ((ngroups - 1 - half) / 2) * 2 + half : -1;
     int ti = 0;
     for (int item = cluster_id; item < nitems; item += nclusters) {
       const Item it = decode_pair(g, item, (int)crank, ntm, ntn, bn, nvalid);
       if (!it.live) continue;
-      const int nkb = it.km.nkb;
-      if (nkb > 0) {
-        mbar_wait(smem_u32(&bar_tfull[ti & 1]), (uint32_t)(ti >> 1) & 1u);
-        tc_fence_after();
-        if (g.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && ti < 16) g.dbg[ti * 8 + 4] = clock64();
-        if (half >= ngroups) {                      // narrow tile: this warp has no column group
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_leader(smem_u32(&bar_tempty[ti & 1]));
-        }
+      mbar_wait(smem_u32(&bar_tfull[ti & 1]), (uint32_t)(ti >> 1) & 1u);
+      tc_fence_after();
+      if (g.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && ti < 16) g.dbg[ti * 8 + 4] = clock64();
+      if (last_g < 0) {                             // narrow tile: this warp has no column group
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(smem_u32(&bar_tempty[ti & 1]));
       }
       const uint32_t tbuf = tmem_d + (uint32_t)((ti & 1) * 2 * bn);   // this tile's accumulator buffer
-      for (int gi = 0; gi < ngroups; ++gi) {
+      for (int gi = half; gi < ngroups; gi += 2) {
         const int col0 = gi * 32, gw = min(32, bn - col0);
         float v[32];
-        if (nkb > 0) {
+        const bool estamp = g.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && ti == 2 && gi == half;
+        unsigned long long e0 = 0, e1 = 0, e2 = 0;
+        if (estamp) e0 = clock64();
+        {
           float w[32];
-          const uint32_t ta = tbuf + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
-          if (gw == 32) { tmem_ld32_nowait(ta, v); tmem_ld32_nowait(ta + (uint32_t)bn, w); }
-          else { tmem_ld16_nowait(ta, v); tmem_ld16_nowait(ta + (uint32_t)bn, w); }
+          // TMEM columns of a buffer (N = 2*bn, CTA0's rows then CTA1's): [main n<bn/2 | corr n<bn/2 | main n>=bn/2 | corr n>=bn/2]
+          const int hh = bn / 2;
+          const int mcol = (col0 / hh) * bn + (col0 % hh);
+          const uint32_t ta = tbuf + ((uint32_t)(quarter * 32) << 16) + (uint32_t)mcol;
+          if (gw == 32) { tmem_ld32_nowait(ta, v); tmem_ld32_nowait(ta + (uint32_t)hh, w); }
+          else { tmem_ld16_nowait(ta, v); tmem_ld16_nowait(ta + (uint32_t)hh, w); }
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (j < gw) v[j] += w[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
-        if (nkb > 0 && gi == last_g) {              // this warp is done with the accumulator
+        if (estamp) { if (v[0] == 123.456f) e1 = 1; e1 += clock64(); }
+        if (gi == last_g) {                          // this warp is done with the accumulator buffer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(smem_u32(&bar_tempty[ti & 1]));
@@ -674,6 +661,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pair_kernel(const GemmAr
                          "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
                          : "memory");
         __syncwarp();
+        if (estamp) e2 = clock64();
         // row-contiguous: 8 lanes x 16 B = one 128-byte line per row, 4 rows per instruction
         const int nb = it.n0 + col0 + c4;
         if (c4 < gw && nb < g.N) {
@@ -711,28 +699,31 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pair_kernel(const GemmAr
           }
         }
         __syncwarp();
+        if (estamp) { g.dbg[300] = e0; g.dbg[301] = e1; g.dbg[302] = e2; g.dbg[303] = clock64(); }
       }
       if (g.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && ti < 16) g.dbg[ti * 8 + 5] = clock64();
-      if (nkb > 0) ++ti;
+      ++ti;
     }
-  } else {
+  } else if (warp == P_MMA_WARP) {
     // ------------------------------ MMA warp ------------------------------
     if (lane == 0 && crank == 0) {
-      // leader: one lane issues the pair's MMAs (M = 256 across the two CTAs, each SM reads its own
-      // 128 rows of A and its own half of B from shared memory)
-      const uint32_t idesc = make_idesc2(bn);
+      // leader: one lane issues the pair's MMAs (M = 256 across the two CTAs)
+      // each K step = 2 instructions of N = 2*bn against the CTA pair's contiguous [B_hi | B_lo] rows:
+      //   A_hi x [B_hi | B_lo] -> [main | corr],   A_lo x [B_hi | B_lo] -> [main += lo*hi | corr += lo*lo (2^-24, harmless)]
+      // the per-instruction cost of tcgen05.mma is ~145 cycles almost independent of N (measured), so two wide
+      // instructions beat three narrow ones by 1.46x; main sees 2 truncating adds per K step instead of 1.
+      const uint32_t idesc = make_idesc2(2 * bn);
       int gk = 0, ti = 0;
       for (int item = cluster_id; item < nitems; item += nclusters) {
         const Item it = decode_pair(g, item, 0, ntm, ntn, bn, nvalid);
         if (!it.live) continue;
         const int nkb = it.km.nkb;
-        if (nkb == 0) continue;
         unsigned long long t0 = 0, t1 = 0, t2 = 0;
         if (g.dbg && blockIdx.x == 0) t0 = clock64();
         mbar_wait(smem_u32(&bar_tempty[ti & 1]), ((uint32_t)(ti >> 1) & 1u) ^ 1u);   // both CTAs drained this buffer's previous tile
-        const uint32_t tbuf = tmem_d + (uint32_t)((ti & 1) * 2 * bn);
         tc_fence_after();
         if (g.dbg && blockIdx.x == 0) t1 = clock64();
+        const uint32_t tbuf = tmem_d + (uint32_t)((ti & 1) * 2 * bn);
         for (int kb = 0; kb < nkb; ++kb) {
           const int q = gk + kb;
           const int s = q % stages;
@@ -745,14 +736,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pair_kernel(const GemmAr
           if (g.dbg && blockIdx.x == 0 && kb == 0) t2 = clock64();
           const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
           const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
-          const uint64_t b_hi = make_desc(sa + 2 * A_TILE_BYTES), b_lo = make_desc(sa + 2 * A_TILE_BYTES + hb);
+          const uint64_t b_all = make_desc(sa + 2 * A_TILE_BYTES);   // bn rows per CTA: [hi half | lo half]
           const int ksteps = (live + 7) / 8;
           for (int j = 0; j < ksteps; ++j) {
             const uint64_t adv = (uint64_t)(j * 2);
             const uint32_t acc = (kb | j) ? 1u : 0u;
-            mma_tf32_2(tbuf + (uint32_t)bn, a_lo + adv, b_hi + adv, idesc, acc);   // correction accumulator
-            mma_tf32_2(tbuf + (uint32_t)bn, a_hi + adv, b_lo + adv, idesc, 1u);
-            mma_tf32_2(tbuf, a_hi + adv, b_hi + adv, idesc, acc);                  // main accumulator
+            mma_tf32_2(tbuf, a_hi + adv, b_all + adv, idesc, acc);
+            mma_tf32_2(tbuf, a_lo + adv, b_all + adv, idesc, 1u);
           }
           mma_commit2_mc(smem_u32(&bar_empty[s]));           // frees the stage in both CTAs
         }
@@ -779,11 +769,53 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pair_kernel(const GemmAr
       }
     }
     __syncwarp();
+  } else {
+    // ------------------------------ producer: A by TMA, B halves by bulk copy ------------------------------
+    if (lane == 0) {
+      int gk = 0;
+      for (int item = cluster_id; item < nitems; item += nclusters) {
+        const Item it = decode_pair(g, item, (int)crank, ntm, ntn, bn, nvalid);
+        if (!it.live) continue;
+        const int nkb = it.km.nkb;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int q = gk + kb;
+          const int s = q % stages;
+          int k0, live;
+          kmap_get(it.km, kb, k0, live);
+          // the stage is free once the pair's MMAs of its previous use retired
+          mbar_wait(smem_u32(&bar_empty[s]), ((uint32_t)(q / stages) & 1u) ^ 1u);
+          const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
+          {
+            // B halves: their expect_tx is posted before the A tile is requested, hence before the
+            // splitters (who wait for the A tile) can arrive on full[s]
+            const unsigned char* tile = g.Bpacked + ((size_t)(it.n0 / bn) * (size_t)((g.K + BK - 1) / BK) + (size_t)(k0 / BK)) * (size_t)(4u * hb);
+            const uint32_t bar = smem_u32(&bar_full[s]);
+            asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(2u * hb) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa + 2 * A_TILE_BYTES),
+                         "l"(tile + (size_t)crank * hb), "r"(hb), "r"(bar)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa + 2 * A_TILE_BYTES + hb),
+                         "l"(tile + 2u * (size_t)hb + (size_t)crank * hb), "r"(hb), "r"(bar)
+                         : "memory");
+          }
+          {
+            // A: 128 rows x 32 floats at (row m0, column k0) straight into the A_hi slot; OOB rows / columns are zero
+            const uint32_t bar = smem_u32(&bar_afull[s]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(A_TILE_BYTES) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(sa),
+                         "l"(&tmapA), "r"(bar), "r"(k0), "r"(it.m0)
+                         : "memory");
+          }
+        }
+        gk += nkb;
+      }
+    }
+    __syncwarp();
   }
 
   tc_fence_before();
   __syncthreads();
-  // do not exit (or free TMEM) while the peer may still multicast into our smem / signal our barriers
+  // do not exit (or free TMEM) while the peer may still signal our barriers
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (warp == P_MMA_WARP) {
@@ -822,7 +854,7 @@ __global__ void pack_b_kernel(const float* __restrict__ W, int ld, int transB, i
 
 struct Plan { int bn, stages, tmem_cols; size_t smem; int stages_pers; size_t smem_pers; };
 // cta_group::2 kernel: tiles <= 128 wide so that two accumulator buffers (main + correction each) fit in 512 TMEM columns
-inline int pair_bn(int N) { const int nt = cdiv(N, 128); int bn = round_up(cdiv(N, nt), 16); return bn > 128 ? 128 : bn; }
+inline int pair_bn(int N) { return N <= 64 ? 64 : 128; }   // bn/2 must be a multiple of 32 (epilogue column groups)
 inline bool al16h(const void* p, int ld) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0)); }
 inline Plan plan_for(int N) {
   Plan p;
@@ -857,9 +889,32 @@ inline cudaError_t tc_gemm_init() {
   GAC_TC_ATTR(true, true, false, false) GAC_TC_ATTR(true, true, true, false)
   GAC_TC_ATTR(false, false, false, true) GAC_TC_ATTR(false, false, true, true)
 #undef GAC_TC_ATTR
-  if ((e = cudaFuncSetAttribute(tc::gemm_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(tc::gemm_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(tc::gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT)) != cudaSuccess) return e;
   return cudaSuccess;
+}
+
+// 2-D tensor map of a row-major fp32 matrix (rows x cols, leading dimension ld) with a 32-column x
+// 128-row box and the 128-byte swizzle the UMMA K-major layout expects; out-of-bounds reads are zero.
+// cuTensorMapEncodeTiled is fetched from the driver at run time (no link-time dependency on libcuda).
+inline bool tc_encode_tmap_2d(CUtensorMap* out, const float* base, int rows, int cols, int ld) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_fn>(p);
+  }
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // The cta_group::2 persistent kernel (TMEM double buffered) passes the whole GPU suite but is, as of
@@ -897,20 +952,24 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   // one-tile-per-CTA kernel because both are bound by shared-memory bandwidth; it is
   // the base for the cta_group::2 version.
   if (g.Bpacked && g.Bpacked_bn > 0) {
-    // packed for the cta_group::2 persistent kernel
-    if (g.transA || g.transC || g.splitk > 1 || !epi_al) return cudaErrorInvalidValue;
+    // packed for the cta_group::2 persistent kernel (A by TMA: needs 16-byte aligned rows)
+    if (g.transA || g.transC || g.splitk > 1 || !epi_al || !veca) return cudaErrorInvalidValue;
     static int nsm2 = 0;
     if (nsm2 == 0) {
       int dev = 0;
       if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm2, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm2 <= 0) nsm2 = 148;
     }
+    CUtensorMap tmap;
+    if (!tc_encode_tmap_2d(&tmap, g.A, g.M, g.K, g.lda)) return cudaErrorNotSupported;
     const int pbn = g.Bpacked_bn;
     const int ntn = cdiv(g.N, pbn), ntm = cdiv(g.M, tc::BM), npairs = ntn * cdiv(ntm, 2);
     const int nclus = npairs < nsm2 / 2 ? npairs : nsm2 / 2;
     const int pstage = 2 * (int)tc::A_TILE_BYTES + 2 * (pbn / 2) * 128;
-    int pst = (tc::SMEM_LIMIT - 1024 - tc::P_EPI_WARPS * tc::P_STG_BYTES) / pstage;
+    const int fixed = 1024 + tc::P_EPI_WARPS * tc::P_STG_BYTES;
+    int pst = (tc::SMEM_LIMIT - fixed) / pstage;
     if (pst > tc::MAX_STAGES) pst = tc::MAX_STAGES;
-    const size_t psmem = (size_t)pst * pstage + 1024 + tc::P_EPI_WARPS * tc::P_STG_BYTES;
+    if (pst < 2) return cudaErrorInvalidValue;
+    const size_t psmem = (size_t)pst * pstage + fixed;
     int tcols = 32;
     while (tcols < 4 * pbn) tcols *= 2;                       // 2 buffers x (main + correction)
     cudaLaunchConfig_t cfg;
@@ -920,8 +979,7 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (veca) return cudaLaunchKernelEx(&cfg, tc::gemm_tc_pair_kernel<true>, g, pbn, pst, tcols, ntm, ntn, npairs);
-    return cudaLaunchKernelEx(&cfg, tc::gemm_tc_pair_kernel<false>, g, pbn, pst, tcols, ntm, ntn, npairs);
+    return cudaLaunchKernelEx(&cfg, tc::gemm_tc_pair_kernel, g, tmap, pbn, pst, tcols, ntm, ntn, npairs);
   }
   if (false) {
   } else if (g.Bpacked && !g.transA && g.splitk <= 1) {

@@ -42,8 +42,5 @@ else:
     for i in range(6):
         r = found[i] - t00
         print(f"{i:3d} start={r[0]:8d} tmem_ok={r[1]:8d} first_full={r[2]:8d} issued={r[3]:8d} | epi_start={r[4]:8d} epi_end={r[5]:8d}")
-    ld = arr[off + 256:off + 256 + 128].reshape(16, 8)
-    print("loader thread 0 (group 0): q  issue->data  data->stage_free  stores  fence  arrive   | start(rel)")
-    for i in range(14):
-        r = ld[i]
-        print(f"  q={int(r[6]):3d} load={r[1]-r[0]:6d} wait_empty={r[2]-r[1]:6d} split+sts={r[3]-r[2]:6d} fence={r[4]-r[3]:6d} arrive={r[5]-r[4]:6d} | {r[0]-t00:8d}")
+    e = arr[off + 300:off + 304]
+    print(f"epilogue group (warp 8, tile 2): tmem ld+wait+add {e[1]-e[0]}  st.shared+syncwarp {e[2]-e[1]}  ld.shared+epilogue+st.global+syncwarp {e[3]-e[2]} cycles")
