@@ -180,7 +180,7 @@ def run_gpu(args):
         B, scaling = B // world, "strong"
     P = B * K
     torch.manual_seed(1234)               # identical replicas
-    agent = GACAgent(A, S, action_samples=K, batch_size=B, device=dev, engine=args.engine, chunk_rows=args.chunk_rows)
+    agent = GACAgent(A, S, action_samples=K, batch_size=B, device=dev, engine=args.engine, chunk_rows=args.chunk_rows, actor=args.actor)
     batch_np, noise_np = synth(S, A, B, K, 1000 * 2 + rank)
     to_dev = lambda d: {k: torch.from_numpy(v).to(dev) for k, v in d.items()}
     batch, noise = to_dev(batch_np), to_dev(noise_np)
@@ -287,10 +287,10 @@ def run_gpu(args):
     if rank == 0:
         pairs_per_step = 2 * P * world
         value = pairs_per_step / (ms_per_step * 1e-3)
-        f_ref, f_min = step_flops(S, A, B, K, m_mean)
+        f_ref, f_min = step_flops(S, A, B, K, m_mean) if args.actor == "AIQN" else (float("nan"), float("nan"))
         pk = peaks()
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.actor == "AIQN":
             Bs = min(B, 32)
             sec, done, cores = time_cpu_reference(S, A, Bs, K, steps=20, warmup=1, budget_s=15.0)
             cpu = {"value": 2 * Bs * K / sec, "unit": "pairs/s", "cores": cores, "kind": "port",
@@ -302,7 +302,7 @@ def run_gpu(args):
                            "global_batch": B * world, "action_samples": K, "parallelism": f"dp{world}",
                            "selected_rows_mean": m_mean, "candidate_rows": 2 * P,
                            "l2": "per-step working set (activations saved for BPTT) is GBs >> 126 MB L2; no flush needed",
-                           "engine": "tcgen05 3xTF32" if args.engine == 0 else "SIMT fp32"},
+                           "engine": "tcgen05 3xTF32" if args.engine == 0 else "SIMT fp32", "actor": args.actor},
                 "steps_per_s": 1e3 / ms_per_step,
                 "step_flops": {"algorithmic_gflop_min": f_min / 1e9, "as_written_gflop": f_ref / 1e9,
                                "achieved_tflops_min": f_min * world / (ms_per_step * 1e-3) / 1e12,
@@ -404,6 +404,7 @@ def main():
     ap.add_argument("--engine", type=int, default=0, help="0 = tcgen05 3xTF32 GEMMs, 1 = SIMT fp32")
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--actor", default="AIQN", choices=["AIQN", "IQN"], help="AIQN = BASELINE.json's actor; IQN = the reference CLI default (main.py:78)")
     ap.add_argument("--sweep-chunks", type=int, default=0, help="walker2d sweep: number of 4096-state chunks (0 = all 1M states)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -8,7 +8,7 @@ from . import _lib  # noqa: F401  (loads the shared library or raises)
 from .agent import GACAgent
 from .engine import Arena, Engine
 from .helpers import ActionSampler, ReplayBuffer, denormalize, normalize, update
-from .networks import (FNN, AutoRegressiveStochasticActor, CosineBasisLinear, Critic, IQNActor, Value)
+from .networks import (FNN, AutoRegressiveStochasticActor, CosineBasisLinear, Critic, IQNActor, StochasticActor, Value)
 
 __all__ = ["GACAgent", "Arena", "Engine", "ActionSampler", "ReplayBuffer", "update", "normalize", "denormalize", "FNN",
-           "AutoRegressiveStochasticActor", "CosineBasisLinear", "Critic", "IQNActor", "Value"]
+           "AutoRegressiveStochasticActor", "CosineBasisLinear", "Critic", "IQNActor", "StochasticActor", "Value"]

@@ -23,7 +23,15 @@ VAR_NAMES = (
     "fnn2.w0", "fnn2.b0", "fnn2.w1", "fnn2.b1", "fnn2.w2", "fnn2.b2",
     "value.w0", "value.b0", "value.w1", "value.b1", "value.w2", "value.b2",
 )
+# IQN actor (StochasticActor): the first eight actor slots, the other five are empty
+VAR_NAMES_IQN = ("actor.wm", "actor.bm", "actor.wn", "actor.bn", "actor.wo", "actor.bo", "actor.ws", "actor.bs",
+                 "actor._8", "actor._9", "actor._10", "actor._11", "actor._12") + VAR_NAMES[13:]
 NET_NAMES = ("actor", "fnn1", "fnn2", "value")
+ACTOR_KINDS = {"AIQN": 0, "IQN": 1}
+
+
+def var_names(kind: int):
+    return VAR_NAMES_IQN if kind == 1 else VAR_NAMES
 
 
 class Layout(C.Structure):
@@ -33,7 +41,7 @@ class Layout(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("S", C.c_int32), ("A", C.c_int32), ("B", C.c_int32), ("K", C.c_int32), ("chunk_rows", C.c_int32),
-                ("engine", C.c_int32)]
+                ("engine", C.c_int32), ("actor_kind", C.c_int32)]
 
 
 class HParams(C.Structure):
@@ -52,6 +60,10 @@ class StepIO(C.Structure):
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
     "gac_layout": (C.c_int, [_I, _I, C.POINTER(Layout)]),
+    "gac_layout_ex": (C.c_int, [_I, _I, _I, C.POINTER(Layout)]),
+    "gac_iqn_forward": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, _P]),
+    "gac_iqn_train_fwd": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, _P, _P]),
+    "gac_iqn_bwd": (C.c_int, [_P, _P, _P, _P, _I]),
     "gac_workspace_bytes": (C.c_size_t, [C.POINTER(Config)]),
     "gac_create": (C.c_int, [C.POINTER(Config), _P, C.c_size_t, _P, C.POINTER(_P)]),
     "gac_destroy": (None, [_P]),
@@ -98,7 +110,7 @@ def check(rc: int):
         raise GacError(f"libgac_b200 error {rc}: {lib.gac_last_error().decode()}")
 
 
-def layout(S: int, A: int) -> Layout:
+def layout(S: int, A: int, kind: int = 0) -> Layout:
     lay = Layout()
-    check(lib.gac_layout(S, A, C.byref(lay)))
+    check(lib.gac_layout_ex(S, A, kind, C.byref(lay)))
     return lay

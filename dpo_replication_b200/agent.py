@@ -10,7 +10,7 @@ import torch
 from . import dist as gdist
 from .engine import Arena, Engine, f32, keras_default_init
 from .helpers import ActionSampler, ReplayBuffer, normalize, update
-from .networks import AutoRegressiveStochasticActor, Critic, Value
+from .networks import AutoRegressiveStochasticActor, Critic, StochasticActor, Value
 
 
 class GACAgent:
@@ -23,9 +23,9 @@ class GACAgent:
         self.gamma, self.action_samples, self.mode, self.beta, self.tau = gamma, action_samples, mode, beta, tau
         self.batch_size = batch_size
         self.normalize_observations, self.q_normalization, self.normalize_rewards = normalize_obs, q_normalization, normalize_rewards
-        if actor != 'AIQN':
-            # StochasticActor (IQN, networks.py:271-323) is row 1 of SURVEY.md §8f ("next")
-            raise NotImplementedError("only the AIQN actor is on the accelerated path")
+        if actor not in ('AIQN', 'IQN'):
+            raise NotImplementedError("actor must be 'AIQN' or 'IQN' (agent.py:65-70)")
+        self.actor_kind = 1 if actor == 'IQN' else 0
         if normalize_obs or normalize_rewards:
             raise NotImplementedError("RunningMeanStd normalisation is out of scope (off by default, agent.py:25)")
         self.obs_rms = None
@@ -34,17 +34,18 @@ class GACAgent:
             raise RuntimeError("dpo_replication_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         S, A = state_dim, action_dim
-        self.arena = Arena(S, A, self.device)
-        self.engine = Engine(S, A, batch_size, action_samples, self.device, chunk_rows=chunk_rows, engine=engine)
+        self.arena = Arena(S, A, self.device, self.actor_kind)
+        self.engine = Engine(S, A, batch_size, action_samples, self.device, chunk_rows=chunk_rows, engine=engine, actor_kind=self.actor_kind)
         mk = dict(arena=self.arena, init=False)
-        self.actor = AutoRegressiveStochasticActor(S, A, role="online", **mk)
-        self.target_actor = AutoRegressiveStochasticActor(S, A, role="target", **mk)
+        actor_cls = StochasticActor if self.actor_kind == 1 else AutoRegressiveStochasticActor      # agent.py:65-70
+        self.actor = actor_cls(S, A, role="online", **mk)
+        self.target_actor = actor_cls(S, A, role="target", **mk)
         self.critics = Critic(S, A, role="online", **mk)
         self.target_critics = Critic(S, A, role="target", **mk)
         self.value = Value(S, role="online", **mk)
         self.target_value = Value(S, role="target", **mk)
         for net in ("actor", "fnn1", "fnn2", "value"):
-            self.arena.load(self.arena.online, net, keras_default_init(S, A, net))
+            self.arena.load(self.arena.online, net, keras_default_init(S, A, "iqn" if (net == "actor" and self.actor_kind == 1) else net))
         # agent.py:114-116: hard copies.  target_value has no variables yet when update() runs in
         # the reference, so it keeps its own independent initialisation.
         update(self.target_actor, self.actor, 1.0)
@@ -114,12 +115,13 @@ class GACAgent:
         s = f32(states, self.device)
         B, K, A = s.shape[0], self.action_samples, self.action_dim
         P = B * K
-        eng = self.engine if B == self.batch_size else Engine(self.state_dim, A, B, K, self.device)
+        eng = self.engine if B == self.batch_size else Engine(self.state_dim, A, B, K, self.device, actor_kind=self.actor_kind)
         n = noise or {}
         g = lambda k, f: f32(n[k], self.device) if k in n else f()
         sidx = torch.arange(B, dtype=torch.int32, device=self.device).repeat(K)            # row = k*B + b
         ar = self.arena
-        ta = eng.aiqn_sample(ar.net_slice(ar.target, "actor"), s, sidx, g("filter_tau", lambda: torch.rand(P, A, device=self.device)))
+        sample = eng.iqn_forward if self.actor_kind == 1 else eng.aiqn_sample
+        ta = sample(ar.net_slice(ar.target, "actor"), s, sidx, g("filter_tau", lambda: torch.rand(P, A, device=self.device)))
         ta = torch.clamp(ta + g("filter_normal", lambda: torch.randn(P, A, device=self.device)) * 0.01, -1, 1)
         ra = g("filter_rand", lambda: torch.rand(P, A, device=self.device) * 2 - 1)
         acts = torch.cat([ta, ra], 0).contiguous()

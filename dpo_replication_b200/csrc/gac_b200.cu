@@ -34,10 +34,19 @@ static void fnn_offsets(int n_in, int64_t off[7]) {
   off[6] = o;
 }
 
-extern "C" int gac_layout(int32_t S, int32_t A, gac_layout_t* out) {
-  if (!out || S <= 0 || A <= 0) return fail(GAC_ERR_INVALID, "gac_layout: bad arguments");
-  const int ar[13] = {GAC_NB, GAC_E, GAC_E, GAC_E, GAC_E, 1, GAC_NB, GAC_E, 2 * GAC_E, GAC_E, 2, S, GAC_E};
-  const int ac[13] = {GAC_E, 1, GAC_E, 1, 1, 1, GAC_E, 1, GAC_G, GAC_G, GAC_G, GAC_E, 1};
+extern "C" int gac_layout(int32_t S, int32_t A, gac_layout_t* out) { return gac_layout_ex(S, A, GAC_ACTOR_AIQN, out); }
+
+extern "C" int gac_layout_ex(int32_t S, int32_t A, int32_t actor_kind, gac_layout_t* out) {
+  if (!out || S <= 0 || A <= 0 || A > GAC_E) return fail(GAC_ERR_INVALID, "gac_layout: bad arguments");
+  if (actor_kind != GAC_ACTOR_AIQN && actor_kind != GAC_ACTOR_IQN) return fail(GAC_ERR_INVALID, "gac_layout: unknown actor kind");
+  int ar[13] = {GAC_NB, GAC_E, GAC_E, GAC_E, GAC_E, 1, GAC_NB, GAC_E, 2 * GAC_E, GAC_E, 2, S, GAC_E};
+  int ac[13] = {GAC_E, 1, GAC_E, 1, 1, 1, GAC_E, 1, GAC_G, GAC_G, GAC_G, GAC_E, 1};
+  if (actor_kind == GAC_ACTOR_IQN) {           // StochasticActor, networks.py:283-302
+    const int d = GAC_E / A, D = d * A;
+    const int ir[13] = {D, 200, GAC_NB, d, 200, A, S, D, 0, 0, 0, 0, 0};
+    const int ic[13] = {200, 1, d, 1, A, 1, D, 1, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 13; ++i) { ar[i] = ir[i]; ac[i] = ic[i]; }
+  }
   int64_t o = 0;
   int v = 0;
   out->net_begin[GAC_NET_ACTOR] = 0;
@@ -86,6 +95,11 @@ struct gac_ctx {
   float *pred_c, *dpred_c;
   const int* bwd_sidx; const float* bwd_states; int bwd_nstates; const int* bwd_drows;  // saved by supervised_fwd
   float *spart, *cpart, *fpart0, *fpart1;
+  // IQN actor scratch (actor_kind == GAC_ACTOR_IQN): sampling (Rs rows) and training (Mc rows)
+  int iq_d, iq_D;
+  float *iq_se_u, *iq_cos, *iq_ne, *iq_me;
+  float *it_x, *it_se, *it_cos, *it_ne, *it_merge, *it_me, *it_dop, *it_dme, *it_dmerge, *it_dne, *it_dse;
+  int* it_live;   // [0] live rows of the chunk, [1] live rows * A
   unsigned char* pack[16]; size_t pack_bytes;   // pre-split / pre-swizzled weight tiles (tc::pack_b_kernel)
 };
 
@@ -115,7 +129,8 @@ int derive(gac_ctx* c) {
   c->NUa = f.B > 1024 ? f.B : 1024;
   if (c->NUa > c->Mc && c->Mc >= f.B) c->NUa = c->Mc > f.B ? c->Mc : f.B;
   c->max_splits = 128;
-  return gac_layout(f.S, f.A, &c->lay);
+  c->iq_d = GAC_E / f.A; c->iq_D = c->iq_d * f.A;
+  return gac_layout_ex(f.S, f.A, f.actor_kind, &c->lay);
 }
 
 size_t partition(gac_ctx* c, void* ws) {
@@ -157,6 +172,15 @@ size_t partition(gac_ctx* c, void* ws) {
   c->spart = b.take<float>((size_t)c->max_splits * GAC_E * GAC_G);
   const size_t maxrows = AM > Rs ? AM : Rs;
   c->cpart = b.take<float>(((maxrows + COLSUM_ROWS - 1) / COLSUM_ROWS + 8192 / 16 + 1) * GAC_G);
+  if (f.actor_kind == GAC_ACTOR_IQN) {
+    const size_t D = c->iq_D;
+    c->iq_se_u = b.take<float>((size_t)c->NUs * D); c->iq_cos = b.take<float>(Rs * A * GAC_NB); c->iq_ne = b.take<float>(Rs * D);
+    c->iq_me = b.take<float>(Rs * 200);
+    c->it_x = b.take<float>(Mc * S); c->it_se = b.take<float>(Mc * D); c->it_cos = b.take<float>(Mc * A * GAC_NB);
+    c->it_ne = b.take<float>(Mc * D); c->it_merge = b.take<float>(Mc * D); c->it_me = b.take<float>(Mc * 200);
+    c->it_dop = b.take<float>(Mc * A); c->it_dme = b.take<float>(Mc * 200); c->it_dmerge = b.take<float>(Mc * D);
+    c->it_dne = b.take<float>(Mc * D); c->it_dse = b.take<float>(Mc * D); c->it_live = b.take<int>(4);
+  }
   const size_t nrb = (AM + FB_ROWS - 1) / FB_ROWS + 1;
   c->fpart0 = b.take<float>(nrb * GAC_G); c->fpart1 = b.take<float>(nrb * GAC_G);
   c->pack_bytes = tc_packed_bytes(GAC_E, GAC_G);
@@ -242,7 +266,7 @@ int run_colsum(gac_ctx* c, const float* X, int ldx, const float* w, int N, long 
   const int nblk = (int)cdiv64(rows, rpb);
   colsum_kernel<<<dim3(cdiv(N, 128), nblk), 128, 0, c->stream>>>(X, ldx, w, N, rows, rv, c->cpart, rpb);
   LAUNCHED(c, "colsum");
-  reduce_cols_kernel<<<cdiv(N, 32), dim3(32, 8), 0, c->stream>>>(c->cpart, nblk, N, dst, accumulate);
+  reduce_cols_kernel<<<cdiv(N, 32), dim3(32, RC_LANES), 0, c->stream>>>(c->cpart, nblk, N, dst, accumulate);
   LAUNCHED(c, "colsum_reduce");
   return GAC_OK;
 }
@@ -349,6 +373,7 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
 
 int aiqn_sample(gac_ctx* c, const float* actor, const float* states_u, int n_states, const int* sidx, const float* taus,
                 int rows, float* actions) {
+  if (c->cfg.actor_kind != GAC_ACTOR_AIQN) return fail(GAC_ERR_INVALID, "gac_aiqn_sample: context was created for the IQN actor");
   if (n_states > c->NUs) return fail(GAC_ERR_WORKSPACE, "gac_aiqn_sample: n_states exceeds the workspace capacity");
   GAC_TRY(state_prep(c, actor, states_u, n_states, c->se_u, c->sx_u));
   const int A = c->cfg.A;
@@ -485,9 +510,9 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   head_bwd_kernel<<<dim3(GAC_E / FB_COLS, nrb_all), FB_COLS, 0, st>>>(c->dop, var(c, actor, 0, GAC_A_W2), c->ay1, AM, rv, c->dy1p,
                                                                       c->fpart0, c->fpart1);
   LAUNCHED(c, "head_bwd");
-  reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, 8), 0, st>>>(c->fpart0, nrb_all, GAC_E, G(GAC_A_B1), acc);
+  reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart0, nrb_all, GAC_E, G(GAC_A_B1), acc);
   LAUNCHED(c, "reduce_cols");
-  reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, 8), 0, st>>>(c->fpart1, nrb_all, GAC_E, G(GAC_A_W2), acc);
+  reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart1, nrb_all, GAC_E, G(GAC_A_W2), acc);
   LAUNCHED(c, "reduce_cols");
   GAC_TRY(wgrad(GAC_E, GAC_E, c->au, GAC_E, c->dy1p, GAC_E, AM, G(GAC_A_W1), true));
   GemmArgs g = gemm_args((int)AM, GAC_E, GAC_E, c->dy1p, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->du, GAC_E);
@@ -496,7 +521,7 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   hadamard_bwd_kernel<<<dim3(GAC_E / FB_COLS, nrb_all), FB_COLS, 0, st>>>(c->du, c->hall + (size_t)Mc * GAC_E, c->ne, AM, rv, c->dne,
                                                                           c->dhu, c->fpart0);
   LAUNCHED(c, "hadamard_bwd");
-  reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, 8), 0, st>>>(c->fpart0, nrb_all, GAC_E, G(GAC_A_BN), acc);
+  reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart0, nrb_all, GAC_E, G(GAC_A_BN), acc);
   LAUNCHED(c, "reduce_cols");
   GAC_TRY(wgrad(GAC_NB, GAC_E, c->cn, GAC_NB, c->dne, GAC_E, AM, G(GAC_A_WN), true));
   // recurrence, reverse time.  mx is overwritten with dmx step by step (it is dead after the forward gates)
@@ -518,9 +543,9 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   }
   // time-parallel weight gradients of the GRU
   GAC_TRY(wgrad(GAC_E, GAC_G, c->hall, GAC_E, c->dmh, GAC_G, AM, G(GAC_A_U), true));
-  reduce_cols_kernel<<<cdiv(GAC_G, 32), dim3(32, 8), 0, st>>>(c->fpart1, A * nrb_step, GAC_G, G(GAC_A_GB) + GAC_G, acc);
+  reduce_cols_kernel<<<cdiv(GAC_G, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart1, A * nrb_step, GAC_G, G(GAC_A_GB) + GAC_G, acc);
   LAUNCHED(c, "reduce_cols");
-  reduce_cols_kernel<<<cdiv(GAC_G, 32), dim3(32, 8), 0, st>>>(c->fpart0, A * nrb_step, GAC_G, G(GAC_A_GB), acc);
+  reduce_cols_kernel<<<cdiv(GAC_G, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart0, A * nrb_step, GAC_G, G(GAC_A_GB), acc);
   LAUNCHED(c, "reduce_cols");
   GAC_TRY(wgrad(GAC_E, GAC_G, c->a_ae, GAC_E, c->mx, GAC_G, AM, G(GAC_A_KX) + (size_t)GAC_E * GAC_G, true));
   g = gemm_args((int)AM, GAC_E, GAC_G, c->mx, GAC_G, kxa, GAC_G, c->du, GAC_E);
@@ -538,6 +563,108 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   GAC_TRY(run_gemm(c, g));
   GAC_TRY(wgrad(S, GAC_E, c->bwd_states, S, c->a_dse_u, GAC_E, NU, G(GAC_A_WS), false));
   GAC_TRY(run_colsum(c, c->a_dse_u, GAC_E, nullptr, GAC_E, NU, RowValid{nullptr, 1}, G(GAC_A_BS), acc));
+  return GAC_OK;
+}
+
+// ---------------------------------- IQN actor (StochasticActor) ----------------------------------
+inline const float* ivar(const gac_ctx* c, const float* base, int v) { return base + c->lay.offsets[v]; }
+inline float* ivar(const gac_ctx* c, float* base, int v) { return base + c->lay.offsets[v]; }
+
+int iqn_forward(gac_ctx* c, const float* actor, const float* states_u, int n_states, const int* sidx, const float* taus, int rows,
+                float* actions) {
+  if (c->cfg.actor_kind != GAC_ACTOR_IQN) return fail(GAC_ERR_INVALID, "gac_iqn_forward: context was not created for the IQN actor");
+  if (n_states > c->NUs) return fail(GAC_ERR_WORKSPACE, "gac_iqn_forward: n_states exceeds the workspace capacity");
+  const int S = c->cfg.S, A = c->cfg.A, d = c->iq_d, D = c->iq_D;
+  cudaStream_t st = c->stream;
+  const RowValid all{nullptr, 1};
+  // state embedding once per unique state (exact hoist), gathered inside the Hadamard kernel
+  GemmArgs g = gemm_args(n_states, D, S, states_u, S, ivar(c, actor, GAC_I_WS), D, c->iq_se_u, D);
+  g.bias = ivar(c, actor, GAC_I_BS); g.act = ACT_LRELU; g.alpha = 0.01f;
+  GAC_TRY(run_gemm(c, g));
+  for (int r0 = 0; r0 < rows; r0 += c->Rs) {
+    const int n = rows - r0 < c->Rs ? rows - r0 : c->Rs;
+    cos_basis_kernel<<<(unsigned)cdiv64((long long)n * A * GAC_NB, 256), 256, 0, st>>>(taus + (size_t)r0 * A, 1, c->iq_cos, n * A, all);
+    LAUNCHED(c, "cos_basis");
+    g = gemm_args(n * A, d, GAC_NB, c->iq_cos, GAC_NB, ivar(c, actor, GAC_I_WN), d, c->iq_ne, d);
+    g.bias = ivar(c, actor, GAC_I_BN); g.act = ACT_LRELU; g.alpha = 0.01f;
+    GAC_TRY(run_gemm(c, g));
+    iqn_merge_kernel<<<(unsigned)cdiv64((long long)n * D, 256), 256, 0, st>>>(c->iq_se_u, sidx + r0, c->iq_ne, n, D, all, c->iq_ne);
+    LAUNCHED(c, "iqn_merge");
+    g = gemm_args(n, 200, D, c->iq_ne, D, ivar(c, actor, GAC_I_WM), 200, c->iq_me, 200);
+    g.bias = ivar(c, actor, GAC_I_BM); g.act = ACT_LRELU; g.alpha = 0.01f;
+    GAC_TRY(run_gemm(c, g));
+    g = gemm_args(n, A, 200, c->iq_me, 200, ivar(c, actor, GAC_I_WO), A, actions + (size_t)r0 * A, A);
+    g.bias = ivar(c, actor, GAC_I_BO); g.act = ACT_TANH;
+    GAC_TRY(run_gemm(c, g));
+  }
+  return GAC_OK;
+}
+
+int iqn_train_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_states, const int* sidx, const float* taus, int max_rows,
+                  const int* d_rows, float* pred) {
+  if (c->cfg.actor_kind != GAC_ACTOR_IQN) return fail(GAC_ERR_INVALID, "gac_iqn_train_fwd: context was not created for the IQN actor");
+  const int S = c->cfg.S, A = c->cfg.A, d = c->iq_d, D = c->iq_D, Mc = c->Mc;
+  if (max_rows > Mc) return fail(GAC_ERR_WORKSPACE, "gac_iqn_train_fwd: max_rows exceeds chunk_rows");
+  cudaStream_t st = c->stream;
+  int* live = c->it_live;
+  if (d_rows) GAC_CUDA(cudaMemcpyAsync(live + 2, d_rows, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  else GAC_CUDA(cudaMemcpyAsync(live + 2, &max_rows, sizeof(int), cudaMemcpyHostToDevice, st));
+  scale_int_kernel<<<1, 32, 0, st>>>(live + 2, A, max_rows, live);
+  LAUNCHED(c, "scale_int");
+  const RowValid rv{live, Mc}, rvA{live + 1, Mc * A};
+  gather_rows_kernel<<<(unsigned)cdiv64((long long)max_rows * S, 256), 256, 0, st>>>(states_u, sidx, max_rows, S, rv, c->it_x);
+  LAUNCHED(c, "gather_rows");
+  GemmArgs g = gemm_args(Mc, D, S, c->it_x, S, ivar(c, actor, GAC_I_WS), D, c->it_se, D);
+  g.bias = ivar(c, actor, GAC_I_BS); g.act = ACT_LRELU; g.alpha = 0.01f; g.dyn_rows = live; g.seg_rows = Mc;
+  GAC_TRY(run_gemm(c, g));
+  cos_basis_kernel<<<(unsigned)cdiv64((long long)max_rows * A * GAC_NB, 256), 256, 0, st>>>(taus, 1, c->it_cos, max_rows * A, rvA);
+  LAUNCHED(c, "cos_basis");
+  g = gemm_args(Mc * A, d, GAC_NB, c->it_cos, GAC_NB, ivar(c, actor, GAC_I_WN), d, c->it_ne, d);
+  g.bias = ivar(c, actor, GAC_I_BN); g.act = ACT_LRELU; g.alpha = 0.01f; g.dyn_rows = live + 1; g.seg_rows = Mc * A;
+  GAC_TRY(run_gemm(c, g));
+  iqn_merge_kernel<<<(unsigned)cdiv64((long long)Mc * D, 256), 256, 0, st>>>(c->it_se, nullptr, c->it_ne, Mc, D, rv, c->it_merge);
+  LAUNCHED(c, "iqn_merge");
+  g = gemm_args(Mc, 200, D, c->it_merge, D, ivar(c, actor, GAC_I_WM), 200, c->it_me, 200);
+  g.bias = ivar(c, actor, GAC_I_BM); g.act = ACT_LRELU; g.alpha = 0.01f; g.dyn_rows = live; g.seg_rows = Mc;
+  GAC_TRY(run_gemm(c, g));
+  g = gemm_args(Mc, A, 200, c->it_me, 200, ivar(c, actor, GAC_I_WO), A, c->pred_c, A);
+  g.bias = ivar(c, actor, GAC_I_BO); g.act = ACT_TANH; g.dyn_rows = live; g.seg_rows = Mc;
+  GAC_TRY(run_gemm(c, g));
+  if (pred) GAC_CUDA(cudaMemcpyAsync(pred, c->pred_c, (size_t)max_rows * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  c->bwd_drows = live;
+  return GAC_OK;
+}
+
+int iqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, int acc) {
+  if (c->cfg.actor_kind != GAC_ACTOR_IQN || !c->bwd_drows) return fail(GAC_ERR_INVALID, "gac_iqn_bwd: no saved IQN forward");
+  const int S = c->cfg.S, A = c->cfg.A, d = c->iq_d, D = c->iq_D, Mc = c->Mc;
+  cudaStream_t st = c->stream;
+  const int* live = c->it_live;
+  const RowValid rv{live, Mc}, rvA{live + 1, Mc * A};
+  auto wgrad = [&](int M, int N, const float* X, int ldx, const float* dY, int ldy, int rows, float* dst, const int* dyn, int seg) {
+    GemmArgs g = gemm_args(M, N, rows, X, ldx, dY, ldy, dst, N);
+    g.transA = 1; g.accumulate = acc; g.dyn_rows = dyn; g.seg_rows = seg; g.valid_on_k = 1;
+    return run_gemm(c, g);
+  };
+  tanh_bwd_kernel<<<(unsigned)cdiv64((long long)Mc * A, 256), 256, 0, st>>>(dpred, c->pred_c, (long long)Mc * A, A, rv, c->it_dop);
+  LAUNCHED(c, "tanh_bwd");
+  GAC_TRY(wgrad(200, A, c->it_me, 200, c->it_dop, A, Mc, ivar(c, grad, GAC_I_WO), live, Mc));
+  GAC_TRY(run_colsum(c, c->it_dop, A, nullptr, A, Mc, rv, ivar(c, grad, GAC_I_BO), acc));
+  GemmArgs g = gemm_args(Mc, 200, A, c->it_dop, A, ivar(c, actor, GAC_I_WO), A, c->it_dme, 200);
+  g.transB = 1; g.gate = c->it_me; g.ldgate = 200; g.gate_alpha = 0.01f; g.dyn_rows = live; g.seg_rows = Mc;
+  GAC_TRY(run_gemm(c, g));
+  GAC_TRY(wgrad(D, 200, c->it_merge, D, c->it_dme, 200, Mc, ivar(c, grad, GAC_I_WM), live, Mc));
+  GAC_TRY(run_colsum(c, c->it_dme, 200, nullptr, 200, Mc, rv, ivar(c, grad, GAC_I_BM), acc));
+  g = gemm_args(Mc, D, 200, c->it_dme, 200, ivar(c, actor, GAC_I_WM), 200, c->it_dmerge, D);
+  g.transB = 1; g.dyn_rows = live; g.seg_rows = Mc;
+  GAC_TRY(run_gemm(c, g));
+  iqn_dmerge_kernel<<<(unsigned)cdiv64((long long)Mc * D, 256), 256, 0, st>>>(c->it_dmerge, c->it_se, c->it_ne, (long long)Mc * D, D, rv,
+                                                                            c->it_dne, c->it_dse);
+  LAUNCHED(c, "iqn_dmerge");
+  GAC_TRY(wgrad(GAC_NB, d, c->it_cos, GAC_NB, c->it_dne, d, Mc * A, ivar(c, grad, GAC_I_WN), live + 1, Mc * A));
+  GAC_TRY(run_colsum(c, c->it_dne, d, nullptr, d, (long long)Mc * A, rvA, ivar(c, grad, GAC_I_BN), acc));
+  GAC_TRY(wgrad(S, D, c->it_x, S, c->it_dse, D, Mc, ivar(c, grad, GAC_I_WS), live, Mc));
+  GAC_TRY(run_colsum(c, c->it_dse, D, nullptr, D, Mc, rv, ivar(c, grad, GAC_I_BS), acc));
   return GAC_OK;
 }
 
@@ -654,6 +781,23 @@ int gac_aiqn_sample(gac_ctx_t* c, const float* actor, const float* states_u, int
   return aiqn_sample(c, actor, states_u, n_states, state_idx, taus, rows, actions);
 }
 
+int gac_iqn_forward(gac_ctx_t* c, const float* actor, const float* states_u, int32_t n_states, const int32_t* state_idx,
+                    const float* taus, int32_t rows, float* actions) {
+  if (!c || !actor || !states_u || !state_idx || !taus || !actions || rows < 0) return fail(GAC_ERR_INVALID, "gac_iqn_forward: bad arguments");
+  return iqn_forward(c, actor, states_u, n_states, state_idx, taus, rows, actions);
+}
+
+int gac_iqn_train_fwd(gac_ctx_t* c, const float* actor, const float* states_u, int32_t n_states, const int32_t* state_idx,
+                      const float* taus, int32_t max_rows, const int32_t* d_rows, float* pred) {
+  if (!c || !actor || !states_u || !state_idx || !taus) return fail(GAC_ERR_INVALID, "gac_iqn_train_fwd: bad arguments");
+  return iqn_train_fwd(c, actor, states_u, n_states, state_idx, taus, max_rows, d_rows, pred);
+}
+
+int gac_iqn_bwd(gac_ctx_t* c, const float* actor, const float* dpred, float* grad_actor, int32_t accumulate) {
+  if (!c || !actor || !dpred || !grad_actor) return fail(GAC_ERR_INVALID, "gac_iqn_bwd: bad arguments");
+  return iqn_bwd(c, actor, dpred, grad_actor, accumulate);
+}
+
 int gac_critic_eval(gac_ctx_t* c, const float* fnn1, const float* fnn2, const float* states_u, const int32_t* state_idx,
                     const float* actions, int32_t rows, float* q) {
   if (!c || !fnn1 || !fnn2 || !states_u || !actions || !q) return fail(GAC_ERR_INVALID, "gac_critic_eval: bad arguments");
@@ -748,7 +892,8 @@ int gac_step_grads(gac_ctx_t* c, const gac_step_io_t* io, const gac_hparams_t* h
   // ---- both target-actor sampling passes in one 2P-row batch (F9) ----
   GAC_CUDA(cudaMemcpyAsync(c->taus2, io->value_tau, (size_t)P * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
   GAC_CUDA(cudaMemcpyAsync(c->taus2 + (size_t)P * A, io->filter_tau, (size_t)P * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  GAC_TRY(aiqn_sample(c, t_actor, io->s, B, c->sidx3, c->taus2, 2 * P, c->acts2));
+  if (c->cfg.actor_kind == GAC_ACTOR_IQN) GAC_TRY(iqn_forward(c, t_actor, io->s, B, c->sidx3, c->taus2, 2 * P, c->acts2));
+  else GAC_TRY(aiqn_sample(c, t_actor, io->s, B, c->sidx3, c->taus2, 2 * P, c->acts2));
   // candidates: [value-pass actions ; clip(target actions + 0.01 N) ; uniform random actions]
   GAC_CUDA(cudaMemcpyAsync(c->cand, c->acts2, (size_t)P * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
   noise_clip_kernel<<<(unsigned)cdiv64((long long)P * A, 256), 256, 0, st>>>(c->acts2 + (size_t)P * A, io->filter_normal, 0.01f,
@@ -781,10 +926,14 @@ int gac_step_grads(gac_ctx_t* c, const gac_step_io_t* io, const gac_hparams_t* h
   for (int ch = 0; ch < c->nchunks; ++ch) {
     const size_t r0 = (size_t)ch * Mc;
     const int maxr = (int)((size_t)2 * P - r0 < (size_t)Mc ? (size_t)2 * P - r0 : (size_t)Mc);
-    GAC_TRY(supervised_fwd(c, o_actor, io->s, B, c->sidx_sel + r0, io->actor_tau + r0 * A, c->act_sel + r0 * A, maxr, c->rows_c + ch, nullptr));
+    if (c->cfg.actor_kind == GAC_ACTOR_IQN)
+      GAC_TRY(iqn_train_fwd(c, o_actor, io->s, B, c->sidx_sel + r0, io->actor_tau + r0 * A, maxr, c->rows_c + ch, nullptr));
+    else
+      GAC_TRY(supervised_fwd(c, o_actor, io->s, B, c->sidx_sel + r0, io->actor_tau + r0 * A, c->act_sel + r0 * A, maxr, c->rows_c + ch, nullptr));
     GAC_TRY(qhuber(c, c->pred_c, c->act_sel + r0 * A, io->actor_tau + r0 * A, hp->mode == 0 ? c->adv_sel + r0 : nullptr, maxr,
                    c->rows_c + ch, A, 1.f, c->dpred_c, stats + 3, 1));
-    GAC_TRY(aiqn_bwd(c, o_actor, c->dpred_c, g_actor, ch > 0));
+    if (c->cfg.actor_kind == GAC_ACTOR_IQN) GAC_TRY(iqn_bwd(c, o_actor, c->dpred_c, g_actor, ch > 0));
+    else GAC_TRY(aiqn_bwd(c, o_actor, c->dpred_c, g_actor, ch > 0));
   }
 
   // optional taps for the parity tests

@@ -49,7 +49,7 @@ inline int round_up(int a, int b) { return cdiv(a, b) * b; }
 // epilogue order: + bias[n]  + add[addidx?addidx[m]:m][n]  -> activation -> * mul[m][n]
 //                 -> * (gate[m][n] > 0 ? 1 : gate_alpha)  -> (+ C_old if accumulate)
 // ------------------------------------------------------------------------------------------
-enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_LRELU2 = 2 /* lrelu(0.01) then lrelu(0.2): networks.py:196 */ };
+enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_LRELU2 = 2 /* lrelu(0.01) then lrelu(0.2): networks.py:196 */, ACT_TANH = 3 };
 
 struct GemmArgs {
   int M, N, K;
@@ -88,6 +88,7 @@ __device__ __forceinline__ float gemm_epilogue(const GemmArgs& g, float acc, int
   if (g.add) v += g.add[(size_t)(g.addidx ? g.addidx[m] : m) * g.ldadd + n];
   if (g.act == ACT_LRELU) v = lrelu_f(v, g.alpha);
   else if (g.act == ACT_LRELU2) v = lrelu_f(lrelu_f(v, 0.01f), 0.2f);
+  else if (g.act == ACT_TANH) v = tanhf(v);
   if (g.mul) v *= g.mul[(size_t)m * g.ldmul + n];
   if (g.gate) v *= (g.gate[(size_t)m * g.ldgate + n] > 0.f ? 1.f : g.gate_alpha);
   if (g.accumulate) v += g.transC ? g.C[(size_t)n * g.ldc + m] : g.C[(size_t)m * g.ldc + n];

@@ -875,7 +875,7 @@ inline Plan plan_for(int N) {
 
 }  // namespace tc
 
-inline bool tc_gemm_supported(const GemmArgs& g) { return g.K >= 8 && g.N >= 32 && g.M >= 64; }
+inline bool tc_gemm_supported(const GemmArgs& g) { return g.K >= 8 && g.N >= 32 && g.M >= 64 && g.act != ACT_TANH; }
 
 template <bool TA, bool TB, bool VEC, bool PACKED>
 inline cudaError_t tc_set_attr() {

@@ -197,25 +197,27 @@ __global__ void __launch_bounds__(FB_COLS) hadamard_bwd_kernel(const float* __re
 }
 
 // dst[n] = (accumulate ? dst[n] : 0) + sum_{s < nsplit} part[s*N + n], fixed order.
-// block (32, 8): 8 row lanes each sum every 8th partial with 4-way ILP, then a fixed-order smem fold.
-__global__ void reduce_cols_kernel(const float* __restrict__ part, int nsplit, int N, float* __restrict__ dst, int accumulate) {
-  __shared__ float sh[8][33];
+// block (32, 32): 32 row lanes each sum every 32nd partial with 4-way ILP, then a fixed-order smem fold.
+constexpr int RC_LANES = 32;
+__global__ void __launch_bounds__(32 * RC_LANES) reduce_cols_kernel(const float* __restrict__ part, int nsplit, int N,
+                                                                   float* __restrict__ dst, int accumulate) {
+  __shared__ float sh[RC_LANES][33];
   const int n = blockIdx.x * 32 + threadIdx.x, ly = threadIdx.y;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (n < N) {
     int s = ly;
-    for (; s + 24 < nsplit; s += 32) {
-      s0 += part[(size_t)s * N + n]; s1 += part[(size_t)(s + 8) * N + n];
-      s2 += part[(size_t)(s + 16) * N + n]; s3 += part[(size_t)(s + 24) * N + n];
+    for (; s + 3 * RC_LANES < nsplit; s += 4 * RC_LANES) {
+      s0 += part[(size_t)s * N + n]; s1 += part[(size_t)(s + RC_LANES) * N + n];
+      s2 += part[(size_t)(s + 2 * RC_LANES) * N + n]; s3 += part[(size_t)(s + 3 * RC_LANES) * N + n];
     }
-    for (; s < nsplit; s += 8) s0 += part[(size_t)s * N + n];
+    for (; s < nsplit; s += RC_LANES) s0 += part[(size_t)s * N + n];
   }
   sh[ly][threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (ly == 0 && n < N) {
     float t = accumulate ? dst[n] : 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
+    for (int k = 0; k < RC_LANES; ++k) t += sh[k][threadIdx.x];
     dst[n] = t;
   }
 }
@@ -578,6 +580,47 @@ __global__ void polyak_kernel(float* __restrict__ t, const float* __restrict__ s
 __global__ void polyak_scalar_kernel(float* __restrict__ t, const float* __restrict__ s, long long n, float one_minus_rho, float rho) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) t[i] = __fadd_rn(__fmul_rn(t[i], one_minus_rho), __fmul_rn(s[i], rho));
+}
+
+// ---- IQN actor (StochasticActor, networks.py:304-323) glue ----
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, int rows, int W, RowValid rv,
+                                   float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * W) return;
+  const int r = i / W, c = i % W;
+  if (!rv(r)) return;                  // dead rows carry uninitialised indices
+  out[i] = src[(size_t)idx[r] * W + c];
+}
+// merge = se[sidx ? sidx[r] : r] * ne   (networks.py:319)
+__global__ void iqn_merge_kernel(const float* __restrict__ se, const int* __restrict__ sidx, const float* __restrict__ ne, int rows,
+                                 int D, RowValid rv, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * D) return;
+  const int r = i / D, c = i % D;
+  if (!rv(r)) return;
+  out[i] = se[(size_t)(sidx ? sidx[r] : r) * D + c] * ne[i];
+}
+// dne = dmerge * se * lrelu'(ne) ; dse = dmerge * ne * lrelu'(se)    (both LeakyReLU(0.01); sign(y) = sign(pre))
+__global__ void iqn_dmerge_kernel(const float* __restrict__ dmerge, const float* __restrict__ se, const float* __restrict__ ne,
+                                  long long n, int D, RowValid rv, float* __restrict__ dne, float* __restrict__ dse) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!rv((int)(i / D))) return;
+  const float d = dmerge[i], s = se[i], e = ne[i];
+  dne[i] = d * s * (e > 0.f ? 1.f : 0.01f);
+  dse[i] = d * e * (s > 0.f ? 1.f : 0.01f);
+}
+// dop = dpred * (1 - out^2)   (tanh output layer)
+__global__ void tanh_bwd_kernel(const float* __restrict__ dpred, const float* __restrict__ out, long long n, int A, RowValid rv,
+                                float* __restrict__ dop) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!rv((int)(i / A))) return;
+  const float o = out[i];
+  dop[i] = dpred[i] * (1.f - o * o);
+}
+__global__ void scale_int_kernel(const int* __restrict__ src, int mul, int cap, int* __restrict__ dst) {
+  if (threadIdx.x == 0) { dst[0] = min(*src, cap); dst[1] = min(*src, cap) * mul; }
 }
 
 // ---- step glue: chunk row counts and the actor gradient normalisation ----

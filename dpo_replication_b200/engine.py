@@ -38,9 +38,10 @@ def f32(x, device) -> torch.Tensor:
 class Arena:
     """Flat parameter storage for the four trainable nets + their targets and Adam slots."""
 
-    def __init__(self, S: int, A: int, device):
-        self.S, self.A, self.device = S, A, device
-        self.lay = _lib.layout(S, A)
+    def __init__(self, S: int, A: int, device, actor_kind: int = 0):
+        self.S, self.A, self.device, self.actor_kind = S, A, device, actor_kind
+        self.names = _lib.var_names(actor_kind)
+        self.lay = _lib.layout(S, A, actor_kind)
         self.n = int(self.lay.offsets[_lib.NVARS])
         z = lambda extra=0: torch.zeros(self.n + extra, dtype=torch.float32, device=device)
         self.online, self.target, self.adam_m, self.adam_v = z(), z(), z(), z()
@@ -57,13 +58,13 @@ class Arena:
         return buf[a:b]
 
     def view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
-        v = _lib.VAR_NAMES.index(name)
+        v = self.names.index(name)
         o, r, c = int(self.lay.offsets[v]), int(self.lay.rows[v]), int(self.lay.cols[v])
         t = buf[o:o + r * c]
         return t.view(r, c) if c > 1 else t
 
     def named(self, buf: torch.Tensor, net: str) -> Dict[str, torch.Tensor]:
-        return {n.split(".", 1)[1]: self.view(buf, n) for n in _lib.VAR_NAMES if n.startswith(net + ".")}
+        return {n.split(".", 1)[1]: self.view(buf, n) for n in self.names if n.startswith(net + ".") and not n.split(".", 1)[1].startswith("_")}
 
     @property
     def stats(self) -> torch.Tensor:
@@ -91,6 +92,11 @@ def keras_default_init(S: int, A: int, net: str, generator=None) -> Dict[str, to
         return q * torch.sign(torch.diagonal(r))
 
     E = 400
+    if net == "iqn":          # StochasticActor, reference GAC/networks.py:283-302
+        d = E // A
+        D = d * A
+        return {"wm": glorot(D, 200), "bm": torch.zeros(200), "wn": glorot(64, d), "bn": torch.zeros(d), "wo": glorot(200, A),
+                "bo": torch.zeros(A), "ws": glorot(S, D), "bs": torch.zeros(D)}
     if net == "actor":
         return {"wa": glorot(64, E), "ba": torch.zeros(E), "w1": glorot(E, E), "b1": torch.zeros(E), "w2": glorot(E, 1),
                 "b2": torch.zeros(1), "wn": glorot(64, E), "bn": torch.zeros(E), "kx": glorot(2 * E, 3 * E),
@@ -104,11 +110,12 @@ def keras_default_init(S: int, A: int, net: str, generator=None) -> Dict[str, to
 class Engine:
     """One gac_ctx bound to the current torch CUDA stream."""
 
-    def __init__(self, S: int, A: int, B: int, K: int, device=None, chunk_rows: int = 0, engine: int = 0):
+    def __init__(self, S: int, A: int, B: int, K: int, device=None, chunk_rows: int = 0, engine: int = 0, actor_kind: int = 0):
         _require_cuda()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.S, self.A, self.B, self.K = S, A, B, K
-        self.cfg = Config(S, A, B, K, chunk_rows, engine)
+        self.actor_kind = actor_kind
+        self.cfg = Config(S, A, B, K, chunk_rows, engine, actor_kind)
         nbytes = lib.gac_workspace_bytes(C.byref(self.cfg))
         if nbytes == 0:
             raise _lib.GacError(f"bad configuration: {lib.gac_last_error().decode()}")
@@ -120,7 +127,7 @@ class Engine:
             h = C.c_void_p()
             check(lib.gac_create(C.byref(self.cfg), C.c_void_p(base), nbytes, C.c_void_p(self.stream.cuda_stream), C.byref(h)))
         self.h = h
-        self.lay = _lib.layout(S, A)
+        self.lay = _lib.layout(S, A, actor_kind)
 
     def __del__(self):
         try:
@@ -157,6 +164,22 @@ class Engine:
         out = self._new(rows, self.A)
         check(lib.gac_aiqn_sample(self.h, ptr(actor), ptr(states_u), states_u.shape[0], ptr(state_idx), ptr(taus), rows, ptr(out)))
         return out
+
+    def iqn_forward(self, actor, states_u, state_idx, taus):
+        rows = taus.shape[0]
+        out = self._new(rows, self.A)
+        check(lib.gac_iqn_forward(self.h, ptr(actor), ptr(states_u), states_u.shape[0], ptr(state_idx), ptr(taus), rows, ptr(out)))
+        return out
+
+    def iqn_train_fwd(self, actor, states_u, state_idx, taus, d_rows=None):
+        rows = taus.shape[0]
+        pred = self._new(rows, self.A)
+        check(lib.gac_iqn_train_fwd(self.h, ptr(actor), ptr(states_u), states_u.shape[0], ptr(state_idx), ptr(taus), rows, ptr(d_rows),
+                                    ptr(pred)))
+        return pred
+
+    def iqn_bwd(self, actor, dpred, grad_actor, accumulate=False):
+        check(lib.gac_iqn_bwd(self.h, ptr(actor), ptr(dpred), ptr(grad_actor), int(accumulate)))
 
     def critic_eval(self, fnn1, fnn2, states_u, state_idx, actions):
         rows = actions.shape[0]

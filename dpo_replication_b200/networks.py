@@ -22,14 +22,14 @@ from .engine import Arena, Engine, f32, keras_default_init
 _ENGINES: Dict[tuple, Engine] = {}
 
 
-def _engine_for(S: int, A: int, rows: int, device) -> Engine:
+def _engine_for(S: int, A: int, rows: int, device, kind: int = 0) -> Engine:
     """Engines for stand-alone network objects, cached by capacity (power-of-two rows)."""
     cap = 128
     while cap < rows:
         cap *= 2
-    key = (S, A, cap, str(device))
+    key = (S, A, cap, str(device), kind)
     if key not in _ENGINES:
-        _ENGINES[key] = Engine(S, A, B=cap, K=1, device=device, chunk_rows=cap)
+        _ENGINES[key] = Engine(S, A, B=cap, K=1, device=device, chunk_rows=cap, actor_kind=kind)
     return _ENGINES[key]
 
 
@@ -43,14 +43,16 @@ class _Net:
     """A network = a named slice of an Arena (its own, or the owning agent's)."""
     net_names: tuple = ()
 
+    actor_kind = 0
+
     def _attach(self, arena: Optional[Arena], role: str, S: int, A: int, device, init: bool):
         self._owns_arena = arena is None
-        self.arena = arena if arena is not None else Arena(S, A, device or _default_device())
+        self.arena = arena if arena is not None else Arena(S, A, device or _default_device(), self.actor_kind)
         self.role = role            # "online" or "target": which arena buffer holds the weights
         self.device = self.arena.device
         if init:
             for net in self.net_names:
-                self.arena.load(self._buf, net, keras_default_init(S, A, net))
+                self.arena.load(self._buf, net, keras_default_init(S, A, "iqn" if (net == "actor" and self.actor_kind == 1) else net))
 
     @property
     def _buf(self) -> torch.Tensor:
@@ -147,13 +149,14 @@ class IQNActor(_Net):
         if taus is None:
             taus = torch.rand(M, A, device=self.device)                      # networks.py:134
         taus = f32(taus, self.device).reshape(M, A)
-        eng = _engine_for(self.state_dim, self.action_dim, M, self.device)
+        eng = _engine_for(self.state_dim, self.action_dim, M, self.device, self.actor_kind)
         sidx = torch.arange(M, dtype=torch.int32, device=self.device)
         base = self._base("actor", self.arena.online)
-        pred = eng.aiqn_supervised_fwd(base, s, sidx, taus, acts)
+        iqn = self.actor_kind == 1
+        pred = eng.iqn_train_fwd(base, s, sidx, taus) if iqn else eng.aiqn_supervised_fwd(base, s, sidx, taus, acts)
         w = adv / adv.sum() if mode == "linear" else torch.ones_like(adv)
         self.last_loss, dpred = eng.qhuber_loss_bwd(pred, acts, taus, w, 1.0 / (M * A))
-        eng.aiqn_bwd(base, dpred, self.arena.net_slice(self.arena.grad, "actor"), accumulate=False)
+        (eng.iqn_bwd if iqn else eng.aiqn_bwd)(base, dpred, self.arena.net_slice(self.arena.grad, "actor"), accumulate=False)
         self._adam_only(eng, ("actor",))
 
 
@@ -179,6 +182,31 @@ class AutoRegressiveStochasticActor(IQNActor):
             acts = f32(supervise_actions, self.device).reshape(rows, -1)
             return eng.aiqn_supervised_fwd(self._base("actor"), s, sidx, taus, acts)
         return eng.aiqn_sample(self._base("actor"), s, sidx, taus)
+
+
+class StochasticActor(IQNActor):
+    """GAC/networks.py:271-323 (IQN): state embedding (S -> d*A) * cosine noise embedding (per action
+    dimension, d = 400 // A) -> Dense(200) -> Dense(A, tanh).  `supervise_actions` is accepted and ignored,
+    exactly as in the reference (:309)."""
+    actor_kind = 1
+
+    def __init__(self, state_dim, action_dim, n_basis_functions=64, *, arena=None, role="online", device=None, init=True):
+        super().__init__(state_dim, action_dim)
+        if n_basis_functions != 64:
+            raise NotImplementedError("the B200 kernels bake n_basis_functions = 64 (reference default)")
+        self.module_type = "StochasticActor"
+        self.noise_embed_dim = 400 // action_dim
+        self._attach(arena, role, state_dim, action_dim, device, init)
+
+    def __call__(self, states, taus, supervise_actions=None):
+        s = f32(states, self.device)
+        if s.dim() == 1:
+            s = s.reshape(1, -1)
+        rows = s.shape[0]
+        taus = f32(taus, self.device).reshape(rows, -1)
+        eng = _engine_for(self.state_dim, self.action_dim, rows, self.device, 1)
+        sidx = torch.arange(rows, dtype=torch.int32, device=self.device)
+        return eng.iqn_forward(self._base("actor"), s, sidx, taus)
 
 
 class FNN(_Net):
@@ -264,8 +292,9 @@ class Value(_Net):
         if taus is None:
             taus = torch.rand(B * K, A, device=self.device)                       # networks.py:473
         sidx = torch.arange(B, dtype=torch.int32, device=self.device).repeat_interleave(K)   # row = b*K + k
-        eng = _engine_for(actor.state_dim, A, B * K, self.device)
-        acts = eng.aiqn_sample(actor._base("actor"), s, sidx, f32(taus, self.device).reshape(B * K, A))
+        eng = _engine_for(actor.state_dim, A, B * K, self.device, actor.actor_kind)
+        sample = eng.iqn_forward if actor.actor_kind == 1 else eng.aiqn_sample
+        acts = sample(actor._base("actor"), s, sidx, f32(taus, self.device).reshape(B * K, A))
         q = eng.critic_eval(critic._base("fnn1"), critic._base("fnn2"), s, sidx, acts)
         v_critic = q.reshape(B, K, 1).mean(dim=1)                                  # networks.py:484-485
         eng_v = _engine_for(self.arena.S, self.arena.A, B, self.device)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GAC_B200_ABI_VERSION 1
+#define GAC_B200_ABI_VERSION 2
 
 enum gac_status {
   GAC_OK = 0,
@@ -48,6 +48,13 @@ enum gac_var {
 };
 enum gac_net { GAC_NET_ACTOR = 0, GAC_NET_FNN1, GAC_NET_FNN2, GAC_NET_VALUE, GAC_NNETS };
 
+/* actor_kind: the AIQN actor (AutoRegressiveStochasticActor, networks.py:144-268) or the IQN actor
+ * (StochasticActor, networks.py:271-323).  With the IQN actor the first eight actor slots hold, in tf.Module
+ * order, merge_embedding_layer (D,200)+(200), noise_embedding_layer (64,d)+(d), output_action_layer (200,A)+(A),
+ * state_embedding_layer (S,D)+(D) with d = 400 / A, D = d*A; the remaining five actor slots are empty. */
+enum gac_actor_kind { GAC_ACTOR_AIQN = 0, GAC_ACTOR_IQN = 1 };
+enum gac_iqn_var { GAC_I_WM = 0, GAC_I_BM, GAC_I_WN, GAC_I_BN, GAC_I_WO, GAC_I_BO, GAC_I_WS, GAC_I_BS };
+
 /* Arena layout for (S, A).  offsets[v] = first float of variable v, rows/cols = its shape
  * (cols = 1 for vectors... biases are (n,) => rows=n, cols=1; gb is (2,1200)).
  * offsets[GAC_NVARS] = arena length in floats (each variable starts on a 128-byte boundary;
@@ -60,7 +67,8 @@ typedef struct gac_layout {
   int64_t net_begin[GAC_NNETS + 1];
 } gac_layout_t;
 
-int gac_layout(int32_t S, int32_t A, gac_layout_t* out /* host */);
+int gac_layout(int32_t S, int32_t A, gac_layout_t* out /* host */);            /* AIQN actor */
+int gac_layout_ex(int32_t S, int32_t A, int32_t actor_kind, gac_layout_t* out /* host */);
 
 /* Static configuration of one agent replica (one per GPU). */
 typedef struct gac_config {
@@ -69,6 +77,7 @@ typedef struct gac_config {
   int32_t K;             /* action_samples                               agent.py:53    */
   int32_t chunk_rows;    /* row chunk for the actor fwd/bwd workspace (0 = min(2*B*K, 65536)) */
   int32_t engine;        /* 0 = tcgen05 3xTF32 GEMMs where available, 1 = SIMT fp32 everywhere */
+  int32_t actor_kind;    /* enum gac_actor_kind                          agent.py:65-70 */
 } gac_config_t;
 
 typedef struct gac_hparams {
@@ -108,6 +117,16 @@ int gac_adam_polyak(gac_ctx_t* ctx, float* online, float* target, float* adam_m,
  * taus: (rows, A); actions out: (rows, A).  actor: arena base of the actor variables. ---- */
 int gac_aiqn_sample(gac_ctx_t* ctx, const float* actor, const float* states_u, int32_t n_states,
                     const int32_t* state_idx, const float* taus, int32_t rows, float* actions);
+
+/* ---- StochasticActor.__call__ (IQN, networks.py:304-323); same argument meaning as gac_aiqn_sample.
+ * Context must have been created with actor_kind = GAC_ACTOR_IQN. ---- */
+int gac_iqn_forward(gac_ctx_t* ctx, const float* actor, const float* states_u, int32_t n_states,
+                    const int32_t* state_idx, const float* taus, int32_t rows, float* actions);
+/* ---- the same forward keeping the activations for gac_iqn_bwd (IQNActor.train, networks.py:137-140) ---- */
+int gac_iqn_train_fwd(gac_ctx_t* ctx, const float* actor, const float* states_u, int32_t n_states,
+                      const int32_t* state_idx, const float* taus, int32_t max_rows, const int32_t* d_rows,
+                      float* pred);
+int gac_iqn_bwd(gac_ctx_t* ctx, const float* actor, const float* dpred, float* grad_actor, int32_t accumulate);
 
 /* ---- Critic.__call__ (networks.py:384-388): q = min(fnn1, fnn2)(concat(s, a)) ---- */
 int gac_critic_eval(gac_ctx_t* ctx, const float* fnn1, const float* fnn2, const float* states_u,

@@ -262,6 +262,79 @@ def aiqn_supervised_backward(cache, dact):
 
 
 # --------------------------------------------------------------------------------------
+# IQN actor (StochasticActor, networks.py:271-323) -- the reference CLI's default actor (main.py:78)
+#   wm (D,200) bm (200)   merge_embedding_layer      D = (400 // A) * A
+#   wn (64,d)  bn (d)     noise_embedding_layer.act_linear (LeakyReLU 0.01), d = 400 // A
+#   wo (200,A) bo (A)     output_action_layer (tanh)
+#   ws (S,D)   bs (D)     state_embedding_layer (LeakyReLU 0.01)
+# --------------------------------------------------------------------------------------
+IQN_KEYS = ("wm", "bm", "wn", "bn", "wo", "bo", "ws", "bs")
+
+
+def iqn_shapes(S, A):
+    d = E // A
+    D = d * A
+    return {"wm": (D, 200), "bm": (200,), "wn": (NB, d), "bn": (d,), "wo": (200, A), "bo": (A,), "ws": (S, D), "bs": (D,)}
+
+
+def init_iqn(rng, S, A, bias_scale=0.0):
+    p = {}
+    for k, shp in iqn_shapes(S, A).items():
+        p[k] = _glorot(rng, shp) if len(shp) == 2 else (bias_scale * rng.standard_normal(shp)).astype(np.float32)
+    return p
+
+
+def iqn_forward(p, states, taus, dtype=np.float32, cache=False):
+    """StochasticActor.__call__, networks.py:304-323 (supervise_actions is ignored there)."""
+    p = cast(p, dtype)
+    states = np.asarray(states, dtype=dtype)
+    taus = _flat2(taus)
+    rows, A = taus.shape
+    d = p["wn"].shape[1]
+    se_pre = states @ p["ws"] + p["bs"]
+    se = lrelu(se_pre, 0.01)                                              # :313
+    cn = cosine_basis(taus, dtype)                                        # (rows*A, 64)
+    ne_pre = cn @ p["wn"] + p["bn"]
+    ne = lrelu(ne_pre, 0.01).reshape(rows, A * d)                         # :315-317
+    merge = se * ne                                                       # :319
+    me_pre = merge @ p["wm"] + p["bm"]
+    me = lrelu(me_pre, 0.01)                                              # :321
+    out = np.tanh(me @ p["wo"] + p["bo"])                                 # :322
+    if cache:
+        return out, dict(p=p, states=states, se=se, se_pre=se_pre, cn=cn, ne=ne, ne_pre=ne_pre.reshape(rows, A * d), merge=merge,
+                         me=me, me_pre=me_pre, out=out, rows=rows, A=A, d=d)
+    return out
+
+
+def iqn_backward(c, dact):
+    p, rows, A, d = c["p"], c["rows"], c["A"], c["d"]
+    g = {}
+    dop = dact * (1 - c["out"] ** 2)
+    g["wo"] = c["me"].T @ dop
+    g["bo"] = dop.sum(0)
+    dme = (dop @ p["wo"].T) * lrelu_grad(c["me_pre"], 0.01)
+    g["wm"] = c["merge"].T @ dme
+    g["bm"] = dme.sum(0)
+    dmerge = dme @ p["wm"].T
+    dne = (dmerge * c["se"] * lrelu_grad(c["ne_pre"], 0.01)).reshape(rows * A, d)
+    g["wn"] = c["cn"].T @ dne
+    g["bn"] = dne.sum(0)
+    dse = dmerge * c["ne"] * lrelu_grad(c["se_pre"], 0.01)
+    g["ws"] = c["states"].T @ dse
+    g["bs"] = dse.sum(0)
+    return g
+
+
+def iqn_train_grads(p, states, actions, advantage, taus, mode="linear", beta=1.0, dtype=np.float32):
+    """IQNActor.train with the IQN forward (networks.py:122-141)."""
+    adv = np.asarray(advantage, dtype).reshape(-1, 1)
+    w = target_density(mode, adv, beta)
+    pred, cache = iqn_forward(p, states, taus, dtype, cache=True)
+    loss, dpred = quantile_huber_loss(pred, np.asarray(_flat2(actions), dtype), np.asarray(_flat2(taus), dtype), w)
+    return iqn_backward(cache, dpred), float(loss), pred, dpred
+
+
+# --------------------------------------------------------------------------------------
 # FNN / Critic / Value
 # --------------------------------------------------------------------------------------
 def fnn_forward(p, x, cache=False):

@@ -103,6 +103,21 @@ class AIQNT:
         return self._head(gru_out * ne).squeeze(-1)
 
 
+class IQNT:
+    """StochasticActor (networks.py:271-323) on a parameter dict of tensors."""
+
+    def __init__(self, p, action_dim):
+        self.p, self.action_dim = p, action_dim
+        self.noise_embedding_layer = CosineBasisLinearT(p["wn"], p["bn"], act=0.01)
+
+    def __call__(self, states, taus, supervise_actions=None):
+        p = self.p
+        se = F.leaky_relu(states @ p["ws"] + p["bs"], 0.01)
+        ne = self.noise_embedding_layer(taus).reshape(states.shape[0], -1)
+        me = F.leaky_relu((se * ne) @ p["wm"] + p["bm"], 0.01)
+        return torch.tanh(me @ p["wo"] + p["bo"])
+
+
 def fnn_t(p, x):
     h = F.leaky_relu(x @ p["w0"] + p["b0"], 0.01)
     h = F.leaky_relu(h @ p["w1"] + p["b1"], 0.01)

@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported(lib):
     raw = C.CDLL(lib.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.lib.gac_abi_version() == 1
+    assert lib.lib.gac_abi_version() == 2
 
 
 @pytest.mark.parametrize("S,A", [(3, 1), (17, 6), (376, 17), (111, 8)])
@@ -80,3 +80,16 @@ def test_product_package_never_imports_the_oracle():
         if f.endswith(".py"):
             src = open(os.path.join(pkg, f)).read()
             assert "oracle" not in src.replace("the oracle", "").replace("by the oracle", ""), f
+
+
+@pytest.mark.parametrize("S,A", [(17, 6), (376, 17), (3, 1)])
+def test_iqn_layout_matches_reference_variable_shapes(lib, S, A):
+    # StochasticActor (networks.py:283-302): 8 actor variables in tf.Module order, then the same three FNNs
+    lay = lib.layout(S, A, 1)
+    shapes = O.iqn_shapes(S, A)
+    for i, k in enumerate(("wm", "bm", "wn", "bn", "wo", "bo", "ws", "bs")):
+        assert lay.rows[i] * lay.cols[i] == int(np.prod(shapes[k])), k
+        assert lay.offsets[i] % 32 == 0
+    assert all(lay.rows[i] == 0 for i in range(8, 13))
+    assert lay.net_begin[1] == lay.offsets[13] and lay.net_begin[4] == lay.offsets[31]
+    assert lib.lib.gac_layout_ex(S, A, 7, C.byref(lib.Layout())) == -1

@@ -194,3 +194,26 @@ def test_golden_fixture_matches_oracle():
     # fp32 oracle stays within tolerance of the fp64 fixture on the teacher-forced path
     sup32, _ = O.aiqn_supervised(nets["actor"], st, tau, tch, np.float32)
     assert np.abs(sup32 - z["stage.supervised"]).max() < 1e-5
+
+
+def test_iqn_actor_matches_torch_autograd():
+    """StochasticActor (IQN, networks.py:271-323): forward + hand-derived backward vs torch autograd, and the
+    reference's shape test (tests/unit/GAC/networks.py:96-130: batch 10, S=20, A=5 -> (10, 5))."""
+    rng = np.random.default_rng(8)
+    S, A, M = 20, 5, 10
+    p = O.init_iqn(rng, S, A, bias_scale=0.1)
+    assert p["wn"].shape == (64, 80) and p["wm"].shape == (400, 200) and O.iqn_shapes(17, 6)["ws"] == (17, 396)
+    s, taus = rng.standard_normal((M, S)), rng.uniform(size=(M, A, 1)).astype(np.float32)
+    acts, adv = rng.uniform(-1, 1, (M, A)).astype(np.float32), rng.uniform(0.1, 1, (M, 1))
+    out = O.iqn_forward(p, s, taus, np.float64)
+    assert out.shape == (M, A)
+    g, loss, pred, _ = O.iqn_train_grads(p, s, acts, adv, taus, dtype=np.float64)
+    tp = T.to_t(p, torch.float64, grad=True)
+    tpred = T.IQNT(tp, A)(torch.tensor(s), torch.tensor(taus.reshape(M, A), dtype=torch.float64))
+    assert np.abs(tpred.detach().numpy() - pred).max() < 1e-12
+    tl = T.huber_quantile_loss_t(tpred, torch.tensor(acts, dtype=torch.float64), torch.tensor(taus.reshape(M, A), dtype=torch.float64),
+                                 torch.tensor(adv / adv.sum()))
+    gr = torch.autograd.grad(tl, list(tp.values()))
+    assert abs(float(tl.detach()) - loss) < 1e-14
+    for k, r in zip(tp.keys(), gr):
+        assert np.abs(g[k] - r.numpy()).max() <= 1e-10 * max(np.abs(r.numpy()).max(), 1e-30), k
