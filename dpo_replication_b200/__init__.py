@@ -7,8 +7,8 @@ Importing the package loads libgac_b200.so and fails loudly if it has not been b
 from . import _lib  # noqa: F401  (loads the shared library or raises)
 from .agent import GACAgent
 from .engine import Arena, Engine
-from .helpers import ActionSampler, ReplayBuffer, denormalize, normalize, update
+from .helpers import ActionSampler, DeviceReplayBuffer, ReplayBuffer, denormalize, normalize, update
 from .networks import (FNN, AutoRegressiveStochasticActor, CosineBasisLinear, Critic, IQNActor, StochasticActor, Value)
 
-__all__ = ["GACAgent", "Arena", "Engine", "ActionSampler", "ReplayBuffer", "update", "normalize", "denormalize", "FNN",
+__all__ = ["GACAgent", "Arena", "Engine", "ActionSampler", "ReplayBuffer", "DeviceReplayBuffer", "update", "normalize", "denormalize", "FNN",
            "AutoRegressiveStochasticActor", "CosineBasisLinear", "Critic", "IQNActor", "StochasticActor", "Value"]

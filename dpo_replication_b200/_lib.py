@@ -81,6 +81,7 @@ SIGNATURES = {
     "gac_td_fwd_bwd": (C.c_int, [_P, _P, _I, _P, _P, _I, _P, _P]),
     "gac_step_grads": (C.c_int, [_P, C.POINTER(StepIO), C.POINTER(HParams)]),
     "gac_step_apply": (C.c_int, [_P, C.POINTER(StepIO), C.POINTER(HParams)]),
+    "gac_replay_gather": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "gac_gemm": (C.c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I]),
     "gac_launch_count": (_L, [_P]),
 }

@@ -9,7 +9,7 @@ import torch
 
 from . import dist as gdist
 from .engine import Arena, Engine, f32, keras_default_init
-from .helpers import ActionSampler, ReplayBuffer, normalize, update
+from .helpers import ActionSampler, DeviceReplayBuffer, ReplayBuffer, normalize, update
 from .networks import AutoRegressiveStochasticActor, Critic, StochasticActor, Value
 
 
@@ -18,7 +18,7 @@ class GACAgent:
 
     def __init__(self, action_dim, state_dim, buffer_size=1000000, action_samples=10, mode='linear', beta=1, tau=5e-3,
                  q_normalization=0.01, gamma=0.99, normalize_obs=False, normalize_rewards=False, batch_size=64,
-                 actor='AIQN', *args, device=None, chunk_rows=0, engine=0, **kwargs):
+                 actor='AIQN', *args, device=None, chunk_rows=0, engine=0, replay_on_device=True, **kwargs):
         self.action_dim, self.state_dim, self.buffer_size = action_dim, state_dim, buffer_size
         self.gamma, self.action_samples, self.mode, self.beta, self.tau = gamma, action_samples, mode, beta, tau
         self.batch_size = batch_size
@@ -51,7 +51,8 @@ class GACAgent:
         update(self.target_actor, self.actor, 1.0)
         update(self.target_critics, self.critics, 1.0)
         self.arena.load(self.arena.target, "value", keras_default_init(S, A, "value"))
-        self.replay = ReplayBuffer(S, A, buffer_size)
+        # the reference keeps a host NumPy ring (helpers.py:33-72); the default here keeps it in HBM
+        self.replay = DeviceReplayBuffer(S, A, buffer_size, self.device) if replay_on_device else ReplayBuffer(S, A, buffer_size)
         self.action_sampler = ActionSampler(self.actor.action_dim)
         self._hp = self.engine.hparams(gamma, tau, q_normalization, beta, mode)
 
@@ -136,6 +137,42 @@ class GACAgent:
     def get_action(self, states):
         """agent.py:218-228."""
         return self.action_sampler.get_actions(self.actor, states)
+
+    # ---- acting path (SURVEY.md §8f rank 3): the batch-1 / small-batch sampler as one CUDA graph ----------
+    def get_action_graphed(self, states, *, taus=None):
+        """Same result as `get_action` for a fixed batch size, replayed from a captured CUDA graph: the
+        A-step autoregressive sampler is ~7 small kernels per action dimension, i.e. launch bound at
+        batch 1 (main.py:119-121,195-203 call it once per environment step).  The graph is captured on
+        first use per batch size; inputs are copied into static buffers, tau is drawn outside the graph."""
+        s = f32(states, self.device)
+        if s.dim() == 1:
+            s = s.reshape(1, -1)
+        rows = s.shape[0]
+        if not hasattr(self, "_act_graphs"):
+            self._act_graphs = {}
+        if rows not in self._act_graphs:
+            st_in = torch.zeros(rows, self.state_dim, device=self.device)
+            tau_in = torch.zeros(rows, self.action_dim, device=self.device)
+            sidx = torch.arange(rows, dtype=torch.int32, device=self.device)
+            base = self.arena.net_slice(self.arena.online, "actor")
+            # the engine launches on the stream it was created on: create it on the capture stream, warm it up
+            # there (lazy module loading, no sync or allocation may happen inside the capture), then capture
+            cap_stream = torch.cuda.Stream(device=self.device)
+            cap_stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(cap_stream):
+                cap_eng = Engine(self.state_dim, self.action_dim, max(rows, 128), 1, self.device, chunk_rows=128, actor_kind=self.actor_kind)
+                cap_fn = cap_eng.iqn_forward if self.actor_kind == 1 else cap_eng.aiqn_sample
+                cap_fn(base, st_in, sidx, tau_in)
+            cap_stream.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=cap_stream):
+                out = cap_fn(base, st_in, sidx, tau_in)
+            self._act_graphs[rows] = (graph, st_in, tau_in, out, cap_eng, sidx)
+        graph, st_in, tau_in, out, _, _ = self._act_graphs[rows]
+        st_in.copy_(s)
+        tau_in.copy_(torch.rand(rows, self.action_dim, device=self.device) if taus is None else f32(taus, self.device).reshape(rows, -1))
+        graph.replay()
+        return out.clone()
 
     def select_perturbed_action(self, state, action_noise=None):
         """agent.py:230-248."""

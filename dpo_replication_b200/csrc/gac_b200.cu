@@ -206,7 +206,7 @@ enum { PK_T_WA = 0, PK_T_KXA, PK_T_U, PK_T_WN, PK_T_W1, PK_O_WA, PK_O_KXA, PK_O_
 // cta_group::2 persistent kernel (128-wide tiles), small ones the one-tile-per-CTA kernel.
 const unsigned char* pack_w(gac_ctx* c, int slot, const float* W, int ld, int K, int N, int transB, int rows) {
   c->pk_bn[slot] = 0;
-  if (c->cfg.engine != 0 || K < 32 || N < 32 || tc_packed_bytes(K, N) > c->pack_bytes) return nullptr;
+  if (c->cfg.engine != 0 || K < 32 || N < 32 || rows < 64 || tc_packed_bytes(K, N) > c->pack_bytes) return nullptr;   // rows < 64: SIMT path
   const int bn = (tc_pair_enabled() && rows >= 1024) ? tc::pair_bn(N) : 0;
   if (tc_pack_b(W, ld, transB, K, N, c->pack[slot], c->stream, bn) != cudaSuccess) return nullptr;
   c->launches++;
@@ -837,6 +837,17 @@ int gac_td_fwd_bwd(gac_ctx_t* c, const float* fnn, int32_t n_in, const float* x,
                    float* loss_out) {
   if (!c || !fnn || !x || !y || !grad_fnn || !loss_out) return fail(GAC_ERR_INVALID, "gac_td_fwd_bwd: bad arguments");
   return td_fwd_bwd(c, fnn, n_in, x, y, rows, grad_fnn, loss_out);
+}
+
+int gac_replay_gather(const float* obs1, const float* obs2, const float* acts, const float* rews, const float* done, const int32_t* idx,
+                      int32_t n, int32_t S, int32_t A, float* s, float* sp, float* a, float* r, float* it, void* stream) {
+  if (!obs1 || !obs2 || !acts || !rews || !done || !idx || !s || !sp || !a || !r || !it || n <= 0 || S <= 0 || A <= 0)
+    return fail(GAC_ERR_INVALID, "gac_replay_gather: bad arguments");
+  const long long total = (long long)n * (2 * S + A + 2);
+  replay_gather_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(obs1, obs2, acts, rews, done, idx, n,
+                                                                                                        S, A, s, sp, a, r, it);
+  GAC_LAUNCH_CHECK("replay_gather");
+  return GAC_OK;
 }
 
 int gac_gemm(gac_ctx_t* c, int32_t engine, const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t transA,

@@ -113,6 +113,37 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs g) {
   }
 }
 
+// Small-M path (M <= 8: the acting path, one state per environment step -- agent.py:218-248): a 128x128 tile
+// would run one serial K loop on a handful of CTAs.  Here a block owns 64 output columns, 8 thread rows split
+// K, partial sums are folded through shared memory in fixed order; loads of B are coalesced along n.
+template <bool TB>
+__global__ void __launch_bounds__(512) gemm_smallm_kernel(const GemmArgs g) {
+  __shared__ float red[8][8][65];
+  const int tx = threadIdx.x, ty = threadIdx.y;          // tx: column in the block, ty: K slice
+  const int n = blockIdx.x * 64 + tx;
+  float acc[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) acc[m] = 0.f;
+  if (n < g.N) {
+    for (int k = ty; k < g.K; k += 8) {
+      const float b = TB ? g.B[(size_t)n * g.ldb + k] : g.B[(size_t)k * g.ldb + n];
+#pragma unroll
+      for (int m = 0; m < 8; ++m)
+        if (m < g.M) acc[m] = fmaf(g.A[(size_t)m * g.lda + k], b, acc[m]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 8; ++m) red[ty][m][tx] = acc[m];
+  __syncthreads();
+  if (ty < g.M && n < g.N) {                             // thread row ty finishes output row m = ty
+    const int m = ty;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][m][tx];
+    g.C[(size_t)m * g.ldc + n] = gemm_epilogue(g, s, m, n);
+  }
+}
+
 // dst[i] = (accumulate ? dst[i] : 0) + sum_z part[z*stride + i]   (fixed order => deterministic)
 __global__ void reduce_splits_kernel(const float* __restrict__ part, long long stride, int nsplit, float* __restrict__ dst,
                                      long long n, int accumulate) {
@@ -124,6 +155,12 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, long long s
 }
 
 inline cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st) {
+  if (g.M <= 8 && !g.transA && !g.transC && g.splitk <= 1 && !g.dyn_rows) {
+    dim3 blk(64, 8);
+    if (g.transB) gemm_smallm_kernel<true><<<cdiv(g.N, 64), blk, 0, st>>>(g);
+    else gemm_smallm_kernel<false><<<cdiv(g.N, 64), blk, 0, st>>>(g);
+    return cudaGetLastError();
+  }
   dim3 grid(cdiv(g.N, 128), cdiv(g.M, 128), g.splitk > 1 ? g.splitk : 1);
   if (g.transA) {
     if (g.transB) gemm_simt_kernel<true, true><<<grid, 256, 0, st>>>(g);

@@ -623,6 +623,23 @@ __global__ void scale_int_kernel(const int* __restrict__ src, int mul, int cap, 
   if (threadIdx.x == 0) { dst[0] = min(*src, cap); dst[1] = min(*src, cap) * mul; }
 }
 
+// ---- ReplayBuffer.sample_batch (helpers.py:65-72): one gather for the five transition arrays ----
+__global__ void replay_gather_kernel(const float* __restrict__ obs1, const float* __restrict__ obs2, const float* __restrict__ acts,
+                                     const float* __restrict__ rews, const float* __restrict__ done, const int* __restrict__ idx, int n,
+                                     int S, int A, float* __restrict__ s, float* __restrict__ sp, float* __restrict__ a,
+                                     float* __restrict__ r, float* __restrict__ it) {
+  const int W = 2 * S + A + 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * W) return;
+  const int row = i / W, c = i % W;
+  const size_t src = (size_t)idx[row];
+  if (c < S) s[(size_t)row * S + c] = obs1[src * S + c];
+  else if (c < 2 * S) sp[(size_t)row * S + (c - S)] = obs2[src * S + (c - S)];
+  else if (c < 2 * S + A) a[(size_t)row * A + (c - 2 * S)] = acts[src * A + (c - 2 * S)];
+  else if (c == 2 * S + A) r[row] = rews[src];
+  else it[row] = done[src];
+}
+
 // ---- step glue: chunk row counts and the actor gradient normalisation ----
 // rows_c[c] = clamp(M - c*chunk, 0, chunk)
 __global__ void chunk_rows_kernel(const int* __restrict__ m, int chunk, int nchunks, int* __restrict__ rows_c) {

@@ -198,6 +198,13 @@ typedef struct gac_step_io {
 int gac_step_grads(gac_ctx_t* ctx, const gac_step_io_t* io /* host */, const gac_hparams_t* hp /* host */);
 int gac_step_apply(gac_ctx_t* ctx, const gac_step_io_t* io /* host */, const gac_hparams_t* hp /* host */);
 
+/* ---- ReplayBuffer.sample_batch (GAC/helpers.py:65-72) on a device-resident ring buffer: gathers the five
+ * transition arrays for `n` indices (int32, drawn by the caller: the reference uses random.sample) in one
+ * kernel.  obs1/obs2 (size,S), acts (size,A), rews/done (size,1) -> s/sp (n,S), a (n,A), r/it (n,1). ---- */
+int gac_replay_gather(const float* obs1, const float* obs2, const float* acts, const float* rews, const float* done,
+                      const int32_t* idx, int32_t n, int32_t S, int32_t A, float* s, float* sp, float* a, float* r,
+                      float* it, void* stream);
+
 /* ---- plain GEMM entry used by the tests and the micro-benchmarks:
  * C(M,N) = A(M,K) * B(K,N), engine 0 = tcgen05 3xTF32, 1 = SIMT fp32,
  * 2 = tcgen05 3xTF32 with B pre-packed as a weight matrix (bulk-copy path). ---- */

@@ -177,3 +177,43 @@ def test_agent_surface(gb):
     assert bool((adv > 0).all())
     with pytest.raises(NotImplementedError):
         gb.GACAgent(2, 4, mode="max")
+
+
+def test_device_replay_buffer_matches_reference_ring(gb):
+    """DeviceReplayBuffer vs the host ReplayBuffer (reference tests/unit/GAC/helpers.py:10-47 semantics: FIFO
+    ring, store writes row `ptr`, sampling without replacement); the on-device gather is bit-exact."""
+    import random
+    S, A, size = 5, 2, 4
+    dev_buf = gb.DeviceReplayBuffer(S, A, size, "cuda")
+    host = gb.ReplayBuffer(S, A, size)
+    rng = np.random.default_rng(3)
+    for i in range(6):                                   # 6 stores into a size-4 ring: rows 0,1 overwritten
+        tr = (rng.standard_normal(S).astype(np.float32), rng.uniform(-1, 1, A).astype(np.float32), float(i), rng.standard_normal(S).astype(np.float32), i == 5)
+        dev_buf.store(*tr); host.store(*tr)
+        if i == 0:
+            assert np.array_equal(dev_buf.obs1_buf[0].cpu().numpy(), tr[0])     # test_store: row 0 written
+    assert dev_buf.size == host.size == 4 and dev_buf.ptr == host.ptr == 2
+    for name in ("obs1_buf", "obs2_buf", "acts_buf", "rews_buf", "done_buf"):
+        assert np.array_equal(getattr(dev_buf, name).cpu().numpy(), getattr(host, name))
+    random.seed(7); a = dev_buf.sample_batch(3)
+    random.seed(7); b = host.sample_batch(3)
+    for k in ("s", "a", "r", "sp", "it"):
+        assert np.array_equal(getattr(a, k).cpu().numpy(), getattr(b, k).numpy()), k
+    assert len(set(dev_buf._last_idx.cpu().tolist())) == 3                       # without replacement
+
+
+@pytest.mark.parametrize("actor", ["AIQN", "IQN"])
+def test_graphed_acting_path_matches_eager(gb, actor):
+    """get_action for a fixed small batch replayed from one CUDA graph gives the same
+    actions as the eager multi-launch path (same tau), and follows weight updates (the graph reads the arena)."""
+    ag = gb.GACAgent(3, 11, action_samples=4, batch_size=8, actor=actor)
+    st = torch.randn(1, 11, device="cuda")
+    tau = torch.rand(1, 3, device="cuda")
+    eager = ag.action_sampler.get_actions(ag.actor, st, taus=tau)
+    g1 = ag.get_action_graphed(st, taus=tau)
+    assert torch.equal(eager, g1)
+    ag.arena.online.mul_(1.01)                      # weights change in place -> the replay must see them
+    eager2 = ag.action_sampler.get_actions(ag.actor, st, taus=tau)
+    g2 = ag.get_action_graphed(st, taus=tau)
+    assert torch.equal(eager2, g2) and not torch.equal(g1, g2)
+    assert tuple(ag.get_action_graphed(torch.randn(11)).shape) == (1, 3)
