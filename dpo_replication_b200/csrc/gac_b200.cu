@@ -7,6 +7,7 @@
 #include "gac_common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gru_step_tc.cuh"
 #include "kernels_elem.cuh"
 
 namespace gac {
@@ -101,6 +102,8 @@ struct gac_ctx {
   float *it_x, *it_se, *it_cos, *it_ne, *it_merge, *it_me, *it_dop, *it_dme, *it_dmerge, *it_dne, *it_dse;
   int* it_live;   // [0] live rows of the chunk, [1] live rows * A
   unsigned char* pack[16]; size_t pack_bytes;   // pre-split / pre-swizzled weight tiles (tc::pack_b_kernel)
+  unsigned char* gru_pack[2];                   // fused GRU-step weights (tc::gru_pack_kernel): target / online actor
+  const unsigned char *gru_t, *gru_o;           // valid for the current call; nullptr = unfused path
 };
 
 namespace {
@@ -187,6 +190,7 @@ size_t partition(gac_ctx* c, void* ws) {
   if (tc_packed_bytes(GAC_G, GAC_E) > c->pack_bytes) c->pack_bytes = tc_packed_bytes(GAC_G, GAC_E);
   c->pack_bytes = (c->pack_bytes + 1023) & ~(size_t)1023;
   for (int i = 0; i < 16; ++i) c->pack[i] = b.take<unsigned char>(c->pack_bytes);
+  for (int i = 0; i < 2; ++i) c->gru_pack[i] = b.take<unsigned char>(tc::GRU_PACK_BYTES);
   return (b.off + 255) & ~(size_t)255;
 }
 
@@ -212,6 +216,25 @@ const unsigned char* pack_w(gac_ctx* c, int slot, const float* W, int ld, int K,
   c->launches++;
   c->pk_bn[slot] = bn;
   return c->pack[slot];
+}
+
+// weights of the fused GRU step (gru_step_tc.cuh); nullptr = not applicable, use the GEMM + gates kernels
+const unsigned char* pack_gru(gac_ctx* c, int which, const float* actor, int rows) {
+  static const bool off = getenv("GAC_NO_FUSED_GRU") != nullptr;
+  if (off || c->cfg.engine != 0 || rows < 64) return nullptr;
+  if (gru_pack(var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, var(c, actor, 0, GAC_A_U), c->gru_pack[which], c->stream) != cudaSuccess)
+    return nullptr;
+  c->launches++;
+  return c->gru_pack[which];
+}
+int run_gru_step(gac_ctx* c, const unsigned char* wpk, const float* actor, const float* sx, const int* sidx, const float* ae,
+                 const float* hprev, float* hout, int rows, const int* dyn, float* z, float* r, float* cc, float* mhh) {
+  tc::GruStepArgs a;
+  a.rows = rows; a.dyn_rows = dyn; a.ae = ae; a.hprev = hprev; a.wpk = wpk; a.sx = sx; a.sidx = sidx;
+  a.b1 = var(c, actor, 0, GAC_A_GB) + GAC_G; a.hout = hout; a.z = z; a.r = r; a.c = cc; a.mhh = mhh;
+  GAC_CUDA(launch_gru_step(a, c->stream));
+  c->launches++;
+  return GAC_OK;
 }
 
 // GEMM dispatch: tcgen05 3xTF32 engine where the shape qualifies, else SIMT; split-K for the
@@ -343,18 +366,23 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
     GemmArgs g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->ae, GAC_E);
     g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.Bpacked = c->pk[PK_T_WA]; g.Bpacked_bn = c->pk_bn[PK_T_WA];
     GAC_TRY(run_gemm(c, g));
-    g = gemm_args(rows, GAC_G, GAC_E, c->ae, GAC_E, kxa, GAC_G, c->mxa, GAC_G);
-    g.Bpacked = c->pk[PK_T_KXA]; g.Bpacked_bn = c->pk_bn[PK_T_KXA];
-    GAC_TRY(run_gemm(c, g));
-    if (d) {
-      g = gemm_args(rows, GAC_G, GAC_E, hprev, GAC_E, var(c, actor, 0, GAC_A_U), GAC_G, c->mh, GAC_G);
-      g.Bpacked = c->pk[PK_T_U]; g.Bpacked_bn = c->pk_bn[PK_T_U];
+    if (c->gru_t) {
+      // both projections + gates in one kernel: mxa / mh never touch HBM
+      GAC_TRY(run_gru_step(c, c->gru_t, actor, c->sx_u, sidx, c->ae, d ? hprev : nullptr, hcur, rows, nullptr, nullptr, nullptr, nullptr, nullptr));
+    } else {
+      g = gemm_args(rows, GAC_G, GAC_E, c->ae, GAC_E, kxa, GAC_G, c->mxa, GAC_G);
+      g.Bpacked = c->pk[PK_T_KXA]; g.Bpacked_bn = c->pk_bn[PK_T_KXA];
       GAC_TRY(run_gemm(c, g));
+      if (d) {
+        g = gemm_args(rows, GAC_G, GAC_E, hprev, GAC_E, var(c, actor, 0, GAC_A_U), GAC_G, c->mh, GAC_G);
+        g.Bpacked = c->pk[PK_T_U]; g.Bpacked_bn = c->pk_bn[PK_T_U];
+        GAC_TRY(run_gemm(c, g));
+      }
+      gru_gates_fwd_kernel<<<(unsigned)cdiv64((long long)rows * GAC_E, 256), 256, 0, st>>>(
+          c->sx_u, sidx, c->mxa, d ? c->mh : nullptr, var(c, actor, 0, GAC_A_GB) + GAC_G, hprev, hcur, nullptr, nullptr, nullptr,
+          nullptr, rows, all);
+      LAUNCHED(c, "gru_gates_fwd");
     }
-    gru_gates_fwd_kernel<<<(unsigned)cdiv64((long long)rows * GAC_E, 256), 256, 0, st>>>(
-        c->sx_u, sidx, c->mxa, d ? c->mh : nullptr, var(c, actor, 0, GAC_A_GB) + GAC_G, hprev, hcur, nullptr, nullptr, nullptr,
-        nullptr, rows, all);
-    LAUNCHED(c, "gru_gates_fwd");
     cos_basis_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(taus + d, A, c->cosb, rows, all);
     LAUNCHED(c, "cos_basis");
     g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->u, GAC_E);
@@ -378,8 +406,11 @@ int aiqn_sample(gac_ctx* c, const float* actor, const float* states_u, int n_sta
   GAC_TRY(state_prep(c, actor, states_u, n_states, c->se_u, c->sx_u));
   const int A = c->cfg.A;
   c->pk[PK_T_WA] = pack_w(c, PK_T_WA, var(c, actor, 0, GAC_A_WA), GAC_E, GAC_NB, GAC_E, 0, rows);
-  c->pk[PK_T_KXA] = pack_w(c, PK_T_KXA, var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, GAC_G, GAC_E, GAC_G, 0, rows);
-  c->pk[PK_T_U] = pack_w(c, PK_T_U, var(c, actor, 0, GAC_A_U), GAC_G, GAC_E, GAC_G, 0, rows);
+  c->gru_t = pack_gru(c, 0, actor, rows);
+  if (!c->gru_t) {
+    c->pk[PK_T_KXA] = pack_w(c, PK_T_KXA, var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, GAC_G, GAC_E, GAC_G, 0, rows);
+    c->pk[PK_T_U] = pack_w(c, PK_T_U, var(c, actor, 0, GAC_A_U), GAC_G, GAC_E, GAC_G, 0, rows);
+  }
   c->pk[PK_T_WN] = pack_w(c, PK_T_WN, var(c, actor, 0, GAC_A_WN), GAC_E, GAC_NB, GAC_E, 0, rows);
   c->pk[PK_T_W1] = pack_w(c, PK_T_W1, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 0, rows);
   for (int r0 = 0; r0 < rows; r0 += c->Rs) {
@@ -443,8 +474,11 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
   GAC_TRY(state_prep(c, actor, states_u, n_states, c->a_se_u, c->a_sx_u));
   const float* kxa_w = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
   c->pk[PK_O_WA] = pack_w(c, PK_O_WA, var(c, actor, 0, GAC_A_WA), GAC_E, GAC_NB, GAC_E, 0, c->Mc);
-  c->pk[PK_O_KXA] = pack_w(c, PK_O_KXA, kxa_w, GAC_G, GAC_E, GAC_G, 0, c->Mc);
-  c->pk[PK_O_U] = pack_w(c, PK_O_U, var(c, actor, 0, GAC_A_U), GAC_G, GAC_E, GAC_G, 0, c->Mc);
+  c->gru_o = pack_gru(c, 1, actor, c->Mc);
+  if (!c->gru_o) {
+    c->pk[PK_O_KXA] = pack_w(c, PK_O_KXA, kxa_w, GAC_G, GAC_E, GAC_G, 0, c->Mc);
+    c->pk[PK_O_U] = pack_w(c, PK_O_U, var(c, actor, 0, GAC_A_U), GAC_G, GAC_E, GAC_G, 0, c->Mc);
+  }
   c->pk[PK_O_WN] = pack_w(c, PK_O_WN, var(c, actor, 0, GAC_A_WN), GAC_E, GAC_NB, GAC_E, 0, c->Mc);
   c->pk[PK_O_W1] = pack_w(c, PK_O_W1, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 0, c->Mc);
   c->pk[PK_O_W1T] = pack_w(c, PK_O_W1T, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 1, c->Mc);
@@ -455,11 +489,18 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
   GemmArgs g = gemm_args((int)AM, GAC_E, GAC_NB, c->ca, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->a_ae, GAC_E);
   g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_WA]; g.Bpacked_bn = c->pk_bn[PK_O_WA];
   GAC_TRY(run_gemm(c, g));
-  g = gemm_args((int)AM, GAC_G, GAC_E, c->a_ae, GAC_E, kxa_w, GAC_G, c->mx, GAC_G);
-  g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_KXA]; g.Bpacked_bn = c->pk_bn[PK_O_KXA];
-  GAC_TRY(run_gemm(c, g));
+  if (!c->gru_o) {
+    g = gemm_args((int)AM, GAC_G, GAC_E, c->a_ae, GAC_E, kxa_w, GAC_G, c->mx, GAC_G);
+    g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_KXA]; g.Bpacked_bn = c->pk_bn[PK_O_KXA];
+    GAC_TRY(run_gemm(c, g));
+  }
   for (int d = 0; d < A; ++d) {
     const size_t o4 = (size_t)d * Mc * GAC_E, o12 = (size_t)d * Mc * GAC_G;
+    if (c->gru_o) {
+      GAC_TRY(run_gru_step(c, c->gru_o, actor, c->a_sx_u, sidx, c->a_ae + o4, d ? c->hall + o4 : nullptr, c->hall + o4 + (size_t)Mc * GAC_E, Mc,
+                           live, c->zs + o4, c->rs + o4, c->cs + o4, c->mhh + o4));
+      continue;
+    }
     if (d) {
       g = gemm_args(Mc, GAC_G, GAC_E, c->hall + o4, GAC_E, var(c, actor, 0, GAC_A_U), GAC_G, c->dmh + o12, GAC_G);
       g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_U]; g.Bpacked_bn = c->pk_bn[PK_O_U];

@@ -70,6 +70,7 @@ struct GemmArgs {
   // split-K: blockIdx.z = split, raw partial (no epilogue) stored at C + z*split_stride
   int splitk; long long split_stride;
   unsigned long long* dbg;               // optional timeline probe (tools/gemm_probe.py --timeline)
+  int probe;                             // timing experiments only (env GAC_TC_PROBE; results are garbage when set)
 };
 
 inline GemmArgs gemm_args(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc) {

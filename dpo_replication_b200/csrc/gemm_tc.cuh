@@ -403,6 +403,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
         for (int j = 0; j < ksteps; ++j) {
           const uint64_t adv = (uint64_t)(j * 2);            // +32 bytes (8 tf32) in the >>4 address field
           const uint32_t acc = (kb | j) ? 1u : 0u;
+          // timing probe (tools/gemm_probe.py): 1 of the 3 passes only => how much of the tile time is MMA-bound
+          if (g.probe == 2) { mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, acc); continue; }
           mma_tf32(tmem_d + (uint32_t)bn, a_lo + adv, b_hi + adv, idesc, acc);   // correction accumulator
           mma_tf32(tmem_d + (uint32_t)bn, a_hi + adv, b_lo + adv, idesc, 1u);
           mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, acc);                  // main accumulator
@@ -939,7 +941,10 @@ inline cudaError_t tc_pack_b(const float* W, int ld, int transB, int K, int N, u
   return cudaGetLastError();
 }
 
-inline cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
+inline cudaError_t launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
+  GemmArgs g = g_in;
+  static const int probe = getenv("GAC_TC_PROBE") ? atoi(getenv("GAC_TC_PROBE")) : 0;
+  g.probe = probe;
   const tc::Plan p = tc::plan_for(g.N);
   dim3 grid(cdiv(g.N, p.bn), cdiv(g.M, tc::BM), g.splitk > 1 ? g.splitk : 1);
   // 16-byte vector accesses need aligned bases and leading dimensions
