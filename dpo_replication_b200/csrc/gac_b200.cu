@@ -230,7 +230,9 @@ const unsigned char* pack_gru(gac_ctx* c, int which, const float* actor, int row
 int run_gru_step(gac_ctx* c, const unsigned char* wpk, const float* actor, const float* sx, const int* sidx, const float* ae,
                  const float* hprev, float* hout, int rows, const int* dyn, float* z, float* r, float* cc, float* mhh) {
   tc::GruStepArgs a;
-  a.rows = rows; a.dyn_rows = dyn; a.ae = ae; a.hprev = hprev; a.wpk = wpk; a.sx = sx; a.sidx = sidx;
+  static const bool timeline = getenv("GAC_GRU_TIMELINE") != nullptr;
+  a.dbg = timeline ? reinterpret_cast<unsigned long long*>(c->spart) : nullptr;   // scratch: idle during the sampler
+  a.probe = 0; a.rows = rows; a.dyn_rows = dyn; a.ae = ae; a.hprev = hprev; a.wpk = wpk; a.sx = sx; a.sidx = sidx;
   a.b1 = var(c, actor, 0, GAC_A_GB) + GAC_G; a.hout = hout; a.z = z; a.r = r; a.c = cc; a.mhh = mhh;
   GAC_CUDA(launch_gru_step(a, c->stream));
   c->launches++;

@@ -219,6 +219,30 @@ __device__ __forceinline__ void store_operand(const float (&x)[NCH][4], uint32_t
   }
 }
 
+// Two-phase variant of store_operand: the hi/lo split happens in registers while the loader is still waiting for
+// its smem stage, so that only the 128-bit stores remain on the stage's critical path (measured: the stage
+// turn-around -- commit -> loader wake-up -> split + store -> arrive -> MMA wake-up -- is ~1,600 cycles, and with
+// two stages per-K-block time is (T_mma + turn-around) / 2; the split is ~350 of those cycles).
+template <int NCH>
+__device__ __forceinline__ void split_operand(float (&x)[NCH][4], float (&l)[NCH][4]) {
+#pragma unroll
+  for (int i = 0; i < NCH; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float h; split_tf32(x[i][j], h, l[i][j]); x[i][j] = h; }
+}
+template <bool TRANS, int NCH>
+__device__ __forceinline__ void store_split(const float (&h)[NCH][4], const float (&l)[NCH][4], uint32_t s_hi, uint32_t s_lo, int rows, int t) {
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    int r, c;
+    chunk_rc<TRANS>(i, t, r, c);
+    if (r >= rows) continue;
+    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(s_hi + off), "f"(h[i][0]), "f"(h[i][1]), "f"(h[i][2]), "f"(h[i][3]));
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "f"(l[i][0]), "f"(l[i][1]), "f"(l[i][2]), "f"(l[i][3]));
+  }
+}
+
 // TB means "B is stored (N, K) row-major" (g.transB); !TB is the natural Keras (K, N).
 template <bool TA, bool TB, bool VEC, bool PACKED>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, int bn, int stages, int tmem_cols) {
@@ -265,6 +289,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
       load_operand<TA, VEC, 8>(xa, g.A, g.lda, m0, m_end, BM, k0, live, t);
       // B tile rows are output columns n; element (n, k) = B(k, n)
       if constexpr (!PACKED) load_operand<!TB, VEC, NB_CH>(xb, g.B, g.ldb, n0, g.N, bn, k0, live, t);
+      float la[8][4];
+      split_operand<8>(xa, la);     // waits for the A loads, not for the stage
       const int s = kb % stages;
       const uint32_t ph = (uint32_t)(kb / stages) & 1u;
       mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
@@ -282,7 +308,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
                        : "memory");
         }
       }
-      store_operand<TA, 8>(xa, sa, sa + A_TILE_BYTES, BM, t);
+      store_split<TA, 8>(xa, la, sa, sa + A_TILE_BYTES, BM, t);
       if constexpr (!PACKED) store_operand<!TB, NB_CH>(xb, sa + 2 * A_TILE_BYTES, sa + 2 * A_TILE_BYTES + (uint32_t)bn * 128u, bn, t);
       fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();

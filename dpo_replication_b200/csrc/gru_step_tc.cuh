@@ -34,9 +34,9 @@ struct GruStepArgs {
   const float* b1;             // recurrent bias (1200)
   float* hout;                 // (rows, 400)
   float *z, *r, *c, *mhh;      // optional saves (rows, 400)
+  int probe;                   // timing experiments (env GAC_GRU_PROBE): results are garbage when set
+  unsigned long long* dbg;     // optional per-CTA phase stamps (tools/gru_probe.py --timeline)
 };
-
-__device__ __forceinline__ float sigmoid_tc(float x) { return 1.f / (1.f + expf(-x)); }
 
 constexpr int GRU_NU = 64;                                      // hidden units per tile
 constexpr int GRU_NT = (GAC_E + GRU_NU - 1) / GRU_NU;           // 7 (the last tile has 16 units)
@@ -83,6 +83,14 @@ __global__ void __launch_bounds__(THREADS, 1) gru_step_tc_kernel(const GruStepAr
   const int jt = blockIdx.x, m0 = blockIdx.y * BM;
   const int m_end = g.dyn_rows ? min(g.rows, *g.dyn_rows) : g.rows;
   if (m0 >= m_end) return;                                       // dead tile (uniform per CTA)
+  unsigned long long* dbg = (g.dbg && tid == 0) ? g.dbg + 8 + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg) {
+    unsigned long long gt; unsigned sm;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    dbg[0] = gt; dbg[1] = clock64(); dbg[7] = sm;
+    if (blockIdx.x == 0 && blockIdx.y == 0) g.dbg[0] = 0x600DC0DE600DC0DEull;
+  }
   const int nu = min(GRU_NU, GAC_E - jt * GRU_NU);               // 64, or 16 for the last tile
   const int nkb = g.hprev ? 2 * GRU_KB : GRU_KB;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -101,6 +109,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_step_tc_kernel(const GruStepAr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
+  if (dbg) dbg[2] = clock64();
 
   if (warp < LOADER_WARPS) {
     // ------------------------------ loaders: two groups alternate K blocks ------------------------------
@@ -108,12 +117,18 @@ __global__ void __launch_bounds__(THREADS, 1) gru_step_tc_kernel(const GruStepAr
     for (int kb = grp; kb < nkb; kb += 2) {
       const int half = kb >= GRU_KB, k0 = (kb - half * GRU_KB) * BK, live = min(BK, GAC_E - k0);
       float xa[8][4];
+      if (g.probe & 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xa[i][0] = xa[i][1] = xa[i][2] = xa[i][3] = 1.f;
+      } else
       load_operand<false, true, 8>(xa, half ? g.hprev : g.ae, GAC_E, m0, m_end, BM, k0, live, t);
+      float la[8][4];
+      split_operand<8>(xa, la);     // waits for the loads, not for the stage
       const int s = kb % GRU_STAGES;
       const uint32_t ph = (uint32_t)(kb / GRU_STAGES) & 1u;
       mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
       const uint32_t sa = smem0 + (uint32_t)s * GRU_STAGE;
-      if (t == 0) {
+      if (t == 0 && !(g.probe & 4)) {
         const uint32_t bytes = 2u * b_lo_off;
         const unsigned char* srcp = g.wpk + ((size_t)jt * 2 * GRU_KB + kb) * GRU_BSLOT;
         const uint32_t bar = smem_u32(&bar_full[s]);
@@ -122,16 +137,54 @@ __global__ void __launch_bounds__(THREADS, 1) gru_step_tc_kernel(const GruStepAr
                      "l"(srcp), "r"(bytes), "r"(bar)
                      : "memory");
       }
-      store_operand<false, 8>(xa, sa, sa + A_TILE_BYTES, BM, t);
+      if (!(g.probe & 8)) store_split<false, 8>(xa, la, sa, sa + A_TILE_BYTES, BM, t);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
     }
     // ------------------------------ epilogue ------------------------------
+    if (dbg) dbg[3] = clock64();
+    // Work split of phase 2: a thread owns one quad of hidden units and walks rows (rpi rows apart); consecutive
+    // lanes = consecutive units of a row, so global traffic is row-contiguous.  Nothing it reads from global
+    // memory depends on the accumulators, so the loads of the first batch of rows are issued BEFORE waiting for the
+    // last MMAs, and those of batch b + 1 before the gate math of batch b (8 warps per SM cannot hide a dependent
+    // sidx -> sx chain per item otherwise: measured 14.7k of a tile's 59k cycles before this).
+    const int quarter = warp & 3, hf = warp >> 2;
+    const int n4 = nu >> 2, rpi = (LOADER_WARPS * 32) / n4;       // rows per pass: 16 (nu = 64) or 64 (nu = 16)
+    const int u4 = tid % n4, rsub = tid / n4;
+    const int u = jt * GRU_NU + 4 * u4;
+    constexpr int IB = 4;                                         // rows per batch
+    const int nbatch = (BM + IB * rpi - 1) / (IB * rpi);          // 2 or 1
+    struct Batch { int sid[IB]; float4 sz[IB], sr[IB], sh[IB], hp[IB]; };
+    auto load_sid = [&](Batch& q, int r0) {
+#pragma unroll
+      for (int b = 0; b < IB; ++b) {
+        const int row = r0 + b * rpi + rsub, m = m0 + row;
+        q.sid[b] = (row < BM && m < m_end) ? g.sidx[m] : -1;
+      }
+    };
+    auto load_rows = [&](Batch& q, int r0) {
+#pragma unroll
+      for (int b = 0; b < IB; ++b) {
+        q.hp[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q.sid[b] < 0) continue;
+        const float* sx = g.sx + (size_t)q.sid[b] * GAC_G + u;
+        q.sz[b] = *reinterpret_cast<const float4*>(sx); q.sr[b] = *reinterpret_cast<const float4*>(sx + GAC_E);
+        q.sh[b] = *reinterpret_cast<const float4*>(sx + 2 * GAC_E);
+        if (g.hprev) q.hp[b] = *reinterpret_cast<const float4*>(g.hprev + (size_t)(m0 + r0 + b * rpi + rsub) * GAC_E + u);
+      }
+    };
+    Batch q0, q1;
+    load_sid(q0, 0);
+    if (nbatch > 1) load_sid(q1, IB * rpi);
+    const float4 bz = *reinterpret_cast<const float4*>(g.b1 + u), br = *reinterpret_cast<const float4*>(g.b1 + GAC_E + u),
+                 bh = *reinterpret_cast<const float4*>(g.b1 + 2 * GAC_E + u);
+    load_rows(q0, 0);
+
     mbar_wait(smem_u32(&bar_accum), 0);
     tc_fence_after();
+    if (dbg) dbg[4] = clock64();
     // phase 1: main + correction -> smem [128][4 nu (+4 pad)] fp32.  All MMAs have retired, so the stages are free.
-    const int quarter = warp & 3, hf = warp >> 2;
     const int ncols = g.hprev ? 4 * nu : 3 * nu;                 // hh columns were never written on the first step
     const int SS = 4 * nu + 4;                                   // row stride in floats (== 4 mod 32: conflict-free v4 stores)
     float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)));
@@ -147,45 +200,44 @@ __global__ void __launch_bounds__(THREADS, 1) gru_step_tc_kernel(const GruStepAr
           *reinterpret_cast<float4*>(srow + ci * 16 + q) = make_float4(v[q] + w[q], v[q + 1] + w[q + 1], v[q + 2] + w[q + 2], v[q + 3] + w[q + 3]);
       }
     }
+    if (nbatch > 1) load_rows(q1, IB * rpi);
     asm volatile("bar.sync 1, 256;" ::: "memory");               // the 8 epilogue warps only
-    // phase 2: (row, 4 units) items; consecutive lanes = consecutive units of a row => coalesced global traffic
-    const int n4 = nu >> 2, total = BM * n4, et = tid;           // tid < 256 here
-    for (int i = et; i < total; i += LOADER_WARPS * 32) {
-      const int row = i / n4, u4 = i - row * n4;
-      const int m = m0 + row;
-      if (m >= m_end) continue;
-      const int u = jt * GRU_NU + 4 * u4;
-      const float* srow = stg + (size_t)row * SS + 4 * u4;
-      const float4 axh = *reinterpret_cast<const float4*>(srow);
-      const float4 az = *reinterpret_cast<const float4*>(srow + nu);
-      const float4 ar = *reinterpret_cast<const float4*>(srow + 2 * nu);
-      float4 ahh = make_float4(0.f, 0.f, 0.f, 0.f), hp = ahh;
-      if (g.hprev) {
-        ahh = *reinterpret_cast<const float4*>(srow + 3 * nu);
-        hp = *reinterpret_cast<const float4*>(g.hprev + (size_t)m * GAC_E + u);
-      }
-      const float* sx = g.sx + (size_t)g.sidx[m] * GAC_G + u;
-      const float4 sz = *reinterpret_cast<const float4*>(sx), sr = *reinterpret_cast<const float4*>(sx + GAC_E),
-                   sh = *reinterpret_cast<const float4*>(sx + 2 * GAC_E);
-      const float4 bz = *reinterpret_cast<const float4*>(g.b1 + u), br = *reinterpret_cast<const float4*>(g.b1 + GAC_E + u),
-                   bh = *reinterpret_cast<const float4*>(g.b1 + 2 * GAC_E + u);
-      float4 ho, zo, ro, co, mo;
-#define GRU_LANE(f)                                                              \
-  {                                                                              \
-    const float hh = ahh.f + bh.f;                                               \
-    const float zz = sigmoid_tc((sz.f + az.f) + bz.f), rr = sigmoid_tc((sr.f + ar.f) + br.f); \
-    const float cc = tanhf((sh.f + axh.f) + rr * hh);                            \
-    ho.f = zz * hp.f + (1.f - zz) * cc; zo.f = zz; ro.f = rr; co.f = cc; mo.f = hh; \
+    if (dbg) dbg[5] = clock64();
+    // phase 2: gate math.  sigmoid / tanh through ex2.approx + fast division: |error| ~ 2e-7, far inside the 1e-5 contract
+    auto sig = [](float x) { return __fdividef(1.f, 1.f + __expf(-x)); };
+    auto tnh = [](float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); };
+    auto gates = [&](const Batch& q, int r0) {
+#pragma unroll
+      for (int b = 0; b < IB; ++b) {
+        if (q.sid[b] < 0) continue;
+        const int row = r0 + b * rpi + rsub;
+        const float* srow = stg + (size_t)row * SS + 4 * u4;
+        const float4 axh = *reinterpret_cast<const float4*>(srow);
+        const float4 az = *reinterpret_cast<const float4*>(srow + nu);
+        const float4 ar = *reinterpret_cast<const float4*>(srow + 2 * nu);
+        float4 ahh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.hprev) ahh = *reinterpret_cast<const float4*>(srow + 3 * nu);
+        float4 ho, zo, ro, co, mo;
+#define GRU_LANE(f)                                                                               \
+  {                                                                                               \
+    const float hh = ahh.f + bh.f;                                                                \
+    const float zz = sig((q.sz[b].f + az.f) + bz.f), rr = sig((q.sr[b].f + ar.f) + br.f);         \
+    const float cc = tnh((q.sh[b].f + axh.f) + rr * hh);                                          \
+    ho.f = zz * q.hp[b].f + (1.f - zz) * cc; zo.f = zz; ro.f = rr; co.f = cc; mo.f = hh;          \
   }
-      GRU_LANE(x) GRU_LANE(y) GRU_LANE(z) GRU_LANE(w)
+        GRU_LANE(x) GRU_LANE(y) GRU_LANE(z) GRU_LANE(w)
 #undef GRU_LANE
-      const size_t o = (size_t)m * GAC_E + u;
-      *reinterpret_cast<float4*>(g.hout + o) = ho;
-      if (g.z) {
-        *reinterpret_cast<float4*>(g.z + o) = zo; *reinterpret_cast<float4*>(g.r + o) = ro;
-        *reinterpret_cast<float4*>(g.c + o) = co; *reinterpret_cast<float4*>(g.mhh + o) = mo;
+        const size_t o = (size_t)(m0 + row) * GAC_E + u;
+        *reinterpret_cast<float4*>(g.hout + o) = ho;
+        if (g.z) {
+          *reinterpret_cast<float4*>(g.z + o) = zo; *reinterpret_cast<float4*>(g.r + o) = ro;
+          *reinterpret_cast<float4*>(g.c + o) = co; *reinterpret_cast<float4*>(g.mhh + o) = mo;
+        }
       }
-    }
+    };
+    gates(q0, 0);
+    if (nbatch > 1) gates(q1, IB * rpi);
+    if (dbg) dbg[6] = clock64();
   } else {
     // ------------------------------ MMA issuer (one lane) ------------------------------
     if (lane == 0) {
@@ -216,6 +268,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_step_tc_kernel(const GruStepAr
             continue;
           }
           const uint32_t acc = (kb | j) ? 1u : 0u;
+          if (g.probe & 1) { mma_tf32(tmem_d + dcol, a_hi + adv, b_hi + adv, id3, acc); continue; }
+          if (g.probe & 16) continue;
           mma_tf32(corr + dcol, a_lo + adv, b_hi + adv, id3, acc);
           mma_tf32(corr + dcol, a_hi + adv, b_lo + adv, id3, 1u);
           mma_tf32(tmem_d + dcol, a_hi + adv, b_hi + adv, id3, acc);
@@ -249,8 +303,11 @@ inline cudaError_t launch_gru_step(const tc::GruStepArgs& g, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr = true;
   }
+  static const int probe = getenv("GAC_GRU_PROBE") ? atoi(getenv("GAC_GRU_PROBE")) : 0;
+  tc::GruStepArgs a = g;
+  a.probe = probe;
   dim3 grid(tc::GRU_NT, cdiv(g.rows, tc::BM));
-  tc::gru_step_tc_kernel<<<grid, tc::THREADS, tc::GRU_SMEM, st>>>(g);
+  tc::gru_step_tc_kernel<<<grid, tc::THREADS, tc::GRU_SMEM, st>>>(a);
   return cudaGetLastError();
 }
 
