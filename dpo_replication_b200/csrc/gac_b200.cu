@@ -102,6 +102,7 @@ struct gac_ctx {
   float *it_x, *it_se, *it_cos, *it_ne, *it_merge, *it_me, *it_dop, *it_dme, *it_dmerge, *it_dne, *it_dse;
   int* it_live;   // [0] live rows of the chunk, [1] live rows * A
   unsigned char* pack[16]; size_t pack_bytes;   // pre-split / pre-swizzled weight tiles (tc::pack_b_kernel)
+  int* seg_info;                                // [unsorted | start[NU] | end[NU]] of the per-state segments (aiqn_bwd)
   unsigned char* gru_pack[2];                   // fused GRU-step weights (tc::gru_pack_kernel): target / online actor
   const unsigned char *gru_t, *gru_o;           // valid for the current call; nullptr = unfused path
 };
@@ -163,7 +164,7 @@ size_t partition(gac_ctx* c, void* ws) {
   c->skip = b.take<int>(GAC_NNETS); c->idx_sel = b.take<int64_t>(2 * P);
   c->a_se_u = b.take<float>((size_t)c->NUa * GAC_E); c->a_sx_u = b.take<float>((size_t)c->NUa * GAC_G);
   c->a_dsx_u = b.take<float>((size_t)c->NUa * GAC_G); c->a_dse_u = b.take<float>((size_t)c->NUa * GAC_E);
-  c->a_states = b.take<float>((size_t)c->NUa * S); c->a_sidx = b.take<int>(Mc);
+  c->a_states = b.take<float>((size_t)c->NUa * S); c->a_sidx = b.take<int>(Mc); c->seg_info = b.take<int>(2 * (size_t)c->NUa + 2);
   c->ca = b.take<float>(AM * GAC_NB); c->cn = b.take<float>(AM * GAC_NB);
   c->a_ae = b.take<float>(AM * GAC_E); c->mx = b.take<float>(AM * GAC_G); c->dmh = b.take<float>(AM * GAC_G);
   c->zs = b.take<float>(AM * GAC_E); c->rs = b.take<float>(AM * GAC_E); c->cs = b.take<float>(AM * GAC_E);
@@ -516,7 +517,7 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
   g = gemm_args((int)AM, GAC_E, GAC_NB, c->cn, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->ne, GAC_E);
   g.bias = var(c, actor, 0, GAC_A_BN); g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_WN]; g.Bpacked_bn = c->pk_bn[PK_O_WN];
   GAC_TRY(run_gemm(c, g));
-  mul_kernel<<<(unsigned)cdiv64(AM * GAC_E, 256), 256, 0, st>>>(c->ne, c->hall + (size_t)Mc * GAC_E, AM * GAC_E, Mc, live, c->au);
+  mul_kernel<<<(unsigned)cdiv64(AM * GAC_E / 4, 256), 256, 0, st>>>(c->ne, c->hall + (size_t)Mc * GAC_E, AM * GAC_E, Mc, live, c->au);
   LAUNCHED(c, "hadamard");
   g = gemm_args((int)AM, GAC_E, GAC_E, c->au, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->ay1, GAC_E);
   g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_W1]; g.Bpacked_bn = c->pk_bn[PK_O_W1];
@@ -598,7 +599,12 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   GAC_TRY(run_colsum(c, c->du, GAC_E, nullptr, GAC_E, AM, rv, G(GAC_A_BA), acc));
   // state half: reduce d(sx) per unique state, then B-row GEMMs
   const int NU = c->bwd_nstates;
-  segment_sum_kernel<<<dim3(NU, cdiv(GAC_G, 256)), 256, 0, st>>>(c->mx, c->bwd_sidx, A, Mc, live, 0, c->a_dsx_u);
+  GAC_CUDA(cudaMemsetAsync(c->seg_info, 0, (size_t)(2 * NU + 1) * sizeof(int), st));
+  segment_ranges_kernel<<<cdiv(Mc, 256), 256, 0, st>>>(c->bwd_sidx, Mc, live, NU, c->seg_info);
+  LAUNCHED(c, "segment_ranges");
+  segment_sum_sorted_kernel<<<dim3(NU, cdiv(GAC_G, 256)), 256, 0, st>>>(c->mx, A, Mc, NU, c->seg_info, 0, c->a_dsx_u);
+  LAUNCHED(c, "segment_sum_sorted");
+  segment_sum_kernel<<<dim3(NU, cdiv(GAC_G, 256)), 256, 0, st>>>(c->mx, c->bwd_sidx, A, Mc, live, 0, c->a_dsx_u, c->seg_info);
   LAUNCHED(c, "segment_sum");
   GAC_TRY(wgrad(GAC_E, GAC_G, c->a_se_u, GAC_E, c->a_dsx_u, GAC_G, NU, G(GAC_A_KX), false));
   g = gemm_args(NU, GAC_E, GAC_G, c->a_dsx_u, GAC_G, var(c, actor, 0, GAC_A_KX), GAC_G, c->a_dse_u, GAC_E);

@@ -80,16 +80,20 @@ __global__ void __launch_bounds__(THREADS, 1) gru_step_tc_kernel(const GruStepAr
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int jt = blockIdx.x, m0 = blockIdx.y * BM;
+  // 1-D grid: all 64-unit tiles first (row-block major, 6 per row block: neighbours share the A rows in L2), the
+  // narrow 16-unit tiles last, where they fill the tail of the last wave
+  const int nmb = (g.rows + BM - 1) / BM, nfull = nmb * (GRU_NT - 1);
+  const int jt = (int)blockIdx.x < nfull ? (int)blockIdx.x % (GRU_NT - 1) : GRU_NT - 1;
+  const int m0 = ((int)blockIdx.x < nfull ? (int)blockIdx.x / (GRU_NT - 1) : (int)blockIdx.x - nfull) * BM;
   const int m_end = g.dyn_rows ? min(g.rows, *g.dyn_rows) : g.rows;
   if (m0 >= m_end) return;                                       // dead tile (uniform per CTA)
-  unsigned long long* dbg = (g.dbg && tid == 0) ? g.dbg + 8 + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  unsigned long long* dbg = (g.dbg && tid == 0) ? g.dbg + 8 + (size_t)blockIdx.x * 8 : nullptr;
   if (dbg) {
     unsigned long long gt; unsigned sm;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
     dbg[0] = gt; dbg[1] = clock64(); dbg[7] = sm;
-    if (blockIdx.x == 0 && blockIdx.y == 0) g.dbg[0] = 0x600DC0DE600DC0DEull;
+    if (blockIdx.x == 0) g.dbg[0] = 0x600DC0DE600DC0DEull;
   }
   const int nu = min(GRU_NU, GAC_E - jt * GRU_NU);               // 64, or 16 for the last tile
   const int nkb = g.hprev ? 2 * GRU_KB : GRU_KB;
@@ -306,7 +310,7 @@ inline cudaError_t launch_gru_step(const tc::GruStepArgs& g, cudaStream_t st) {
   static const int probe = getenv("GAC_GRU_PROBE") ? atoi(getenv("GAC_GRU_PROBE")) : 0;
   tc::GruStepArgs a = g;
   a.probe = probe;
-  dim3 grid(tc::GRU_NT, cdiv(g.rows, tc::BM));
+  dim3 grid(tc::GRU_NT * cdiv(g.rows, tc::BM));
   tc::gru_step_tc_kernel<<<grid, tc::THREADS, tc::GRU_SMEM, st>>>(a);
   return cudaGetLastError();
 }

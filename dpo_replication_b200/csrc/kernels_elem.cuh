@@ -315,12 +315,14 @@ __global__ void head_dop_kernel(const float* __restrict__ dpred, const float* __
 }
 
 // ---- out = a * b on live rows (u = ne * h, networks.py:220/:265) ----
+// out = a * b over (rows, 400) activations, 128-bit accesses; dead rows (row % seg >= *dyn) are skipped
 __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, int seg, const int* dyn,
                            float* __restrict__ out) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  if (dyn && (int)((idx / GAC_E) % seg) >= *dyn) return;
-  out[idx] = a[idx] * b[idx];
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // float4 index; GAC_E / 4 = 100 per row
+  if (i4 * 4 >= n) return;
+  if (dyn && (int)((i4 / (GAC_E / 4)) % seg) >= *dyn) return;
+  const float4 x = reinterpret_cast<const float4*>(a)[i4], y = reinterpret_cast<const float4*>(b)[i4];
+  reinterpret_cast<float4*>(out)[i4] = make_float4(x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w);
 }
 
 // row -> state index of the 3P candidate rows of one step: [0,P) state-major
@@ -470,11 +472,48 @@ __global__ void compact_scatter_kernel(const float* __restrict__ q, const float*
   if (threadIdx.x == 0) blk_adv[blockIdx.x] = t;
 }
 
+// ---- fast path of the per-state reduction below for a SORTED row -> state map (the advantage filter emits rows in
+// ascending flat index, so sidx is non-decreasing): segment boundaries are found by comparing neighbours, and each
+// block then streams only its own rows.  info = [unsorted flag | start[NU] | end[NU]], zeroed before. ----
+__global__ void segment_ranges_kernel(const int* __restrict__ sidx, int seg, const int* dyn, int nstates, int* __restrict__ info) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nvalid = dyn ? min(*dyn, seg) : seg;
+  if (j >= nvalid) return;
+  const int b = sidx[j];
+  if (b < 0 || b >= nstates) { info[0] = 1; return; }
+  if (j == 0) info[1 + b] = 0;
+  else {
+    const int a = sidx[j - 1];
+    if (a > b) info[0] = 1;
+    else if (a < b) { info[1 + b] = j; if (a >= 0) info[1 + nstates + a] = j; }
+  }
+  if (j == nvalid - 1) info[1 + nstates + b] = nvalid;
+}
+__global__ void segment_sum_sorted_kernel(const float* __restrict__ dmx, int A, int seg, int nstates, const int* __restrict__ info,
+                                          int accumulate, float* __restrict__ dsx_u) {
+  if (info[0]) return;                              // unsorted: segment_sum_kernel does the work
+  const int b = blockIdx.x;
+  const int n = blockIdx.y * 256 + threadIdx.x;     // 256 threads, 5 slabs cover 1200 (tail masked)
+  if (n >= GAC_G) return;
+  const int j0 = info[1 + b], j1 = info[1 + nstates + b];
+  float s = accumulate ? dsx_u[(size_t)b * GAC_G + n] : 0.f;
+  for (int d = 0; d < A; ++d) {
+    const float* p = dmx + ((size_t)d * seg + j0) * GAC_G + n;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    int j = j0;
+    for (; j + 3 < j1; j += 4, p += 4 * GAC_G) { t0 += p[0]; t1 += p[GAC_G]; t2 += p[2 * GAC_G]; t3 += p[3 * GAC_G]; }
+    for (; j < j1; ++j, p += GAC_G) t0 += p[0];
+    s += (t0 + t1) + (t2 + t3);
+  }
+  dsx_u[(size_t)b * GAC_G + n] = s;
+}
+
 // ---- per-unique-state reduction of d(sx): dsx_u[b][n] (+)= sum over live rows j of this
 // chunk with sidx[j] == b of sum_d dmx[(d*seg + j)][n].  One block per (state, column slab);
 // the block scans the chunk's sidx in order, so the summation order is fixed. ----
 __global__ void segment_sum_kernel(const float* __restrict__ dmx, const int* __restrict__ sidx, int A, int seg,
-                                   const int* dyn, int accumulate, float* __restrict__ dsx_u) {
+                                   const int* dyn, int accumulate, float* __restrict__ dsx_u, const int* only_if) {
+  if (only_if && !*only_if) return;               // the sorted fast path took it
   __shared__ int list[256];
   __shared__ int wcnt[8];
   __shared__ int nlist;
