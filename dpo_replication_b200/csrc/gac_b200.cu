@@ -103,6 +103,7 @@ struct gac_ctx {
   int* it_live;   // [0] live rows of the chunk, [1] live rows * A
   unsigned char* pack[16]; size_t pack_bytes;   // pre-split / pre-swizzled weight tiles (tc::pack_b_kernel)
   int* seg_info;                                // [unsorted | start[NU] | end[NU]] of the per-state segments (aiqn_bwd)
+  unsigned char* gru_pack16[2]; tc::GruScales* gru_sc[2];   // 3xFP16 variant: tiles + power-of-two scales (device)
   unsigned char* gru_pack[2];                   // fused GRU-step weights (tc::gru_pack_kernel): target / online actor
   const unsigned char *gru_t, *gru_o;           // valid for the current call; nullptr = unfused path
 };
@@ -192,6 +193,8 @@ size_t partition(gac_ctx* c, void* ws) {
   c->pack_bytes = (c->pack_bytes + 1023) & ~(size_t)1023;
   for (int i = 0; i < 16; ++i) c->pack[i] = b.take<unsigned char>(c->pack_bytes);
   for (int i = 0; i < 2; ++i) c->gru_pack[i] = b.take<unsigned char>(tc::GRU_PACK_BYTES);
+  for (int i = 0; i < 2; ++i) c->gru_pack16[i] = b.take<unsigned char>(tc::GRU_PACK16_BYTES);
+  for (int i = 0; i < 2; ++i) c->gru_sc[i] = b.take<tc::GruScales>(1);
   return (b.off + 255) & ~(size_t)255;
 }
 
@@ -222,19 +225,24 @@ const unsigned char* pack_w(gac_ctx* c, int slot, const float* W, int ld, int K,
 // weights of the fused GRU step (gru_step_tc.cuh); nullptr = not applicable, use the GEMM + gates kernels
 const unsigned char* pack_gru(gac_ctx* c, int which, const float* actor, int rows) {
   static const bool off = getenv("GAC_NO_FUSED_GRU") != nullptr;
+  static const bool tf32_only = getenv("GAC_GRU_TF32") != nullptr;   // A/B switch: skip the 3xFP16 variant
   if (off || c->cfg.engine != 0 || rows < 64) return nullptr;
-  if (gru_pack(var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, var(c, actor, 0, GAC_A_U), c->gru_pack[which], c->stream) != cudaSuccess)
+  if (gru_pack(var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, var(c, actor, 0, GAC_A_U), var(c, actor, 0, GAC_A_WA), var(c, actor, 0, GAC_A_BA),
+               c->gru_pack[which], c->gru_pack16[which], tf32_only ? nullptr : c->gru_sc[which], c->stream) != cudaSuccess)
     return nullptr;
-  c->launches++;
+  c->launches += tf32_only ? 1 : 3;
   return c->gru_pack[which];
 }
-int run_gru_step(gac_ctx* c, const unsigned char* wpk, const float* actor, const float* sx, const int* sidx, const float* ae,
+int run_gru_step(gac_ctx* c, int which, const float* actor, const float* sx, const int* sidx, const float* ae,
                  const float* hprev, float* hout, int rows, const int* dyn, float* z, float* r, float* cc, float* mhh) {
-  tc::GruStepArgs a;
   static const bool timeline = getenv("GAC_GRU_TIMELINE") != nullptr;
+  static const bool tf32_only = getenv("GAC_GRU_TF32") != nullptr;
+  tc::GruStepArgs a;
   a.dbg = timeline ? reinterpret_cast<unsigned long long*>(c->spart) : nullptr;   // scratch: idle during the sampler
-  a.probe = 0; a.rows = rows; a.dyn_rows = dyn; a.ae = ae; a.hprev = hprev; a.wpk = wpk; a.sx = sx; a.sidx = sidx;
+  a.sc = tf32_only ? nullptr : c->gru_sc[which];
+  a.rows = rows; a.dyn_rows = dyn; a.ae = ae; a.hprev = hprev; a.wpk = c->gru_pack[which]; a.sx = sx; a.sidx = sidx;
   a.b1 = var(c, actor, 0, GAC_A_GB) + GAC_G; a.hout = hout; a.z = z; a.r = r; a.c = cc; a.mhh = mhh;
+  a.wpk16 = tf32_only ? nullptr : c->gru_pack16[which];
   GAC_CUDA(launch_gru_step(a, c->stream));
   c->launches++;
   return GAC_OK;
@@ -371,7 +379,7 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
     GAC_TRY(run_gemm(c, g));
     if (c->gru_t) {
       // both projections + gates in one kernel: mxa / mh never touch HBM
-      GAC_TRY(run_gru_step(c, c->gru_t, actor, c->sx_u, sidx, c->ae, d ? hprev : nullptr, hcur, rows, nullptr, nullptr, nullptr, nullptr, nullptr));
+      GAC_TRY(run_gru_step(c, 0, actor, c->sx_u, sidx, c->ae, d ? hprev : nullptr, hcur, rows, nullptr, nullptr, nullptr, nullptr, nullptr));
     } else {
       g = gemm_args(rows, GAC_G, GAC_E, c->ae, GAC_E, kxa, GAC_G, c->mxa, GAC_G);
       g.Bpacked = c->pk[PK_T_KXA]; g.Bpacked_bn = c->pk_bn[PK_T_KXA];
@@ -500,7 +508,7 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
   for (int d = 0; d < A; ++d) {
     const size_t o4 = (size_t)d * Mc * GAC_E, o12 = (size_t)d * Mc * GAC_G;
     if (c->gru_o) {
-      GAC_TRY(run_gru_step(c, c->gru_o, actor, c->a_sx_u, sidx, c->a_ae + o4, d ? c->hall + o4 : nullptr, c->hall + o4 + (size_t)Mc * GAC_E, Mc,
+      GAC_TRY(run_gru_step(c, 1, actor, c->a_sx_u, sidx, c->a_ae + o4, d ? c->hall + o4 : nullptr, c->hall + o4 + (size_t)Mc * GAC_E, Mc,
                            live, c->zs + o4, c->rs + o4, c->cs + o4, c->mhh + o4));
       continue;
     }
