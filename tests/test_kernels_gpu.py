@@ -134,6 +134,44 @@ def test_aiqn_sampler(gb, engine, S, A, rows, nstates):
     assert_close(sup, sup_ref, FWD_RTOL, "teacher-forced forward")
 
 
+# The fused GRU-step kernel runs 3xFP16 with power-of-two scales derived from the weights (gru_step_tc.cuh): the
+# result must not depend on the magnitudes of the four operands.  wa = ba = 0 gives a zero bound on the action
+# embedding => no valid scaling => the in-kernel 3xTF32 fallback is the one that runs.
+@pytest.mark.parametrize("s_kx,s_u,s_wa", [(1.0, 1.0, 1.0), (64.0, 1 / 64.0, 1.0), (1 / 256.0, 4.0, 8.0), (1.0, 1.0, 40.0),
+                                           (1e-3, 1e-3, 1e-2), (1.0, 1.0, 0.0)])
+def test_gru_step_operand_scales(gb, s_kx, s_u, s_wa):
+    S, A, rows, nstates = 17, 6, 300, 10
+    rng = np.random.default_rng(11)
+    p = O.init_actor(rng, S, A, bias_scale=0.05)
+    p = {k: np.array(v, copy=True) for k, v in p.items()}
+    p["kx"] *= np.float32(s_kx); p["u"] *= np.float32(s_u); p["wa"] *= np.float32(s_wa); p["ba"] *= np.float32(s_wa)
+    eng = make_engine(gb, S, A, 512, 1, 0)
+    ar = load_actor(gb, S, A, p)
+    su = rng.standard_normal((nstates, S)).astype(np.float32)
+    sidx = rng.integers(0, nstates, rows).astype(np.int32)
+    taus = rng.uniform(size=(rows, A)).astype(np.float32)
+    teacher = rng.uniform(-1, 1, size=(rows, A)).astype(np.float32)
+    sup = eng.aiqn_supervised_fwd(ar.net_slice(ar.online, "actor"), dev(su), dev(sidx, torch.int32), dev(taus), dev(teacher)).cpu().numpy()
+    sup_ref, _ = O.aiqn_supervised(p, su[sidx], taus, teacher, np.float64)
+    assert np.isfinite(sup).all()
+    assert_close(sup, sup_ref, FWD_RTOL, f"teacher-forced forward, scales {s_kx} {s_u} {s_wa}")
+
+
+# the arithmetic variant is chosen once per process from the environment: re-run the actor tests in a child process
+@pytest.mark.parametrize("env", ["GAC_GRU_TF32", "GAC_NO_FUSED_GRU"])
+def test_actor_paths_other_variants(env):
+    import os
+    import subprocess
+    import sys
+    e = dict(os.environ)
+    e[env] = "1"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(root, "tests", "test_kernels_gpu.py"), "-k",
+                        "aiqn_sampler or actor_loss_and_bptt or golden_stage or gru_step_operand"], env=e, cwd=root, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 def test_critic_and_value_eval(gb, engine):
     S, A, rows, nst = 17, 6, 777, 40
