@@ -102,6 +102,7 @@ struct gac_ctx {
   float *it_x, *it_se, *it_cos, *it_ne, *it_merge, *it_me, *it_dop, *it_dme, *it_dmerge, *it_dne, *it_dse;
   int* it_live;   // [0] live rows of the chunk, [1] live rows * A
   unsigned char* pack[16]; size_t pack_bytes;   // pre-split / pre-swizzled weight tiles (tc::pack_b_kernel)
+  int *seg_hist, *seg_perm;                     // per-block state histograms / rows grouped by state
   int* seg_info;                                // [unsorted | start[NU] | end[NU]] of the per-state segments (aiqn_bwd)
   unsigned char* gru_pack16[2]; tc::GruScales* gru_sc[2];   // 3xFP16 variant: tiles + power-of-two scales (device)
   unsigned char* gru_pack[2];                   // fused GRU-step weights (tc::gru_pack_kernel): target / online actor
@@ -166,6 +167,7 @@ size_t partition(gac_ctx* c, void* ws) {
   c->a_se_u = b.take<float>((size_t)c->NUa * GAC_E); c->a_sx_u = b.take<float>((size_t)c->NUa * GAC_G);
   c->a_dsx_u = b.take<float>((size_t)c->NUa * GAC_G); c->a_dse_u = b.take<float>((size_t)c->NUa * GAC_E);
   c->a_states = b.take<float>((size_t)c->NUa * S); c->a_sidx = b.take<int>(Mc); c->seg_info = b.take<int>(2 * (size_t)c->NUa + 2);
+  c->seg_hist = b.take<int>((size_t)((Mc + SEG_BLOCK - 1) / SEG_BLOCK) * c->NUa); c->seg_perm = b.take<int>(Mc);
   c->ca = b.take<float>(AM * GAC_NB); c->cn = b.take<float>(AM * GAC_NB);
   c->a_ae = b.take<float>(AM * GAC_E); c->mx = b.take<float>(AM * GAC_G); c->dmh = b.take<float>(AM * GAC_G);
   c->zs = b.take<float>(AM * GAC_E); c->rs = b.take<float>(AM * GAC_E); c->cs = b.take<float>(AM * GAC_E);
@@ -230,7 +232,7 @@ const unsigned char* pack_gru(gac_ctx* c, int which, const float* actor, int row
   if (gru_pack(var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, var(c, actor, 0, GAC_A_U), var(c, actor, 0, GAC_A_WA), var(c, actor, 0, GAC_A_BA),
                c->gru_pack[which], c->gru_pack16[which], tf32_only ? nullptr : c->gru_sc[which], c->stream) != cudaSuccess)
     return nullptr;
-  c->launches += tf32_only ? 1 : 3;
+  c->launches += tf32_only ? 1 : 4;
   return c->gru_pack[which];
 }
 int run_gru_step(gac_ctx* c, int which, const float* actor, const float* sx, const int* sidx, const float* ae,
@@ -607,12 +609,16 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   GAC_TRY(run_colsum(c, c->du, GAC_E, nullptr, GAC_E, AM, rv, G(GAC_A_BA), acc));
   // state half: reduce d(sx) per unique state, then B-row GEMMs
   const int NU = c->bwd_nstates;
-  GAC_CUDA(cudaMemsetAsync(c->seg_info, 0, (size_t)(2 * NU + 1) * sizeof(int), st));
-  segment_ranges_kernel<<<cdiv(Mc, 256), 256, 0, st>>>(c->bwd_sidx, Mc, live, NU, c->seg_info);
-  LAUNCHED(c, "segment_ranges");
-  segment_sum_sorted_kernel<<<dim3(NU, cdiv(GAC_G, 256)), 256, 0, st>>>(c->mx, A, Mc, NU, c->seg_info, 0, c->a_dsx_u);
-  LAUNCHED(c, "segment_sum_sorted");
-  segment_sum_kernel<<<dim3(NU, cdiv(GAC_G, 256)), 256, 0, st>>>(c->mx, c->bwd_sidx, A, Mc, live, 0, c->a_dsx_u, c->seg_info);
+  // rows grouped by state with a stable counting sort (block histograms -> scan -> ranked scatter), then one block
+  // per (state, column slab) streams exactly its rows in ascending row order: deterministic, no atomics on floats
+  const int nsb = cdiv(Mc, SEG_BLOCK);
+  seg_hist_kernel<<<nsb, SEG_BLOCK, NU * sizeof(int), st>>>(c->bwd_sidx, Mc, live, NU, c->seg_hist);
+  LAUNCHED(c, "seg_hist");
+  seg_scan_kernel<<<1, 1024, 0, st>>>(c->seg_hist, nsb, NU, c->seg_info);
+  LAUNCHED(c, "seg_scan");
+  seg_scatter_kernel<<<nsb, SEG_BLOCK, 0, st>>>(c->bwd_sidx, Mc, live, NU, c->seg_hist, c->seg_perm);
+  LAUNCHED(c, "seg_scatter");
+  segment_sum_kernel<<<dim3(NU, cdiv(GAC_G, 256)), 256, 0, st>>>(c->mx, c->seg_perm, c->seg_info, A, Mc, NU, 0, c->a_dsx_u);
   LAUNCHED(c, "segment_sum");
   GAC_TRY(wgrad(GAC_E, GAC_G, c->a_se_u, GAC_E, c->a_dsx_u, GAC_G, NU, G(GAC_A_KX), false));
   g = gemm_args(NU, GAC_E, GAC_G, c->a_dsx_u, GAC_G, var(c, actor, 0, GAC_A_KX), GAC_G, c->a_dse_u, GAC_E);

@@ -95,19 +95,23 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// Power-of-two scales of the 3xFP16 variant (one block).  Weight maxima -> [1, 2) after scaling.
-__global__ void gru_scales_kernel(const float* __restrict__ kxa, const float* __restrict__ U, const float* __restrict__ wa,
-                                  const float* __restrict__ ba, GruScales* __restrict__ out) {
-  __shared__ float red[3][32];
+// Power-of-two scales of the 3xFP16 variant.  Pass 1 (many blocks): maxima of |kx_a|, |U| and of the action-embedding
+// bound into three uint slots (non-negative floats order like their bit patterns; the slots are zeroed before);
+// any non-finite value poisons the bound with +inf.  Pass 2 (one thread): the scales.
+__global__ void gru_amax_kernel(const float* __restrict__ kxa, const float* __restrict__ U, const float* __restrict__ wa,
+                                const float* __restrict__ ba, unsigned int* __restrict__ slots) {
   float mk = 0.f, mu = 0.f, mb = 0.f;
   bool bad = false;
-  for (int i = threadIdx.x; i < GAC_E * GAC_G; i += blockDim.x) {
-    const float a = fabsf(kxa[i]), b = fabsf(U[i]);
-    bad |= !(a <= 3e38f) || !(b <= 3e38f);
-    mk = fmaxf(mk, a); mu = fmaxf(mu, b);
+  const int n4 = GAC_E * GAC_G / 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(kxa)[i], b = reinterpret_cast<const float4*>(U)[i];
+    const float ma = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
+    const float mbb = fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)));
+    bad |= !(fabsf(a.x) + fabsf(a.y) + fabsf(a.z) + fabsf(a.w) <= 3e38f) || !(fabsf(b.x) + fabsf(b.y) + fabsf(b.z) + fabsf(b.w) <= 3e38f);
+    mk = fmaxf(mk, ma); mu = fmaxf(mu, mbb);
   }
-  for (int j = threadIdx.x; j < GAC_E; j += blockDim.x) {      // |ae_j| <= sum_i |wa_ij| + |ba_j|  (|cos| <= 1, LeakyReLU is 1-Lipschitz)
-    float sacc = fabsf(ba[j]);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < GAC_E; j += gridDim.x * blockDim.x) {
+    float sacc = fabsf(ba[j]);                                  // |ae_j| <= sum_i |wa_ij| + |ba_j|  (|cos| <= 1, LeakyReLU is 1-Lipschitz)
     for (int i = 0; i < GAC_NB; ++i) sacc += fabsf(wa[(size_t)i * GAC_E + j]);
     bad |= !(sacc <= 3e38f);
     mb = fmaxf(mb, sacc);
@@ -118,30 +122,30 @@ __global__ void gru_scales_kernel(const float* __restrict__ kxa, const float* __
     mk = fmaxf(mk, __shfl_xor_sync(0xffffffffu, mk, o)); mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, o));
     mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
   }
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { red[0][w] = mk; red[1][w] = mu; red[2][w] = mb; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < (int)blockDim.x / 32; ++i) { mk = fmaxf(mk, red[0][i]); mu = fmaxf(mu, red[1][i]); mb = fmaxf(mb, red[2][i]); }
-    GruScales r;
-    r.ok = 0; r.s_ae = r.s_kx = r.s_u = r.inv_unit = 1.f; r.pad[0] = r.pad[1] = r.pad[2] = 0;
-    if (mk > 0.f && mu > 0.f && mb > 0.f && mk < 1e30f && mu < 1e30f && mb < 1e30f) {
-      int ek, eu, eb;
-      frexpf(mk, &ek); frexpf(mu, &eu); frexpf(mb, &eb);       // x = f * 2^e, f in [0.5, 1)
-      // U' = U * 2^(1-eu) in [1,2); unit = s_u.  kx' in [1,2) wants s_kx = 2^(1-ek), which fixes s_ae = 2^(ek-eu);
-      // bound the scaled ae by 2^14 (fp16 max is 2^16): shift the excess onto kx.
-      int ea = ek - eu;                                        // log2 s_ae
-      if (eb + ea > 14) ea = 14 - eb;
-      if (eb + ea < -8) ea = -8 - eb;
-      const int esk = (1 - eu) - ea;                           // log2 s_kx
-      const int kx_top = ek + esk;                             // scaled |kx| < 2^kx_top
-      if (kx_top <= 15 && kx_top >= -8 && abs(ea) < 100 && abs(esk) < 100 && abs(eu) < 100) {
-        r.s_ae = ldexpf(1.f, ea); r.s_kx = ldexpf(1.f, esk); r.s_u = ldexpf(1.f, 1 - eu); r.inv_unit = ldexpf(1.f, eu - 1);
-        r.ok = 1;
-      }
-    }
-    *out = r;
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(slots, __float_as_uint(mk)); atomicMax(slots + 1, __float_as_uint(mu)); atomicMax(slots + 2, __float_as_uint(mb));
   }
+}
+__global__ void gru_scales_kernel(const unsigned int* __restrict__ slots, GruScales* __restrict__ out) {
+  const float mk = __uint_as_float(slots[0]), mu = __uint_as_float(slots[1]), mb = __uint_as_float(slots[2]);
+  GruScales r;
+  r.ok = 0; r.s_ae = r.s_kx = r.s_u = r.inv_unit = 1.f; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+  if (mk > 0.f && mu > 0.f && mb > 0.f && mk < 1e30f && mu < 1e30f && mb < 1e30f) {
+    int ek, eu, eb;
+    frexpf(mk, &ek); frexpf(mu, &eu); frexpf(mb, &eb);         // x = f * 2^e, f in [0.5, 1)
+    // U' = U * 2^(1-eu) in [1,2); unit = s_u.  kx' in [1,2) wants s_kx = 2^(1-ek), which fixes s_ae = 2^(ek-eu);
+    // bound the scaled ae by 2^14 (fp16 max is 2^16): shift the excess onto kx.
+    int ea = ek - eu;                                          // log2 s_ae
+    if (eb + ea > 14) ea = 14 - eb;
+    if (eb + ea < -8) ea = -8 - eb;
+    const int esk = (1 - eu) - ea;                             // log2 s_kx
+    const int kx_top = ek + esk;                               // scaled |kx| < 2^kx_top
+    if (kx_top <= 15 && kx_top >= -8 && abs(ea) < 100 && abs(esk) < 100 && abs(eu) < 100) {
+      r.s_ae = ldexpf(1.f, ea); r.s_kx = ldexpf(1.f, esk); r.s_u = ldexpf(1.f, 1 - eu); r.inv_unit = ldexpf(1.f, eu - 1);
+      r.ok = 1;
+    }
+  }
+  *out = r;
 }
 
 // Pre-split, pre-swizzled weights.  Slot (tile j, block kb2): kb2 < KB -> rows k of kx_a, gate order [h z r];
@@ -465,7 +469,11 @@ __global__ void __launch_bounds__(THREADS, 1) gru_step_tc_kernel(const GruStepAr
 inline cudaError_t gru_pack(const float* kxa, const float* U, const float* wa, const float* ba, unsigned char* out32, unsigned char* out16,
                             tc::GruScales* sc, cudaStream_t st) {
   if (sc) {
-    tc::gru_scales_kernel<<<1, 1024, 0, st>>>(kxa, U, wa, ba, sc);
+    unsigned int* slots = reinterpret_cast<unsigned int*>(sc->pad);   // 3 scratch words inside the struct (rewritten by pass 2)
+    cudaError_t e = cudaMemsetAsync(slots, 0, 3 * sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+    tc::gru_amax_kernel<<<60, 256, 0, st>>>(kxa, U, wa, ba, slots);
+    tc::gru_scales_kernel<<<1, 1, 0, st>>>(slots, sc);
     const long long t16 = (long long)tc::GRU_NT * 2 * tc::GRU_KB16 * 3 * tc::GRU_NU * 8;
     tc::gru_pack_kernel<true><<<(unsigned)cdiv64(t16, 256), 256, 0, st>>>(kxa, U, out16, sc);
   }

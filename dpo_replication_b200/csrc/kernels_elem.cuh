@@ -472,80 +472,92 @@ __global__ void compact_scatter_kernel(const float* __restrict__ q, const float*
   if (threadIdx.x == 0) blk_adv[blockIdx.x] = t;
 }
 
-// ---- fast path of the per-state reduction below for a SORTED row -> state map (the advantage filter emits rows in
-// ascending flat index, so sidx is non-decreasing): segment boundaries are found by comparing neighbours, and each
-// block then streams only its own rows.  info = [unsorted flag | start[NU] | end[NU]], zeroed before. ----
-__global__ void segment_ranges_kernel(const int* __restrict__ sidx, int seg, const int* dyn, int nstates, int* __restrict__ info) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- per-unique-state reduction of d(sx): dsx_u[b][n] (+)= sum over live rows j of this chunk with sidx[j] == b of
+// sum_d dmx[(d*seg + j)][n].  The rows are first grouped by state with a STABLE counting sort (the live list mixes a
+// state-major and a sample-major tiling, so it is not sorted): per-block histograms, a scan over (state, block), and a
+// scatter where a row's slot is base[block][state] + its rank among the block's earlier rows of the same state.
+// Every state's rows end up in ascending row order, so the float summation order is fixed. ----
+constexpr int SEG_BLOCK = 256;
+__global__ void seg_hist_kernel(const int* __restrict__ sidx, int seg, const int* dyn, int nstates, int* __restrict__ hist) {
+  extern __shared__ int sh_hist[];
+  for (int i = threadIdx.x; i < nstates; i += blockDim.x) sh_hist[i] = 0;
+  __syncthreads();
+  const int j = blockIdx.x * SEG_BLOCK + threadIdx.x;
   const int nvalid = dyn ? min(*dyn, seg) : seg;
-  if (j >= nvalid) return;
-  const int b = sidx[j];
-  if (b < 0 || b >= nstates) { info[0] = 1; return; }
-  if (j == 0) info[1 + b] = 0;
-  else {
-    const int a = sidx[j - 1];
-    if (a > b) info[0] = 1;
-    else if (a < b) { info[1 + b] = j; if (a >= 0) info[1 + nstates + a] = j; }
+  if (j < nvalid) {
+    const int b = sidx[j];
+    if (b >= 0 && b < nstates) atomicAdd(&sh_hist[b], 1);       // integer: order-independent
   }
-  if (j == nvalid - 1) info[1 + nstates + b] = nvalid;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nstates; i += blockDim.x) hist[(size_t)blockIdx.x * nstates + i] = sh_hist[i];
 }
-__global__ void segment_sum_sorted_kernel(const float* __restrict__ dmx, int A, int seg, int nstates, const int* __restrict__ info,
-                                          int accumulate, float* __restrict__ dsx_u) {
-  if (info[0]) return;                              // unsorted: segment_sum_kernel does the work
+// hist[blk][b] -> exclusive base of (blk, b) in the grouped list; info = [start[nstates] | end[nstates]]
+__global__ void seg_scan_kernel(int* __restrict__ hist, int nblk, int nstates, int* __restrict__ info) {
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < nstates; b0 += blockDim.x) {
+    const int b = b0 + threadIdx.x;
+    int tot = 0;
+    if (b < nstates)
+      for (int k = 0; k < nblk; ++k) { const int v = hist[(size_t)k * nstates + b]; hist[(size_t)k * nstates + b] = tot; tot += v; }
+    // exclusive scan of tot over the states of this pass (blockDim.x <= 1024): warp scan + warp totals
+    __shared__ int wsum[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int k = 0; k < w; ++k) woff += wsum[k];
+    const int start = carry + woff + inc - tot;
+    if (b < nstates) {
+      info[b] = start; info[nstates + b] = start + tot;
+      for (int k = 0; k < nblk; ++k) hist[(size_t)k * nstates + b] += start;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = start + tot;
+    __syncthreads();
+  }
+}
+__global__ void seg_scatter_kernel(const int* __restrict__ sidx, int seg, const int* dyn, int nstates, const int* __restrict__ base,
+                                   int* __restrict__ perm) {
+  __shared__ int sb[SEG_BLOCK];
+  const int j = blockIdx.x * SEG_BLOCK + threadIdx.x;
+  const int nvalid = dyn ? min(*dyn, seg) : seg;
+  const int b = j < nvalid ? sidx[j] : -1;
+  sb[threadIdx.x] = b;
+  __syncthreads();
+  if (b < 0 || b >= nstates) return;
+  int rank = 0;
+  for (int t = 0; t < (int)threadIdx.x; ++t) rank += sb[t] == b;
+  perm[base[(size_t)blockIdx.x * nstates + b] + rank] = j;
+}
+__global__ void segment_sum_kernel(const float* __restrict__ dmx, const int* __restrict__ perm, const int* __restrict__ info, int A, int seg,
+                                   int nstates, int accumulate, float* __restrict__ dsx_u) {
   const int b = blockIdx.x;
   const int n = blockIdx.y * 256 + threadIdx.x;     // 256 threads, 5 slabs cover 1200 (tail masked)
-  if (n >= GAC_G) return;
-  const int j0 = info[1 + b], j1 = info[1 + nstates + b];
-  float s = accumulate ? dsx_u[(size_t)b * GAC_G + n] : 0.f;
-  for (int d = 0; d < A; ++d) {
-    const float* p = dmx + ((size_t)d * seg + j0) * GAC_G + n;
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-    int j = j0;
-    for (; j + 3 < j1; j += 4, p += 4 * GAC_G) { t0 += p[0]; t1 += p[GAC_G]; t2 += p[2 * GAC_G]; t3 += p[3 * GAC_G]; }
-    for (; j < j1; ++j, p += GAC_G) t0 += p[0];
-    s += (t0 + t1) + (t2 + t3);
-  }
-  dsx_u[(size_t)b * GAC_G + n] = s;
-}
-
-// ---- per-unique-state reduction of d(sx): dsx_u[b][n] (+)= sum over live rows j of this
-// chunk with sidx[j] == b of sum_d dmx[(d*seg + j)][n].  One block per (state, column slab);
-// the block scans the chunk's sidx in order, so the summation order is fixed. ----
-__global__ void segment_sum_kernel(const float* __restrict__ dmx, const int* __restrict__ sidx, int A, int seg,
-                                   const int* dyn, int accumulate, float* __restrict__ dsx_u, const int* only_if) {
-  if (only_if && !*only_if) return;               // the sorted fast path took it
-  __shared__ int list[256];
-  __shared__ int wcnt[8];
-  __shared__ int nlist;
-  const int b = blockIdx.x;
-  const int n = blockIdx.y * 256 + threadIdx.x;   // 256 threads, 5 slabs cover 1200 (tail masked)
-  const int nvalid = dyn ? min(*dyn, seg) : seg;
+  const int j0 = info[b], j1 = info[nstates + b];
+  __shared__ int rows[256];
   float s = (accumulate && n < GAC_G) ? dsx_u[(size_t)b * GAC_G + n] : 0.f;
-  for (int base = 0; base < nvalid; base += 256) {
-    const int j = base + threadIdx.x;
-    const bool hit = j < nvalid && sidx[j] == b;
-    const unsigned bal = __ballot_sync(0xffffffffu, hit);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) wcnt[w] = __popc(bal);
+  for (int base = j0; base < j1; base += 256) {
+    const int cnt = min(256, j1 - base);
     __syncthreads();
-    int off = 0;
-    for (int k = 0; k < w; ++k) off += wcnt[k];
-    if (hit) list[off + __popc(bal & ((1u << lane) - 1u))] = j;
-    if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < 8; ++k) t += wcnt[k]; nlist = t; }
+    if ((int)threadIdx.x < cnt) rows[threadIdx.x] = perm[base + threadIdx.x];
     __syncthreads();
     if (n < GAC_G)
-      for (int e = 0; e < nlist; ++e) {
-        const int jj = list[e];
-        float t0 = 0.f, t1 = 0.f;
-        int d = 0;
-        for (; d + 1 < A; d += 2) {
-          t0 += dmx[((size_t)d * seg + jj) * GAC_G + n];
-          t1 += dmx[((size_t)(d + 1) * seg + jj) * GAC_G + n];
+      for (int d = 0; d < A; ++d) {
+        const float* p = dmx + (size_t)d * seg * GAC_G + n;
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+        int e = 0;
+        for (; e + 3 < cnt; e += 4) {
+          t0 += p[(size_t)rows[e] * GAC_G]; t1 += p[(size_t)rows[e + 1] * GAC_G];
+          t2 += p[(size_t)rows[e + 2] * GAC_G]; t3 += p[(size_t)rows[e + 3] * GAC_G];
         }
-        if (d < A) t0 += dmx[((size_t)d * seg + jj) * GAC_G + n];
-        s += t0 + t1;
+        for (; e < cnt; ++e) t0 += p[(size_t)rows[e] * GAC_G];
+        s += (t0 + t1) + (t2 + t3);
       }
-    __syncthreads();
   }
   if (n < GAC_G) dsx_u[(size_t)b * GAC_G + n] = s;
 }
