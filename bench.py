@@ -51,6 +51,11 @@ def step_flops(S, A, B, K, M):
     return f_ref, f_min
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE gru_step_tc_kernel launch from the ncu --set full capture
+# (profiles/r1b_gru_step_full_raw.csv), keyed by rows
+GRU_TRAFFIC_BYTES = {}
+
+
 def peaks():
     """Measured roofline denominators (driver-written MEASURED_PEAKS.json) or the stated fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -252,34 +257,63 @@ def run_gpu(args):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms = float(ms2.item()) / args.steps
 
-    # ---- roofline of the dominant kernel: the tcgen05 3xTF32 GEMM at the step's dominant shape
-    # (rows x 400) * (400 x 1200) with rows = 2P, timed live with CUDA events on the same stream ----
+    # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream.
+    # AIQN actor on the tcgen05 engine: gru_step_tc_kernel (one GRU step of the sampler on its 2P candidate rows: both
+    # input projections + gates, 3xFP16 arithmetic; profiles/r1b_launches_summary.txt: the largest single kernel of
+    # the step).  Algorithmic flops per launch = 2 * rows * (400 + 400) * 1200 (the GRU's two
+    # projections).  Otherwise: the packed-weight GEMM (rows x 400) * (400 x 1200). ----
     roof = None
     if rank == 0:
         eng = agent.engine
         rows = 2 * P
-        a = torch.randn(rows, 400, device=dev)
-        w = torch.randn(400, 1200, device=dev)
         n_rep = 20
-        keng = 2 if args.engine == 0 else 1          # the step's forward GEMMs use the packed-weight path
-        for _ in range(3):
-            eng.gemm(a, w, engine=keng)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(n_rep):
-            eng.gemm(a, w, engine=keng)
-        e1.record()
-        torch.cuda.synchronize()
-        kms = e0.elapsed_time(e1) / n_rep
         pk = peaks()
-        tf32_peak = pk["bf16_burst"] / 2.0
-        peak = tf32_peak / 3.0 if args.engine == 0 else 74.0
-        ach = 2.0 * rows * 400 * 1200 / (kms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<3xTF32, packed weights> (incl. the 5 us weight pack)" if args.engine == 0 else "gemm_simt_kernel",
-                "shape": f"({rows}x400)*(400x1200)", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None, "ms_per_launch": kms,
-                "peak_source": (f"{pk['source']} bf16 burst {pk['bf16_burst']} TF/s / 2 (TF32) / 3 (3xTF32 passes)" if args.engine == 0
-                                else "fp32 SIMT: 148 SM x 128 FMA x 2 x 1.965 GHz")}
+        if args.actor == "AIQN" and args.engine == 0:
+            ar = agent.arena
+            actor = ar.net_slice(ar.target, "actor")
+            states = torch.randn(B, S, device=dev)
+            sidx = torch.arange(B, device=dev, dtype=torch.int32).repeat_interleave(2 * K)
+            wa, ba = ar.view(ar.target, "actor.wa"), ar.view(ar.target, "actor.ba")
+            ae = torch.nn.functional.leaky_relu(torch.cos(torch.rand(rows, 1, device=dev) * 2 - 1) @ wa[:1] + ba, 0.2)   # inside the actor's bound
+            h = torch.tanh(torch.randn(rows, 400, device=dev))
+            eng.gru_step(actor, states, sidx, ae, h, actor_inputs=True)
+            for _ in range(3):
+                eng.gru_step(actor, states, sidx, ae, h, reuse=True, actor_inputs=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n_rep):
+                eng.gru_step(actor, states, sidx, ae, h, reuse=True, actor_inputs=True)
+            e1.record()
+            torch.cuda.synchronize()
+            kms = e0.elapsed_time(e1) / n_rep
+            ach = 2.0 * rows * 800 * 1200 / (kms * 1e-3) / 1e12
+            peak = pk["bf16_burst"] / 3.0
+            roof = {"bound": "tensor", "kernel": "gru_step_tc_kernel (3xFP16: kind::f16 MMAs, 3 passes per product)",
+                    "shape": f"rows={rows}: [ae | h_prev] ({rows}x800) * [kx_a ; U] (800x1200) + gates", "achieved": ach, "peak": peak,
+                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": GRU_TRAFFIC_BYTES.get(rows), "ms_per_launch": kms,
+                    "algorithmic_bytes": rows * 400 * 4 * 3,
+                    "peak_source": f"{pk['source']} bf16 burst {pk['bf16_burst']} TF/s / 3 (three fp16 passes per fp32 product)"}
+        else:
+            a = torch.randn(rows, 400, device=dev)
+            w = torch.randn(400, 1200, device=dev)
+            keng = 2 if args.engine == 0 else 1          # the step's forward GEMMs use the packed-weight path
+            for _ in range(3):
+                eng.gemm(a, w, engine=keng)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n_rep):
+                eng.gemm(a, w, engine=keng)
+            e1.record()
+            torch.cuda.synchronize()
+            kms = e0.elapsed_time(e1) / n_rep
+            tf32_peak = pk["bf16_burst"] / 2.0
+            peak = tf32_peak / 3.0 if args.engine == 0 else 74.0
+            ach = 2.0 * rows * 400 * 1200 / (kms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<3xTF32, packed weights> (incl. the 5 us weight pack)" if args.engine == 0 else "gemm_simt_kernel",
+                    "shape": f"({rows}x400)*(400x1200)", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": None, "ms_per_launch": kms,
+                    "peak_source": (f"{pk['source']} bf16 burst {pk['bf16_burst']} TF/s / 2 (TF32) / 3 (3xTF32 passes)" if args.engine == 0
+                                    else "fp32 SIMT: 148 SM x 128 FMA x 2 x 1.965 GHz")}
 
     hbm = hbm_kernels(agent, dev) if (rank == 0 and world == 1) else None
     if world > 1:
@@ -302,7 +336,7 @@ def run_gpu(args):
                            "global_batch": B * world, "action_samples": K, "parallelism": f"dp{world}",
                            "selected_rows_mean": m_mean, "candidate_rows": 2 * P,
                            "l2": "per-step working set (activations saved for BPTT) is GBs >> 126 MB L2; no flush needed",
-                           "engine": "tcgen05 3xTF32" if args.engine == 0 else "SIMT fp32", "actor": args.actor},
+                           "engine": "tcgen05 3xTF32 GEMMs, 3xFP16 GRU step" if args.engine == 0 else "SIMT fp32", "actor": args.actor},
                 "steps_per_s": 1e3 / ms_per_step,
                 "step_flops": {"algorithmic_gflop_min": f_min / 1e9, "as_written_gflop": f_ref / 1e9,
                                "achieved_tflops_min": f_min * world / (ms_per_step * 1e-3) / 1e12,

@@ -61,6 +61,7 @@ _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
     "gac_layout": (C.c_int, [_I, _I, C.POINTER(Layout)]),
     "gac_layout_ex": (C.c_int, [_I, _I, _I, C.POINTER(Layout)]),
+    "gac_gru_step": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _I, _P, _I]),
     "gac_iqn_forward": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, _P]),
     "gac_iqn_train_fwd": (C.c_int, [_P, _P, _P, _I, _P, _P, _I, _P, _P]),
     "gac_iqn_bwd": (C.c_int, [_P, _P, _P, _P, _I]),

@@ -236,12 +236,12 @@ const unsigned char* pack_gru(gac_ctx* c, int which, const float* actor, int row
   return c->gru_pack[which];
 }
 int run_gru_step(gac_ctx* c, int which, const float* actor, const float* sx, const int* sidx, const float* ae,
-                 const float* hprev, float* hout, int rows, const int* dyn, float* z, float* r, float* cc, float* mhh) {
+                 const float* hprev, float* hout, int rows, const int* dyn, float* z, float* r, float* cc, float* mhh, bool bounded = true) {
   static const bool timeline = getenv("GAC_GRU_TIMELINE") != nullptr;
   static const bool tf32_only = getenv("GAC_GRU_TF32") != nullptr;
   tc::GruStepArgs a;
   a.dbg = timeline ? reinterpret_cast<unsigned long long*>(c->spart) : nullptr;   // scratch: idle during the sampler
-  a.sc = tf32_only ? nullptr : c->gru_sc[which];
+  a.sc = (tf32_only || !bounded) ? nullptr : c->gru_sc[which];   // 3xFP16 needs operands bounded by the weights
   a.rows = rows; a.dyn_rows = dyn; a.ae = ae; a.hprev = hprev; a.wpk = c->gru_pack[which]; a.sx = sx; a.sidx = sidx;
   a.b1 = var(c, actor, 0, GAC_A_GB) + GAC_G; a.hout = hout; a.z = z; a.r = r; a.c = cc; a.mhh = mhh;
   a.wpk16 = tf32_only ? nullptr : c->gru_pack16[which];
@@ -842,6 +842,42 @@ int gac_aiqn_sample(gac_ctx_t* c, const float* actor, const float* states_u, int
                     const float* taus, int32_t rows, float* actions) {
   if (!c || !actor || !states_u || !state_idx || !taus || !actions || rows < 0) return fail(GAC_ERR_INVALID, "gac_aiqn_sample: bad arguments");
   return aiqn_sample(c, actor, states_u, n_states, state_idx, taus, rows, actions);
+}
+
+int gac_gru_step(gac_ctx_t* c, const float* actor, const float* states_u, int32_t n_states, const int32_t* state_idx,
+                 const float* action_emb, const float* h_prev, int32_t rows, float* h_out, int32_t flags) {
+  const bool reuse = flags & GAC_GRU_REUSE;
+  if (!c || !actor || !states_u || !state_idx || !action_emb || !h_out || rows < 0) return fail(GAC_ERR_INVALID, "gac_gru_step: bad arguments");
+  if (c->cfg.actor_kind != GAC_ACTOR_AIQN) return fail(GAC_ERR_INVALID, "gac_gru_step: context was created for the IQN actor");
+  if (n_states > c->NUs) return fail(GAC_ERR_WORKSPACE, "gac_gru_step: n_states exceeds the workspace capacity");
+  if (rows > c->Rs) return fail(GAC_ERR_WORKSPACE, "gac_gru_step: rows exceeds the sampler chunk");
+  if (rows == 0) return GAC_OK;
+  cudaStream_t st = c->stream;
+  const float* kxa = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
+  if (!reuse) {
+    GAC_TRY(state_prep(c, actor, states_u, n_states, c->se_u, c->sx_u));
+    c->gru_t = pack_gru(c, 0, actor, rows);
+    if (!c->gru_t) {
+      c->pk[PK_T_KXA] = pack_w(c, PK_T_KXA, kxa, GAC_G, GAC_E, GAC_G, 0, rows);
+      c->pk[PK_T_U] = pack_w(c, PK_T_U, var(c, actor, 0, GAC_A_U), GAC_G, GAC_E, GAC_G, 0, rows);
+    }
+  }
+  if (c->gru_t)
+    return run_gru_step(c, 0, actor, c->sx_u, state_idx, action_emb, h_prev, h_out, rows, nullptr, nullptr, nullptr, nullptr, nullptr,
+                        (flags & GAC_GRU_ACTOR_INPUTS) != 0);
+  GemmArgs g = gemm_args(rows, GAC_G, GAC_E, action_emb, GAC_E, kxa, GAC_G, c->mxa, GAC_G);
+  g.Bpacked = c->pk[PK_T_KXA]; g.Bpacked_bn = c->pk_bn[PK_T_KXA];
+  GAC_TRY(run_gemm(c, g));
+  if (h_prev) {
+    g = gemm_args(rows, GAC_G, GAC_E, h_prev, GAC_E, var(c, actor, 0, GAC_A_U), GAC_G, c->mh, GAC_G);
+    g.Bpacked = c->pk[PK_T_U]; g.Bpacked_bn = c->pk_bn[PK_T_U];
+    GAC_TRY(run_gemm(c, g));
+  }
+  gru_gates_fwd_kernel<<<(unsigned)cdiv64((long long)rows * GAC_E, 256), 256, 0, st>>>(
+      c->sx_u, state_idx, c->mxa, h_prev ? c->mh : nullptr, var(c, actor, 0, GAC_A_GB) + GAC_G, h_prev, h_out, nullptr, nullptr, nullptr,
+      nullptr, rows, RowValid{nullptr, 1});
+  LAUNCHED(c, "gru_gates_fwd");
+  return GAC_OK;
 }
 
 int gac_iqn_forward(gac_ctx_t* c, const float* actor, const float* states_u, int32_t n_states, const int32_t* state_idx,

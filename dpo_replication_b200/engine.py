@@ -165,6 +165,15 @@ class Engine:
         check(lib.gac_aiqn_sample(self.h, ptr(actor), ptr(states_u), states_u.shape[0], ptr(state_idx), ptr(taus), rows, ptr(out)))
         return out
 
+    def gru_step(self, actor, states_u, state_idx, action_emb, h_prev=None, reuse=False, actor_inputs=False):
+        """One GRU(400) step of the AIQN actor (reference GAC/networks.py:166): h' = GRU([se[state_idx] | action_emb], h_prev).
+        actor_inputs: action_emb / h_prev come from the actor itself (bounded by its weights) -> 3xFP16 variant allowed."""
+        rows = action_emb.shape[0]
+        out = self._new(rows, 400)
+        check(lib.gac_gru_step(self.h, ptr(actor), ptr(states_u), states_u.shape[0], ptr(state_idx), ptr(action_emb), ptr(h_prev), rows,
+                               ptr(out), int(reuse) | (2 if actor_inputs else 0)))
+        return out
+
     def iqn_forward(self, actor, states_u, state_idx, taus):
         rows = taus.shape[0]
         out = self._new(rows, self.A)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GAC_B200_ABI_VERSION 2
+#define GAC_B200_ABI_VERSION 3
 
 enum gac_status {
   GAC_OK = 0,
@@ -117,6 +117,22 @@ int gac_adam_polyak(gac_ctx_t* ctx, float* online, float* target, float* adam_m,
  * taus: (rows, A); actions out: (rows, A).  actor: arena base of the actor variables. ---- */
 int gac_aiqn_sample(gac_ctx_t* ctx, const float* actor, const float* states_u, int32_t n_states,
                     const int32_t* state_idx, const float* taus, int32_t rows, float* actions);
+
+/* ---- one step of the actor's GRU (tf.keras.layers.GRU(400) cell, reset_after=True, gate order [z|r|h];
+ * networks.py:166 / the per-dimension loop 205-225 and 258-262):
+ *   h_out = GRU(x = [state_embedding(states_u)[state_idx] | action_emb], h_prev)
+ * action_emb, h_prev, h_out: (rows, 400); h_prev == NULL means h_prev = 0 (first action dimension).
+ * rows <= 2*B*K.  On the tcgen05 engine this is ONE kernel: both input projections, the gate math and the
+ * state update (csrc/gru_step_tc.cuh).  flags:
+ *   GAC_GRU_REUSE          states_u and the actor's weights are unchanged since the previous call on this context
+ *                          (skips the per-state projection and the weight packing);
+ *   GAC_GRU_ACTOR_INPUTS   action_emb is the actor's own embedding LeakyReLU(cos(.) wa + ba) and |h_prev| < 1, i.e.
+ *                          both are bounded by the weights: allows the 3xFP16 arithmetic variant (same accuracy,
+ *                          half the tensor-core instructions).  Without it the 3xTF32 variant runs, which has
+ *                          fp32's exponent range. ---- */
+enum { GAC_GRU_REUSE = 1, GAC_GRU_ACTOR_INPUTS = 2 };
+int gac_gru_step(gac_ctx_t* ctx, const float* actor, const float* states_u, int32_t n_states, const int32_t* state_idx,
+                 const float* action_emb, const float* h_prev, int32_t rows, float* h_out, int32_t flags);
 
 /* ---- StochasticActor.__call__ (IQN, networks.py:304-323); same argument meaning as gac_aiqn_sample.
  * Context must have been created with actor_kind = GAC_ACTOR_IQN. ---- */

@@ -134,6 +134,34 @@ def test_aiqn_sampler(gb, engine, S, A, rows, nstates):
     assert_close(sup, sup_ref, FWD_RTOL, "teacher-forced forward")
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("bounded", [False, True])
+@pytest.mark.parametrize("rows,nstates,first", [(300, 10, False), (300, 10, True), (1000, 7, False), (40, 40, False)])
+def test_gru_step_entry(gb, engine, rows, nstates, first, bounded):
+    """gac_gru_step against the oracle's Keras-GRU cell (reset_after, [z|r|h]) on identical inputs."""
+    S, A = 17, 6
+    rng = np.random.default_rng(5)
+    p = O.init_actor(rng, S, A, bias_scale=0.05)
+    eng = make_engine(gb, S, A, 1024, 1, engine)
+    ar = load_actor(gb, S, A, p)
+    su = rng.standard_normal((nstates, S)).astype(np.float32)
+    sidx = rng.integers(0, nstates, rows).astype(np.int32)
+    if bounded:    # the actor's own embedding (|ae| <= sum|wa| + |ba|): the 3xFP16 variant may run
+        ae = O.cosine_basis_linear(rng.uniform(-1, 1, (rows, 1)).astype(np.float32), p["wa"], p["ba"], np.float32, 0.2)[:, 0, :]
+    else:          # arbitrary caller data, far beyond that bound: 3xTF32 variant
+        ae = (5.0 * rng.standard_normal((rows, 400))).astype(np.float32)
+    h = np.tanh(rng.standard_normal((rows, 400))).astype(np.float32)
+    p64 = O.cast(p, np.float64)
+    se, _ = O.state_embed(p64, su.astype(np.float64))
+    x = np.concatenate([se[sidx], ae.astype(np.float64)], axis=1)
+    ref, _ = O.gru_step(p64, x, np.zeros((rows, 400)) if first else h.astype(np.float64))
+    actor = ar.net_slice(ar.online, "actor")
+    got = eng.gru_step(actor, dev(su), dev(sidx, torch.int32), dev(ae), None if first else dev(h), actor_inputs=bounded)
+    assert_close(got.cpu().numpy(), ref, FWD_RTOL, "gru step")
+    got2 = eng.gru_step(actor, dev(su), dev(sidx, torch.int32), dev(ae), None if first else dev(h), reuse=True, actor_inputs=bounded)
+    assert torch.equal(got, got2)
+
+
 # The fused GRU-step kernel runs 3xFP16 with power-of-two scales derived from the weights (gru_step_tc.cuh): the
 # result must not depend on the magnitudes of the four operands.  wa = ba = 0 gives a zero bound on the action
 # embedding => no valid scaling => the in-kernel 3xTF32 fallback is the one that runs.
