@@ -52,7 +52,7 @@ def main():
         rec = arr[hits[0] + 8: hits[0] + 8 + 8 * n].reshape(n, 8)      # stamps of the LAST launch (step d = A-1)
         t0 = rec[:, 0].min()
         names = ["setup", "loader loop", "wait accum", "phase1 (TMEM->smem)", "phase2 (gates+IO)"]
-        for label, sel in (("nu=64 tiles", np.arange(n) < n // 7 * 6), ("nu=16 tiles", np.arange(n) >= n // 7 * 6)):
+        for label, sel in (("nu=64 tiles", np.arange(n) % 7 != 6), ("nu=16 tiles", np.arange(n) % 7 == 6)):
             r = rec[sel]
             d = np.diff(r[:, 1:7], axis=1)
             print(f"{label}: n={r.shape[0]}  " + "  ".join(f"{nm} {d[:, i].mean():8.0f}" for i, nm in enumerate(names)) +
