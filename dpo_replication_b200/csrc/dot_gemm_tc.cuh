@@ -1,0 +1,326 @@
+// "Dense -> LeakyReLU -> Dense(1)" as ONE tcgen05 kernel (sm_100a): the hidden layer never reaches HBM.
+//
+//   part[row][tile] = sum_{n in tile} w2[n] * lrelu_alpha( (A * W)[row][n] + bias[n] )
+//
+// The reference ends every network with this pair: the actor head dense_layer_2(dense_layer_1(h * noise_embedding))
+// (networks.py:171-174, 221) and the 400 -> 300 -> 1 tail of every FNN (networks.py:345-358).  Unfused, the hidden
+// activations (rows x N fp32) are written by the GEMM epilogue -- at HBM write speed, overlapping no MMA work -- and read
+// back by a row-dot kernel.  Here a CTA owns 128 rows x bn <= 256 hidden columns; its epilogue reads the accumulators
+// lane-per-row straight from TMEM, applies bias + LeakyReLU, multiplies by the output weights and reduces along the row in
+// registers: 4 bytes per row and tile leave the SM.  The (at most two) tile partials are added by the consumer in a fixed
+// order (plus the output bias and the output nonlinearity).
+//
+// Same pipeline as gru_step_tc.cuh (two loader groups, packed weights by cp.async.bulk, dual TMEM accumulators) and the same
+// two arithmetic variants: 3xTF32, or 3xFP16 when the caller can bound the A operand (DotScales.ok, see gru_step_tc.cuh).
+#pragma once
+#include "gru_step_tc.cuh"
+
+namespace gac {
+namespace tc {
+
+struct DotScales {
+  float s_a, s_w, inv_unit;    // A' = A * s_a, W' = W * s_w, accumulators in units of s_a * s_w
+  int ok;
+  unsigned int slots[4];       // scratch of the two-pass maxima
+};
+
+struct DotGemmArgs {
+  int rows;                    // M
+  const int* dyn_rows;         // optional device row count
+  const float* A; int lda;     // (rows, K) row-major, 16-byte aligned rows
+  int K, N, bn, ntiles;        // K multiple of 16; N hidden columns in ntiles tiles of bn (multiple of 16, <= 256)
+  const unsigned char* wpk;    // dot_pack_kernel<false> tiles
+  const unsigned char* wpk16;  // dot_pack_kernel<true> tiles (used when sc->ok)
+  const DotScales* sc;         // nullptr: 3xTF32 only
+  const float* bias;           // (N)
+  const float* w2;             // (N) output weights
+  float alpha;                 // LeakyReLU slope
+  float* part;                 // (rows, ntiles)
+};
+
+constexpr int DOT_STAGES = 2;
+inline int dot_kblocks(int K, bool f16) { return f16 ? (K + BK16 - 1) / BK16 : (K + BK - 1) / BK; }
+inline size_t dot_pack_bytes(int K, int bn, int ntiles, bool f16) { return (size_t)ntiles * dot_kblocks(K, f16) * 2 * bn * 128; }
+inline int dot_smem_bytes(int bn) { return DOT_STAGES * (2 * (int)A_TILE_BYTES + 2 * bn * 128) + 1024 + 2 * bn * 4 + 256 * 4; }
+
+// W is (K, N) row-major.  Slot (tile j, block kb) = [hi | lo], bn rows (hidden columns) x 128 bytes, 128B-swizzled.
+template <bool F16>
+__global__ void dot_pack_kernel(const float* __restrict__ W, int K, int N, int bn, int ntiles, unsigned char* __restrict__ out,
+                                const DotScales* __restrict__ sc) {
+  constexpr int BKE = F16 ? BK16 : BK, CE = F16 ? 8 : 4;
+  const int KB = (K + BKE - 1) / BKE;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_slot = (long long)bn * 8;
+  if (idx >= (long long)ntiles * KB * per_slot) return;
+  if (F16 && !sc->ok) return;
+  const int c = idx % 8, r = (idx / 8) % bn;
+  const int slot = idx / per_slot, kb = slot % KB, j = slot / KB;
+  const int n = j * bn + r;
+  float x[CE];
+#pragma unroll
+  for (int e = 0; e < CE; ++e) {
+    const int k = kb * BKE + CE * c + e;
+    x[e] = (k < K && n < N) ? W[(size_t)k * N + n] : 0.f;
+  }
+  unsigned char* base = out + (size_t)slot * (2 * (size_t)bn * 128);
+  const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+  if constexpr (F16) {
+    const float sw = sc->s_w;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_f16x2(x[2 * e] * sw, x[2 * e + 1] * sw, h[e], l[e]);
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(base + (size_t)bn * 128 + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  } else {
+    float h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_tf32(x[e], h[e], l[e]);
+    *reinterpret_cast<float4*>(base + off) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(base + (size_t)bn * 128 + off) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// slots[0] = max |W| (n elements); slots[1] = max_j (sum_i |E_ij| + |e_j|): the bound of |cosine_embedding * E + e|
+// (and of its product with a GRU state, |h| < 1).  Non-finite values poison slot 1 with +inf.  Slots zeroed before.
+__global__ void dot_amax_kernel(const float* __restrict__ W, int n, const float* __restrict__ E, const float* __restrict__ e, int nb,
+                                int ne, unsigned int* __restrict__ slots) {
+  float mw = 0.f, mb = 0.f;
+  bool bad = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float a = fabsf(W[i]);
+    bad |= !(a <= 3e38f);
+    mw = fmaxf(mw, a);
+  }
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ne; j += gridDim.x * blockDim.x) {
+    float s = fabsf(e[j]);
+    for (int i = 0; i < nb; ++i) s += fabsf(E[(size_t)i * ne + j]);
+    bad |= !(s <= 3e38f);
+    mb = fmaxf(mb, s);
+  }
+  if (bad) mb = __int_as_float(0x7f800000);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o)); }
+  if ((threadIdx.x & 31) == 0) { atomicMax(slots, __float_as_uint(mw)); atomicMax(slots + 1, __float_as_uint(mb)); }
+}
+__global__ void dot_scales_kernel(DotScales* __restrict__ sc) {
+  const float mw = __uint_as_float(sc->slots[0]), mb = __uint_as_float(sc->slots[1]);
+  sc->ok = 0; sc->s_a = sc->s_w = sc->inv_unit = 1.f;
+  if (mw > 0.f && mb > 0.f && mw < 1e30f && mb < 1e30f) {
+    int ew, eb;
+    frexpf(mw, &ew); frexpf(mb, &eb);
+    if (abs(ew) < 100 && abs(eb) < 100) {
+      const int ea = 13 - eb, es = 1 - ew;                       // |A'| < 2^13, |W'| in [1, 2)
+      sc->s_a = ldexpf(1.f, ea); sc->s_w = ldexpf(1.f, es); sc->inv_unit = ldexpf(1.f, -(ea + es));
+      sc->ok = 1;
+    }
+  }
+}
+
+template <bool F16>
+__device__ __forceinline__ void dot_gemm_body(const DotGemmArgs& g) {
+  constexpr int BKE = F16 ? BK16 : BK;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[DOT_STAGES], bar_empty[DOT_STAGES], bar_accum;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bn = g.bn, jt = (int)blockIdx.x % g.ntiles, m0 = ((int)blockIdx.x / g.ntiles) * BM, n0 = jt * bn;
+  const int m_end = g.dyn_rows ? min(g.rows, *g.dyn_rows) : g.rows;
+  if (m0 >= m_end) return;
+  const int nkb = (g.K + BKE - 1) / BKE;
+  const uint32_t stage_bytes = 2 * A_TILE_BYTES + 2 * (uint32_t)bn * 128u;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)) + DOT_STAGES * stage_bytes);
+  float* w2_s = bias_s + bn;
+  float* part_s = w2_s + bn;                                     // [2][128]
+
+  if (tid == 0) {
+    for (int s = 0; s < DOT_STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), LOADER_WARPS / 2); mbar_init(smem_u32(&bar_empty[s]), 1); }
+    mbar_init(smem_u32(&bar_accum), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == LOADER_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < bn; i += THREADS) {
+    const int n = n0 + i;
+    bias_s[i] = n < g.N ? g.bias[n] : 0.f;
+    w2_s[i] = n < g.N ? g.w2[n] : 0.f;                           // padded columns contribute nothing
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  if (warp < LOADER_WARPS) {
+    // ------------------------------ loaders: two groups alternate K blocks ------------------------------
+    const int grp = warp >> 2, t = tid & (GROUP - 1);
+    const float s_a = F16 ? g.sc->s_a : 1.f;
+    float x16[16][4];
+    auto load16 = [&](int kb) {                                  // see gru_step_tc.cuh: sector-exact float4 mapping
+      const int k0 = kb * BKE, live = min(BKE, g.K - k0);
+      const int kq = t & 15;
+      const float* src = g.A + (size_t)(m0 + (t >> 4)) * g.lda + k0 + 4 * kq;
+      const bool klive = kb < nkb && 4 * kq < live;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (klive && m0 + (t >> 4) + 8 * i < m_end) {
+          const float4 v = *reinterpret_cast<const float4*>(src + (size_t)(8 * i) * g.lda);
+          x16[i][0] = v.x; x16[i][1] = v.y; x16[i][2] = v.z; x16[i][3] = v.w;
+        } else {
+          x16[i][0] = x16[i][1] = x16[i][2] = x16[i][3] = 0.f;
+        }
+      }
+    };
+    if constexpr (F16) load16(grp);
+    for (int kb = grp; kb < nkb; kb += 2) {
+      const int k0 = kb * BKE, live = min(BKE, g.K - k0);
+      float xa[8][4], la[8][4];
+      uint32_t h16[16][2], l16[16][2];
+      if constexpr (!F16) {
+        load_operand<false, true, 8>(xa, g.A, g.lda, m0, m_end, BM, k0, live, t);
+        split_operand<8>(xa, la);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          split_f16x2(x16[i][0] * s_a, x16[i][1] * s_a, h16[i][0], l16[i][0]);
+          split_f16x2(x16[i][2] * s_a, x16[i][3] * s_a, h16[i][1], l16[i][1]);
+        }
+        load16(kb + 2);
+      }
+      const int s = kb % DOT_STAGES;
+      const uint32_t ph = (uint32_t)(kb / DOT_STAGES) & 1u;
+      mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+      const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
+      if (t == 0) {
+        const uint32_t bytes = 2u * (uint32_t)bn * 128u;
+        const unsigned char* srcp = (F16 ? g.wpk16 : g.wpk) + ((size_t)jt * nkb + kb) * bytes;
+        const uint32_t bar = smem_u32(&bar_full[s]);
+        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa + 2 * A_TILE_BYTES),
+                     "l"(srcp), "r"(bytes), "r"(bar)
+                     : "memory");
+      }
+      if constexpr (!F16) {
+        store_split<false, 8>(xa, la, sa, sa + A_TILE_BYTES, BM, t);
+      } else {
+        const int kq = t & 15;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int r = (t >> 4) + 8 * i;
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)(((kq >> 1) ^ (r & 7)) << 4) + (uint32_t)(kq & 1) * 8u;
+          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sa + off), "r"(h16[i][0]), "r"(h16[i][1]));
+          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sa + A_TILE_BYTES + off), "r"(l16[i][0]), "r"(l16[i][1]));
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+    }
+    // ------------------------------ epilogue: bias, LeakyReLU, dot with w2 along the row, from TMEM ------------------------------
+    mbar_wait(smem_u32(&bar_accum), 0);
+    tc_fence_after();
+    const int quarter = warp & 3, hf = warp >> 2;
+    const int nch = bn / 16, c0 = hf ? (nch + 1) / 2 : 0, c1 = hf ? nch : (nch + 1) / 2;
+    const float inv_unit = F16 ? g.sc->inv_unit : 1.f, alpha = g.alpha;
+    float acc = 0.f;
+    for (int ci = c0; ci < c1; ++ci) {
+      float v[16], w[16];
+      const uint32_t ta = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ci * 16);
+      tmem_ld16(ta, v);
+      tmem_ld16(ta + 256u, w);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        float y = F16 ? (v[q] + w[q] * (1.f / 2048.f)) * inv_unit : v[q] + w[q];
+        y += bias_s[ci * 16 + q];
+        y = y > 0.f ? y : alpha * y;
+        acc = fmaf(y, w2_s[ci * 16 + q], acc);
+      }
+    }
+    part_s[hf * BM + quarter * 32 + lane] = acc;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (hf == 0) {
+      const int row = quarter * 32 + lane;
+      if (m0 + row < m_end) g.part[(size_t)(m0 + row) * g.ntiles + jt] = part_s[row] + part_s[BM + row];
+    }
+  } else {
+    // ------------------------------ MMA issuer (one lane) ------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = F16 ? make_idesc_f16(bn) : make_idesc(bn);
+      const uint32_t corr = tmem_d + 256u;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int k0 = kb * BKE, live = min(BKE, g.K - k0);
+        const int s = kb % DOT_STAGES;
+        const uint32_t ph = (uint32_t)(kb / DOT_STAGES) & 1u;
+        mbar_wait(smem_u32(&bar_full[s]), ph);
+        tc_fence_after();
+        const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
+        const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
+        const uint64_t b_hi = make_desc(sa + 2 * A_TILE_BYTES), b_lo = make_desc(sa + 2 * A_TILE_BYTES + (uint32_t)bn * 128u);
+        const int ksteps = F16 ? (live + 15) / 16 : (live + 7) / 8;
+        for (int j = 0; j < ksteps; ++j) {
+          const uint64_t adv = (uint64_t)(j * 2);
+          const uint32_t acc = (kb | j) ? 1u : 0u;
+          if constexpr (F16) {
+            mma_f16(corr, a_lo + adv, b_hi + adv, idesc, acc);
+            mma_f16(corr, a_hi + adv, b_lo + adv, idesc, 1u);
+            mma_f16(tmem_d, a_hi + adv, b_hi + adv, idesc, acc);
+          } else {
+            mma_tf32(corr, a_lo + adv, b_hi + adv, idesc, acc);
+            mma_tf32(corr, a_hi + adv, b_lo + adv, idesc, 1u);
+            mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, acc);
+          }
+        }
+        mma_commit(smem_u32(&bar_empty[s]));
+      }
+      mma_commit(smem_u32(&bar_accum));
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == LOADER_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) dot_gemm_tc_kernel(const DotGemmArgs g) {
+  if (g.sc && g.sc->ok) dot_gemm_body<true>(g);
+  else dot_gemm_body<false>(g);
+}
+
+}  // namespace tc
+
+// weights -> packed tiles of both variants; bound_E / bound_e (nb x ne, ne): the embedding that bounds the A operand, or
+// nullptr when no bound is known (3xTF32 only)
+inline cudaError_t dot_pack(const float* W, int K, int N, int bn, int ntiles, const float* bound_E, const float* bound_e, int nb, int ne,
+                            unsigned char* out32, unsigned char* out16, tc::DotScales* sc, cudaStream_t st) {
+  if (sc && bound_E) {
+    cudaError_t e = cudaMemsetAsync(sc, 0, sizeof(tc::DotScales), st);
+    if (e != cudaSuccess) return e;
+    tc::dot_amax_kernel<<<40, 256, 0, st>>>(W, K * N, bound_E, bound_e, nb, ne, reinterpret_cast<unsigned int*>(sc) + 4);
+    tc::dot_scales_kernel<<<1, 1, 0, st>>>(sc);
+    const long long t16 = (long long)ntiles * tc::dot_kblocks(K, true) * bn * 8;
+    tc::dot_pack_kernel<true><<<(unsigned)cdiv64(t16, 256), 256, 0, st>>>(W, K, N, bn, ntiles, out16, sc);
+  }
+  const long long t32 = (long long)ntiles * tc::dot_kblocks(K, false) * bn * 8;
+  tc::dot_pack_kernel<false><<<(unsigned)cdiv64(t32, 256), 256, 0, st>>>(W, K, N, bn, ntiles, out32, nullptr);
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch_dot_gemm(const tc::DotGemmArgs& g, cudaStream_t st) {
+  static int attr_bytes = 0;
+  const int smem = tc::dot_smem_bytes(g.bn);
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(tc::dot_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_bytes = smem;
+  }
+  dim3 grid(g.ntiles * cdiv(g.rows, tc::BM));
+  tc::dot_gemm_tc_kernel<<<grid, tc::THREADS, smem, st>>>(g);
+  return cudaGetLastError();
+}
+
+}  // namespace gac

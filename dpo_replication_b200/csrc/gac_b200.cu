@@ -8,6 +8,9 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "gru_step_tc.cuh"
+#include "dot_gemm_tc.cuh"
+
+constexpr int HEAD_BN = 208, HEAD_NT = 2;   // actor head: 400 hidden columns in two 208-wide tiles (dual accumulators fit TMEM)
 #include "kernels_elem.cuh"
 
 namespace gac {
@@ -104,6 +107,8 @@ struct gac_ctx {
   unsigned char* pack[16]; size_t pack_bytes;   // pre-split / pre-swizzled weight tiles (tc::pack_b_kernel)
   int *seg_hist, *seg_perm;                     // per-block state histograms / rows grouped by state
   int* seg_info;                                // [unsorted | start[NU] | end[NU]] of the per-state segments (aiqn_bwd)
+  // fused actor head of the sampler (dot_gemm_tc.cuh): w1 tiles of both variants, scales, per-row tile partials
+  unsigned char *head_pack32, *head_pack16; tc::DotScales* head_sc; float* head_part; bool head_fused;
   unsigned char* gru_pack16[2]; tc::GruScales* gru_sc[2];   // 3xFP16 variant: tiles + power-of-two scales (device)
   unsigned char* gru_pack[2];                   // fused GRU-step weights (tc::gru_pack_kernel): target / online actor
   const unsigned char *gru_t, *gru_o;           // valid for the current call; nullptr = unfused path
@@ -197,6 +202,9 @@ size_t partition(gac_ctx* c, void* ws) {
   for (int i = 0; i < 2; ++i) c->gru_pack[i] = b.take<unsigned char>(tc::GRU_PACK_BYTES);
   for (int i = 0; i < 2; ++i) c->gru_pack16[i] = b.take<unsigned char>(tc::GRU_PACK16_BYTES);
   for (int i = 0; i < 2; ++i) c->gru_sc[i] = b.take<tc::GruScales>(1);
+  c->head_pack32 = b.take<unsigned char>(tc::dot_pack_bytes(GAC_E, HEAD_BN, HEAD_NT, false));
+  c->head_pack16 = b.take<unsigned char>(tc::dot_pack_bytes(GAC_E, HEAD_BN, HEAD_NT, true));
+  c->head_sc = b.take<tc::DotScales>(1); c->head_part = b.take<float>((size_t)Rs * HEAD_NT);
   return (b.off + 255) & ~(size_t)255;
 }
 
@@ -374,8 +382,10 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
   float* hprev = c->hA; float* hcur = c->hB;
   const float* kxa = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
   for (int d = 0; d < A; ++d) {
-    cos_basis_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(d ? actions + d - 1 : nullptr, A, c->cosb, rows, all);
-    LAUNCHED(c, "cos_basis");
+    if (!(d && c->head_fused)) {   // the fused head's finish kernel already wrote cos(a_{d-1})
+      cos_basis_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(d ? actions + d - 1 : nullptr, A, c->cosb, rows, all);
+      LAUNCHED(c, "cos_basis");
+    }
     GemmArgs g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->ae, GAC_E);
     g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.Bpacked = c->pk[PK_T_WA]; g.Bpacked_bn = c->pk_bn[PK_T_WA];
     GAC_TRY(run_gemm(c, g));
@@ -401,12 +411,25 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
     g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->u, GAC_E);
     g.bias = var(c, actor, 0, GAC_A_BN); g.mul = hcur; g.ldmul = GAC_E; g.Bpacked = c->pk[PK_T_WN]; g.Bpacked_bn = c->pk_bn[PK_T_WN];
     GAC_TRY(run_gemm(c, g));
-    g = gemm_args(rows, GAC_E, GAC_E, c->u, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->y1, GAC_E);
-    g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f; g.Bpacked = c->pk[PK_T_W1]; g.Bpacked_bn = c->pk_bn[PK_T_W1];
-    GAC_TRY(run_gemm(c, g));
-    rowdot_kernel<<<cdiv(rows * 32, 256), 256, 0, st>>>(c->y1, GAC_E, var(c, actor, 0, GAC_A_W2), var(c, actor, 0, GAC_A_B2),
-                                                       nullptr, nullptr, nullptr, GAC_E, rows, 1, actions + d, A, nullptr, 0, all);
-    LAUNCHED(c, "rowdot_tanh");
+    if (c->head_fused) {
+      static const bool tf32_only = getenv("GAC_HEAD_TF32") != nullptr;
+      tc::DotGemmArgs q;
+      q.rows = rows; q.dyn_rows = nullptr; q.A = c->u; q.lda = GAC_E; q.K = GAC_E; q.N = GAC_E; q.bn = HEAD_BN; q.ntiles = HEAD_NT;
+      q.wpk = c->head_pack32; q.wpk16 = c->head_pack16; q.sc = tf32_only ? nullptr : c->head_sc;
+      q.bias = var(c, actor, 0, GAC_A_B1); q.w2 = var(c, actor, 0, GAC_A_W2); q.alpha = 0.01f; q.part = c->head_part;
+      GAC_CUDA(launch_dot_gemm(q, st));
+      c->launches++;
+      head_finish_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(c->head_part, HEAD_NT, var(c, actor, 0, GAC_A_B2), actions + d, A,
+                                                                   d + 1 < A ? c->cosb : nullptr, rows);
+      LAUNCHED(c, "head_finish");
+    } else {
+      g = gemm_args(rows, GAC_E, GAC_E, c->u, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->y1, GAC_E);
+      g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f; g.Bpacked = c->pk[PK_T_W1]; g.Bpacked_bn = c->pk_bn[PK_T_W1];
+      GAC_TRY(run_gemm(c, g));
+      rowdot_kernel<<<cdiv(rows * 32, 256), 256, 0, st>>>(c->y1, GAC_E, var(c, actor, 0, GAC_A_W2), var(c, actor, 0, GAC_A_B2),
+                                                         nullptr, nullptr, nullptr, GAC_E, rows, 1, actions + d, A, nullptr, 0, all);
+      LAUNCHED(c, "rowdot_tanh");
+    }
     float* t = hprev; hprev = hcur; hcur = t;
   }
   return GAC_OK;
@@ -425,7 +448,20 @@ int aiqn_sample(gac_ctx* c, const float* actor, const float* states_u, int n_sta
     c->pk[PK_T_U] = pack_w(c, PK_T_U, var(c, actor, 0, GAC_A_U), GAC_G, GAC_E, GAC_G, 0, rows);
   }
   c->pk[PK_T_WN] = pack_w(c, PK_T_WN, var(c, actor, 0, GAC_A_WN), GAC_E, GAC_NB, GAC_E, 0, rows);
-  c->pk[PK_T_W1] = pack_w(c, PK_T_W1, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 0, rows);
+  {
+    // fused head (w1 GEMM + LeakyReLU + w2 row dot in one kernel); |h * noise_embedding| is bounded by the noise embedding's weights
+    static const bool off = getenv("GAC_NO_FUSED_HEAD") != nullptr;
+    static const bool tf32_only = getenv("GAC_HEAD_TF32") != nullptr;
+    c->head_fused = !off && c->cfg.engine == 0 && rows >= 64;
+    if (c->head_fused) {
+      GAC_CUDA(dot_pack(var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, HEAD_BN, HEAD_NT, tf32_only ? nullptr : var(c, actor, 0, GAC_A_WN),
+                        var(c, actor, 0, GAC_A_BN), GAC_NB, GAC_E, c->head_pack32, c->head_pack16, c->head_sc, c->stream));
+      c->launches += tf32_only ? 1 : 4;
+      c->pk[PK_T_W1] = nullptr;
+    } else {
+      c->pk[PK_T_W1] = pack_w(c, PK_T_W1, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 0, rows);
+    }
+  }
   for (int r0 = 0; r0 < rows; r0 += c->Rs) {
     const int n = rows - r0 < c->Rs ? rows - r0 : c->Rs;
     GAC_TRY(aiqn_sample_rows(c, actor, sidx + r0, taus + (size_t)r0 * A, n, actions + (size_t)r0 * A));

@@ -246,6 +246,21 @@ __global__ void rowdot_kernel(const float* __restrict__ x, int ldx, const float*
   }
 }
 
+// ---- consumer of dot_gemm_tc_kernel's tile partials for the actor head (networks.py:221): a = tanh(sum_t part[r][t] + b2),
+// written to actions[r*inc_out]; when cosb != nullptr also the cosine basis of a (the next dimension's action
+// embedding input, networks.py:44-47 / 208-210), 64 threads per row. ----
+__global__ void head_finish_kernel(const float* __restrict__ part, int ntiles, const float* __restrict__ b2, float* __restrict__ out,
+                                   int inc_out, float* __restrict__ cosb, int rows) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = idx >> 6, i = idx & 63;
+  if (r >= rows) return;
+  float s = part[(size_t)r * ntiles];
+  for (int t = 1; t < ntiles; ++t) s += part[(size_t)r * ntiles + t];
+  const float a = tanhf(s + b2[0]);
+  if (i == 0) out[(size_t)r * inc_out] = a;
+  if (cosb) cosb[idx] = cosf(__fmul_rn(a, c_ipi[i]));
+}
+
 // ---- agent.py:189-190: a = clip(a + 0.01*n, -1, 1) ----
 __global__ void noise_clip_kernel(const float* __restrict__ a, const float* __restrict__ nrm, float scale, long long n,
                                   float* __restrict__ out) {
