@@ -10,6 +10,10 @@
 // registers: 4 bytes per row and tile leave the SM.  The (at most two) tile partials are added by the consumer in a fixed
 // order (plus the output bias and the output nonlinearity).
 //
+// Mode 1 (store) turns the same pipeline into a plain GEMM C = A * W (+ LeakyReLU' gate, + accumulate) for the actor's
+// input-gradient (dgrad) contractions; its A operand is a gradient tensor whose magnitude is tracked by the kernels that
+// produce it (an atomicMax of |x| per block, order-independent), so the 3xFP16 variant applies there too.
+//
 // Same pipeline as gru_step_tc.cuh (two loader groups, packed weights by cp.async.bulk, dual TMEM accumulators) and the same
 // two arithmetic variants: 3xTF32, or 3xFP16 when the caller can bound the A operand (DotScales.ok, see gru_step_tc.cuh).
 #pragma once
@@ -21,7 +25,7 @@ namespace tc {
 struct DotScales {
   float s_a, s_w, inv_unit;    // A' = A * s_a, W' = W * s_w, accumulators in units of s_a * s_w
   int ok;
-  unsigned int slots[4];       // scratch of the two-pass maxima
+  unsigned int slots[4];       // [0] max |W|, [1] bound / max of |A| (float bit patterns), [2] log2 s_w, [3] weights usable
 };
 
 struct DotGemmArgs {
@@ -36,6 +40,11 @@ struct DotGemmArgs {
   const float* w2;             // (N) output weights
   float alpha;                 // LeakyReLU slope
   float* part;                 // (rows, ntiles)
+  // mode 1: C (rows, N) = A * W, optionally times (gate > 0 ? 1 : gate_alpha), optionally added to C
+  int mode, seg_rows;          // seg_rows > 0: rows come in segments of seg_rows of which the first *dyn_rows are live
+  float* C; int ldc;
+  const float* gate; int ldgate; float gate_alpha;
+  int accumulate;
 };
 
 constexpr int DOT_STAGES = 2;
@@ -44,15 +53,16 @@ inline size_t dot_pack_bytes(int K, int bn, int ntiles, bool f16) { return (size
 inline int dot_smem_bytes(int bn) { return DOT_STAGES * (2 * (int)A_TILE_BYTES + 2 * bn * 128) + 1024 + 2 * bn * 4 + 256 * 4; }
 
 // W is (K, N) row-major.  Slot (tile j, block kb) = [hi | lo], bn rows (hidden columns) x 128 bytes, 128B-swizzled.
+// transW: the operand is W^T, i.e. element (k, n) = W[n * ldw + k] (dgrad against a Keras (in, out) kernel).
 template <bool F16>
-__global__ void dot_pack_kernel(const float* __restrict__ W, int K, int N, int bn, int ntiles, unsigned char* __restrict__ out,
-                                const DotScales* __restrict__ sc) {
+__global__ void dot_pack_kernel(const float* __restrict__ W, int ldw, int transW, int K, int N, int bn, int ntiles,
+                                unsigned char* __restrict__ out, const DotScales* __restrict__ sc) {
   constexpr int BKE = F16 ? BK16 : BK, CE = F16 ? 8 : 4;
   const int KB = (K + BKE - 1) / BKE;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long per_slot = (long long)bn * 8;
   if (idx >= (long long)ntiles * KB * per_slot) return;
-  if (F16 && !sc->ok) return;
+  if (F16 && !sc->slots[3]) return;
   const int c = idx % 8, r = (idx / 8) % bn;
   const int slot = idx / per_slot, kb = slot % KB, j = slot / KB;
   const int n = j * bn + r;
@@ -60,12 +70,12 @@ __global__ void dot_pack_kernel(const float* __restrict__ W, int K, int N, int b
 #pragma unroll
   for (int e = 0; e < CE; ++e) {
     const int k = kb * BKE + CE * c + e;
-    x[e] = (k < K && n < N) ? W[(size_t)k * N + n] : 0.f;
+    x[e] = (k < K && n < N) ? (transW ? W[(size_t)n * ldw + k] : W[(size_t)k * ldw + n]) : 0.f;
   }
   unsigned char* base = out + (size_t)slot * (2 * (size_t)bn * 128);
   const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
   if constexpr (F16) {
-    const float sw = sc->s_w;
+    const float sw = ldexpf(1.f, (int)sc->slots[2]);
     uint32_t h[4], l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) split_f16x2(x[2 * e] * sw, x[2 * e + 1] * sw, h[e], l[e]);
@@ -82,12 +92,12 @@ __global__ void dot_pack_kernel(const float* __restrict__ W, int K, int N, int b
 
 // slots[0] = max |W| (n elements); slots[1] = max_j (sum_i |E_ij| + |e_j|): the bound of |cosine_embedding * E + e|
 // (and of its product with a GRU state, |h| < 1).  Non-finite values poison slot 1 with +inf.  Slots zeroed before.
-__global__ void dot_amax_kernel(const float* __restrict__ W, int n, const float* __restrict__ E, const float* __restrict__ e, int nb,
-                                int ne, unsigned int* __restrict__ slots) {
+__global__ void dot_amax_kernel(const float* __restrict__ W, int ldw, int wr, int wc, const float* __restrict__ E,
+                                const float* __restrict__ e, int nb, int ne, unsigned int* __restrict__ slots) {
   float mw = 0.f, mb = 0.f;
   bool bad = false;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float a = fabsf(W[i]);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wr * wc; i += gridDim.x * blockDim.x) {
+    const float a = fabsf(W[(size_t)(i / wc) * ldw + i % wc]);
     bad |= !(a <= 3e38f);
     mw = fmaxf(mw, a);
   }
@@ -97,20 +107,31 @@ __global__ void dot_amax_kernel(const float* __restrict__ W, int n, const float*
     bad |= !(s <= 3e38f);
     mb = fmaxf(mb, s);
   }
-  if (bad) mb = __int_as_float(0x7f800000);
+  if (bad) mw = mb = __int_as_float(0x7f800000);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o)); }
   if ((threadIdx.x & 31) == 0) { atomicMax(slots, __float_as_uint(mw)); atomicMax(slots + 1, __float_as_uint(mb)); }
 }
-__global__ void dot_scales_kernel(DotScales* __restrict__ sc) {
-  const float mw = __uint_as_float(sc->slots[0]), mb = __uint_as_float(sc->slots[1]);
-  sc->ok = 0; sc->s_a = sc->s_w = sc->inv_unit = 1.f;
-  if (mw > 0.f && mb > 0.f && mw < 1e30f && mb < 1e30f) {
-    int ew, eb;
-    frexpf(mw, &ew); frexpf(mb, &eb);
-    if (abs(ew) < 100 && abs(eb) < 100) {
-      const int ea = 13 - eb, es = 1 - ew;                       // |A'| < 2^13, |W'| in [1, 2)
-      sc->s_a = ldexpf(1.f, ea); sc->s_w = ldexpf(1.f, es); sc->inv_unit = ldexpf(1.f, -(ea + es));
+// weight half of the scales (at pack time): slots[2] = log2 s_w with |W * s_w| in [1, 2), slots[3] = usable
+__global__ void dot_wscale_kernel(DotScales* __restrict__ sc) {
+  const float mw = __uint_as_float(sc->slots[0]);
+  int ew = 0, okw = 0;
+  if (mw > 0.f && mw < 1e30f) { frexpf(mw, &ew); okw = abs(ew) < 100; }
+  sc->slots[2] = (unsigned int)(1 - ew); sc->slots[3] = (unsigned int)okw;
+  sc->s_w = ldexpf(1.f, 1 - ew);
+  sc->ok = 0; sc->s_a = 1.f; sc->inv_unit = 1.f;
+}
+// operand half (just before the GEMM): the bound of |A| comes from slots[1] (weights-derived) or from a producer's
+// running maximum (a_amax): |A * s_a| < 2^13
+__global__ void dot_ascale_kernel(DotScales* __restrict__ sc, const unsigned int* __restrict__ a_amax) {
+  const float mb = __uint_as_float(a_amax ? *a_amax : sc->slots[1]);
+  sc->ok = 0; sc->s_a = 1.f; sc->inv_unit = 1.f;
+  if (sc->slots[3] && mb > 0.f && mb < 1e30f) {
+    int eb;
+    frexpf(mb, &eb);
+    if (abs(eb) < 100) {
+      const int ea = 13 - eb, es = (int)sc->slots[2];
+      sc->s_a = ldexpf(1.f, ea); sc->inv_unit = ldexpf(1.f, -(ea + es));
       sc->ok = 1;
     }
   }
@@ -125,7 +146,17 @@ __device__ __forceinline__ void dot_gemm_body(const DotGemmArgs& g) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bn = g.bn, jt = (int)blockIdx.x % g.ntiles, m0 = ((int)blockIdx.x / g.ntiles) * BM, n0 = jt * bn;
-  const int m_end = g.dyn_rows ? min(g.rows, *g.dyn_rows) : g.rows;
+  int m_end = g.rows;
+  if (g.dyn_rows) {
+    const int nvalid = *g.dyn_rows;
+    if (g.seg_rows > 0) {                                       // segments of seg_rows (a multiple of 128) rows, the first nvalid live
+      const int in_seg = m0 % g.seg_rows;
+      if (in_seg >= nvalid) return;
+      m_end = min(g.rows, m0 - in_seg + nvalid);
+    } else {
+      m_end = min(g.rows, nvalid);
+    }
+  }
   if (m0 >= m_end) return;
   const int nkb = (g.K + BKE - 1) / BKE;
   const uint32_t stage_bytes = 2 * A_TILE_BYTES + 2 * (uint32_t)bn * 128u;
@@ -143,11 +174,12 @@ __device__ __forceinline__ void dot_gemm_body(const DotGemmArgs& g) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < bn; i += THREADS) {
-    const int n = n0 + i;
-    bias_s[i] = n < g.N ? g.bias[n] : 0.f;
-    w2_s[i] = n < g.N ? g.w2[n] : 0.f;                           // padded columns contribute nothing
-  }
+  if (g.mode == 0)
+    for (int i = tid; i < bn; i += THREADS) {
+      const int n = n0 + i;
+      bias_s[i] = n < g.N ? g.bias[n] : 0.f;
+      w2_s[i] = n < g.N ? g.w2[n] : 0.f;                         // padded columns contribute nothing
+    }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -224,6 +256,37 @@ __device__ __forceinline__ void dot_gemm_body(const DotGemmArgs& g) {
     const int quarter = warp & 3, hf = warp >> 2;
     const int nch = bn / 16, c0 = hf ? (nch + 1) / 2 : 0, c1 = hf ? nch : (nch + 1) / 2;
     const float inv_unit = F16 ? g.sc->inv_unit : 1.f, alpha = g.alpha;
+    if (g.mode == 1) {
+      // store epilogue: lane = row; 16-column chunks, 128-bit accesses (N, ldc, ldgate multiples of 4, aligned bases)
+      const int m = m0 + quarter * 32 + lane;
+      const bool m_ok = m < m_end;
+      for (int ci = c0; ci < c1; ++ci) {
+        float v[16], w[16];
+        const uint32_t ta = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ci * 16);
+        tmem_ld16(ta, v);
+        tmem_ld16(ta + 256u, w);
+        const int nb = n0 + ci * 16;
+        if (!m_ok || nb >= g.N) continue;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = F16 ? (v[q] + w[q] * (1.f / 2048.f)) * inv_unit : v[q] + w[q];
+        float* crow = g.C + (size_t)m * g.ldc + nb;
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+          if (nb + q >= g.N) break;
+          float4 x = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+          if (g.gate) {
+            const float4 b = *reinterpret_cast<const float4*>(g.gate + (size_t)m * g.ldgate + nb + q);
+            const float ga = g.gate_alpha;
+            x.x *= b.x > 0.f ? 1.f : ga; x.y *= b.y > 0.f ? 1.f : ga; x.z *= b.z > 0.f ? 1.f : ga; x.w *= b.w > 0.f ? 1.f : ga;
+          }
+          if (g.accumulate) {
+            const float4 b = *reinterpret_cast<const float4*>(crow + q);
+            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+          }
+          *reinterpret_cast<float4*>(crow + q) = x;
+        }
+      }
+    } else {
     float acc = 0.f;
     for (int ci = c0; ci < c1; ++ci) {
       float v[16], w[16];
@@ -243,6 +306,7 @@ __device__ __forceinline__ void dot_gemm_body(const DotGemmArgs& g) {
     if (hf == 0) {
       const int row = quarter * 32 + lane;
       if (m0 + row < m_end) g.part[(size_t)(m0 + row) * g.ntiles + jt] = part_s[row] + part_s[BM + row];
+    }
     }
   } else {
     // ------------------------------ MMA issuer (one lane) ------------------------------
@@ -293,20 +357,27 @@ __global__ void __launch_bounds__(THREADS, 1) dot_gemm_tc_kernel(const DotGemmAr
 
 }  // namespace tc
 
-// weights -> packed tiles of both variants; bound_E / bound_e (nb x ne, ne): the embedding that bounds the A operand, or
-// nullptr when no bound is known (3xTF32 only)
-inline cudaError_t dot_pack(const float* W, int K, int N, int bn, int ntiles, const float* bound_E, const float* bound_e, int nb, int ne,
-                            unsigned char* out32, unsigned char* out16, tc::DotScales* sc, cudaStream_t st) {
-  if (sc && bound_E) {
+// weights -> packed tiles of both variants.  bound_E / bound_e (nb x ne, ne): the embedding whose weights bound the A operand
+// (slots[1]); nullptr when the bound comes from a producer's running maximum at launch time.  sc == nullptr: 3xTF32 only.
+inline cudaError_t dot_pack(const float* W, int ldw, int transW, int K, int N, int bn, int ntiles, const float* bound_E, const float* bound_e,
+                            int nb, int ne, unsigned char* out32, unsigned char* out16, tc::DotScales* sc, cudaStream_t st) {
+  if (sc) {
     cudaError_t e = cudaMemsetAsync(sc, 0, sizeof(tc::DotScales), st);
     if (e != cudaSuccess) return e;
-    tc::dot_amax_kernel<<<40, 256, 0, st>>>(W, K * N, bound_E, bound_e, nb, ne, reinterpret_cast<unsigned int*>(sc) + 4);
-    tc::dot_scales_kernel<<<1, 1, 0, st>>>(sc);
+    // |W| over the (K x N) or (N x K) matrix: rows of ldw floats, `cols` used
+    const int wr = transW ? N : K, wc = transW ? K : N;
+    tc::dot_amax_kernel<<<40, 256, 0, st>>>(W, ldw, wr, wc, bound_E, bound_e, nb, bound_E ? ne : 0, reinterpret_cast<unsigned int*>(sc) + 4);
+    tc::dot_wscale_kernel<<<1, 1, 0, st>>>(sc);
     const long long t16 = (long long)ntiles * tc::dot_kblocks(K, true) * bn * 8;
-    tc::dot_pack_kernel<true><<<(unsigned)cdiv64(t16, 256), 256, 0, st>>>(W, K, N, bn, ntiles, out16, sc);
+    tc::dot_pack_kernel<true><<<(unsigned)cdiv64(t16, 256), 256, 0, st>>>(W, ldw, transW, K, N, bn, ntiles, out16, sc);
   }
   const long long t32 = (long long)ntiles * tc::dot_kblocks(K, false) * bn * 8;
-  tc::dot_pack_kernel<false><<<(unsigned)cdiv64(t32, 256), 256, 0, st>>>(W, K, N, bn, ntiles, out32, nullptr);
+  tc::dot_pack_kernel<false><<<(unsigned)cdiv64(t32, 256), 256, 0, st>>>(W, ldw, transW, K, N, bn, ntiles, out32, nullptr);
+  return cudaGetLastError();
+}
+// operand half of the scales, right before the launch (a_amax == nullptr: the weights-derived bound in the struct)
+inline cudaError_t dot_ascale(tc::DotScales* sc, const unsigned int* a_amax, cudaStream_t st) {
+  tc::dot_ascale_kernel<<<1, 1, 0, st>>>(sc, a_amax);
   return cudaGetLastError();
 }
 

@@ -107,6 +107,9 @@ struct gac_ctx {
   unsigned char* pack[16]; size_t pack_bytes;   // pre-split / pre-swizzled weight tiles (tc::pack_b_kernel)
   int *seg_hist, *seg_perm;                     // per-block state histograms / rows grouped by state
   int* seg_info;                                // [unsorted | start[NU] | end[NU]] of the per-state segments (aiqn_bwd)
+  // input-gradient GEMMs of the actor's backward on dot_gemm_tc.cuh (store mode): W1^T, U^T, kx_a^T tiles of both variants,
+  // scales, and the running |x| maxima written by the kernels that produce their A operands ([0] dmx/dmh, [2] dy1p)
+  unsigned char *dg_pack32[3], *dg_pack16[3]; tc::DotScales* dg_sc[3]; unsigned int* dg_amax; bool dg_fused;
   // fused actor head of the sampler (dot_gemm_tc.cuh): w1 tiles of both variants, scales, per-row tile partials
   unsigned char *head_pack32, *head_pack16; tc::DotScales* head_sc; float* head_part; bool head_fused;
   unsigned char* gru_pack16[2]; tc::GruScales* gru_sc[2];   // 3xFP16 variant: tiles + power-of-two scales (device)
@@ -205,6 +208,13 @@ size_t partition(gac_ctx* c, void* ws) {
   c->head_pack32 = b.take<unsigned char>(tc::dot_pack_bytes(GAC_E, HEAD_BN, HEAD_NT, false));
   c->head_pack16 = b.take<unsigned char>(tc::dot_pack_bytes(GAC_E, HEAD_BN, HEAD_NT, true));
   c->head_sc = b.take<tc::DotScales>(1); c->head_part = b.take<float>((size_t)Rs * HEAD_NT);
+  for (int i = 0; i < 3; ++i) {
+    const int Kd = i == 0 ? GAC_E : GAC_G;
+    c->dg_pack32[i] = b.take<unsigned char>(tc::dot_pack_bytes(Kd, HEAD_BN, HEAD_NT, false));
+    c->dg_pack16[i] = b.take<unsigned char>(tc::dot_pack_bytes(Kd, HEAD_BN, HEAD_NT, true));
+    c->dg_sc[i] = b.take<tc::DotScales>(1);
+  }
+  c->dg_amax = b.take<unsigned int>(4);
   return (b.off + 255) & ~(size_t)255;
 }
 
@@ -417,6 +427,7 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
       q.rows = rows; q.dyn_rows = nullptr; q.A = c->u; q.lda = GAC_E; q.K = GAC_E; q.N = GAC_E; q.bn = HEAD_BN; q.ntiles = HEAD_NT;
       q.wpk = c->head_pack32; q.wpk16 = c->head_pack16; q.sc = tf32_only ? nullptr : c->head_sc;
       q.bias = var(c, actor, 0, GAC_A_B1); q.w2 = var(c, actor, 0, GAC_A_W2); q.alpha = 0.01f; q.part = c->head_part;
+      q.mode = 0; q.seg_rows = 0; q.C = nullptr; q.ldc = 0; q.gate = nullptr; q.ldgate = 0; q.gate_alpha = 0.f; q.accumulate = 0;
       GAC_CUDA(launch_dot_gemm(q, st));
       c->launches++;
       head_finish_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(c->head_part, HEAD_NT, var(c, actor, 0, GAC_A_B2), actions + d, A,
@@ -454,9 +465,10 @@ int aiqn_sample(gac_ctx* c, const float* actor, const float* states_u, int n_sta
     static const bool tf32_only = getenv("GAC_HEAD_TF32") != nullptr;
     c->head_fused = !off && c->cfg.engine == 0 && rows >= 64;
     if (c->head_fused) {
-      GAC_CUDA(dot_pack(var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, HEAD_BN, HEAD_NT, tf32_only ? nullptr : var(c, actor, 0, GAC_A_WN),
-                        var(c, actor, 0, GAC_A_BN), GAC_NB, GAC_E, c->head_pack32, c->head_pack16, c->head_sc, c->stream));
-      c->launches += tf32_only ? 1 : 4;
+      GAC_CUDA(dot_pack(var(c, actor, 0, GAC_A_W1), GAC_E, 0, GAC_E, GAC_E, HEAD_BN, HEAD_NT, var(c, actor, 0, GAC_A_WN),
+                        var(c, actor, 0, GAC_A_BN), GAC_NB, GAC_E, c->head_pack32, c->head_pack16, tf32_only ? nullptr : c->head_sc, c->stream));
+      if (!tf32_only) GAC_CUDA(dot_ascale(c->head_sc, nullptr, c->stream));
+      c->launches += tf32_only ? 1 : 5;
       c->pk[PK_T_W1] = nullptr;
     } else {
       c->pk[PK_T_W1] = pack_w(c, PK_T_W1, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 0, rows);
@@ -530,9 +542,23 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
   }
   c->pk[PK_O_WN] = pack_w(c, PK_O_WN, var(c, actor, 0, GAC_A_WN), GAC_E, GAC_NB, GAC_E, 0, c->Mc);
   c->pk[PK_O_W1] = pack_w(c, PK_O_W1, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 0, c->Mc);
-  c->pk[PK_O_W1T] = pack_w(c, PK_O_W1T, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 1, c->Mc);
-  c->pk[PK_O_UT] = pack_w(c, PK_O_UT, var(c, actor, 0, GAC_A_U), GAC_G, GAC_G, GAC_E, 1, c->Mc);
-  c->pk[PK_O_KXAT] = pack_w(c, PK_O_KXAT, kxa_w, GAC_G, GAC_G, GAC_E, 1, c->Mc);
+  {
+    // the three input-gradient contractions of the backward (x W^T): 3xFP16 with the A bound tracked by the producers
+    static const bool off = getenv("GAC_NO_F16_DGRAD") != nullptr;
+    c->dg_fused = !off && c->cfg.engine == 0 && c->Mc >= 128 && c->Mc % 128 == 0;
+    if (c->dg_fused) {
+      const float* W[3] = {var(c, actor, 0, GAC_A_W1), var(c, actor, 0, GAC_A_U), kxa_w};
+      for (int i = 0; i < 3; ++i)
+        GAC_CUDA(dot_pack(W[i], i == 0 ? GAC_E : GAC_G, 1, i == 0 ? GAC_E : GAC_G, GAC_E, HEAD_BN, HEAD_NT, nullptr, nullptr, 0, 0,
+                          c->dg_pack32[i], c->dg_pack16[i], c->dg_sc[i], st));
+      c->launches += 12;
+      c->pk[PK_O_W1T] = c->pk[PK_O_UT] = c->pk[PK_O_KXAT] = nullptr;
+    } else {
+      c->pk[PK_O_W1T] = pack_w(c, PK_O_W1T, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 1, c->Mc);
+      c->pk[PK_O_UT] = pack_w(c, PK_O_UT, var(c, actor, 0, GAC_A_U), GAC_G, GAC_G, GAC_E, 1, c->Mc);
+      c->pk[PK_O_KXAT] = pack_w(c, PK_O_KXAT, kxa_w, GAC_G, GAC_G, GAC_E, 1, c->Mc);
+    }
+  }
   cos_basis_seq_kernel<<<(unsigned)cdiv64(AM * GAC_NB, 256), 256, 0, st>>>(teacher, taus, A, Mc, c->ca, c->cn, live);
   LAUNCHED(c, "cos_basis_seq");
   GemmArgs g = gemm_args((int)AM, GAC_E, GAC_NB, c->ca, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->a_ae, GAC_E);
@@ -592,13 +618,28 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
     if (dyn) { g.dyn_rows = live; g.seg_rows = Mc; g.valid_on_k = 1; }
     return run_gemm(c, g);
   };
+  // C (rows, 400) = X (rows, K) * W^T through dot_gemm_tc.cuh (store mode); which: 0 = W1, 1 = U, 2 = kx_a
+  auto dgrad = [&](int which, const float* X, int ldx, int K, long long rows, float* Cdst, const float* gate, float gate_alpha, int accumulate,
+                   const unsigned int* amax) -> int {
+    GAC_CUDA(dot_ascale(c->dg_sc[which], amax, st));
+    tc::DotGemmArgs q;
+    q.rows = (int)rows; q.dyn_rows = live; q.seg_rows = Mc; q.A = X; q.lda = ldx; q.K = K; q.N = GAC_E; q.bn = HEAD_BN; q.ntiles = HEAD_NT;
+    q.wpk = c->dg_pack32[which]; q.wpk16 = c->dg_pack16[which]; q.sc = c->dg_sc[which];
+    q.bias = nullptr; q.w2 = nullptr; q.alpha = 0.f; q.part = nullptr;
+    q.mode = 1; q.C = Cdst; q.ldc = GAC_E; q.gate = gate; q.ldgate = GAC_E; q.gate_alpha = gate_alpha; q.accumulate = accumulate;
+    GAC_CUDA(launch_dot_gemm(q, st));
+    c->launches += 2;
+    return GAC_OK;
+  };
+  if (c->dg_fused) GAC_CUDA(cudaMemsetAsync(c->dg_amax, 0, 4 * sizeof(unsigned int), st));
+  unsigned int* amax_g = c->dg_fused ? c->dg_amax : nullptr;
   // head
   head_dop_kernel<<<(unsigned)cdiv64(AM, 256), 256, 0, st>>>(dpred, c->pred_c, A, Mc, live, c->dop);
   LAUNCHED(c, "head_dop");
   GAC_TRY(run_colsum(c, c->dop, 1, nullptr, 1, AM, rv, G(GAC_A_B2), acc));
   const int nrb_all = (int)cdiv64(AM, FB_ROWS);
   head_bwd_kernel<<<dim3(GAC_E / FB_COLS, nrb_all), FB_COLS, 0, st>>>(c->dop, var(c, actor, 0, GAC_A_W2), c->ay1, AM, rv, c->dy1p,
-                                                                      c->fpart0, c->fpart1);
+                                                                      c->fpart0, c->fpart1, amax_g ? amax_g + 2 : nullptr);
   LAUNCHED(c, "head_bwd");
   reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart0, nrb_all, GAC_E, G(GAC_A_B1), acc);
   LAUNCHED(c, "reduce_cols");
@@ -606,8 +647,12 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   LAUNCHED(c, "reduce_cols");
   GAC_TRY(wgrad(GAC_E, GAC_E, c->au, GAC_E, c->dy1p, GAC_E, AM, G(GAC_A_W1), true));
   GemmArgs g = gemm_args((int)AM, GAC_E, GAC_E, c->dy1p, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->du, GAC_E);
-  g.transB = 1; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_W1T]; g.Bpacked_bn = c->pk_bn[PK_O_W1T];
-  GAC_TRY(run_gemm(c, g));
+  if (c->dg_fused) {
+    GAC_TRY(dgrad(0, c->dy1p, GAC_E, GAC_E, AM, c->du, nullptr, 0.f, 0, amax_g + 2));
+  } else {
+    g.transB = 1; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_W1T]; g.Bpacked_bn = c->pk_bn[PK_O_W1T];
+    GAC_TRY(run_gemm(c, g));
+  }
   hadamard_bwd_kernel<<<dim3(GAC_E / FB_COLS, nrb_all), FB_COLS, 0, st>>>(c->du, c->hall + (size_t)Mc * GAC_E, c->ne, AM, rv, c->dne,
                                                                           c->dhu, c->fpart0);
   LAUNCHED(c, "hadamard_bwd");
@@ -621,9 +666,12 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
     const size_t o4 = (size_t)d * Mc * GAC_E, o12 = (size_t)d * Mc * GAC_G;
     gru_gates_bwd_kernel<<<dim3(GAC_E / FB_COLS, nrb_step), FB_COLS, 0, st>>>(
         dh_next, c->dhu + o4, c->zs + o4, c->rs + o4, c->cs + o4, c->mhh + o4, d ? c->hall + o4 : nullptr, c->mx + o12, c->dmh + o12,
-        carry, Mc, rv, c->fpart0 + (size_t)d * nrb_step * GAC_G, c->fpart1 + (size_t)d * nrb_step * GAC_G);
+        carry, Mc, rv, c->fpart0 + (size_t)d * nrb_step * GAC_G, c->fpart1 + (size_t)d * nrb_step * GAC_G, amax_g);
     LAUNCHED(c, "gru_gates_bwd");
-    if (d) {
+    if (d && c->dg_fused) {
+      // running maximum over the steps done so far: an upper bound of this step's |dmh|
+      GAC_TRY(dgrad(1, c->dmh + o12, GAC_G, GAC_G, Mc, carry, nullptr, 0.f, 1, amax_g));
+    } else if (d) {
       g = gemm_args(Mc, GAC_E, GAC_G, c->dmh + o12, GAC_G, var(c, actor, 0, GAC_A_U), GAC_G, carry, GAC_E);
       g.transB = 1; g.accumulate = 1; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_UT]; g.Bpacked_bn = c->pk_bn[PK_O_UT];
       GAC_TRY(run_gemm(c, g));
@@ -638,9 +686,13 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   reduce_cols_kernel<<<cdiv(GAC_G, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart0, A * nrb_step, GAC_G, G(GAC_A_GB), acc);
   LAUNCHED(c, "reduce_cols");
   GAC_TRY(wgrad(GAC_E, GAC_G, c->a_ae, GAC_E, c->mx, GAC_G, AM, G(GAC_A_KX) + (size_t)GAC_E * GAC_G, true));
-  g = gemm_args((int)AM, GAC_E, GAC_G, c->mx, GAC_G, kxa, GAC_G, c->du, GAC_E);
-  g.transB = 1; g.gate = c->a_ae; g.ldgate = GAC_E; g.gate_alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_KXAT]; g.Bpacked_bn = c->pk_bn[PK_O_KXAT];
-  GAC_TRY(run_gemm(c, g));
+  if (c->dg_fused) {
+    GAC_TRY(dgrad(2, c->mx, GAC_G, GAC_G, AM, c->du, c->a_ae, 0.2f, 0, amax_g));
+  } else {
+    g = gemm_args((int)AM, GAC_E, GAC_G, c->mx, GAC_G, kxa, GAC_G, c->du, GAC_E);
+    g.transB = 1; g.gate = c->a_ae; g.ldgate = GAC_E; g.gate_alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_KXAT]; g.Bpacked_bn = c->pk_bn[PK_O_KXAT];
+    GAC_TRY(run_gemm(c, g));
+  }
   GAC_TRY(wgrad(GAC_NB, GAC_E, c->ca, GAC_NB, c->du, GAC_E, AM, G(GAC_A_WA), true));
   GAC_TRY(run_colsum(c, c->du, GAC_E, nullptr, GAC_E, AM, rv, G(GAC_A_BA), acc));
   // state half: reduce d(sx) per unique state, then B-row GEMMs

@@ -108,6 +108,18 @@ __global__ void gru_gates_fwd_kernel(const float* __restrict__ sx_u, const int* 
   if (zs) { zs[idx] = z; rs_[idx] = r; cs[idx] = c; mhhs[idx] = hh; }
 }
 
+// Running maximum of |x| of a tensor a kernel writes (the bound the 3xFP16 GEMMs scale their A operand with): one
+// shared-memory atomicMax per thread, one global atomicMax per block; maxima are order-independent, so this is
+// deterministic.  Non-negative floats order like their bit patterns; NaN / inf come out >= 0x7f800000 and disable FP16.
+__device__ __forceinline__ void block_amax(float m, unsigned int* __restrict__ slot) {
+  __shared__ unsigned int sh_amax;
+  if (threadIdx.x == 0) sh_amax = 0u;
+  __syncthreads();
+  atomicMax(&sh_amax, __float_as_uint(fabsf(m)) & 0x7fffffffu);
+  __syncthreads();
+  if (threadIdx.x == 0 && sh_amax) atomicMax(slot, sh_amax);
+}
+
 // Producer kernels below also emit per-row-block column sums (bias gradients) so that no second
 // pass over the activations is needed.  Layout: block = FB_COLS threads (one column each) x
 // FB_ROWS rows; thread loops over the rows with 4-way ILP; partial sums go to
@@ -123,12 +135,12 @@ __global__ void __launch_bounds__(FB_COLS) gru_gates_bwd_kernel(const float* __r
                                      const float* __restrict__ cs, const float* __restrict__ mhhs,
                                      const float* __restrict__ hprev, float* __restrict__ dmx, float* __restrict__ dmh,
                                      float* __restrict__ dh_carry, int rows, RowValid rv, float* __restrict__ part_mx,
-                                     float* __restrict__ part_mh) {
+                                     float* __restrict__ part_mh, unsigned int* __restrict__ amax /* [0] |dmx|, [1] |dmh| or null */) {
   const int j = blockIdx.x * FB_COLS + threadIdx.x;
   const int r0 = blockIdx.y * FB_ROWS;
   const int nvalid = rv.dyn ? min(*rv.dyn, rows) : rows;
   const int r1 = min(r0 + FB_ROWS, nvalid);
-  float sz = 0.f, sr = 0.f, sc = 0.f, scr = 0.f;
+  float sz = 0.f, sr = 0.f, sc = 0.f, scr = 0.f, mx = 0.f;
 #pragma unroll 4
   for (int row = r0; row < r1; ++row) {
     const size_t idx = (size_t)row * GAC_E + j;
@@ -143,11 +155,14 @@ __global__ void __launch_bounds__(FB_COLS) gru_gates_bwd_kernel(const float* __r
     dmh[o] = dzp; dmh[o + GAC_E] = drp; dmh[o + 2 * GAC_E] = dcp * r;
     dh_carry[idx] = dh * z;
     sz += dzp; sr += drp; sc += dcp; scr += dcp * r;
+    mx = fmaxf(mx, fmaxf(fabsf(dzp), fmaxf(fabsf(drp), fabsf(dcp))));      // |dcp * r| <= |dcp|: one bound serves both tensors
+    if (!(fabsf(dzp) + fabsf(drp) + fabsf(dcp) <= 3e38f)) mx = __int_as_float(0x7f800000);
   }
   float* pm = part_mx + (size_t)blockIdx.y * GAC_G + j;
   float* ph = part_mh + (size_t)blockIdx.y * GAC_G + j;
   pm[0] = sz; pm[GAC_E] = sr; pm[2 * GAC_E] = sc;
   ph[0] = sz; ph[GAC_E] = sr; ph[2 * GAC_E] = scr;
+  if (amax) block_amax(mx, amax);
 }
 
 // dy1p[r][j] = dop[r] * w2[j] * lrelu'(y1[r][j]); partial sums: sum_r dy1p (d b1) and
@@ -155,13 +170,13 @@ __global__ void __launch_bounds__(FB_COLS) gru_gates_bwd_kernel(const float* __r
 __global__ void __launch_bounds__(FB_COLS) head_bwd_kernel(const float* __restrict__ dop, const float* __restrict__ w2,
                                                            const float* __restrict__ y1, long long rows, RowValid rv,
                                                            float* __restrict__ dy1p, float* __restrict__ part_b1,
-                                                           float* __restrict__ part_w2) {
+                                                           float* __restrict__ part_w2, unsigned int* __restrict__ amax /* |dy1p| or null */) {
   const int j = blockIdx.x * FB_COLS + threadIdx.x;
   const long long r0 = (long long)blockIdx.y * FB_ROWS;
   long long r1 = min(rows, r0 + FB_ROWS);
   if (rv.dyn) { const long long seg0 = (r0 / rv.seg) * rv.seg; r1 = min(r1, seg0 + min(*rv.dyn, rv.seg)); }
   const float w = w2[j];
-  float sb = 0.f, sw = 0.f;
+  float sb = 0.f, sw = 0.f, mx = 0.f;
 #pragma unroll 4
   for (long long row = r0; row < r1; ++row) {
     const size_t idx = (size_t)row * GAC_E + j;
@@ -169,9 +184,12 @@ __global__ void __launch_bounds__(FB_COLS) head_bwd_kernel(const float* __restri
     const float g = d * w * (y > 0.f ? 1.f : 0.01f);
     dy1p[idx] = g;
     sb += g; sw += y * d;
+    mx = fmaxf(mx, fabsf(g));
+    if (!(fabsf(g) <= 3e38f)) mx = __int_as_float(0x7f800000);
   }
   part_b1[(size_t)blockIdx.y * GAC_E + j] = sb;
   part_w2[(size_t)blockIdx.y * GAC_E + j] = sw;
+  if (amax) block_amax(mx, amax);
 }
 
 // dne = du * h ; dhu = du * ne ; partial column sums of dne (gradient of the noise-embedding bias)
