@@ -10,6 +10,7 @@
 #include "gru_step_tc.cuh"
 #include "dot_gemm_tc.cuh"
 
+constexpr int FNN_BN = 160, FNN_NT = 2;     // FNN tail: 300 hidden columns in two 160-wide tiles
 constexpr int HEAD_BN = 208, HEAD_NT = 2;   // actor head: 400 hidden columns in two 208-wide tiles (dual accumulators fit TMEM)
 #include "kernels_elem.cuh"
 
@@ -110,6 +111,8 @@ struct gac_ctx {
   // input-gradient GEMMs of the actor's backward on dot_gemm_tc.cuh (store mode): W1^T, U^T, kx_a^T tiles of both variants,
   // scales, and the running |x| maxima written by the kernels that produce their A operands ([0] dmx/dmh, [2] dy1p)
   unsigned char *dg_pack32[3], *dg_pack16[3]; tc::DotScales* dg_sc[3]; unsigned int* dg_amax; bool dg_fused;
+  // fused tails (400 -> 300 -> 1) of the twin critics in critic_eval
+  unsigned char *cr_pack32[2], *cr_pack16[2]; tc::DotScales* cr_sc[2]; float* cr_part[2]; unsigned int* cr_bound;
   // fused actor head of the sampler (dot_gemm_tc.cuh): w1 tiles of both variants, scales, per-row tile partials
   unsigned char *head_pack32, *head_pack16; tc::DotScales* head_sc; float* head_part; bool head_fused;
   unsigned char* gru_pack16[2]; tc::GruScales* gru_sc[2];   // 3xFP16 variant: tiles + power-of-two scales (device)
@@ -215,6 +218,12 @@ size_t partition(gac_ctx* c, void* ws) {
     c->dg_sc[i] = b.take<tc::DotScales>(1);
   }
   c->dg_amax = b.take<unsigned int>(4);
+  for (int i = 0; i < 2; ++i) {
+    c->cr_pack32[i] = b.take<unsigned char>(tc::dot_pack_bytes(GAC_H1, FNN_BN, FNN_NT, false));
+    c->cr_pack16[i] = b.take<unsigned char>(tc::dot_pack_bytes(GAC_H1, FNN_BN, FNN_NT, true));
+    c->cr_sc[i] = b.take<tc::DotScales>(1); c->cr_part[i] = b.take<float>((size_t)Rs * FNN_NT);
+  }
+  c->cr_bound = b.take<unsigned int>(4);
   return (b.off + 255) & ~(size_t)255;
 }
 
@@ -353,21 +362,59 @@ int value_eval(gac_ctx* c, const float* value, const float* states, int rows, fl
 }
 
 int critic_eval(gac_ctx* c, const float* f1, const float* f2, const float* states_u, const int* sidx, const float* actions,
-                int rows, float* q) {
+                int rows, float* q, int n_states = 0) {
   const int S = c->cfg.S, A = c->cfg.A, W = S + A;
+  cudaStream_t st = c->stream;
   int64_t off[7];
   fnn_offsets(W, off);
-  const unsigned char* pk1 = rows >= 1024 ? pack_w(c, PK_C_F1, f1 + off[2], GAC_H2, GAC_H1, GAC_H2, 0, rows < c->Rs ? rows : (rows % c->Rs ? rows % c->Rs : c->Rs)) : nullptr;
-  const unsigned char* pk2 = rows >= 1024 ? pack_w(c, PK_C_F2, f2 + off[2], GAC_H2, GAC_H1, GAC_H2, 0, rows < c->Rs ? rows : (rows % c->Rs ? rows % c->Rs : c->Rs)) : nullptr;
+  // Fused tail (dot_gemm_tc.cuh): layer 2 + LeakyReLU + output dot in one kernel, 3xFP16 with the bound of the first
+  // hidden layer derived from the weights and the batch's states (|action| <= 1).  Needs the number of unique states.
+  static const bool off_env = getenv("GAC_NO_FUSED_CRITIC") != nullptr;
+  const bool fused = !off_env && c->cfg.engine == 0 && rows >= 1024 && n_states > 0 && sidx != nullptr;
+  const float* fn[2] = {f1, f2};
+  const unsigned char *pk1 = nullptr, *pk2 = nullptr;
+  if (fused) {
+    GAC_CUDA(cudaMemsetAsync(c->cr_bound, 0, 4 * sizeof(unsigned int), st));
+    for (int i = 0; i < 2; ++i) {
+      fnn_bound_kernel<<<1, 512, W * sizeof(float), st>>>(states_u, n_states, S, W, fn[i] + off[0], fn[i] + off[1], GAC_H1, c->cr_bound + i);
+      LAUNCHED(c, "fnn_bound");
+      GAC_CUDA(dot_pack(fn[i] + off[2], GAC_H2, 0, GAC_H1, GAC_H2, FNN_BN, FNN_NT, nullptr, nullptr, 0, 0, c->cr_pack32[i], c->cr_pack16[i],
+                        c->cr_sc[i], st));
+      GAC_CUDA(dot_ascale(c->cr_sc[i], c->cr_bound + i, st));
+      c->launches += 5;
+    }
+  } else if (rows >= 1024) {
+    const int prow = rows < c->Rs ? rows : (rows % c->Rs ? rows % c->Rs : c->Rs);
+    pk1 = pack_w(c, PK_C_F1, f1 + off[2], GAC_H2, GAC_H1, GAC_H2, 0, prow);
+    pk2 = pack_w(c, PK_C_F2, f2 + off[2], GAC_H2, GAC_H1, GAC_H2, 0, prow);
+  }
   for (int r0 = 0; r0 < rows; r0 += c->Rs) {
     const int n = rows - r0 < c->Rs ? rows - r0 : c->Rs;
-    concat_gather_kernel<<<(unsigned)cdiv64((long long)n * W, 256), 256, 0, c->stream>>>(
+    concat_gather_kernel<<<(unsigned)cdiv64((long long)n * W, 256), 256, 0, st>>>(
         states_u, sidx ? sidx + r0 : nullptr, actions + (size_t)r0 * A, S, A, n, c->cx);
     LAUNCHED(c, "concat_gather");
+    if (fused) {
+      float* h0[2] = {c->ch0a, c->ch0b};
+      for (int i = 0; i < 2; ++i) {
+        GemmArgs g = gemm_args(n, GAC_H1, W, c->cx, W, fn[i] + off[0], GAC_H1, h0[i], GAC_H1);
+        g.bias = fn[i] + off[1]; g.act = ACT_LRELU; g.alpha = 0.01f;
+        GAC_TRY(run_gemm(c, g));
+        tc::DotGemmArgs d;
+        d.rows = n; d.dyn_rows = nullptr; d.seg_rows = 0; d.A = h0[i]; d.lda = GAC_H1; d.K = GAC_H1; d.N = GAC_H2; d.bn = FNN_BN; d.ntiles = FNN_NT;
+        d.wpk = c->cr_pack32[i]; d.wpk16 = c->cr_pack16[i]; d.sc = c->cr_sc[i];
+        d.bias = fn[i] + off[3]; d.w2 = fn[i] + off[4]; d.alpha = 0.01f; d.part = c->cr_part[i];
+        d.mode = 0; d.C = nullptr; d.ldc = 0; d.gate = nullptr; d.ldgate = 0; d.gate_alpha = 0.f; d.accumulate = 0;
+        GAC_CUDA(launch_dot_gemm(d, st));
+        c->launches++;
+      }
+      critic_finish_kernel<<<cdiv(n, 256), 256, 0, st>>>(c->cr_part[0], c->cr_part[1], FNN_NT, f1 + off[5], f2 + off[5], q + r0, n);
+      LAUNCHED(c, "critic_finish");
+      continue;
+    }
     GAC_TRY(fnn_forward(c, f1, W, c->cx, n, c->ch0a, c->ch1a, pk1, c->pk_bn[PK_C_F1]));
     GAC_TRY(fnn_forward(c, f2, W, c->cx, n, c->ch0b, c->ch1b, pk2, c->pk_bn[PK_C_F2]));
-    rowdot_kernel<<<cdiv(n * 32, 256), 256, 0, c->stream>>>(c->ch1a, GAC_H2, f1 + off[4], f1 + off[5], c->ch1b, f2 + off[4],
-                                                           f2 + off[5], GAC_H2, n, 0, q + r0, 1, nullptr, 0, RowValid{nullptr, 1});
+    rowdot_kernel<<<cdiv(n * 32, 256), 256, 0, st>>>(c->ch1a, GAC_H2, f1 + off[4], f1 + off[5], c->ch1b, f2 + off[4],
+                                                     f2 + off[5], GAC_H2, n, 0, q + r0, 1, nullptr, 0, RowValid{nullptr, 1});
     LAUNCHED(c, "rowdot_min");
   }
   return GAC_OK;
@@ -1098,7 +1145,7 @@ int gac_step_grads(gac_ctx_t* c, const gac_step_io_t* io, const gac_hparams_t* h
                                                                            (long long)P * A, c->cand + (size_t)P * A);
   LAUNCHED(c, "noise_clip");
   GAC_CUDA(cudaMemcpyAsync(c->cand + (size_t)2 * P * A, io->filter_rand, (size_t)P * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  GAC_TRY(critic_eval(c, t_f1, t_f2, io->s, c->sidx3, c->cand, 3 * P, c->q3));
+  GAC_TRY(critic_eval(c, t_f1, t_f2, io->s, c->sidx3, c->cand, 3 * P, c->q3, B));
 
   // ---- Value.train (networks.py:483-496) ----
   mean_k_kernel<<<cdiv(B * 32, 256), 256, 0, st>>>(c->q3, K, B, c->td_vcrit);

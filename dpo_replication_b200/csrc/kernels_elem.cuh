@@ -279,6 +279,41 @@ __global__ void head_finish_kernel(const float* __restrict__ part, int ntiles, c
   if (cosb) cosb[idx] = cosf(__fmul_rn(a, c_ipi[i]));
 }
 
+// ---- consumer of the tile partials of the twin critics' fused tails (networks.py:388): q = min over the two nets of
+// (sum_t part[r][t] + b2) ----
+__global__ void critic_finish_kernel(const float* __restrict__ part1, const float* __restrict__ part2, int ntiles, const float* __restrict__ b2a,
+                                     const float* __restrict__ b2b, float* __restrict__ q, int rows) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float s1 = part1[(size_t)r * ntiles], s2 = part2[(size_t)r * ntiles];
+  for (int t = 1; t < ntiles; ++t) { s1 += part1[(size_t)r * ntiles + t]; s2 += part2[(size_t)r * ntiles + t]; }
+  q[r] = fminf(s1 + b2a[0], s2 + b2b[0]);
+}
+
+// ---- bound of the first hidden layer of an FNN over concat(state, action) inputs, |action| <= 1:
+// |h0_j| <= sum_{i<S} |w0_ij| max_b |s_bi| + sum_{i>=S} |w0_ij| + |b0_j|   (LeakyReLU is 1-Lipschitz through 0).
+// One block; result (float bits) max-ed into *slot, +inf on non-finite input. ----
+__global__ void fnn_bound_kernel(const float* __restrict__ states, int n, int S, int W, const float* __restrict__ w0,
+                                 const float* __restrict__ b0, int H, unsigned int* __restrict__ slot) {
+  extern __shared__ float xmax[];               // W floats
+  for (int i = threadIdx.x; i < W; i += blockDim.x) {
+    float m = 1.f;
+    if (i < S) { m = 0.f; for (int b = 0; b < n; ++b) m = fmaxf(m, fabsf(states[(size_t)b * S + i])); if (!(m <= 3e38f)) m = __int_as_float(0x7f800000); }
+    xmax[i] = m;
+  }
+  __syncthreads();
+  float mb = 0.f;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    float sacc = fabsf(b0[j]);
+    for (int i = 0; i < W; ++i) sacc += fabsf(w0[(size_t)i * H + j]) * xmax[i];
+    if (!(sacc <= 3e38f)) sacc = __int_as_float(0x7f800000);
+    mb = fmaxf(mb, sacc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(mb));
+}
+
 // ---- agent.py:189-190: a = clip(a + 0.01*n, -1, 1) ----
 __global__ void noise_clip_kernel(const float* __restrict__ a, const float* __restrict__ nrm, float scale, long long n,
                                   float* __restrict__ out) {
