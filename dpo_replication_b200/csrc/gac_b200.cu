@@ -318,6 +318,27 @@ int run_gemm(gac_ctx* c, GemmArgs g) {
       return GAC_OK;
     }
   }
+  // Small problems (the B-row TD nets, the per-state projections): a handful of tiles would walk K serially on a few
+  // SMs -- latency bound, 17-70 us for a few MFLOP.  Spread K over the chip and apply the epilogue in the reduction.
+  static const bool no_small_split = getenv("GAC_NO_SMALL_SPLITK") != nullptr;
+  if (!no_small_split && !g.valid_on_k && !g.dyn_rows && g.K >= 128 && g.M > 8 && (size_t)g.M * g.N <= (size_t)GAC_E * GAC_G && g.act != ACT_TANH) {
+    const int tiles = tc ? cdiv(g.M, tc::BM) * cdiv(g.N, tc::plan_for(g.N).bn) : cdiv(g.M, 128) * cdiv(g.N, 128);
+    int splits = cdiv(g.K, 64);                                // 64-wide K slices (two tcgen05 K blocks)
+    if (splits > 148 / tiles) splits = 148 / tiles;
+    if (splits > c->max_splits) splits = c->max_splits;
+    if (tiles <= 24 && splits >= 2) {
+      GemmArgs p = g;
+      p.C = c->spart; p.ldc = g.N; p.transC = 0; p.splitk = splits; p.split_stride = (long long)g.M * g.N;
+      p.bias = nullptr; p.add = nullptr; p.mul = nullptr; p.gate = nullptr; p.act = ACT_NONE; p.accumulate = 0;
+      p.Bpacked = nullptr; p.Bpacked_bn = 0;                   // K-split tiles read B through the register path
+      if (tc) GAC_CUDA(launch_gemm_tc(p, st)); else GAC_CUDA(launch_gemm_simt(p, st));
+      c->launches++;
+      const long long n = (long long)g.M * g.N;
+      reduce_splits_epi_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(c->spart, splits, g);
+      LAUNCHED(c, "reduce_splits_epi");
+      return GAC_OK;
+    }
+  }
   if (tc) GAC_CUDA(launch_gemm_tc(g, st)); else GAC_CUDA(launch_gemm_simt(g, st));
   c->launches++;
   return GAC_OK;

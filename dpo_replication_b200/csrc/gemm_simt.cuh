@@ -154,6 +154,19 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, long long s
   dst[i] = s;
 }
 
+// split-K reduction for SMALL problems: part holds nsplit dense (M, N) partial products; the fused epilogue of the
+// original GEMM (bias, activation, gates, accumulate, transposed store) is applied to the fixed-order sum.
+__global__ void reduce_splits_epi_kernel(const float* __restrict__ part, int nsplit, const GemmArgs g) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long mn = (long long)g.M * g.N;
+  if (i >= mn) return;
+  const int m = (int)(i / g.N), n = (int)(i - (long long)m * g.N);
+  float s = 0.f;
+  for (int z = 0; z < nsplit; ++z) s += part[(size_t)z * mn + i];
+  const size_t ci = g.transC ? (size_t)n * g.ldc + m : (size_t)m * g.ldc + n;
+  g.C[ci] = gemm_epilogue(g, s, m, n);
+}
+
 inline cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 8 && !g.transA && !g.transC && g.splitk <= 1 && !g.dyn_rows) {
     dim3 blk(64, 8);
