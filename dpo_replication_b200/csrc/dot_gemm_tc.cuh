@@ -96,11 +96,12 @@ __global__ void dot_amax_kernel(const float* __restrict__ W, int ldw, int wr, in
                                 const float* __restrict__ e, int nb, int ne, unsigned int* __restrict__ slots) {
   float mw = 0.f, mb = 0.f;
   bool bad = false;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wr * wc; i += gridDim.x * blockDim.x) {
-    const float a = fabsf(W[(size_t)(i / wc) * ldw + i % wc]);
-    bad |= !(a <= 3e38f);
-    mw = fmaxf(mw, a);
-  }
+  for (int r = blockIdx.x; r < wr; r += gridDim.x)
+    for (int cc = threadIdx.x; cc < wc; cc += blockDim.x) {
+      const float a = fabsf(W[(size_t)r * ldw + cc]);
+      bad |= !(a <= 3e38f);
+      mw = fmaxf(mw, a);
+    }
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ne; j += gridDim.x * blockDim.x) {
     float s = fabsf(e[j]);
     for (int i = 0; i < nb; ++i) s += fabsf(E[(size_t)i * ne + j]);
@@ -366,7 +367,7 @@ inline cudaError_t dot_pack(const float* W, int ldw, int transW, int K, int N, i
     if (e != cudaSuccess) return e;
     // |W| over the (K x N) or (N x K) matrix: rows of ldw floats, `cols` used
     const int wr = transW ? N : K, wc = transW ? K : N;
-    tc::dot_amax_kernel<<<40, 256, 0, st>>>(W, ldw, wr, wc, bound_E, bound_e, nb, bound_E ? ne : 0, reinterpret_cast<unsigned int*>(sc) + 4);
+    tc::dot_amax_kernel<<<148, 256, 0, st>>>(W, ldw, wr, wc, bound_E, bound_e, nb, bound_E ? ne : 0, reinterpret_cast<unsigned int*>(sc) + 4);
     tc::dot_wscale_kernel<<<1, 1, 0, st>>>(sc);
     const long long t16 = (long long)ntiles * tc::dot_kblocks(K, true) * bn * 8;
     tc::dot_pack_kernel<true><<<(unsigned)cdiv64(t16, 256), 256, 0, st>>>(W, ldw, transW, K, N, bn, ntiles, out16, sc);

@@ -76,6 +76,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
+// MN-major operands (bit 15: A, bit 16: B): the operand's M / N index is the contiguous one in shared memory.
+// For 4-byte (tf32) elements the only MN-major layout the tensor core accepts is SWIZZLE_128B_BASE32B (layout type 1;
+// cute: Swizzle<2,5,2> o ((4,8,m),(4,k)) : ((1,4,LBO),(32,SBO))): groups of 32 consecutive M/N elements (128 bytes) form
+// one row of a 4-row (4 k) 512-byte atom whose 32-byte units are XOR-ed with the row index (address bits [5,7) ^= bits
+// [7,9)); consecutive groups are LBO apart, consecutive 4-k atoms SBO apart.  This kernel stores a 32-deep K block of one
+// group contiguously (32 k-rows x 128 B = 4096 B = LBO, SBO = 512 B), so one K step (8 k = 2 atoms) advances the start
+// address by 1024 bytes.  A weight-gradient operand -- an activation matrix (batch rows, features) read as (features,
+// batch) -- is copied into this layout row by row with 128-bit loads and stores: no transposition anywhere.
+__device__ __forceinline__ uint32_t make_idesc_major(int n, bool a_mn, bool b_mn) {
+  return make_idesc(n) | (a_mn ? 1u << 15 : 0u) | (b_mn ? 1u << 16 : 0u);
+}
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -243,6 +257,37 @@ __device__ __forceinline__ void store_split(const float (&h)[NCH][4], const floa
   }
 }
 
+// ---- MN-major staging: element (r, k) = src[(k0 + k) * ld + row0 + r], r contiguous in memory ----
+// 16-byte chunk q = t + 128 i of the (32 k) x (4 NCH chunks per k-row) tile: k = q / CPR, 4 rows starting at 4 (q % CPR).
+// A warp reads one k-row segment of 512 contiguous bytes; the chunk lands at group (r / 32), row k, 32-byte unit
+// ((r / 8) & 3) ^ (k & 3), half (r / 4) & 1.
+template <int NCH>
+__device__ __forceinline__ void load_mn(float (&x)[NCH][4], const float* __restrict__ src, int ld, int row0, int row_end, int rows,
+                                        int k0, int live, int t) {
+  constexpr int CPR = NCH * 4;                                  // chunks per k-row: 32 (128 rows) or 64 (256 rows)
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int q = t + GROUP * i, k = q / CPR, r4 = 4 * (q % CPR);
+    x[i][0] = x[i][1] = x[i][2] = x[i][3] = 0.f;
+    if (r4 < rows && row0 + r4 < row_end && k < live) {          // rows, row_end are multiples of 4 on this path
+      const float4 v = *reinterpret_cast<const float4*>(src + (size_t)(k0 + k) * ld + row0 + r4);
+      x[i][0] = v.x; x[i][1] = v.y; x[i][2] = v.z; x[i][3] = v.w;
+    }
+  }
+}
+template <int NCH>
+__device__ __forceinline__ void store_mn(const float (&h)[NCH][4], const float (&l)[NCH][4], uint32_t s_hi, uint32_t s_lo, int rows, int t) {
+  constexpr int CPR = NCH * 4;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int q = t + GROUP * i, k = q / CPR, c4 = q % CPR;
+    if (4 * c4 >= rows) continue;
+    const uint32_t off = (uint32_t)(c4 >> 3) * 4096u + (uint32_t)k * 128u + (uint32_t)(((((c4 & 7) >> 1) ^ (k & 3)) << 5) | ((c4 & 1) << 4));
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(s_hi + off), "f"(h[i][0]), "f"(h[i][1]), "f"(h[i][2]), "f"(h[i][3]));
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "f"(l[i][0]), "f"(l[i][1]), "f"(l[i][2]), "f"(l[i][3]));
+  }
+}
+
 // TB means "B is stored (N, K) row-major" (g.transB); !TB is the natural Keras (K, N).
 template <bool TA, bool TB, bool VEC, bool PACKED>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, int bn, int stages, int tmem_cols) {
@@ -261,7 +306,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
   const KMap km = make_kmap(g, nvalid, blockIdx.z);
   const int nkb = km.nkb;
 
-  const uint32_t stage_bytes = 2 * A_TILE_BYTES + 2 * (uint32_t)bn * 128u;
+  // operands whose M / N index is contiguous in memory (transposed A, (K, N) row-major B) are staged MN-major when
+  // 128-bit accesses are possible; an MN-major B tile is padded to whole 32-column groups
+  constexpr bool A_MN = TA && VEC, B_MN = !TB && VEC && !PACKED;
+  const uint32_t b_tile = B_MN ? (uint32_t)((bn + 31) & ~31) * 128u : (uint32_t)bn * 128u;
+  const uint32_t stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
   if (tid == 0) {
@@ -286,9 +335,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
       kmap_get(km, kb, k0, live);
       constexpr int NB_CH = PACKED ? 8 : 16;
       float xa[8][4], xb[NB_CH][4];
-      load_operand<TA, VEC, 8>(xa, g.A, g.lda, m0, m_end, BM, k0, live, t);
+      if constexpr (A_MN) load_mn<8>(xa, g.A, g.lda, m0, m_end, BM, k0, live, t);
+      else load_operand<TA, VEC, 8>(xa, g.A, g.lda, m0, m_end, BM, k0, live, t);
       // B tile rows are output columns n; element (n, k) = B(k, n)
-      if constexpr (!PACKED) load_operand<!TB, VEC, NB_CH>(xb, g.B, g.ldb, n0, g.N, bn, k0, live, t);
+      if constexpr (B_MN) load_mn<NB_CH>(xb, g.B, g.ldb, n0, g.N, bn, k0, live, t);
+      else if constexpr (!PACKED) load_operand<!TB, VEC, NB_CH>(xb, g.B, g.ldb, n0, g.N, bn, k0, live, t);
       float la[8][4];
       split_operand<8>(xa, la);     // waits for the A loads, not for the stage
       const int s = kb % stages;
@@ -308,8 +359,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
                        : "memory");
         }
       }
-      store_split<TA, 8>(xa, la, sa, sa + A_TILE_BYTES, BM, t);
-      if constexpr (!PACKED) store_operand<!TB, NB_CH>(xb, sa + 2 * A_TILE_BYTES, sa + 2 * A_TILE_BYTES + (uint32_t)bn * 128u, bn, t);
+      if constexpr (A_MN) store_mn<8>(xa, la, sa, sa + A_TILE_BYTES, BM, t);
+      else store_split<TA, 8>(xa, la, sa, sa + A_TILE_BYTES, BM, t);
+      if constexpr (B_MN) {
+        float lb[NB_CH][4];
+        split_operand<NB_CH>(xb, lb);
+        store_mn<NB_CH>(xb, lb, sa + 2 * A_TILE_BYTES, sa + 2 * A_TILE_BYTES + b_tile, bn, t);
+      } else if constexpr (!PACKED) {
+        store_operand<!TB, NB_CH>(xb, sa + 2 * A_TILE_BYTES, sa + 2 * A_TILE_BYTES + b_tile, bn, t);
+      }
       fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
@@ -414,7 +472,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
   } else {
     // ------------------------------ MMA issuer (one lane) ------------------------------
     if (lane == 0 && nkb > 0) {
-      const uint32_t idesc = make_idesc(bn);
+      const uint32_t idesc = make_idesc_major(bn, A_MN, B_MN);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % stages;
         const uint32_t ph = (uint32_t)(kb / stages) & 1u;
@@ -422,18 +480,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
         kmap_get(km, kb, k0, live);
         mbar_wait(smem_u32(&bar_full[s]), ph);
         tc_fence_after();
-        const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
-        const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
-        const uint64_t b_hi = make_desc(sa + 2 * A_TILE_BYTES), b_lo = make_desc(sa + 2 * A_TILE_BYTES + (uint32_t)bn * 128u);
+        const uint32_t sa = smem0 + (uint32_t)s * stage_bytes, sb = sa + 2 * A_TILE_BYTES;
+        const uint64_t a_hi = A_MN ? make_desc_mn(sa) : make_desc(sa), a_lo = A_MN ? make_desc_mn(sa + A_TILE_BYTES) : make_desc(sa + A_TILE_BYTES);
+        const uint64_t b_hi = B_MN ? make_desc_mn(sb) : make_desc(sb), b_lo = B_MN ? make_desc_mn(sb + b_tile) : make_desc(sb + b_tile);
         const int ksteps = (live + 7) / 8;
         for (int j = 0; j < ksteps; ++j) {
-          const uint64_t adv = (uint64_t)(j * 2);            // +32 bytes (8 tf32) in the >>4 address field
+          // one K step = 8 tf32: +32 bytes along a K-major row, +8 k-rows (1024 bytes) in an MN-major tile (>>4 units)
+          const uint64_t adva = (uint64_t)(A_MN ? j * 64 : j * 2), advb = (uint64_t)(B_MN ? j * 64 : j * 2);
           const uint32_t acc = (kb | j) ? 1u : 0u;
           // timing probe (tools/gemm_probe.py): 1 of the 3 passes only => how much of the tile time is MMA-bound
-          if (g.probe == 2) { mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, acc); continue; }
-          mma_tf32(tmem_d + (uint32_t)bn, a_lo + adv, b_hi + adv, idesc, acc);   // correction accumulator
-          mma_tf32(tmem_d + (uint32_t)bn, a_hi + adv, b_lo + adv, idesc, 1u);
-          mma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, acc);                  // main accumulator
+          if (g.probe == 2) { mma_tf32(tmem_d, a_hi + adva, b_hi + advb, idesc, acc); continue; }
+          mma_tf32(tmem_d + (uint32_t)bn, a_lo + adva, b_hi + advb, idesc, acc);   // correction accumulator
+          mma_tf32(tmem_d + (uint32_t)bn, a_hi + adva, b_lo + advb, idesc, 1u);
+          mma_tf32(tmem_d, a_hi + adva, b_hi + advb, idesc, acc);                  // main accumulator
         }
         mma_commit(smem_u32(&bar_empty[s]));                 // stage reusable once these MMAs retire
       }
@@ -974,9 +1033,15 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
   const tc::Plan p = tc::plan_for(g.N);
   dim3 grid(cdiv(g.N, p.bn), cdiv(g.M, tc::BM), g.splitk > 1 ? g.splitk : 1);
   // 16-byte vector accesses need aligned bases and leading dimensions
-  const bool veca = (g.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
-  const bool vec = veca && (g.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
-#define GAC_TC_LAUNCH(a, b, c, d) tc::gemm_tc_kernel<a, b, c, d><<<grid, tc::THREADS, p.smem, st>>>(g, p.bn, p.stages, p.tmem_cols)
+  // (MN-major staging reads float4 over 4 consecutive rows / columns: their count must be a multiple of 4)
+  const bool veca = (g.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) && (!g.transA || g.M % 4 == 0);
+  const bool vec = veca && (g.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && (g.transB || g.Bpacked || g.N % 4 == 0);
+  // an MN-major B tile is padded to whole 32-column groups (hi and lo tile of every stage)
+  const size_t stage_l = 2 * (size_t)tc::A_TILE_BYTES + 2 * (size_t)((p.bn + 31) & ~31) * 128;
+  int stages_l = p.stages;
+  while (stages_l > 2 && stages_l * stage_l + 1024 > (size_t)tc::SMEM_LIMIT) --stages_l;
+  const size_t smem_l = stages_l * stage_l + 1024;
+#define GAC_TC_LAUNCH(a, b, c, d) tc::gemm_tc_kernel<a, b, c, d><<<grid, tc::THREADS, smem_l, st>>>(g, p.bn, stages_l, p.tmem_cols)
   const bool epi_al = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && tc::al16h(g.bias, 4) &&
                       tc::al16h(g.add, g.ldadd) && tc::al16h(g.mul, g.ldmul) && tc::al16h(g.gate, g.ldgate);
   // Opt-in (GAC_TC_PERSISTENT=1): validated by the full GPU suite, measured no faster than the

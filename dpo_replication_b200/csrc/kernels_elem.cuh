@@ -295,11 +295,13 @@ __global__ void critic_finish_kernel(const float* __restrict__ part1, const floa
 // One block; result (float bits) max-ed into *slot, +inf on non-finite input. ----
 __global__ void fnn_bound_kernel(const float* __restrict__ states, int n, int S, int W, const float* __restrict__ w0,
                                  const float* __restrict__ b0, int H, unsigned int* __restrict__ slot) {
-  extern __shared__ float xmax[];               // W floats
-  for (int i = threadIdx.x; i < W; i += blockDim.x) {
-    float m = 1.f;
-    if (i < S) { m = 0.f; for (int b = 0; b < n; ++b) m = fmaxf(m, fabsf(states[(size_t)b * S + i])); if (!(m <= 3e38f)) m = __int_as_float(0x7f800000); }
-    xmax[i] = m;
+  extern __shared__ float xmax[];               // W floats (as uint bit patterns while reducing)
+  unsigned int* xbits = reinterpret_cast<unsigned int*>(xmax);
+  for (int i = threadIdx.x; i < W; i += blockDim.x) xbits[i] = i < S ? 0u : __float_as_uint(1.f);
+  __syncthreads();
+  for (int e = threadIdx.x; e < n * S; e += blockDim.x) {
+    const float a = fabsf(states[e]);
+    atomicMax(&xbits[e % S], (a <= 3e38f) ? __float_as_uint(a) : 0x7f800000u);
   }
   __syncthreads();
   float mb = 0.f;
