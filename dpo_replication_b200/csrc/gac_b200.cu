@@ -111,6 +111,8 @@ struct gac_ctx {
   // input-gradient GEMMs of the actor's backward on dot_gemm_tc.cuh (store mode): W1^T, U^T, kx_a^T tiles of both variants,
   // scales, and the running |x| maxima written by the kernels that produce their A operands ([0] dmx/dmh, [2] dy1p)
   unsigned char *dg_pack32[3], *dg_pack16[3]; tc::DotScales* dg_sc[3]; unsigned int* dg_amax; bool dg_fused;
+  // 3xFP16 weight-gradient GEMMs of the actor (dW1, dU, dkx_a): scales per site, embedding bounds ([1] noise, [3] action)
+  WgScales* wg_sc; unsigned int* wg_bound; bool wg_f16; unsigned long long* dbg_buf;
   // fused tails (400 -> 300 -> 1) of the twin critics in critic_eval
   unsigned char *cr_pack32[2], *cr_pack16[2]; tc::DotScales* cr_sc[2]; float* cr_part[2]; unsigned int* cr_bound;
   // fused actor head of the sampler (dot_gemm_tc.cuh): w1 tiles of both variants, scales, per-row tile partials
@@ -224,6 +226,8 @@ size_t partition(gac_ctx* c, void* ws) {
     c->cr_sc[i] = b.take<tc::DotScales>(1); c->cr_part[i] = b.take<float>((size_t)Rs * FNN_NT);
   }
   c->cr_bound = b.take<unsigned int>(4);
+  c->wg_sc = b.take<WgScales>(4); c->wg_bound = b.take<unsigned int>(4);
+  c->dbg_buf = b.take<unsigned long long>(8 + 8 * 4096);   // per-CTA phase stamps of one GEMM launch (GAC_WGRAD_TIMELINE)
   return (b.off + 255) & ~(size_t)255;
 }
 
@@ -282,6 +286,8 @@ int run_gru_step(gac_ctx* c, int which, const float* actor, const float* sx, con
 int run_gemm(gac_ctx* c, GemmArgs g) {
   cudaStream_t st = c->stream;
   if (g.M <= 0 || g.N <= 0) return GAC_OK;
+  const WgScales* f16_in = g.f16;
+  g.f16 = nullptr;
   const bool tc = c->cfg.engine == 0 && tc_gemm_supported(g);
   if (g.valid_on_k || g.K >= 8192) {
     // weight-gradient shape: small output, long reduction over activation rows => split-K.
@@ -293,6 +299,7 @@ int run_gemm(gac_ctx* c, GemmArgs g) {
       w.A = g.B; w.lda = g.ldb; w.transA = 1;      // A'(m', k) = dY[k][m']
       w.B = g.A; w.ldb = g.lda; w.transB = 0;      // B'(k, n') = X[k][n']
       w.transC = 1;                                // C'(m', n') -> dW[n'][m'],  ldc = original N
+      w.f16 = f16_in;                              // the 3xFP16 scales are laid out for this swapped product (A' = dY, B' = X)
       g = w;
     }
     const int tiles = tc ? cdiv(g.M, tc::BM) * cdiv(g.N, tc::plan_for(g.N).bn) : cdiv(g.M, 128) * cdiv(g.N, 128);
@@ -614,6 +621,16 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
     // the three input-gradient contractions of the backward (x W^T): 3xFP16 with the A bound tracked by the producers
     static const bool off = getenv("GAC_NO_F16_DGRAD") != nullptr;
     c->dg_fused = !off && c->cfg.engine == 0 && c->Mc >= 128 && c->Mc % 128 == 0;
+    // opt-in (GAC_F16_WGRAD=1): validated by the GPU suite, measured no faster -- the weight-gradient GEMMs are bound by
+    // operand delivery (2,000 cycles per K block with 6 or with 12 MMAs, tools/wgrad_timeline.py), not by the tensor pipe
+    static const bool wg_on = getenv("GAC_F16_WGRAD") != nullptr;
+    c->wg_f16 = c->dg_fused && wg_on;
+    if (c->wg_f16) {
+      GAC_CUDA(cudaMemsetAsync(c->wg_bound, 0, 4 * sizeof(unsigned int), st));
+      tc::dot_amax_kernel<<<4, 256, 0, st>>>(nullptr, 0, 0, 0, var(c, actor, 0, GAC_A_WN), var(c, actor, 0, GAC_A_BN), GAC_NB, GAC_E, c->wg_bound);
+      tc::dot_amax_kernel<<<4, 256, 0, st>>>(nullptr, 0, 0, 0, var(c, actor, 0, GAC_A_WA), var(c, actor, 0, GAC_A_BA), GAC_NB, GAC_E, c->wg_bound + 2);
+      c->launches += 2;
+    }
     if (c->dg_fused) {
       const float* W[3] = {var(c, actor, 0, GAC_A_W1), var(c, actor, 0, GAC_A_U), kxa_w};
       for (int i = 0; i < 3; ++i)
@@ -680,9 +697,18 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   const long long AM = (long long)A * Mc;
   const float* kxa = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
   auto G = [&](int v) { return var(c, grad, 0, v); };
-  auto wgrad = [&](int M, int N, const float* X, int ldx, const float* dY, int ldy, long long rows, float* dst, bool dyn) {
+  // site >= 0: 3xFP16 with |dY| from the producers' running maximum (amax_dy) and |X| <= *bound_x (or bound_const)
+  auto wgrad = [&](int M, int N, const float* X, int ldx, const float* dY, int ldy, long long rows, float* dst, bool dyn, int site = -1,
+                   const unsigned int* amax_dy = nullptr, const unsigned int* bound_x = nullptr, float bound_const = 1.f) -> int {
     GemmArgs g = gemm_args(M, N, (int)rows, X, ldx, dY, ldy, dst, N);
     g.transA = 1; g.accumulate = acc;
+    if (site >= 0 && c->wg_f16) {
+      wg_scale_kernel<<<1, 1, 0, st>>>(c->wg_sc + site, amax_dy, bound_x, bound_const);
+      LAUNCHED(c, "wg_scale");
+      g.f16 = c->wg_sc + site;
+    }
+    static const bool timeline = getenv("GAC_WGRAD_TIMELINE") != nullptr;
+    if (timeline && site == 2) g.dbg = c->dbg_buf;           // the kx_a weight gradient: (2, 10, splits) CTAs
     if (dyn) { g.dyn_rows = live; g.seg_rows = Mc; g.valid_on_k = 1; }
     return run_gemm(c, g);
   };
@@ -713,7 +739,7 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   LAUNCHED(c, "reduce_cols");
   reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart1, nrb_all, GAC_E, G(GAC_A_W2), acc);
   LAUNCHED(c, "reduce_cols");
-  GAC_TRY(wgrad(GAC_E, GAC_E, c->au, GAC_E, c->dy1p, GAC_E, AM, G(GAC_A_W1), true));
+  GAC_TRY(wgrad(GAC_E, GAC_E, c->au, GAC_E, c->dy1p, GAC_E, AM, G(GAC_A_W1), true, 0, c->dg_amax + 2, c->wg_bound + 1));
   GemmArgs g = gemm_args((int)AM, GAC_E, GAC_E, c->dy1p, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->du, GAC_E);
   if (c->dg_fused) {
     GAC_TRY(dgrad(0, c->dy1p, GAC_E, GAC_E, AM, c->du, nullptr, 0.f, 0, amax_g + 2));
@@ -748,12 +774,12 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
     carry = carry == c->dhc0 ? c->dhc1 : c->dhc0;
   }
   // time-parallel weight gradients of the GRU
-  GAC_TRY(wgrad(GAC_E, GAC_G, c->hall, GAC_E, c->dmh, GAC_G, AM, G(GAC_A_U), true));
+  GAC_TRY(wgrad(GAC_E, GAC_G, c->hall, GAC_E, c->dmh, GAC_G, AM, G(GAC_A_U), true, 1, c->dg_amax, nullptr, 1.f));
   reduce_cols_kernel<<<cdiv(GAC_G, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart1, A * nrb_step, GAC_G, G(GAC_A_GB) + GAC_G, acc);
   LAUNCHED(c, "reduce_cols");
   reduce_cols_kernel<<<cdiv(GAC_G, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart0, A * nrb_step, GAC_G, G(GAC_A_GB), acc);
   LAUNCHED(c, "reduce_cols");
-  GAC_TRY(wgrad(GAC_E, GAC_G, c->a_ae, GAC_E, c->mx, GAC_G, AM, G(GAC_A_KX) + (size_t)GAC_E * GAC_G, true));
+  GAC_TRY(wgrad(GAC_E, GAC_G, c->a_ae, GAC_E, c->mx, GAC_G, AM, G(GAC_A_KX) + (size_t)GAC_E * GAC_G, true, 2, c->dg_amax, c->wg_bound + 3));
   if (c->dg_fused) {
     GAC_TRY(dgrad(2, c->mx, GAC_G, GAC_G, AM, c->du, c->a_ae, 0.2f, 0, amax_g));
   } else {

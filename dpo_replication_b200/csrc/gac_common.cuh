@@ -51,6 +51,8 @@ inline int round_up(int a, int b) { return cdiv(a, b) * b; }
 // ------------------------------------------------------------------------------------------
 enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_LRELU2 = 2 /* lrelu(0.01) then lrelu(0.2): networks.py:196 */, ACT_TANH = 3 };
 
+struct WgScales { float s_a, s_b, inv_unit; int ok; };
+
 struct GemmArgs {
   int M, N, K;
   const float* A; int lda; int transA;  // transA: A(m,k) = A[k*lda + m]
@@ -70,6 +72,9 @@ struct GemmArgs {
   // split-K: blockIdx.z = split, raw partial (no epilogue) stored at C + z*split_stride
   int splitk; long long split_stride;
   unsigned long long* dbg;               // optional timeline probe (tools/gemm_probe.py --timeline)
+  // 3xFP16 variant of the weight-gradient GEMM (both operands MN-major activations with known magnitude bounds):
+  // device struct {s_a, s_b, inv_unit, ok}, nullptr = 3xTF32
+  const struct WgScales* f16;
   int probe;                             // timing experiments only (env GAC_TC_PROBE; results are garbage when set)
 };
 

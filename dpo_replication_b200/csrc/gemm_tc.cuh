@@ -26,6 +26,7 @@
 //              gac_common.cuh (bias, gathered add, LeakyReLU, Hadamard, LeakyReLU', accumulate).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "gac_common.cuh"
@@ -90,6 +91,50 @@ __device__ __forceinline__ uint32_t make_idesc_major(int n, bool a_mn, bool b_mn
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {     // kind::f16: D = F32, A = B = F16 (format 0), K-major
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// x (already scaled) -> fp16 hi and fp16 lo' = (x - hi) * 2^11, two values per 32-bit word
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);                   // one cvt.rn.f16x2.f32
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((x0 - hf.x) * 2048.f, (x1 - hf.y) * 2048.f);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// MN-major fp16 operand tile (standard SWIZZLE_128B: 64 M/N elements = 128 bytes per row, 8-row atoms, 16-byte chunks XOR
+// row & 7): a 32-deep K block of one 64-element group is stored contiguously (32 k-rows x 128 B = 4096 B = LBO), 8-k atoms
+// are SBO = 1024 B apart, and one K step (16 k) advances the start address by 2048 bytes.
+__device__ __forceinline__ uint64_t make_desc_mn16(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// float4 of 4 consecutive M/N elements (already scaled) at k -> 4 hi + 4 lo' halves, 8 bytes each
+template <int NCH>
+__device__ __forceinline__ void store_mn16(const float (&x)[NCH][4], float scale, uint32_t s_hi, uint32_t s_lo, int rows, int t) {
+  constexpr int CPR = NCH * 4;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int q = t + 128 * i, k = q / CPR, c4 = q % CPR;
+    if (4 * c4 >= rows) continue;
+    uint32_t h0, h1, l0, l1;
+    split_f16x2(x[i][0] * scale, x[i][1] * scale, h0, l0);
+    split_f16x2(x[i][2] * scale, x[i][3] * scale, h1, l1);
+    const uint32_t off = (uint32_t)(c4 >> 4) * 4096u + (uint32_t)k * 128u + (uint32_t)(((((c4 & 15) >> 1) ^ (k & 7)) << 4) | ((c4 & 1) << 3));
+    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(s_hi + off), "r"(h0), "r"(h1));
+    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(s_lo + off), "r"(l0), "r"(l1));
+  }
+}
+
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -305,6 +350,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
 
   const KMap km = make_kmap(g, nvalid, blockIdx.z);
   const int nkb = km.nkb;
+  // optional per-CTA phase stamps (tools/wgrad_timeline.py): [globaltimer, start, setup, loaders done, accum ready, end, nkb, smid]
+  unsigned long long* dbg = (g.dbg && tid == 0) ? g.dbg + 8 + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg) {
+    unsigned long long gt; unsigned sm;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    dbg[0] = gt; dbg[1] = clock64(); dbg[6] = (unsigned long long)nkb; dbg[7] = sm;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { g.dbg[0] = 0x600DC0DE600DC0DFull; g.dbg[1] = (unsigned long long)gridDim.x * gridDim.y * gridDim.z; }
+  }
 
   // operands whose M / N index is contiguous in memory (transposed A, (K, N) row-major B) are staged MN-major when
   // 128-bit accesses are possible; an MN-major B tile is padded to whole 32-column groups
@@ -312,9 +366,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
   const uint32_t b_tile = B_MN ? (uint32_t)((bn + 31) & ~31) * 128u : (uint32_t)bn * 128u;
   const uint32_t stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // 3xFP16 variant (weight gradients with bounded operands): fp16 tiles are half the bytes, so the same allocation holds
+  // more stages; K blocks stay 32 deep (the live-block enumeration is shared), 2 K steps of 16 per block
+  const bool f16 = A_MN && B_MN && g.f16 != nullptr && g.f16->ok != 0;
+  const uint32_t a_tile16 = 2u * 4096u, b_tile16 = (uint32_t)((bn + 63) / 64) * 4096u, stage16 = 2 * a_tile16 + 2 * b_tile16;
+  const int stages16 = min(MAX_STAGES, (int)(((uint32_t)stages * stage_bytes) / stage16));
+  const int nstg = f16 ? stages16 : stages;
 
   if (tid == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&bar_full[s]), LOADER_WARPS / 2); mbar_init(smem_u32(&bar_empty[s]), 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), LOADER_WARPS / 2); mbar_init(smem_u32(&bar_empty[s]), 1); }
     mbar_init(smem_u32(&bar_accum), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -326,11 +386,33 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
+  if (dbg) dbg[2] = clock64();
 
   if (warp < LOADER_WARPS) {
     // ------------------------------ loaders: two groups alternate K blocks ------------------------------
     const int grp = warp >> 2, t = tid & (GROUP - 1);
-    for (int kb = grp; kb < nkb; kb += 2) {
+    if constexpr (A_MN && B_MN) {
+      if (f16) {
+        const float s_a = g.f16->s_a, s_b = g.f16->s_b;
+        for (int kb = grp; kb < nkb; kb += 2) {
+          int k0, live;
+          kmap_get(km, kb, k0, live);
+          float xa[8][4], xb[16][4];
+          load_mn<8>(xa, g.A, g.lda, m0, m_end, BM, k0, live, t);          // rows k >= live come back as zeros
+          load_mn<16>(xb, g.B, g.ldb, n0, g.N, bn, k0, live, t);
+          const int s = kb % nstg;
+          const uint32_t ph = (uint32_t)(kb / nstg) & 1u;
+          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+          const uint32_t sa = smem0 + (uint32_t)s * stage16;
+          store_mn16<8>(xa, s_a, sa, sa + a_tile16, BM, t);
+          store_mn16<16>(xb, s_b, sa + 2 * a_tile16, sa + 2 * a_tile16 + b_tile16, bn, t);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+        }
+      }
+    }
+    for (int kb = grp; kb < (f16 ? 0 : nkb); kb += 2) {
       int k0, live;
       kmap_get(km, kb, k0, live);
       constexpr int NB_CH = PACKED ? 8 : 16;
@@ -373,10 +455,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
       if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
     }
     // ------------------------------ epilogue ------------------------------
+    if (dbg) dbg[3] = clock64();
     if (nkb > 0) {
       mbar_wait(smem_u32(&bar_accum), 0);
       tc_fence_after();
     }
+    if (dbg) dbg[4] = clock64();
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
     const int m = m0 + quarter * 32 + lane;
     const bool m_ok = m < m_end;
@@ -393,8 +477,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
         const uint32_t ta = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ci * 16);
         tmem_ld16(ta, v);
         tmem_ld16(ta + (uint32_t)bn, w);
+        if (f16) {      // correction passes carry lo' = lo * 2^11; the accumulators are in units of s_a * s_b
+          const float inv = g.f16->inv_unit;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += w[j];
+          for (int j = 0; j < 16; ++j) v[j] = (v[j] + w[j] * (1.f / 2048.f)) * inv;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += w[j];
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -469,9 +559,33 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
         }
       }
     }
+    if (dbg) dbg[5] = clock64();
   } else {
     // ------------------------------ MMA issuer (one lane) ------------------------------
-    if (lane == 0 && nkb > 0) {
+    if (lane == 0 && nkb > 0 && f16) {
+      const uint32_t idesc = make_idesc_f16(bn) | (1u << 15) | (1u << 16);   // both operands MN-major
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % nstg;
+        const uint32_t ph = (uint32_t)(kb / nstg) & 1u;
+        int k0, live;
+        kmap_get(km, kb, k0, live);
+        mbar_wait(smem_u32(&bar_full[s]), ph);
+        tc_fence_after();
+        const uint32_t sa = smem0 + (uint32_t)s * stage16, sb = sa + 2 * a_tile16;
+        const uint64_t a_hi = make_desc_mn16(sa), a_lo = make_desc_mn16(sa + a_tile16);
+        const uint64_t b_hi = make_desc_mn16(sb), b_lo = make_desc_mn16(sb + b_tile16);
+        const int ksteps = (live + 15) / 16;
+        for (int j = 0; j < ksteps; ++j) {
+          const uint64_t adv = (uint64_t)(j * 128);              // 16 k-rows x 128 bytes, >> 4
+          const uint32_t acc = (kb | j) ? 1u : 0u;
+          mma_f16(tmem_d + (uint32_t)bn, a_lo + adv, b_hi + adv, idesc, acc);
+          mma_f16(tmem_d + (uint32_t)bn, a_hi + adv, b_lo + adv, idesc, 1u);
+          mma_f16(tmem_d, a_hi + adv, b_hi + adv, idesc, acc);
+        }
+        mma_commit(smem_u32(&bar_empty[s]));
+      }
+      mma_commit(smem_u32(&bar_accum));
+    } else if (lane == 0 && nkb > 0) {
       const uint32_t idesc = make_idesc_major(bn, A_MN, B_MN);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % stages;

@@ -33,8 +33,6 @@
 //       (non-finite or absurd weights) the device flag `ok` stays 0, this variant exits at once and the 3xTF32
 //       variant, in the same launch does the work (the kernel branches on the flag).
 #pragma once
-#include <cuda_fp16.h>
-
 #include "gemm_tc.cuh"
 
 namespace gac {
@@ -73,27 +71,6 @@ constexpr size_t GRU_PACK_BYTES = (size_t)GRU_NT * 2 * GRU_KB * GRU_BSLOT;   // 
 constexpr int BK16 = 64;                                        // fp16 elements per 128-byte swizzle row
 constexpr int GRU_KB16 = (GAC_E + BK16 - 1) / BK16;             // 7 K blocks per operand half
 constexpr size_t GRU_PACK16_BYTES = (size_t)GRU_NT * 2 * GRU_KB16 * GRU_BSLOT;   // 4.7 MB
-
-__device__ __forceinline__ uint32_t make_idesc_f16(int n) {     // kind::f16: D = F32, A = B = F16 (format 0), K-major
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// x (already scaled) -> fp16 hi and fp16 lo' = (x - hi) * 2^11, two values per 32-bit word
-__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(x0, x1);                   // one cvt.rn.f16x2.f32
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn((x0 - hf.x) * 2048.f, (x1 - hf.y) * 2048.f);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
 
 // Power-of-two scales of the 3xFP16 variant.  Pass 1 (many blocks): maxima of |kx_a|, |U| and of the action-embedding
 // bound into three uint slots (non-negative floats order like their bit patterns; the slots are zeroed before);

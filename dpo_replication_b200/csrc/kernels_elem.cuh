@@ -120,6 +120,22 @@ __device__ __forceinline__ void block_amax(float m, unsigned int* __restrict__ s
   if (threadIdx.x == 0 && sh_amax) atomicMax(slot, sh_amax);
 }
 
+// Scales of the 3xFP16 weight-gradient GEMM dW = X^T dY, right before its launch: |dY| from the producers' running maximum,
+// |X| from a weights-derived bound (bound_x) or a constant (activations in [-1, 1]).  Scaled operands stay below 2^13.
+__global__ void wg_scale_kernel(WgScales* __restrict__ sc, const unsigned int* __restrict__ amax_dy, const unsigned int* __restrict__ bound_x,
+                                float bound_const) {
+  const float ma = __uint_as_float(*amax_dy), mb = bound_x ? __uint_as_float(*bound_x) : bound_const;
+  sc->ok = 0; sc->s_a = sc->s_b = sc->inv_unit = 1.f;
+  if (ma > 0.f && mb > 0.f && ma < 1e30f && mb < 1e30f) {
+    int ea, eb;
+    frexpf(ma, &ea); frexpf(mb, &eb);
+    if (abs(ea) < 100 && abs(eb) < 100) {
+      sc->s_a = ldexpf(1.f, 13 - ea); sc->s_b = ldexpf(1.f, 13 - eb); sc->inv_unit = ldexpf(1.f, ea + eb - 26);
+      sc->ok = 1;
+    }
+  }
+}
+
 // Producer kernels below also emit per-row-block column sums (bias gradients) so that no second
 // pass over the activations is needed.  Layout: block = FB_COLS threads (one column each) x
 // FB_ROWS rows; thread loops over the rows with 4-way ILP; partial sums go to
