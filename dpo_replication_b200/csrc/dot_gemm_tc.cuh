@@ -45,6 +45,7 @@ struct DotGemmArgs {
   float* C; int ldc;
   const float* gate; int ldgate; float gate_alpha;
   int accumulate;
+  int act_lrelu;               // mode 1: y = lrelu_alpha(acc + bias) before gate / accumulate (bias may be nullptr)
 };
 
 constexpr int DOT_STAGES = 2;
@@ -175,11 +176,11 @@ __device__ __forceinline__ void dot_gemm_body(const DotGemmArgs& g) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (g.mode == 0)
+  if (g.mode == 0 || g.bias)
     for (int i = tid; i < bn; i += THREADS) {
       const int n = n0 + i;
-      bias_s[i] = n < g.N ? g.bias[n] : 0.f;
-      w2_s[i] = n < g.N ? g.w2[n] : 0.f;                         // padded columns contribute nothing
+      bias_s[i] = (n < g.N && g.bias) ? g.bias[n] : 0.f;
+      w2_s[i] = (n < g.N && g.w2) ? g.w2[n] : 0.f;               // padded columns contribute nothing
     }
   tc_fence_before();
   __syncthreads();
@@ -270,6 +271,14 @@ __device__ __forceinline__ void dot_gemm_body(const DotGemmArgs& g) {
         if (!m_ok || nb >= g.N) continue;
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = F16 ? (v[q] + w[q] * (1.f / 2048.f)) * inv_unit : v[q] + w[q];
+        if (g.bias) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] += bias_s[ci * 16 + q];
+        }
+        if (g.act_lrelu) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = v[q] > 0.f ? v[q] : alpha * v[q];
+        }
         float* crow = g.C + (size_t)m * g.ldc + nb;
 #pragma unroll
         for (int q = 0; q < 16; q += 4) {

@@ -110,6 +110,7 @@ struct gac_ctx {
   int* seg_info;                                // [unsorted | start[NU] | end[NU]] of the per-state segments (aiqn_bwd)
   // input-gradient GEMMs of the actor's backward on dot_gemm_tc.cuh (store mode): W1^T, U^T, kx_a^T tiles of both variants,
   // scales, and the running |x| maxima written by the kernels that produce their A operands ([0] dmx/dmh, [2] dy1p)
+  unsigned char *w1f_pack32, *w1f_pack16; tc::DotScales* w1f_sc;   // training forward head GEMM (au * W1 + b1, LeakyReLU)
   unsigned char *dg_pack32[3], *dg_pack16[3]; tc::DotScales* dg_sc[3]; unsigned int* dg_amax; bool dg_fused;
   // 3xFP16 weight-gradient GEMMs of the actor (dW1, dU, dkx_a): scales per site, embedding bounds ([1] noise, [3] action)
   WgScales* wg_sc; unsigned int* wg_bound; bool wg_f16; unsigned long long* dbg_buf;
@@ -220,6 +221,9 @@ size_t partition(gac_ctx* c, void* ws) {
     c->dg_sc[i] = b.take<tc::DotScales>(1);
   }
   c->dg_amax = b.take<unsigned int>(4);
+  c->w1f_pack32 = b.take<unsigned char>(tc::dot_pack_bytes(GAC_E, HEAD_BN, HEAD_NT, false));
+  c->w1f_pack16 = b.take<unsigned char>(tc::dot_pack_bytes(GAC_E, HEAD_BN, HEAD_NT, true));
+  c->w1f_sc = b.take<tc::DotScales>(1);
   for (int i = 0; i < 2; ++i) {
     c->cr_pack32[i] = b.take<unsigned char>(tc::dot_pack_bytes(GAC_H1, FNN_BN, FNN_NT, false));
     c->cr_pack16[i] = b.take<unsigned char>(tc::dot_pack_bytes(GAC_H1, FNN_BN, FNN_NT, true));
@@ -431,7 +435,7 @@ int critic_eval(gac_ctx* c, const float* f1, const float* f2, const float* state
         d.rows = n; d.dyn_rows = nullptr; d.seg_rows = 0; d.A = h0[i]; d.lda = GAC_H1; d.K = GAC_H1; d.N = GAC_H2; d.bn = FNN_BN; d.ntiles = FNN_NT;
         d.wpk = c->cr_pack32[i]; d.wpk16 = c->cr_pack16[i]; d.sc = c->cr_sc[i];
         d.bias = fn[i] + off[3]; d.w2 = fn[i] + off[4]; d.alpha = 0.01f; d.part = c->cr_part[i];
-        d.mode = 0; d.C = nullptr; d.ldc = 0; d.gate = nullptr; d.ldgate = 0; d.gate_alpha = 0.f; d.accumulate = 0;
+        d.mode = 0; d.C = nullptr; d.ldc = 0; d.gate = nullptr; d.ldgate = 0; d.gate_alpha = 0.f; d.accumulate = 0; d.act_lrelu = 0;
         GAC_CUDA(launch_dot_gemm(d, st));
         c->launches++;
       }
@@ -502,7 +506,7 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
       q.rows = rows; q.dyn_rows = nullptr; q.A = c->u; q.lda = GAC_E; q.K = GAC_E; q.N = GAC_E; q.bn = HEAD_BN; q.ntiles = HEAD_NT;
       q.wpk = c->head_pack32; q.wpk16 = c->head_pack16; q.sc = tf32_only ? nullptr : c->head_sc;
       q.bias = var(c, actor, 0, GAC_A_B1); q.w2 = var(c, actor, 0, GAC_A_W2); q.alpha = 0.01f; q.part = c->head_part;
-      q.mode = 0; q.seg_rows = 0; q.C = nullptr; q.ldc = 0; q.gate = nullptr; q.ldgate = 0; q.gate_alpha = 0.f; q.accumulate = 0;
+      q.mode = 0; q.seg_rows = 0; q.C = nullptr; q.ldc = 0; q.gate = nullptr; q.ldgate = 0; q.gate_alpha = 0.f; q.accumulate = 0; q.act_lrelu = 0;
       GAC_CUDA(launch_dot_gemm(q, st));
       c->launches++;
       head_finish_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(c->head_part, HEAD_NT, var(c, actor, 0, GAC_A_B2), actions + d, A,
@@ -636,7 +640,11 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
       for (int i = 0; i < 3; ++i)
         GAC_CUDA(dot_pack(W[i], i == 0 ? GAC_E : GAC_G, 1, i == 0 ? GAC_E : GAC_G, GAC_E, HEAD_BN, HEAD_NT, nullptr, nullptr, 0, 0,
                           c->dg_pack32[i], c->dg_pack16[i], c->dg_sc[i], st));
-      c->launches += 12;
+      // forward head GEMM of the training pass: |h * noise_embedding| is bounded by the noise embedding's weights
+      GAC_CUDA(dot_pack(var(c, actor, 0, GAC_A_W1), GAC_E, 0, GAC_E, GAC_E, HEAD_BN, HEAD_NT, var(c, actor, 0, GAC_A_WN), var(c, actor, 0, GAC_A_BN),
+                        GAC_NB, GAC_E, c->w1f_pack32, c->w1f_pack16, c->w1f_sc, st));
+      GAC_CUDA(dot_ascale(c->w1f_sc, nullptr, st));
+      c->launches += 17;
       c->pk[PK_O_W1T] = c->pk[PK_O_UT] = c->pk[PK_O_KXAT] = nullptr;
     } else {
       c->pk[PK_O_W1T] = pack_w(c, PK_O_W1T, var(c, actor, 0, GAC_A_W1), GAC_E, GAC_E, GAC_E, 1, c->Mc);
@@ -676,9 +684,19 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
   GAC_TRY(run_gemm(c, g));
   mul_kernel<<<(unsigned)cdiv64(AM * GAC_E / 4, 256), 256, 0, st>>>(c->ne, c->hall + (size_t)Mc * GAC_E, AM * GAC_E, Mc, live, c->au);
   LAUNCHED(c, "hadamard");
-  g = gemm_args((int)AM, GAC_E, GAC_E, c->au, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->ay1, GAC_E);
-  g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_W1]; g.Bpacked_bn = c->pk_bn[PK_O_W1];
-  GAC_TRY(run_gemm(c, g));
+  if (c->dg_fused) {
+    tc::DotGemmArgs q;
+    q.rows = (int)AM; q.dyn_rows = live; q.seg_rows = Mc; q.A = c->au; q.lda = GAC_E; q.K = GAC_E; q.N = GAC_E; q.bn = HEAD_BN; q.ntiles = HEAD_NT;
+    q.wpk = c->w1f_pack32; q.wpk16 = c->w1f_pack16; q.sc = c->w1f_sc;
+    q.bias = var(c, actor, 0, GAC_A_B1); q.w2 = nullptr; q.alpha = 0.01f; q.part = nullptr;
+    q.mode = 1; q.C = c->ay1; q.ldc = GAC_E; q.gate = nullptr; q.ldgate = 0; q.gate_alpha = 0.f; q.accumulate = 0; q.act_lrelu = 1;
+    GAC_CUDA(launch_dot_gemm(q, st));
+    c->launches++;
+  } else {
+    g = gemm_args((int)AM, GAC_E, GAC_E, c->au, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->ay1, GAC_E);
+    g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_W1]; g.Bpacked_bn = c->pk_bn[PK_O_W1];
+    GAC_TRY(run_gemm(c, g));
+  }
   for (int d = 0; d < A; ++d) {
     rowdot_kernel<<<cdiv(Mc * 32, 256), 256, 0, st>>>(c->ay1 + (size_t)d * Mc * GAC_E, GAC_E, var(c, actor, 0, GAC_A_W2),
                                                      var(c, actor, 0, GAC_A_B2), nullptr, nullptr, nullptr, GAC_E, Mc, 1,
@@ -718,9 +736,10 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
     GAC_CUDA(dot_ascale(c->dg_sc[which], amax, st));
     tc::DotGemmArgs q;
     q.rows = (int)rows; q.dyn_rows = live; q.seg_rows = Mc; q.A = X; q.lda = ldx; q.K = K; q.N = GAC_E; q.bn = HEAD_BN; q.ntiles = HEAD_NT;
-    q.wpk = c->dg_pack32[which]; q.wpk16 = c->dg_pack16[which]; q.sc = c->dg_sc[which];
+    static const bool dg_tf32 = getenv("GAC_DGRAD_TF32") != nullptr;   // A/B switch: same pipeline, 3xTF32 arithmetic
+    q.wpk = c->dg_pack32[which]; q.wpk16 = c->dg_pack16[which]; q.sc = dg_tf32 ? nullptr : c->dg_sc[which];
     q.bias = nullptr; q.w2 = nullptr; q.alpha = 0.f; q.part = nullptr;
-    q.mode = 1; q.C = Cdst; q.ldc = GAC_E; q.gate = gate; q.ldgate = GAC_E; q.gate_alpha = gate_alpha; q.accumulate = accumulate;
+    q.mode = 1; q.C = Cdst; q.ldc = GAC_E; q.gate = gate; q.ldgate = GAC_E; q.gate_alpha = gate_alpha; q.accumulate = accumulate; q.act_lrelu = 0;
     GAC_CUDA(launch_dot_gemm(q, st));
     c->launches += 2;
     return GAC_OK;

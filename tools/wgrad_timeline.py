@@ -12,14 +12,15 @@ import __graft_entry__ as ge  # noqa: E402
 
 ge.build()
 import dpo_replication_b200 as g  # noqa: E402
-from oracle import gac_oracle as O  # noqa: E402  (synthetic batch generator only)
 
 
 def main():
     S, A, B, K = 17, 6, 256, 64
     agent = g.GACAgent(A, S, action_samples=K, batch_size=B, device="cuda")
     rng = np.random.default_rng(0)
-    batch = O.make_batch(rng, S, A, B)
+    batch = dict(s=rng.standard_normal((B, S)).astype(np.float32), a=rng.uniform(-1, 1, (B, A)).astype(np.float32),
+                 r=rng.standard_normal((B, 1)).astype(np.float32), sp=rng.standard_normal((B, S)).astype(np.float32),
+                 it=(rng.uniform(size=(B, 1)) > 0.05).astype(np.float32))
     for _ in range(3):
         agent.train_on_batch(batch)
     torch.cuda.synchronize()
