@@ -113,7 +113,7 @@ struct gac_ctx {
   unsigned char *w1f_pack32, *w1f_pack16; tc::DotScales* w1f_sc;   // training forward head GEMM (au * W1 + b1, LeakyReLU)
   unsigned char *dg_pack32[3], *dg_pack16[3]; tc::DotScales* dg_sc[3]; unsigned int* dg_amax; bool dg_fused;
   // 3xFP16 weight-gradient GEMMs of the actor (dW1, dU, dkx_a): scales per site, embedding bounds ([1] noise, [3] action)
-  WgScales* wg_sc; unsigned int* wg_bound; bool wg_f16; unsigned long long* dbg_buf;
+  WgScales* wg_sc; unsigned int* wg_bound; bool wg_f16; unsigned char* wg_xpack; unsigned long long* dbg_buf;
   // fused tails (400 -> 300 -> 1) of the twin critics in critic_eval
   unsigned char *cr_pack32[2], *cr_pack16[2]; tc::DotScales* cr_sc[2]; float* cr_part[2]; unsigned int* cr_bound;
   // fused actor head of the sampler (dot_gemm_tc.cuh): w1 tiles of both variants, scales, per-row tile partials
@@ -231,6 +231,7 @@ size_t partition(gac_ctx* c, void* ws) {
   }
   c->cr_bound = b.take<unsigned int>(4);
   c->wg_sc = b.take<WgScales>(4); c->wg_bound = b.take<unsigned int>(4);
+  c->wg_xpack = b.take<unsigned char>(wg_pack_x_bytes((long long)AM, GAC_E));
   c->dbg_buf = b.take<unsigned long long>(8 + 8 * 4096);   // per-CTA phase stamps of one GEMM launch (GAC_WGRAD_TIMELINE)
   return (b.off + 255) & ~(size_t)255;
 }
@@ -291,7 +292,8 @@ int run_gemm(gac_ctx* c, GemmArgs g) {
   cudaStream_t st = c->stream;
   if (g.M <= 0 || g.N <= 0) return GAC_OK;
   const WgScales* f16_in = g.f16;
-  g.f16 = nullptr;
+  const unsigned char* bpk_in = g.Bpk16;
+  g.f16 = nullptr; g.Bpk16 = nullptr;
   const bool tc = c->cfg.engine == 0 && tc_gemm_supported(g);
   if (g.valid_on_k || g.K >= 8192) {
     // weight-gradient shape: small output, long reduction over activation rows => split-K.
@@ -303,7 +305,7 @@ int run_gemm(gac_ctx* c, GemmArgs g) {
       w.A = g.B; w.lda = g.ldb; w.transA = 1;      // A'(m', k) = dY[k][m']
       w.B = g.A; w.ldb = g.lda; w.transB = 0;      // B'(k, n') = X[k][n']
       w.transC = 1;                                // C'(m', n') -> dW[n'][m'],  ldc = original N
-      w.f16 = f16_in;                              // the 3xFP16 scales are laid out for this swapped product (A' = dY, B' = X)
+      w.f16 = f16_in; w.Bpk16 = bpk_in;            // the 3xFP16 scales / packed X are laid out for this swapped product (A' = dY, B' = X)
       g = w;
     }
     const int tiles = tc ? cdiv(g.M, tc::BM) * cdiv(g.N, tc::plan_for(g.N).bn) : cdiv(g.M, 128) * cdiv(g.N, 128);
@@ -625,10 +627,12 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
     // the three input-gradient contractions of the backward (x W^T): 3xFP16 with the A bound tracked by the producers
     static const bool off = getenv("GAC_NO_F16_DGRAD") != nullptr;
     c->dg_fused = !off && c->cfg.engine == 0 && c->Mc >= 128 && c->Mc % 128 == 0;
-    // opt-in (GAC_F16_WGRAD=1): validated by the GPU suite, measured no faster -- the weight-gradient GEMMs are bound by
-    // operand delivery (2,000 cycles per K block with 6 or with 12 MMAs, tools/wgrad_timeline.py), not by the tensor pipe
-    static const bool wg_on = getenv("GAC_F16_WGRAD") != nullptr;
-    c->wg_f16 = c->dg_fused && wg_on;
+    // 3xFP16 for the three large weight gradients (dW1, dU, dkx_a): the X operand is pre-split into fp16 tiles once
+    // (wg_pack_x_kernel) and fetched by bulk copies, so only dY goes through registers.  (3xFP16 with both operands
+    // register-staged was no faster than 3xTF32: the loop is bound by the loaders' instruction work, not by the
+    // tensor pipe -- tools/wgrad_timeline.py.)  GAC_NO_F16_WGRAD=1 restores 3xTF32.
+    static const bool wg_off = getenv("GAC_NO_F16_WGRAD") != nullptr;
+    c->wg_f16 = c->dg_fused && !wg_off;
     if (c->wg_f16) {
       GAC_CUDA(cudaMemsetAsync(c->wg_bound, 0, 4 * sizeof(unsigned int), st));
       tc::dot_amax_kernel<<<4, 256, 0, st>>>(nullptr, 0, 0, 0, var(c, actor, 0, GAC_A_WN), var(c, actor, 0, GAC_A_BN), GAC_NB, GAC_E, c->wg_bound);
@@ -724,6 +728,11 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
       wg_scale_kernel<<<1, 1, 0, st>>>(c->wg_sc + site, amax_dy, bound_x, bound_const);
       LAUNCHED(c, "wg_scale");
       g.f16 = c->wg_sc + site;
+      if (dyn && M == GAC_E && ldx == GAC_E && rows == AM && c->cfg.engine == 0) {
+        GAC_CUDA(wg_pack_x(X, ldx, M, Mc, A, live, c->wg_sc + site, c->wg_xpack, st));
+        c->launches++;
+        g.Bpk16 = c->wg_xpack;
+      }
     }
     static const bool timeline = getenv("GAC_WGRAD_TIMELINE") != nullptr;
     if (timeline && site == 2) g.dbg = c->dbg_buf;           // the kx_a weight gradient: (2, 10, splits) CTAs

@@ -75,6 +75,7 @@ struct GemmArgs {
   // 3xFP16 variant of the weight-gradient GEMM (both operands MN-major activations with known magnitude bounds):
   // device struct {s_a, s_b, inv_unit, ok}, nullptr = 3xTF32
   const struct WgScales* f16;
+  const unsigned char* Bpk16;            // 3xFP16 weight gradients: the X operand pre-split into MN-major fp16 tiles (wg_pack_x_kernel)
   int probe;                             // timing experiments only (env GAC_TC_PROBE; results are garbage when set)
 };
 

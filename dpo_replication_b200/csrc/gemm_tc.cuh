@@ -399,13 +399,26 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
           kmap_get(km, kb, k0, live);
           float xa[8][4], xb[16][4];
           load_mn<8>(xa, g.A, g.lda, m0, m_end, BM, k0, live, t);          // rows k >= live come back as zeros
-          load_mn<16>(xb, g.B, g.ldb, n0, g.N, bn, k0, live, t);
+          if (!g.Bpk16) load_mn<16>(xb, g.B, g.ldb, n0, g.N, bn, k0, live, t);
           const int s = kb % nstg;
           const uint32_t ph = (uint32_t)(kb / nstg) & 1u;
           mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
           const uint32_t sa = smem0 + (uint32_t)s * stage16;
+          if (g.Bpk16) {
+            // the X operand was pre-split into fp16 tiles by wg_pack_x_kernel: one bulk copy per K block, no register work
+            if (t == 0) {
+              const uint32_t bytes = 2u * b_tile16;
+              const unsigned char* srcp = g.Bpk16 + ((size_t)(k0 / BK) * gridDim.x + blockIdx.x) * bytes;
+              const uint32_t bar = smem_u32(&bar_full[s]);
+              asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa + 2 * a_tile16),
+                           "l"(srcp), "r"(bytes), "r"(bar)
+                           : "memory");
+            }
+          } else {
+            store_mn16<16>(xb, s_b, sa + 2 * a_tile16, sa + 2 * a_tile16 + b_tile16, bn, t);
+          }
           store_mn16<8>(xa, s_a, sa, sa + a_tile16, BM, t);
-          store_mn16<16>(xb, s_b, sa + 2 * a_tile16, sa + 2 * a_tile16 + b_tile16, bn, t);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
@@ -1137,6 +1150,45 @@ inline cudaError_t tc_pack_b(const float* W, int ld, int transB, int K, int N, u
   if (bn == 0) bn = tc::plan_for(N).bn;
   const long long total = (long long)cdiv(N, bn) * cdiv(K, tc::BK) * bn * 8;
   tc::pack_b_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(W, ld, transB, K, N, bn, out);
+  return cudaGetLastError();
+}
+
+// X operand of a weight-gradient GEMM (activations, (nseg * seg rows, ncols) fp32, the first *live rows of every segment
+// live) -> MN-major fp16 hi / lo' tiles, one [hi | lo] slot per (32-row K block, n-tile): exactly the shared-memory image the
+// 3xFP16 path of gemm_tc_kernel<1,0,1,0> stages for its B operand, so the GEMM fetches it with one bulk copy per K block.
+// Dead K blocks are skipped; rows beyond `live` inside the last live block are zero.
+namespace tc {
+__global__ void wg_pack_x_kernel(const float* __restrict__ X, int ldx, int ncols, int seg, const int* __restrict__ live, const WgScales* __restrict__ sc,
+                                 int bn, int ntiles, unsigned char* __restrict__ out) {
+  const int blk = blockIdx.x, sg = blockIdx.y, j = blockIdx.z;
+  const int nvalid = live ? min(*live, seg) : seg;
+  if (blk * BK >= nvalid || !sc->ok) return;
+  const float scale = sc->s_b;
+  const uint32_t b_tile16 = (uint32_t)((bn + 63) / 64) * 4096u;
+  unsigned char* slot = out + ((size_t)((size_t)sg * (seg / BK) + blk) * ntiles + j) * (2 * (size_t)b_tile16);
+  const int n0 = j * bn, cpr = bn / 4;                          // float4 chunks per k-row of this tile
+  for (int idx = threadIdx.x; idx < BK * cpr; idx += blockDim.x) {
+    const int k = idx / cpr, c4 = idx - k * cpr, n = n0 + 4 * c4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (blk * BK + k < nvalid && n < ncols) v = *reinterpret_cast<const float4*>(X + ((size_t)sg * seg + blk * BK + k) * ldx + n);
+    uint32_t h0, h1, l0, l1;
+    split_f16x2(v.x * scale, v.y * scale, h0, l0);
+    split_f16x2(v.z * scale, v.w * scale, h1, l1);
+    const uint32_t off = (uint32_t)(c4 >> 4) * 4096u + (uint32_t)k * 128u + (uint32_t)(((((c4 & 15) >> 1) ^ (k & 7)) << 4) | ((c4 & 1) << 3));
+    *reinterpret_cast<uint2*>(slot + off) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(slot + b_tile16 + off) = make_uint2(l0, l1);
+  }
+}
+}  // namespace tc
+inline size_t wg_pack_x_bytes(long long rows, int ncols) {
+  const tc::Plan p = tc::plan_for(ncols);
+  return (size_t)(rows / tc::BK) * cdiv(ncols, p.bn) * 2 * (size_t)((p.bn + 63) / 64) * 4096;
+}
+inline cudaError_t wg_pack_x(const float* X, int ldx, int ncols, int seg, int nseg, const int* live, const WgScales* sc, unsigned char* out,
+                             cudaStream_t st) {
+  const tc::Plan p = tc::plan_for(ncols);
+  dim3 grid(seg / tc::BK, nseg, cdiv(ncols, p.bn));
+  tc::wg_pack_x_kernel<<<grid, 256, 0, st>>>(X, ldx, ncols, seg, live, sc, p.bn, cdiv(ncols, p.bn), out);
   return cudaGetLastError();
 }
 
