@@ -317,6 +317,36 @@ def test_actor_loss_and_bptt(gb, engine, S, A, M, nst, live):
     assert_close(ar.named(ar.grad, "actor")["u"].cpu().numpy(), 2 * g_ref["u"], GRAD_RTOL, "accumulate")
 
 
+# The backward's input- and weight-gradient GEMMs run 3xFP16 with scales taken from running maxima of the gradient tensors
+# (chunk sizes that are multiples of 128): the result must be scale-covariant over many orders of magnitude, and all-zero
+# gradients (no usable scale) must fall back cleanly.
+@pytest.mark.parametrize("gscale", [1.0, 1e-7, 3e4, 0.0])
+def test_actor_bptt_gradient_scales(gb, gscale):
+    S, A, M, nst = 17, 6, 256, 24
+    rng = np.random.default_rng(15)
+    p = O.init_actor(rng, S, A, bias_scale=0.05)
+    eng = make_engine(gb, S, A, 128, 1, 0)          # chunk = 2 * 128 * 1 = 256 rows
+    ar = load_actor(gb, S, A, p)
+    su = rng.standard_normal((nst, S)).astype(np.float32)
+    sidx = rng.integers(0, nst, M).astype(np.int32)
+    taus = rng.uniform(size=(M, A)).astype(np.float32)
+    acts = rng.uniform(-1, 1, (M, A)).astype(np.float32)
+    adv = rng.uniform(0.05, 1.0, M).astype(np.float32)
+    base = ar.net_slice(ar.online, "actor")
+    pred = eng.aiqn_supervised_fwd(base, dev(su), dev(sidx, torch.int32), dev(taus), dev(acts))
+    g_ref, _, pred_ref, dpred_ref = O.actor_train_grads(p, su[sidx], acts, adv[:, None], taus, "linear", 1.0, np.float64)
+    assert_close(pred.cpu().numpy(), pred_ref, FWD_RTOL, "supervised forward")
+    eng.aiqn_bwd(base, dev((dpred_ref * gscale).astype(np.float32)), ar.net_slice(ar.grad, "actor"))
+    got = ar.named(ar.grad, "actor")
+    for k, g in g_ref.items():
+        x = got[k].cpu().numpy().reshape(g.shape)
+        assert np.isfinite(x).all(), k
+        if gscale == 0.0:
+            assert float(np.abs(x).max()) == 0.0, k
+        else:
+            assert_close(x / gscale, g, GRAD_RTOL, f"actor grad {k} at gradient scale {gscale}")
+
+
 def test_golden_stage_vectors(gb):
     import importlib.util, os
     here = os.path.dirname(os.path.abspath(__file__))
