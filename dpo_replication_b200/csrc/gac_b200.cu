@@ -474,7 +474,7 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
   const float* kxa = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
   for (int d = 0; d < A; ++d) {
     if (!(d && c->head_fused)) {   // the fused head's finish kernel already wrote cos(a_{d-1})
-      cos_basis_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(d ? actions + d - 1 : nullptr, A, c->cosb, rows, all);
+      cos_basis_kernel<<<cdiv(rows * (GAC_NB / 4), 256), 256, 0, st>>>(d ? actions + d - 1 : nullptr, A, c->cosb, rows, all);
       LAUNCHED(c, "cos_basis");
     }
     GemmArgs g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->ae, GAC_E);
@@ -497,7 +497,7 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
           nullptr, rows, all);
       LAUNCHED(c, "gru_gates_fwd");
     }
-    cos_basis_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(taus + d, A, c->cosb, rows, all);
+    cos_basis_kernel<<<cdiv(rows * (GAC_NB / 4), 256), 256, 0, st>>>(taus + d, A, c->cosb, rows, all);
     LAUNCHED(c, "cos_basis");
     g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->u, GAC_E);
     g.bias = var(c, actor, 0, GAC_A_BN); g.mul = hcur; g.ldmul = GAC_E; g.Bpacked = c->pk[PK_T_WN]; g.Bpacked_bn = c->pk_bn[PK_T_WN];
@@ -511,7 +511,7 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
       q.mode = 0; q.seg_rows = 0; q.C = nullptr; q.ldc = 0; q.gate = nullptr; q.ldgate = 0; q.gate_alpha = 0.f; q.accumulate = 0; q.act_lrelu = 0;
       GAC_CUDA(launch_dot_gemm(q, st));
       c->launches++;
-      head_finish_kernel<<<cdiv(rows * GAC_NB, 256), 256, 0, st>>>(c->head_part, HEAD_NT, var(c, actor, 0, GAC_A_B2), actions + d, A,
+      head_finish_kernel<<<cdiv(rows * (GAC_NB / 4), 256), 256, 0, st>>>(c->head_part, HEAD_NT, var(c, actor, 0, GAC_A_B2), actions + d, A,
                                                                    d + 1 < A ? c->cosb : nullptr, rows);
       LAUNCHED(c, "head_finish");
     } else {
@@ -656,7 +656,7 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
       c->pk[PK_O_KXAT] = pack_w(c, PK_O_KXAT, kxa_w, GAC_G, GAC_G, GAC_E, 1, c->Mc);
     }
   }
-  cos_basis_seq_kernel<<<(unsigned)cdiv64(AM * GAC_NB, 256), 256, 0, st>>>(teacher, taus, A, Mc, c->ca, c->cn, live);
+  cos_basis_seq_kernel<<<(unsigned)cdiv64(AM * (GAC_NB / 4), 256), 256, 0, st>>>(teacher, taus, A, Mc, c->ca, c->cn, live);
   LAUNCHED(c, "cos_basis_seq");
   GemmArgs g = gemm_args((int)AM, GAC_E, GAC_NB, c->ca, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->a_ae, GAC_E);
   g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_WA]; g.Bpacked_bn = c->pk_bn[PK_O_WA];
@@ -856,7 +856,7 @@ int iqn_forward(gac_ctx* c, const float* actor, const float* states_u, int n_sta
   GAC_TRY(run_gemm(c, g));
   for (int r0 = 0; r0 < rows; r0 += c->Rs) {
     const int n = rows - r0 < c->Rs ? rows - r0 : c->Rs;
-    cos_basis_kernel<<<(unsigned)cdiv64((long long)n * A * GAC_NB, 256), 256, 0, st>>>(taus + (size_t)r0 * A, 1, c->iq_cos, n * A, all);
+    cos_basis_kernel<<<(unsigned)cdiv64((long long)n * A * (GAC_NB / 4), 256), 256, 0, st>>>(taus + (size_t)r0 * A, 1, c->iq_cos, n * A, all);
     LAUNCHED(c, "cos_basis");
     g = gemm_args(n * A, d, GAC_NB, c->iq_cos, GAC_NB, ivar(c, actor, GAC_I_WN), d, c->iq_ne, d);
     g.bias = ivar(c, actor, GAC_I_BN); g.act = ACT_LRELU; g.alpha = 0.01f;
@@ -890,7 +890,7 @@ int iqn_train_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_s
   GemmArgs g = gemm_args(Mc, D, S, c->it_x, S, ivar(c, actor, GAC_I_WS), D, c->it_se, D);
   g.bias = ivar(c, actor, GAC_I_BS); g.act = ACT_LRELU; g.alpha = 0.01f; g.dyn_rows = live; g.seg_rows = Mc;
   GAC_TRY(run_gemm(c, g));
-  cos_basis_kernel<<<(unsigned)cdiv64((long long)max_rows * A * GAC_NB, 256), 256, 0, st>>>(taus, 1, c->it_cos, max_rows * A, rvA);
+  cos_basis_kernel<<<(unsigned)cdiv64((long long)max_rows * A * (GAC_NB / 4), 256), 256, 0, st>>>(taus, 1, c->it_cos, max_rows * A, rvA);
   LAUNCHED(c, "cos_basis");
   g = gemm_args(Mc * A, d, GAC_NB, c->it_cos, GAC_NB, ivar(c, actor, GAC_I_WN), d, c->it_ne, d);
   g.bias = ivar(c, actor, GAC_I_BN); g.act = ACT_LRELU; g.alpha = 0.01f; g.dyn_rows = live + 1; g.seg_rows = Mc * A;

@@ -33,12 +33,14 @@ __device__ __forceinline__ float block_sum(float v, float* sh /* >= 32 floats */
 }
 
 // ---- cosine basis: out[r][i] = cos(fl32(x[r*incx] * i_pi[i]))   networks.py:44-47 ----
+// 4 basis functions per thread (one 128-bit store), 16 threads per row.
 __global__ void cos_basis_kernel(const float* __restrict__ x, int incx, float* __restrict__ out, int rows, RowValid rv) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = idx >> 6, i = idx & 63;
+  const int r = idx >> 4, i = (idx & 15) * 4;
   if (r >= rows || !rv(r)) return;
   const float xv = x ? x[(size_t)r * incx] : 0.f;
-  out[idx] = cosf(__fmul_rn(xv, c_ipi[i]));
+  reinterpret_cast<float4*>(out)[idx] = make_float4(cosf(__fmul_rn(xv, c_ipi[i])), cosf(__fmul_rn(xv, c_ipi[i + 1])),
+                                                    cosf(__fmul_rn(xv, c_ipi[i + 2])), cosf(__fmul_rn(xv, c_ipi[i + 3])));
 }
 
 // teacher-forced "shifted action": step d reads action d-1 (0 for d == 0)   networks.py:253-255
@@ -46,15 +48,17 @@ __global__ void cos_basis_kernel(const float* __restrict__ x, int incx, float* _
 __global__ void cos_basis_seq_kernel(const float* __restrict__ teacher, const float* __restrict__ taus, int A, int seg,
                                      float* __restrict__ ca, float* __restrict__ cn, const int* dyn) {
   const int nvalid = dyn ? *dyn : seg;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = idx & 63;
-  const long long rs = idx >> 6;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // 4 basis functions per thread
+  const int i = (int)(idx & 15) * 4;
+  const long long rs = idx >> 4;
   if (rs >= (long long)A * seg) return;
   const int d = rs / seg, r = rs % seg;
   if (r >= nvalid) return;
-  const float prev = d == 0 ? 0.f : teacher[(size_t)r * A + d - 1];
-  ca[idx] = cosf(__fmul_rn(prev, c_ipi[i]));
-  cn[idx] = cosf(__fmul_rn(taus[(size_t)r * A + d], c_ipi[i]));
+  const float prev = d == 0 ? 0.f : teacher[(size_t)r * A + d - 1], tau = taus[(size_t)r * A + d];
+  reinterpret_cast<float4*>(ca)[idx] = make_float4(cosf(__fmul_rn(prev, c_ipi[i])), cosf(__fmul_rn(prev, c_ipi[i + 1])),
+                                                   cosf(__fmul_rn(prev, c_ipi[i + 2])), cosf(__fmul_rn(prev, c_ipi[i + 3])));
+  reinterpret_cast<float4*>(cn)[idx] = make_float4(cosf(__fmul_rn(tau, c_ipi[i])), cosf(__fmul_rn(tau, c_ipi[i + 1])),
+                                                   cosf(__fmul_rn(tau, c_ipi[i + 2])), cosf(__fmul_rn(tau, c_ipi[i + 3])));
 }
 
 // ---- x = concat(states[sidx[r]], actions[r])   networks.py:385 ----
@@ -285,14 +289,16 @@ __global__ void rowdot_kernel(const float* __restrict__ x, int ldx, const float*
 // embedding input, networks.py:44-47 / 208-210), 64 threads per row. ----
 __global__ void head_finish_kernel(const float* __restrict__ part, int ntiles, const float* __restrict__ b2, float* __restrict__ out,
                                    int inc_out, float* __restrict__ cosb, int rows) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = idx >> 6, i = idx & 63;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // 16 threads per row, 4 basis functions each
+  const int r = idx >> 4, i = (idx & 15) * 4;
   if (r >= rows) return;
   float s = part[(size_t)r * ntiles];
   for (int t = 1; t < ntiles; ++t) s += part[(size_t)r * ntiles + t];
   const float a = tanhf(s + b2[0]);
   if (i == 0) out[(size_t)r * inc_out] = a;
-  if (cosb) cosb[idx] = cosf(__fmul_rn(a, c_ipi[i]));
+  if (cosb)
+    reinterpret_cast<float4*>(cosb)[idx] = make_float4(cosf(__fmul_rn(a, c_ipi[i])), cosf(__fmul_rn(a, c_ipi[i + 1])),
+                                                       cosf(__fmul_rn(a, c_ipi[i + 2])), cosf(__fmul_rn(a, c_ipi[i + 3])));
 }
 
 // ---- consumer of the tile partials of the twin critics' fused tails (networks.py:388): q = min over the two nets of
