@@ -116,6 +116,7 @@ struct gac_ctx {
   WgScales* wg_sc; unsigned int* wg_bound; bool wg_f16; unsigned char* wg_xpack; unsigned long long* dbg_buf;
   // fused tails (400 -> 300 -> 1) of the twin critics in critic_eval
   unsigned char *cr_pack32[2], *cr_pack16[2]; tc::DotScales* cr_sc[2]; float* cr_part[2]; unsigned int* cr_bound;
+  float* cr_sx0[2];                             // state half of the critics' first layer per unique state (n_states, 400)
   // fused actor head of the sampler (dot_gemm_tc.cuh): w1 tiles of both variants, scales, per-row tile partials
   unsigned char *head_pack32, *head_pack16; tc::DotScales* head_sc; float* head_part; bool head_fused;
   unsigned char* gru_pack16[2]; tc::GruScales* gru_sc[2];   // 3xFP16 variant: tiles + power-of-two scales (device)
@@ -228,6 +229,7 @@ size_t partition(gac_ctx* c, void* ws) {
     c->cr_pack32[i] = b.take<unsigned char>(tc::dot_pack_bytes(GAC_H1, FNN_BN, FNN_NT, false));
     c->cr_pack16[i] = b.take<unsigned char>(tc::dot_pack_bytes(GAC_H1, FNN_BN, FNN_NT, true));
     c->cr_sc[i] = b.take<tc::DotScales>(1); c->cr_part[i] = b.take<float>((size_t)Rs * FNN_NT);
+    c->cr_sx0[i] = b.take<float>((size_t)c->NUs * GAC_H1);
   }
   c->cr_bound = b.take<unsigned int>(4);
   c->wg_sc = b.take<WgScales>(4); c->wg_bound = b.take<unsigned int>(4);
@@ -404,7 +406,7 @@ int critic_eval(gac_ctx* c, const float* f1, const float* f2, const float* state
   // Fused tail (dot_gemm_tc.cuh): layer 2 + LeakyReLU + output dot in one kernel, 3xFP16 with the bound of the first
   // hidden layer derived from the weights and the batch's states (|action| <= 1).  Needs the number of unique states.
   static const bool off_env = getenv("GAC_NO_FUSED_CRITIC") != nullptr;
-  const bool fused = !off_env && c->cfg.engine == 0 && rows >= 1024 && n_states > 0 && sidx != nullptr;
+  const bool fused = !off_env && c->cfg.engine == 0 && rows >= 1024 && n_states > 0 && n_states <= c->NUs && sidx != nullptr;
   const float* fn[2] = {f1, f2};
   const unsigned char *pk1 = nullptr, *pk2 = nullptr;
   if (fused) {
@@ -416,6 +418,10 @@ int critic_eval(gac_ctx* c, const float* f1, const float* f2, const float* state
                         c->cr_sc[i], st));
       GAC_CUDA(dot_ascale(c->cr_sc[i], c->cr_bound + i, st));
       c->launches += 5;
+      // state half of layer 1, once per unique state: sx0 = s_u W0[:S] + b0
+      GemmArgs g0 = gemm_args(n_states, GAC_H1, S, states_u, S, fn[i] + off[0], GAC_H1, c->cr_sx0[i], GAC_H1);
+      g0.bias = fn[i] + off[1];
+      GAC_TRY(run_gemm(c, g0));
     }
   } else if (rows >= 1024) {
     const int prow = rows < c->Rs ? rows : (rows % c->Rs ? rows % c->Rs : c->Rs);
@@ -424,15 +430,13 @@ int critic_eval(gac_ctx* c, const float* f1, const float* f2, const float* state
   }
   for (int r0 = 0; r0 < rows; r0 += c->Rs) {
     const int n = rows - r0 < c->Rs ? rows - r0 : c->Rs;
-    concat_gather_kernel<<<(unsigned)cdiv64((long long)n * W, 256), 256, 0, st>>>(
-        states_u, sidx ? sidx + r0 : nullptr, actions + (size_t)r0 * A, S, A, n, c->cx);
-    LAUNCHED(c, "concat_gather");
     if (fused) {
       float* h0[2] = {c->ch0a, c->ch0b};
       for (int i = 0; i < 2; ++i) {
-        GemmArgs g = gemm_args(n, GAC_H1, W, c->cx, W, fn[i] + off[0], GAC_H1, h0[i], GAC_H1);
-        g.bias = fn[i] + off[1]; g.act = ACT_LRELU; g.alpha = 0.01f;
-        GAC_TRY(run_gemm(c, g));
+        // layer 1: gathered state half + A FMAs per output (no (S + A)-deep GEMM over every candidate row)
+        fnn_l1_gather_kernel<<<(unsigned)cdiv64((long long)n * (GAC_H1 / 4), 256), 256, 0, st>>>(
+            c->cr_sx0[i], sidx + r0, actions + (size_t)r0 * A, fn[i] + off[0] + (size_t)S * GAC_H1, A, GAC_H1, n, h0[i]);
+        LAUNCHED(c, "fnn_l1_gather");
         tc::DotGemmArgs d;
         d.rows = n; d.dyn_rows = nullptr; d.seg_rows = 0; d.A = h0[i]; d.lda = GAC_H1; d.K = GAC_H1; d.N = GAC_H2; d.bn = FNN_BN; d.ntiles = FNN_NT;
         d.wpk = c->cr_pack32[i]; d.wpk16 = c->cr_pack16[i]; d.sc = c->cr_sc[i];
@@ -445,6 +449,9 @@ int critic_eval(gac_ctx* c, const float* f1, const float* f2, const float* state
       LAUNCHED(c, "critic_finish");
       continue;
     }
+    concat_gather_kernel<<<(unsigned)cdiv64((long long)n * W, 256), 256, 0, st>>>(
+        states_u, sidx ? sidx + r0 : nullptr, actions + (size_t)r0 * A, S, A, n, c->cx);
+    LAUNCHED(c, "concat_gather");
     GAC_TRY(fnn_forward(c, f1, W, c->cx, n, c->ch0a, c->ch1a, pk1, c->pk_bn[PK_C_F1]));
     GAC_TRY(fnn_forward(c, f2, W, c->cx, n, c->ch0b, c->ch1b, pk2, c->pk_bn[PK_C_F2]));
     rowdot_kernel<<<cdiv(n * 32, 256), 256, 0, st>>>(c->ch1a, GAC_H2, f1 + off[4], f1 + off[5], c->ch1b, f2 + off[4],

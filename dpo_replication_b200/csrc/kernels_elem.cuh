@@ -301,6 +301,27 @@ __global__ void head_finish_kernel(const float* __restrict__ part, int ntiles, c
                                                        cosf(__fmul_rn(a, c_ipi[i + 2])), cosf(__fmul_rn(a, c_ipi[i + 3])));
 }
 
+// ---- first hidden layer of an FNN over concat(state, action) with the state half hoisted per unique state
+// (networks.py:385-388): h0[r] = lrelu_0.01( sx0[sidx[r]] + a[r] * W0[S:] ), sx0 = s_u W0[:S] + b0 (n_states rows).
+// One thread per (row, 4 columns): A FMAs per output instead of a (S + A)-deep GEMM over every candidate row. ----
+__global__ void fnn_l1_gather_kernel(const float* __restrict__ sx0, const int* __restrict__ sidx, const float* __restrict__ actions,
+                                     const float* __restrict__ w0a, int A, int H, int rows, float* __restrict__ h0) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int hq = H >> 2;
+  if (idx >= (long long)rows * hq) return;
+  const int r = (int)(idx / hq), c = (int)(idx - (long long)r * hq) * 4;
+  float4 v = *reinterpret_cast<const float4*>(sx0 + (size_t)sidx[r] * H + c);
+  const float* a = actions + (size_t)r * A;
+  for (int i = 0; i < A; ++i) {
+    const float ai = a[i];
+    const float4 w = *reinterpret_cast<const float4*>(w0a + (size_t)i * H + c);
+    v.x = fmaf(ai, w.x, v.x); v.y = fmaf(ai, w.y, v.y); v.z = fmaf(ai, w.z, v.z); v.w = fmaf(ai, w.w, v.w);
+  }
+  v.x = v.x > 0.f ? v.x : 0.01f * v.x; v.y = v.y > 0.f ? v.y : 0.01f * v.y;
+  v.z = v.z > 0.f ? v.z : 0.01f * v.z; v.w = v.w > 0.f ? v.w : 0.01f * v.w;
+  *reinterpret_cast<float4*>(h0 + (size_t)r * H + c) = v;
+}
+
 // ---- consumer of the tile partials of the twin critics' fused tails (networks.py:388): q = min over the two nets of
 // (sum_t part[r][t] + b2) ----
 __global__ void critic_finish_kernel(const float* __restrict__ part1, const float* __restrict__ part2, int ntiles, const float* __restrict__ b2a,
