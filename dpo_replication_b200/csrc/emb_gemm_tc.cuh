@@ -1,0 +1,241 @@
+// CosineBasisLinear as ONE tcgen05 kernel (sm_100a):  C[r, :] = act( cos(x_r * i * pi)_{i=1..64} * W + b ) (* mul[r, :])
+// (networks.py:17-62: the action embedding, LeakyReLU(0.2) outside, and the noise embedding, multiplied by the GRU
+// state right after -- networks.py:208-210, 219-221).
+//
+// As two kernels (cosine basis, then a K = 64 GEMM with 208-wide tiles) this path spent 50-65 us per 32768 rows on 6 us of
+// tensor-core work: every row block was visited twice (two N tiles), the basis went through HBM, and the stores dominate.
+// Here a CTA owns 128 complete rows: the 128 x 64 basis is computed in registers (never stored), W (64 x 400, pre-split fp16
+// hi / lo, 100 KB) arrives by one bulk copy, 24 MMAs (4 K steps x 3 passes x 2 column halves) accumulate all 400 columns in
+// TMEM, and the epilogue applies bias / LeakyReLU / the Hadamard factor and writes the rows: the kernel runs at the speed
+// of its output stream.
+//
+// Arithmetic: 3xFP16 with ONE accumulator.  |cos| <= 1 is scaled by 2^13 and W by a power of two from its scanned maximum
+// (emb_scale_kernel); lo = x' - hi is kept UNSCALED so that all three passes share a unit -- its absolute precision
+// (fp16 subnormal spacing 2^-24 against operands of ~2^13) is 2^-37 relative, and with only 12 MMAs per column the
+// accumulate truncation (<= 12 x 2^-24) needs no separate correction accumulator.  Non-finite / absurd weights clear the
+// device flag and the CTA computes its tile with plain fp32 FMAs instead.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace gac {
+namespace tc {
+
+struct EmbScales { float s_w, inv_unit; int ok; unsigned int amax[2]; int pad[3]; };
+
+struct EmbArgs {
+  int rows;                      // M
+  const int* dyn_rows; int seg_rows;   // optional device row count (rows come in segments of seg_rows, the first *dyn_rows live)
+  const float* x; int incx;      // x_r = x[r * incx]; nullptr = 0 (first action dimension)
+  const unsigned char* wpk;      // emb_pack_kernel output: [hi | lo], 400 rows (n) x 128 bytes (64 k), K-major SWIZZLE_128B
+  const EmbScales* sc;
+  const float* W;                // (64, 400) fp32, for the fallback
+  const float* bias;             // (400)
+  int act; float alpha;          // 1: LeakyReLU(alpha)
+  const float* mul; int ldmul;   // optional (rows, 400) Hadamard factor applied last
+  float* C; int ldc;             // (rows, 400)
+};
+
+constexpr uint32_t EMB_W_TILE = (uint32_t)GAC_E * 128u;          // 51,200 B per hi / lo
+constexpr uint32_t EMB_A_TILE = (uint32_t)BM * 128u;             // 16 KB per hi / lo
+constexpr int EMB_SMEM = 2 * EMB_W_TILE + 2 * EMB_A_TILE + 1024;
+
+__global__ void emb_scale_kernel(EmbScales* __restrict__ sc) {
+  const float mw = __uint_as_float(sc->amax[0]);
+  sc->ok = 0; sc->s_w = 1.f; sc->inv_unit = 1.f;
+  if (mw > 0.f && mw < 1e30f) {
+    int ew;
+    frexpf(mw, &ew);
+    if (abs(ew) < 100) { sc->s_w = ldexpf(1.f, 13 - ew); sc->inv_unit = ldexpf(1.f, ew - 26); sc->ok = 1; }   // |W'| < 2^13, A' = cos * 2^13
+  }
+}
+// W (64, 400) row-major -> fp16 hi | lo (unscaled lo), B-operand image: row n, 16-byte chunk (k / 8) ^ (n & 7)
+__global__ void emb_pack_kernel(const float* __restrict__ W, const EmbScales* __restrict__ sc, unsigned char* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= GAC_E * 8 || !sc->ok) return;
+  const int c = idx & 7, n = idx >> 3;
+  const float s = sc->s_w;
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float x0 = W[(size_t)(8 * c + 2 * e) * GAC_E + n] * s, x1 = W[(size_t)(8 * c + 2 * e + 1) * GAC_E + n] * s;
+    const __half2 hh = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    h[e] = *reinterpret_cast<const uint32_t*>(&hh); l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  const uint32_t off = (uint32_t)n * 128u + (uint32_t)((c ^ (n & 7)) << 4);
+  *reinterpret_cast<uint4*>(out + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(out + EMB_W_TILE + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_acc;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM;
+  int m_end = g.rows;
+  if (g.dyn_rows) {
+    const int nvalid = *g.dyn_rows;
+    if (g.seg_rows > 0) {
+      const int in_seg = m0 % g.seg_rows;
+      if (in_seg >= nvalid) return;
+      m_end = min(g.rows, m0 - in_seg + nvalid);
+    } else {
+      m_end = min(g.rows, nvalid);
+    }
+  }
+  if (m0 >= m_end) return;
+  const bool ok = g.sc->ok != 0;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sw_hi = smem0, sw_lo = smem0 + EMB_W_TILE, sa_hi = smem0 + 2 * EMB_W_TILE, sa_lo = sa_hi + EMB_A_TILE;
+
+  if (!ok) {
+    // fallback: plain fp32 (one thread per (row, column) pair, strided); correct for any finite weights
+    for (int i = tid; i < BM * GAC_E; i += THREADS) {
+      const int r = i / GAC_E, n = i - r * GAC_E, m = m0 + r;
+      if (m >= m_end) continue;
+      const float xv = g.x ? g.x[(size_t)m * g.incx] : 0.f;
+      float acc = 0.f;
+      for (int k = 0; k < GAC_NB; ++k) acc = fmaf(cosf(__fmul_rn(xv, c_ipi[k])), g.W[(size_t)k * GAC_E + n], acc);
+      float v = acc + g.bias[n];
+      if (g.act) v = v > 0.f ? v : g.alpha * v;
+      if (g.mul) v *= g.mul[(size_t)m * g.ldmul + n];
+      g.C[(size_t)m * g.ldc + n] = v;
+    }
+    return;
+  }
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar_w), 1); mbar_init(smem_u32(&bar_a), LOADER_WARPS); mbar_init(smem_u32(&bar_acc), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == LOADER_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  if (warp < LOADER_WARPS) {
+    if (tid == 0) {   // the whole pre-split weight matrix: one bulk copy
+      const uint32_t bar = smem_u32(&bar_w), bytes = 2 * EMB_W_TILE;
+      // the barrier has one pending arrival: this thread's arrive carries the expected byte count
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sw_hi), "l"(g.wpk), "r"(bytes),
+                   "r"(bar)
+                   : "memory");
+    }
+    // ---- the 128 x 64 cosine basis, straight into the A operand: thread = (row, half of the 64 k) ----
+    {
+      const int r = tid >> 1, kh = tid & 1, m = m0 + r;
+      const float xv = (m < m_end && g.x) ? g.x[(size_t)m * g.incx] : 0.f;
+      const bool live = m < m_end;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {            // 16-byte chunks (8 k each) of this thread's half row
+        const int c = kh * 4 + cc;
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = 8 * c + 2 * e;
+          const float x0 = live ? cosf(__fmul_rn(xv, c_ipi[k])) * 8192.f : 0.f, x1 = live ? cosf(__fmul_rn(xv, c_ipi[k + 1])) * 8192.f : 0.f;
+          const __half2 hh = __floats2half2_rn(x0, x1);
+          const float2 hf = __half22float2(hh);
+          const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+          h[e] = *reinterpret_cast<const uint32_t*>(&hh); l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sa_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]));
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sa_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_a));
+    }
+    // ---- epilogue: lane = row, 25 chunks of 16 columns split over the two warp halves ----
+    mbar_wait(smem_u32(&bar_acc), 0);
+    tc_fence_after();
+    const int quarter = warp & 3, hf = warp >> 2;
+    const int m = m0 + quarter * 32 + lane;
+    const bool m_ok = m < m_end;
+    const float inv = g.sc->inv_unit, alpha = g.alpha;
+    constexpr int NCH = GAC_E / 16;                // 25
+    for (int ci = hf ? (NCH + 1) / 2 : 0; ci < (hf ? NCH : (NCH + 1) / 2); ++ci) {
+      float v[16];
+      tmem_ld16(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ci * 16), v);
+      if (!m_ok) continue;
+      const int nb = ci * 16;
+      const float4* b4 = reinterpret_cast<const float4*>(g.bias + nb);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b = b4[q];
+        v[4 * q] = v[4 * q] * inv + b.x; v[4 * q + 1] = v[4 * q + 1] * inv + b.y; v[4 * q + 2] = v[4 * q + 2] * inv + b.z; v[4 * q + 3] = v[4 * q + 3] * inv + b.w;
+      }
+      if (g.act) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = v[q] > 0.f ? v[q] : alpha * v[q];
+      }
+      if (g.mul) {
+        const float4* m4 = reinterpret_cast<const float4*>(g.mul + (size_t)m * g.ldmul + nb);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float4 b = m4[q]; v[4 * q] *= b.x; v[4 * q + 1] *= b.y; v[4 * q + 2] *= b.z; v[4 * q + 3] *= b.w; }
+      }
+      float* crow = g.C + (size_t)m * g.ldc + nb;
+#pragma unroll
+      for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(crow + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+    }
+  } else {
+    if (lane == 0) {
+      mbar_wait(smem_u32(&bar_w), 0);
+      mbar_wait(smem_u32(&bar_a), 0);
+      tc_fence_after();
+      const uint32_t id256 = make_idesc_f16(256), id144 = make_idesc_f16(GAC_E - 256);
+      const uint64_t a_hi = make_desc(sa_hi), a_lo = make_desc(sa_lo);
+      const uint64_t b_hi = make_desc(sw_hi), b_lo = make_desc(sw_lo);
+      const uint64_t nb2 = (uint64_t)((256u * 128u) >> 4);       // second column part: B rows 256..399
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                              // K = 64 = 4 steps of 16
+        const uint64_t adv = (uint64_t)(j * 2);
+        const uint32_t acc = j ? 1u : 0u;
+        mma_f16(tmem_d, a_hi + adv, b_hi + adv, id256, acc);
+        mma_f16(tmem_d, a_lo + adv, b_hi + adv, id256, 1u);
+        mma_f16(tmem_d, a_hi + adv, b_lo + adv, id256, 1u);
+        mma_f16(tmem_d + 256u, a_hi + adv, b_hi + nb2 + adv, id144, acc);
+        mma_f16(tmem_d + 256u, a_lo + adv, b_hi + nb2 + adv, id144, 1u);
+        mma_f16(tmem_d + 256u, a_hi + adv, b_lo + nb2 + adv, id144, 1u);
+      }
+      mma_commit(smem_u32(&bar_acc));
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == LOADER_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512) : "memory");
+  }
+}
+
+}  // namespace tc
+
+inline cudaError_t emb_pack(const float* W, tc::EmbScales* sc, unsigned char* out, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(sc, 0, sizeof(tc::EmbScales), st);
+  if (e != cudaSuccess) return e;
+  tc::dot_amax_kernel<<<16, 256, 0, st>>>(W, GAC_E, GAC_NB, GAC_E, nullptr, nullptr, 0, 0, sc->amax);
+  tc::emb_scale_kernel<<<1, 1, 0, st>>>(sc);
+  tc::emb_pack_kernel<<<cdiv(GAC_E * 8, 256), 256, 0, st>>>(W, sc, out);
+  return cudaGetLastError();
+}
+inline cudaError_t launch_emb_gemm(const tc::EmbArgs& g, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc::emb_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::EMB_SMEM);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  tc::emb_gemm_tc_kernel<<<cdiv(g.rows, tc::BM), tc::THREADS, tc::EMB_SMEM, st>>>(g);
+  return cudaGetLastError();
+}
+
+}  // namespace gac

@@ -13,6 +13,7 @@
 constexpr int FNN_BN = 160, FNN_NT = 2;     // FNN tail: 300 hidden columns in two 160-wide tiles
 constexpr int HEAD_BN = 208, HEAD_NT = 2;   // actor head: 400 hidden columns in two 208-wide tiles (dual accumulators fit TMEM)
 #include "kernels_elem.cuh"
+#include "emb_gemm_tc.cuh"
 
 namespace gac {
 thread_local char g_err[512] = {0};
@@ -114,6 +115,8 @@ struct gac_ctx {
   unsigned char *dg_pack32[3], *dg_pack16[3]; tc::DotScales* dg_sc[3]; unsigned int* dg_amax; bool dg_fused;
   // 3xFP16 weight-gradient GEMMs of the actor (dW1, dU, dkx_a): scales per site, embedding bounds ([1] noise, [3] action)
   WgScales* wg_sc; unsigned int* wg_bound; bool wg_f16; unsigned char* wg_xpack; unsigned long long* dbg_buf;
+  // cosine embeddings of the sampler as one kernel each (emb_gemm_tc.cuh): [0] action embedding, [1] noise embedding
+  unsigned char* emb_pack_buf[2]; tc::EmbScales* emb_sc[2]; bool emb_fused;
   // fused tails (400 -> 300 -> 1) of the twin critics in critic_eval
   unsigned char *cr_pack32[2], *cr_pack16[2]; tc::DotScales* cr_sc[2]; float* cr_part[2]; unsigned int* cr_bound;
   float* cr_sx0[2];                             // state half of the critics' first layer per unique state (n_states, 400)
@@ -232,6 +235,7 @@ size_t partition(gac_ctx* c, void* ws) {
     c->cr_sx0[i] = b.take<float>((size_t)c->NUs * GAC_H1);
   }
   c->cr_bound = b.take<unsigned int>(4);
+  for (int i = 0; i < 2; ++i) { c->emb_pack_buf[i] = b.take<unsigned char>(2 * tc::EMB_W_TILE); c->emb_sc[i] = b.take<tc::EmbScales>(1); }
   c->wg_sc = b.take<WgScales>(4); c->wg_bound = b.take<unsigned int>(4);
   c->wg_xpack = b.take<unsigned char>(wg_pack_x_bytes((long long)AM, GAC_E));
   c->dbg_buf = b.take<unsigned long long>(8 + 8 * 4096);   // per-CTA phase stamps of one GEMM launch (GAC_WGRAD_TIMELINE)
@@ -480,13 +484,27 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
   float* hprev = c->hA; float* hcur = c->hB;
   const float* kxa = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
   for (int d = 0; d < A; ++d) {
-    if (!(d && c->head_fused)) {   // the fused head's finish kernel already wrote cos(a_{d-1})
-      cos_basis_kernel<<<cdiv(rows * (GAC_NB / 4), 256), 256, 0, st>>>(d ? actions + d - 1 : nullptr, A, c->cosb, rows, all);
-      LAUNCHED(c, "cos_basis");
+    GemmArgs g;
+    // cosine embedding (basis + Dense + activation [+ Hadamard]) as one kernel; x_r = x[r * A]
+    auto embed = [&](int which, const float* x, const float* W, const float* bias, int act, float alpha, const float* mul, float* out) -> int {
+      tc::EmbArgs e;
+      e.rows = rows; e.dyn_rows = nullptr; e.seg_rows = 0; e.x = x; e.incx = A; e.wpk = c->emb_pack_buf[which]; e.sc = c->emb_sc[which];
+      e.W = W; e.bias = bias; e.act = act; e.alpha = alpha; e.mul = mul; e.ldmul = GAC_E; e.C = out; e.ldc = GAC_E;
+      GAC_CUDA(launch_emb_gemm(e, st));
+      c->launches++;
+      return GAC_OK;
+    };
+    if (c->emb_fused) {
+      GAC_TRY(embed(0, d ? actions + d - 1 : nullptr, var(c, actor, 0, GAC_A_WA), var(c, actor, 0, GAC_A_BA), 1, 0.2f, nullptr, c->ae));
+    } else {
+      if (!(d && c->head_fused)) {   // the fused head's finish kernel already wrote cos(a_{d-1})
+        cos_basis_kernel<<<cdiv(rows * (GAC_NB / 4), 256), 256, 0, st>>>(d ? actions + d - 1 : nullptr, A, c->cosb, rows, all);
+        LAUNCHED(c, "cos_basis");
+      }
+      g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->ae, GAC_E);
+      g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.Bpacked = c->pk[PK_T_WA]; g.Bpacked_bn = c->pk_bn[PK_T_WA];
+      GAC_TRY(run_gemm(c, g));
     }
-    GemmArgs g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->ae, GAC_E);
-    g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.Bpacked = c->pk[PK_T_WA]; g.Bpacked_bn = c->pk_bn[PK_T_WA];
-    GAC_TRY(run_gemm(c, g));
     if (c->gru_t) {
       // both projections + gates in one kernel: mxa / mh never touch HBM
       GAC_TRY(run_gru_step(c, 0, actor, c->sx_u, sidx, c->ae, d ? hprev : nullptr, hcur, rows, nullptr, nullptr, nullptr, nullptr, nullptr));
@@ -504,11 +522,15 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
           nullptr, rows, all);
       LAUNCHED(c, "gru_gates_fwd");
     }
-    cos_basis_kernel<<<cdiv(rows * (GAC_NB / 4), 256), 256, 0, st>>>(taus + d, A, c->cosb, rows, all);
-    LAUNCHED(c, "cos_basis");
-    g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->u, GAC_E);
-    g.bias = var(c, actor, 0, GAC_A_BN); g.mul = hcur; g.ldmul = GAC_E; g.Bpacked = c->pk[PK_T_WN]; g.Bpacked_bn = c->pk_bn[PK_T_WN];
-    GAC_TRY(run_gemm(c, g));
+    if (c->emb_fused) {
+      GAC_TRY(embed(1, taus + d, var(c, actor, 0, GAC_A_WN), var(c, actor, 0, GAC_A_BN), 0, 0.f, hcur, c->u));
+    } else {
+      cos_basis_kernel<<<cdiv(rows * (GAC_NB / 4), 256), 256, 0, st>>>(taus + d, A, c->cosb, rows, all);
+      LAUNCHED(c, "cos_basis");
+      g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->u, GAC_E);
+      g.bias = var(c, actor, 0, GAC_A_BN); g.mul = hcur; g.ldmul = GAC_E; g.Bpacked = c->pk[PK_T_WN]; g.Bpacked_bn = c->pk_bn[PK_T_WN];
+      GAC_TRY(run_gemm(c, g));
+    }
     if (c->head_fused) {
       static const bool tf32_only = getenv("GAC_HEAD_TF32") != nullptr;
       tc::DotGemmArgs q;
@@ -519,7 +541,7 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
       GAC_CUDA(launch_dot_gemm(q, st));
       c->launches++;
       head_finish_kernel<<<cdiv(rows * (GAC_NB / 4), 256), 256, 0, st>>>(c->head_part, HEAD_NT, var(c, actor, 0, GAC_A_B2), actions + d, A,
-                                                                   d + 1 < A ? c->cosb : nullptr, rows);
+                                                                   (d + 1 < A && !c->emb_fused) ? c->cosb : nullptr, rows);
       LAUNCHED(c, "head_finish");
     } else {
       g = gemm_args(rows, GAC_E, GAC_E, c->u, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->y1, GAC_E);
@@ -540,6 +562,15 @@ int aiqn_sample(gac_ctx* c, const float* actor, const float* states_u, int n_sta
   if (n_states > c->NUs) return fail(GAC_ERR_WORKSPACE, "gac_aiqn_sample: n_states exceeds the workspace capacity");
   GAC_TRY(state_prep(c, actor, states_u, n_states, c->se_u, c->sx_u));
   const int A = c->cfg.A;
+  {
+    static const bool emb_off = getenv("GAC_NO_FUSED_EMB") != nullptr;
+    c->emb_fused = !emb_off && c->cfg.engine == 0 && rows >= 64;
+    if (c->emb_fused) {
+      GAC_CUDA(emb_pack(var(c, actor, 0, GAC_A_WA), c->emb_sc[0], c->emb_pack_buf[0], c->stream));
+      GAC_CUDA(emb_pack(var(c, actor, 0, GAC_A_WN), c->emb_sc[1], c->emb_pack_buf[1], c->stream));
+      c->launches += 6;
+    }
+  }
   c->pk[PK_T_WA] = pack_w(c, PK_T_WA, var(c, actor, 0, GAC_A_WA), GAC_E, GAC_NB, GAC_E, 0, rows);
   c->gru_t = pack_gru(c, 0, actor, rows);
   if (!c->gru_t) {
