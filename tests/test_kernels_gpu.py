@@ -186,7 +186,8 @@ def test_gru_step_operand_scales(gb, s_kx, s_u, s_wa):
 
 
 # the arithmetic variant is chosen once per process from the environment: re-run the actor tests in a child process
-@pytest.mark.parametrize("env", ["GAC_GRU_TF32", "GAC_NO_FUSED_GRU", "GAC_NO_FUSED_HEAD", "GAC_HEAD_TF32", "GAC_NO_F16_DGRAD", "GAC_NO_F16_WGRAD", "GAC_NO_FUSED_EMB"])
+@pytest.mark.parametrize("env", ["GAC_GRU_TF32", "GAC_NO_FUSED_GRU", "GAC_NO_FUSED_HEAD", "GAC_HEAD_TF32", "GAC_NO_F16_DGRAD", "GAC_NO_F16_WGRAD", "GAC_NO_FUSED_EMB", "GAC_NO_FUSED_CRITIC", "GAC_DGRAD_TF32",
+                                 "GAC_NO_SMALL_SPLITK"])
 def test_actor_paths_other_variants(env):
     import os
     import subprocess
@@ -194,9 +195,10 @@ def test_actor_paths_other_variants(env):
     e = dict(os.environ)
     e[env] = "1"
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(root, "tests", "test_kernels_gpu.py"), "-k",
-                        "aiqn_sampler or actor_loss_and_bptt or golden_stage or gru_step_operand"], env=e, cwd=root, capture_output=True,
-                       text=True, timeout=600)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(root, "tests", "test_kernels_gpu.py"),
+                        os.path.join(root, "tests", "test_step_gpu.py"), "-k",
+                        "aiqn_sampler or actor_loss_and_bptt or golden_stage or gru_step_operand or gradient_scales or td_fwd_bwd or "
+                        "pendulum_step or halfcheetah_dims"], env=e, cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
