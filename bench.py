@@ -237,16 +237,20 @@ def run_gpu(args):
     stats_host = torch.zeros(8).pin_memory()
     h2d = sum(v.numel() * 4 for v in pinned.values())
 
+    m_e2e = torch.zeros(1, device=dev)
+
     def e2e_step():
         b = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
         agent.train_on_batch(b)                              # RNG drawn on device, as the reference's tf.random does
         stats_host.copy_(agent.arena.stats, non_blocking=True)
+        m_e2e.add_(agent.arena.stats[5])                     # fresh random draws every step => its own selected-row count
 
     for _ in range(3):
         e2e_step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    m_e2e.zero_()
     e0.record()
     for _ in range(args.steps):
         e2e_step()
@@ -259,7 +263,7 @@ def run_gpu(args):
 
     # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream.
     # AIQN actor on the tcgen05 engine: gru_step_tc_kernel (one GRU step of the sampler on its 2P candidate rows: both
-    # input projections + gates, 3xFP16 arithmetic; profiles/r1b_launches_summary.txt: the largest single kernel of
+    # input projections + gates, 3xFP16 arithmetic; profiles/r1c_launches_summary.txt: the largest single kernel of
     # the step).  Algorithmic flops per launch = 2 * rows * (400 + 400) * 1200 (the GRU's two
     # projections).  Otherwise: the packed-weight GEMM (rows x 400) * (400 x 1200). ----
     roof = None
@@ -343,7 +347,9 @@ def run_gpu(args):
                                "frac_of_3xtf32_peak": f_min / (ms_per_step * 1e-3) / 1e12 / (pk["bf16_sustained"] / 6.0)},
                 "clocks": clk, "gpu_launches": int(launches),
                 "e2e": {"value": pairs_per_step / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms},
+                        "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms,
+                        "selected_rows_mean": float(m_e2e.item()) / args.steps / world,
+                        "note": "fresh device-side random draws every step (the kernel-only loop replays one fixed draw), so the data-dependent number of selected rows differs"},
                 "roofline": roof, "cpu_baseline": cpu, "hbm_kernels": hbm}
         print(json.dumps(line))
     if world > 1:
