@@ -46,6 +46,7 @@ struct DotGemmArgs {
   const float* gate; int ldgate; float gate_alpha;
   int accumulate;
   int act_lrelu;               // mode 1: y = lrelu_alpha(acc + bias) before gate / accumulate (bias may be nullptr)
+  unsigned long long* dbg;     // optional per-CTA phase stamps (GAC_DGRAD_TIMELINE, tools/wgrad_timeline.py --dgrad)
 };
 
 constexpr int DOT_STAGES = 2;
@@ -161,6 +162,14 @@ __device__ __forceinline__ void dot_gemm_body(const DotGemmArgs& g) {
   }
   if (m0 >= m_end) return;
   const int nkb = (g.K + BKE - 1) / BKE;
+  unsigned long long* dbg = (g.dbg && tid == 0) ? g.dbg + 8 + (size_t)blockIdx.x * 8 : nullptr;
+  if (dbg) {
+    unsigned long long gt; unsigned sm;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    dbg[0] = gt; dbg[1] = clock64(); dbg[6] = (unsigned long long)nkb; dbg[7] = sm;
+    if (blockIdx.x == 0) { g.dbg[0] = 0x600DC0DE600DC0DFull; g.dbg[1] = gridDim.x; }
+  }
   const uint32_t stage_bytes = 2 * A_TILE_BYTES + 2 * (uint32_t)bn * 128u;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   float* bias_s = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)) + DOT_STAGES * stage_bytes);
@@ -186,6 +195,7 @@ __device__ __forceinline__ void dot_gemm_body(const DotGemmArgs& g) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
+  if (dbg) dbg[2] = clock64();
 
   if (warp < LOADER_WARPS) {
     // ------------------------------ loaders: two groups alternate K blocks ------------------------------
@@ -253,12 +263,67 @@ __device__ __forceinline__ void dot_gemm_body(const DotGemmArgs& g) {
       if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
     }
     // ------------------------------ epilogue: bias, LeakyReLU, dot with w2 along the row, from TMEM ------------------------------
+    if (dbg) dbg[3] = clock64();
     mbar_wait(smem_u32(&bar_accum), 0);
     tc_fence_after();
+    if (dbg) dbg[4] = clock64();
     const int quarter = warp & 3, hf = warp >> 2;
     const int nch = bn / 16, c0 = hf ? (nch + 1) / 2 : 0, c1 = hf ? nch : (nch + 1) / 2;
     const float inv_unit = F16 ? g.sc->inv_unit : 1.f, alpha = g.alpha;
-    if (g.mode == 1) {
+    if (g.mode == 1 && (g.gate || g.accumulate)) {
+      // store epilogue with per-element operands (gate / accumulate): lane-per-row global loads would serialise a
+      // dependent load -> multiply -> store chain per 16-column chunk (measured 24.6k of a 59k-cycle tile).  Stage the
+      // scaled sums through the idle pipeline smem instead and walk (row, 4 columns) items so that every global access is
+      // row-contiguous and the operand loads of IB items are in flight together.
+      const int SS = bn + 4;                                    // floats; (bn + 4) / 4 is odd => conflict-free 128-bit row stores
+      float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)));
+      {
+        float* srow = stg + (size_t)(quarter * 32 + lane) * SS;
+        for (int ci = c0; ci < c1; ++ci) {
+          float v[16], w[16];
+          const uint32_t ta = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ci * 16);
+          tmem_ld16(ta, v);
+          tmem_ld16(ta + 256u, w);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            float y = F16 ? (v[q] + w[q] * (1.f / 2048.f)) * inv_unit : v[q] + w[q];
+            if (g.bias) y += bias_s[ci * 16 + q];
+            if (g.act_lrelu) y = y > 0.f ? y : alpha * y;
+            v[q] = y;
+          }
+#pragma unroll
+          for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(srow + ci * 16 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int n4 = bn >> 2, total = BM * n4;
+      constexpr int IB = 4;
+      const float ga = g.gate_alpha;
+      for (int i0 = tid; i0 < total; i0 += IB * LOADER_WARPS * 32) {
+        float4 gt[IB], ac[IB];
+        int row[IB], col[IB];
+        bool okk[IB];
+#pragma unroll
+        for (int u = 0; u < IB; ++u) {
+          const int i = i0 + u * LOADER_WARPS * 32;
+          row[u] = i / n4;
+          col[u] = 4 * (i - row[u] * n4);
+          okk[u] = i < total && m0 + row[u] < m_end && n0 + col[u] < g.N;
+          if (!okk[u]) continue;
+          const size_t mrow = (size_t)(m0 + row[u]);
+          if (g.gate) gt[u] = *reinterpret_cast<const float4*>(g.gate + mrow * g.ldgate + n0 + col[u]);
+          if (g.accumulate) ac[u] = *reinterpret_cast<const float4*>(g.C + mrow * g.ldc + n0 + col[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < IB; ++u) {
+          if (!okk[u]) continue;
+          float4 x = *reinterpret_cast<const float4*>(stg + (size_t)row[u] * SS + col[u]);
+          if (g.gate) { x.x *= gt[u].x > 0.f ? 1.f : ga; x.y *= gt[u].y > 0.f ? 1.f : ga; x.z *= gt[u].z > 0.f ? 1.f : ga; x.w *= gt[u].w > 0.f ? 1.f : ga; }
+          if (g.accumulate) { x.x += ac[u].x; x.y += ac[u].y; x.z += ac[u].z; x.w += ac[u].w; }
+          *reinterpret_cast<float4*>(g.C + (size_t)(m0 + row[u]) * g.ldc + n0 + col[u]) = x;
+        }
+      }
+    } else     if (g.mode == 1) {
       // store epilogue: lane = row; 16-column chunks, 128-bit accesses (N, ldc, ldgate multiples of 4, aligned bases)
       const int m = m0 + quarter * 32 + lane;
       const bool m_ok = m < m_end;
@@ -318,6 +383,7 @@ __device__ __forceinline__ void dot_gemm_body(const DotGemmArgs& g) {
       if (m0 + row < m_end) g.part[(size_t)(m0 + row) * g.ntiles + jt] = part_s[row] + part_s[BM + row];
     }
     }
+    if (dbg) dbg[5] = clock64();
   } else {
     // ------------------------------ MMA issuer (one lane) ------------------------------
     if (lane == 0) {

@@ -445,7 +445,7 @@ int critic_eval(gac_ctx* c, const float* f1, const float* f2, const float* state
         d.rows = n; d.dyn_rows = nullptr; d.seg_rows = 0; d.A = h0[i]; d.lda = GAC_H1; d.K = GAC_H1; d.N = GAC_H2; d.bn = FNN_BN; d.ntiles = FNN_NT;
         d.wpk = c->cr_pack32[i]; d.wpk16 = c->cr_pack16[i]; d.sc = c->cr_sc[i];
         d.bias = fn[i] + off[3]; d.w2 = fn[i] + off[4]; d.alpha = 0.01f; d.part = c->cr_part[i];
-        d.mode = 0; d.C = nullptr; d.ldc = 0; d.gate = nullptr; d.ldgate = 0; d.gate_alpha = 0.f; d.accumulate = 0; d.act_lrelu = 0;
+        d.mode = 0; d.C = nullptr; d.ldc = 0; d.gate = nullptr; d.ldgate = 0; d.gate_alpha = 0.f; d.accumulate = 0; d.act_lrelu = 0; d.dbg = nullptr;
         GAC_CUDA(launch_dot_gemm(d, st));
         c->launches++;
       }
@@ -537,7 +537,7 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
       q.rows = rows; q.dyn_rows = nullptr; q.A = c->u; q.lda = GAC_E; q.K = GAC_E; q.N = GAC_E; q.bn = HEAD_BN; q.ntiles = HEAD_NT;
       q.wpk = c->head_pack32; q.wpk16 = c->head_pack16; q.sc = tf32_only ? nullptr : c->head_sc;
       q.bias = var(c, actor, 0, GAC_A_B1); q.w2 = var(c, actor, 0, GAC_A_W2); q.alpha = 0.01f; q.part = c->head_part;
-      q.mode = 0; q.seg_rows = 0; q.C = nullptr; q.ldc = 0; q.gate = nullptr; q.ldgate = 0; q.gate_alpha = 0.f; q.accumulate = 0; q.act_lrelu = 0;
+      q.mode = 0; q.seg_rows = 0; q.C = nullptr; q.ldc = 0; q.gate = nullptr; q.ldgate = 0; q.gate_alpha = 0.f; q.accumulate = 0; q.act_lrelu = 0; q.dbg = nullptr;
       GAC_CUDA(launch_dot_gemm(q, st));
       c->launches++;
       head_finish_kernel<<<cdiv(rows * (GAC_NB / 4), 256), 256, 0, st>>>(c->head_part, HEAD_NT, var(c, actor, 0, GAC_A_B2), actions + d, A,
@@ -731,7 +731,7 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
     q.rows = (int)AM; q.dyn_rows = live; q.seg_rows = Mc; q.A = c->au; q.lda = GAC_E; q.K = GAC_E; q.N = GAC_E; q.bn = HEAD_BN; q.ntiles = HEAD_NT;
     q.wpk = c->w1f_pack32; q.wpk16 = c->w1f_pack16; q.sc = c->w1f_sc;
     q.bias = var(c, actor, 0, GAC_A_B1); q.w2 = nullptr; q.alpha = 0.01f; q.part = nullptr;
-    q.mode = 1; q.C = c->ay1; q.ldc = GAC_E; q.gate = nullptr; q.ldgate = 0; q.gate_alpha = 0.f; q.accumulate = 0; q.act_lrelu = 1;
+    q.mode = 1; q.C = c->ay1; q.ldc = GAC_E; q.gate = nullptr; q.ldgate = 0; q.gate_alpha = 0.f; q.accumulate = 0; q.act_lrelu = 1; q.dbg = nullptr;
     GAC_CUDA(launch_dot_gemm(q, st));
     c->launches++;
   } else {
@@ -787,6 +787,8 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
     q.wpk = c->dg_pack32[which]; q.wpk16 = c->dg_pack16[which]; q.sc = dg_tf32 ? nullptr : c->dg_sc[which];
     q.bias = nullptr; q.w2 = nullptr; q.alpha = 0.f; q.part = nullptr;
     q.mode = 1; q.C = Cdst; q.ldc = GAC_E; q.gate = gate; q.ldgate = GAC_E; q.gate_alpha = gate_alpha; q.accumulate = accumulate; q.act_lrelu = 0;
+    static const bool dg_timeline = getenv("GAC_DGRAD_TIMELINE") != nullptr;
+    q.dbg = (dg_timeline && which == 2) ? c->dbg_buf : nullptr;   // the kx_a input gradient
     GAC_CUDA(launch_dot_gemm(q, st));
     c->launches += 2;
     return GAC_OK;

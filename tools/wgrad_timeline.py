@@ -33,7 +33,7 @@ def main():
     rec = arr[hits[0] + 8: hits[0] + 8 + 8 * n].reshape(n, 8)
     rec = rec[rec[:, 6] > 0]
     d = np.diff(rec[:, 1:6], axis=1)
-    names = ["setup", "loader+MMA loop", "wait last MMAs", "epilogue"]
+    names = ["setup", "loader+MMA loop", "wait last MMAs", "epilogue"]   # (GAC_DGRAD_TIMELINE=1: the kx_a input-gradient dot-GEMM instead)
     print(f"{rec.shape[0]} CTAs with work of {n}; K blocks per CTA: mean {rec[:, 6].mean():.1f}")
     print("  ".join(f"{nm} {d[:, i].mean():9.0f}" for i, nm in enumerate(names)), f"  total {(rec[:, 5] - rec[:, 1]).mean():9.0f} cycles")
     print(f"loop cycles per K block: {(d[:, 1] / rec[:, 6]).mean():.0f}")
