@@ -3,6 +3,7 @@ declares; layout and argument validation need no GPU."""
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -93,3 +94,20 @@ def test_iqn_layout_matches_reference_variable_shapes(lib, S, A):
     assert all(lay.rows[i] == 0 for i in range(8, 13))
     assert lay.net_begin[1] == lay.offsets[13] and lay.net_begin[4] == lay.offsets[31]
     assert lib.lib.gac_layout_ex(S, A, 7, C.byref(lib.Layout())) == -1
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference-equivalent CPU path) prints ONE JSON line with the contract's keys;
+    it needs no GPU and never touches the CUDA library."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "pendulum", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "impl", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "pairs/s"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
