@@ -109,7 +109,7 @@ def test_adam_polyak(gb, engine):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("S,A,rows,nstates", [(3, 1, 64, 64), (17, 6, 300, 10), (11, 3, 129, 129)])
+@pytest.mark.parametrize("S,A,rows,nstates", [(3, 1, 64, 64), (17, 6, 300, 10), (11, 3, 129, 129), (40, 17, 256, 16)])
 def test_aiqn_sampler(gb, engine, S, A, rows, nstates):
     rng = np.random.default_rng(2)
     p = O.init_actor(rng, S, A, bias_scale=0.05)
@@ -279,7 +279,8 @@ def test_td_fwd_bwd(gb, engine, n_in, rows):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("S,A,M,nst,live", [(3, 1, 64, 16, None), (17, 6, 200, 24, None), (9, 3, 256, 256, 131), (5, 2, 128, 8, 0)])
+@pytest.mark.parametrize("S,A,M,nst,live", [(3, 1, 64, 16, None), (17, 6, 200, 24, None), (9, 3, 256, 256, 131), (5, 2, 128, 8, 0),
+                                           (40, 17, 256, 16, 200)])
 def test_actor_loss_and_bptt(gb, engine, S, A, M, nst, live):
     rng = np.random.default_rng(5)
     p = O.init_actor(rng, S, A, bias_scale=0.05)
