@@ -154,37 +154,58 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_a));
     }
-    // ---- epilogue: lane = row, 25 chunks of 16 columns split over the two warp halves ----
+    // ---- epilogue.  The accumulators are read lane-per-row from TMEM; writing (and reading the Hadamard factor) that way
+    // would touch 32 different rows with 16 bytes each per instruction.  Instead the sums go through the now idle weight /
+    // basis smem in two column halves (208 + 192), and (row, 4 columns) items make every global access row-contiguous,
+    // with the Hadamard loads of four items in flight. ----
     mbar_wait(smem_u32(&bar_acc), 0);
     tc_fence_after();
     const int quarter = warp & 3, hf = warp >> 2;
-    const int m = m0 + quarter * 32 + lane;
-    const bool m_ok = m < m_end;
     const float inv = g.sc->inv_unit, alpha = g.alpha;
-    constexpr int NCH = GAC_E / 16;                // 25
-    for (int ci = hf ? (NCH + 1) / 2 : 0; ci < (hf ? NCH : (NCH + 1) / 2); ++ci) {
-      float v[16];
-      tmem_ld16(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ci * 16), v);
-      if (!m_ok) continue;
-      const int nb = ci * 16;
-      const float4* b4 = reinterpret_cast<const float4*>(g.bias + nb);
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)));
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int cbeg = half ? 13 : 0, cend = half ? 25 : 13;      // 16-column chunks of this half: 208 / 192 columns
+      const int wcols = (cend - cbeg) * 16, SS = wcols + 4;       // (wcols + 4) / 4 is odd: conflict-free 128-bit row stores
+      const int nmine = (cend - cbeg + 1 - hf) / 2;               // chunks cbeg + hf, cbeg + hf + 2, ...
+      float* srow = stg + (size_t)(quarter * 32 + lane) * SS;
+      for (int j = 0; j < nmine; ++j) {
+        const int ci = cbeg + hf + 2 * j;
+        float v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ci * 16), v);
+        const float4* b4 = reinterpret_cast<const float4*>(g.bias + ci * 16);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 b = b4[q];
-        v[4 * q] = v[4 * q] * inv + b.x; v[4 * q + 1] = v[4 * q + 1] * inv + b.y; v[4 * q + 2] = v[4 * q + 2] * inv + b.z; v[4 * q + 3] = v[4 * q + 3] * inv + b.w;
+        for (int q = 0; q < 4; ++q) {
+          const float4 bb = b4[q];
+          float4 o = make_float4(v[4 * q] * inv + bb.x, v[4 * q + 1] * inv + bb.y, v[4 * q + 2] * inv + bb.z, v[4 * q + 3] * inv + bb.w);
+          if (g.act) { o.x = o.x > 0.f ? o.x : alpha * o.x; o.y = o.y > 0.f ? o.y : alpha * o.y; o.z = o.z > 0.f ? o.z : alpha * o.z; o.w = o.w > 0.f ? o.w : alpha * o.w; }
+          *reinterpret_cast<float4*>(srow + (ci - cbeg) * 16 + 4 * q) = o;
+        }
       }
-      if (g.act) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int n4 = wcols >> 2, total = BM * n4, col0 = cbeg * 16;
+      constexpr int IB = 4;
+      for (int i0 = tid; i0 < total; i0 += IB * LOADER_WARPS * 32) {
+        float4 ml[IB];
+        int row[IB], col[IB];
+        bool okk[IB];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = v[q] > 0.f ? v[q] : alpha * v[q];
+        for (int u = 0; u < IB; ++u) {
+          const int i = i0 + u * LOADER_WARPS * 32;
+          row[u] = i / n4;
+          col[u] = 4 * (i - row[u] * n4);
+          okk[u] = i < total && m0 + row[u] < m_end;
+          if (okk[u] && g.mul) ml[u] = *reinterpret_cast<const float4*>(g.mul + (size_t)(m0 + row[u]) * g.ldmul + col0 + col[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < IB; ++u) {
+          if (!okk[u]) continue;
+          float4 x = *reinterpret_cast<const float4*>(stg + (size_t)row[u] * SS + col[u]);
+          if (g.mul) { x.x *= ml[u].x; x.y *= ml[u].y; x.z *= ml[u].z; x.w *= ml[u].w; }
+          *reinterpret_cast<float4*>(g.C + (size_t)(m0 + row[u]) * g.ldc + col0 + col[u]) = x;
+        }
       }
-      if (g.mul) {
-        const float4* m4 = reinterpret_cast<const float4*>(g.mul + (size_t)m * g.ldmul + nb);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const float4 b = m4[q]; v[4 * q] *= b.x; v[4 * q + 1] *= b.y; v[4 * q + 2] *= b.z; v[4 * q + 3] *= b.w; }
-      }
-      float* crow = g.C + (size_t)m * g.ldc + nb;
-#pragma unroll
-      for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(crow + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");             // the staging area is rewritten by the second half
     }
   } else {
     if (lane == 0) {
