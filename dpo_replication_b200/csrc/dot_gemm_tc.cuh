@@ -113,7 +113,13 @@ __global__ void dot_amax_kernel(const float* __restrict__ W, int ldw, int wr, in
   if (bad) mw = mb = __int_as_float(0x7f800000);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o)); }
-  if ((threadIdx.x & 31) == 0) { atomicMax(slots, __float_as_uint(mw)); atomicMax(slots + 1, __float_as_uint(mb)); }
+  // one global atomic per block and slot (a thousand same-address atomics serialise at L2 for longer than the scan takes)
+  __shared__ unsigned int sh_max[2];
+  if (threadIdx.x < 2) sh_max[threadIdx.x] = 0u;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { atomicMax(&sh_max[0], __float_as_uint(mw)); atomicMax(&sh_max[1], __float_as_uint(mb)); }
+  __syncthreads();
+  if (threadIdx.x < 2 && sh_max[threadIdx.x]) atomicMax(slots + threadIdx.x, sh_max[threadIdx.x]);
 }
 // weight half of the scales (at pack time): slots[2] = log2 s_w with |W * s_w| in [1, 2), slots[3] = usable
 __global__ void dot_wscale_kernel(DotScales* __restrict__ sc) {

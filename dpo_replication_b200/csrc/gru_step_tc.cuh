@@ -99,9 +99,14 @@ __global__ void gru_amax_kernel(const float* __restrict__ kxa, const float* __re
     mk = fmaxf(mk, __shfl_xor_sync(0xffffffffu, mk, o)); mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, o));
     mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
   }
+  __shared__ unsigned int sh_max[3];                           // one global atomic per block and slot
+  if (threadIdx.x < 3) sh_max[threadIdx.x] = 0u;
+  __syncthreads();
   if ((threadIdx.x & 31) == 0) {
-    atomicMax(slots, __float_as_uint(mk)); atomicMax(slots + 1, __float_as_uint(mu)); atomicMax(slots + 2, __float_as_uint(mb));
+    atomicMax(&sh_max[0], __float_as_uint(mk)); atomicMax(&sh_max[1], __float_as_uint(mu)); atomicMax(&sh_max[2], __float_as_uint(mb));
   }
+  __syncthreads();
+  if (threadIdx.x < 3 && sh_max[threadIdx.x]) atomicMax(slots + threadIdx.x, sh_max[threadIdx.x]);
 }
 __global__ void gru_scales_kernel(const unsigned int* __restrict__ slots, GruScales* __restrict__ out) {
   const float mk = __uint_as_float(slots[0]), mu = __uint_as_float(slots[1]), mb = __uint_as_float(slots[2]);
