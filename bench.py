@@ -34,6 +34,7 @@ CONFIGS = {
     "ant": (111, 8, 16384, 256),          # configs[3]: B is the GLOBAL batch, split over ranks (strong scaling)
     "walker2d": (17, 6, 1000000, 32),     # configs[4]: forward-only sampler sweep over 1M states x 32 + Polyak bandwidth
 }
+CONFIG_NUM = {"pendulum": 1, "halfcheetah": 2, "humanoid": 3, "ant": 4, "walker2d": 5}
 METRIC = "GAC sampled (s,a) pairs/s through full train steps (HalfCheetah dims; steps/s in steps_per_s)"
 
 
@@ -51,9 +52,30 @@ def step_flops(S, A, B, K, M):
     return f_ref, f_min
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE gru_step_tc_kernel launch from the ncu --set full capture
-# (profiles/r1b_gru_step_full_raw.csv), keyed by rows
-GRU_TRAFFIC_BYTES = {32768: 111866368 + 33870336}
+def csrc_hash():
+    """sha256 over the kernel sources: ties a measured-traffic record to the code it was captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "dpo_replication_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(kernel, rows):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel`, from the `ncu --set full` capture that
+    tools/ncu_traffic.py summarised into profiles/traffic.json.  Only returned when that capture was taken from the
+    kernel sources as they are now (same csrc hash); otherwise null -- never a number from older code."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, "no capture"
+    rec = json.load(open(p)).get(kernel)
+    if not rec or rec.get("rows") != rows:
+        return None, "no capture for this kernel / row count"
+    if rec.get("csrc_hash") != csrc_hash():
+        return None, f"capture {rec.get('source')} is from older kernel sources"
+    return rec["dram_bytes_read"] + rec["dram_bytes_write"], rec.get("source")
 
 
 def peaks():
@@ -103,55 +125,90 @@ class ClockSampler:
         return out
 
 
-def synth(S, A, B, K, seed):
-    from oracle import gac_oracle as O   # bench: synthetic-input recipe shared with the tests (not on the timed path)
-    rng = np.random.default_rng(seed)
-    return O.make_batch(rng, S, A, B), O.make_noise(rng, A, B, K)
+def _synth_module():
+    """dpo_replication_b200/synth.py loaded BY PATH (NumPy only): the reference arm must not import the package, which
+    would load libgac_b200.so into the CPU process."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_gac_synth", os.path.join(ROOT, "dpo_replication_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+WEIGHT_SEED = 1234
+
+
+def synth(S, A, B, K, cfg_index, rank):
+    """Initial agent state (identical on every rank and in both arms) and rank `rank`'s replay batch + RNG draws."""
+    sy = _synth_module()
+    nets = sy.agent_state(np.random.default_rng(WEIGHT_SEED), S, A)
+    rng = np.random.default_rng(1000 * cfg_index + rank)         # SURVEY.md 8d: seed = 1000 * config# + rank
+    return nets, sy.replay_batch(rng, S, A, B), sy.step_noise(rng, A, B, K)
+
+
+def bench_config(name, S, A, B, K, world, scaling):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": f"{name}: S={S} A={A} B={B}/GPU K={K} full GAC train step (AIQN actor, twin critic, value)",
+            "global_batch": B * world, "action_samples": K, "parallelism": f"dp{world}", "scaling": scaling,
+            "candidate_rows_per_gpu": 2 * B * K,
+            "l2": "per-step working set (activations saved for BPTT) is GBs >> 126 MB L2; no flush needed",
+            "v_target": "after one step, target/online value.b2 shifted by median(q - v) of that step's candidates (about half are selected)"}
 
 
 # ---------------------------------------------------------------------------------------------
 # reference arm: the reference-equivalent CPU path (TensorFlow is not installable -- DESIGN.md)
 # ---------------------------------------------------------------------------------------------
-def time_cpu_reference(S, A, B, K, steps, warmup, budget_s=None):
+def time_cpu_reference(name, S, A, B, K, steps, warmup, budget_s=None):
+    """The reference-equivalent CPU path (oracle/torch_ref.py: torch-CPU eager, op for op as GAC/networks.py + agent.py)
+    on the SAME initial state, batch, draws and V_target centring as the GPU arm, all host threads."""
     import torch
-    from oracle import gac_oracle as O
     from oracle import torch_ref as T
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    rng = np.random.default_rng(1)
-    nets = O.make_agent(rng, S, A)
-    nets["target_value"]["b2"] = nets["target_value"]["b2"] - np.float32(0.0)
+    nets, batch, noise = synth(S, A, B, K, CONFIG_NUM[name], 0)
     agent = T.TorchGAC(nets, A, K)
-    batch, noise = O.make_batch(rng, S, A, B), O.make_noise(rng, A, B, K)
+    info = agent.train_one_step(batch, noise)                    # the GPU arm's centring step
+    shift = float((info["filter"]["q"] - info["filter"]["v"]).median())
+    with torch.no_grad():
+        agent.n["target_value"]["b2"] += shift
+        agent.n["value"]["b2"] += shift
     for _ in range(warmup):
         agent.train_one_step(batch, noise)
     t0 = time.perf_counter()
-    done = 0
+    done, msum = 0, 0
     for _ in range(steps):
-        agent.train_one_step(batch, noise)
+        msum += agent.train_one_step(batch, noise)["M"]
         done += 1
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return dt / done, done, cores
+    return dt / done, done, cores, msum / done
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     S, A, B, K = CONFIGS[args.config]
-    Bs = min(B, 32)                       # bounded sample: 32 of the 256 states per step, same K
-    sec, done, cores = time_cpu_reference(S, A, Bs, K, args.steps, args.warmup)
-    pairs = 2 * Bs * K / sec
+    scaling = "weak"
+    if args.config == "ant":
+        B, scaling = B // world, "strong"
+    if args.config in ("ant", "walker2d"):
+        print(json.dumps({"impl": "reference", "unavailable": f"the CPU path is timed on the metric's config only, not on --config {args.config}"}))
+        return 0
+    # one step = the full B-state batch of ONE rank (at N = 1: the whole job's batch; at N > 1 the bounded sample is one
+    # rank's shard of the N*B global batch -- the rate, pairs/s, does not depend on the sample size)
+    sec, done, cores, m_mean = time_cpu_reference(args.config, S, A, B, K, args.steps, args.warmup)
+    pairs = 2 * B * K / sec
+    sample = f"{done} full train steps on {B} states x K={K}" + ("" if world == 1 else f" (one rank's shard of the {B * world}-state global batch)")
     line = {"impl": "reference", "metric": METRIC, "value": pairs, "unit": "pairs/s", "n_gpus": args.gpus, "steps": done,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3 * (B / Bs), "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config}: S={S} A={A} B={B} K={K} full GAC train step",
-                       "note": "reference-equivalent CPU path (torch-CPU eager op-for-op mirror; TensorFlow not installable)"},
-            "steps_per_s": 1.0 / (sec * (B / Bs)),
-            "cpu_baseline": {"value": pairs, "unit": "pairs/s", "cores": cores, "kind": "port",
-                             "sample": f"{done} full train steps on {Bs} of the {B} states (K={K}); ms_per_step scaled x{B // Bs} to the full batch"},
+            "config": bench_config(args.config, S, A, B, K, world, scaling),
+            "steps_per_s": 1.0 / sec, "selected_rows_mean": m_mean,
+            "note": "reference-equivalent CPU path (torch-CPU eager op-for-op mirror of GAC/networks.py + agent.py; TensorFlow is not installable here)",
+            "cpu_baseline": {"value": pairs, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": pairs, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -184,9 +241,11 @@ def run_gpu(args):
     if args.config == "ant":              # strong scaling on the fixed global batch
         B, scaling = B // world, "strong"
     P = B * K
-    torch.manual_seed(1234)               # identical replicas
+    torch.manual_seed(1234 + rank)        # device-side draws of the e2e loop differ per rank; the weights come from synth()
     agent = GACAgent(A, S, action_samples=K, batch_size=B, device=dev, engine=args.engine, chunk_rows=args.chunk_rows, actor=args.actor)
-    batch_np, noise_np = synth(S, A, B, K, 1000 * 2 + rank)
+    nets_np, batch_np, noise_np = synth(S, A, B, K, CONFIG_NUM[args.config], rank)
+    if args.actor == "AIQN":
+        agent.load_state(nets_np)         # the same initial state as the reference arm (and on every rank)
     to_dev = lambda d: {k: torch.from_numpy(v).to(dev) for k, v in d.items()}
     batch, noise = to_dev(batch_np), to_dev(noise_np)
 
@@ -294,7 +353,8 @@ def run_gpu(args):
             peak = pk["bf16_burst"] / 3.0
             roof = {"bound": "tensor", "kernel": "gru_step_tc_kernel (3xFP16: kind::f16 MMAs, 3 passes per product)",
                     "shape": f"rows={rows}: [ae | h_prev] ({rows}x800) * [kx_a ; U] (800x1200) + gates", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": GRU_TRAFFIC_BYTES.get(rows), "ms_per_launch": kms,
+                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": measured_traffic("gru_step_tc_kernel", rows)[0],
+                    "traffic_source": measured_traffic("gru_step_tc_kernel", rows)[1], "ms_per_launch": kms,
                     "algorithmic_bytes": rows * 400 * 4 * 3,
                     "peak_source": f"{pk['source']} bf16 burst {pk['bf16_burst']} TF/s / 3 (three fp16 passes per fp32 product)"}
         else:
@@ -322,39 +382,118 @@ def run_gpu(args):
     hbm = hbm_kernels(agent, dev) if (rank == 0 and world == 1) else None
     if world > 1:
         dist.barrier()
+    ant = None
+    if args.config == "halfcheetah" and args.actor == "AIQN" and not args.no_ant:
+        try:
+            ant = ant_strong_probe(dev, rank, world, engine=args.engine)
+        except Exception as exc:                                         # the probe must never take the headline line down
+            ant = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if rank == 0:
         pairs_per_step = 2 * P * world
         value = pairs_per_step / (ms_per_step * 1e-3)
         f_ref, f_min = step_flops(S, A, B, K, m_mean) if args.actor == "AIQN" else (float("nan"), float("nan"))
         pk = peaks()
         cpu = None
-        if world == 1 and not args.no_cpu_baseline and args.actor == "AIQN":
-            Bs = min(B, 32)
-            sec, done, cores = time_cpu_reference(S, A, Bs, K, steps=20, warmup=1, budget_s=15.0)
-            cpu = {"value": 2 * Bs * K / sec, "unit": "pairs/s", "cores": cores, "kind": "port",
-                   "sample": f"{done} full train steps of the reference-equivalent torch-CPU path on {Bs} of the {B} states (K={K})"}
+        if world == 1 and not args.no_cpu_baseline and args.actor == "AIQN" and args.config in ("halfcheetah", "pendulum"):
+            sec, done, cores, m_cpu = time_cpu_reference(args.config, S, A, B, K, steps=20, warmup=0, budget_s=15.0)
+            cpu = {"value": 2 * B * K / sec, "unit": "pairs/s", "cores": cores, "kind": "port", "selected_rows_mean": m_cpu,
+                   "sample": f"{done} full train steps of the reference-equivalent torch-CPU path on the same {B} states x K={K}, same initial state, draws and V_target centring"}
+        cfg = bench_config(args.config, S, A, B, K, world, scaling)
+        tf = f_min * world / (ms_per_step * 1e-3) / 1e12
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": f"{args.config}: S={S} A={A} B={B}/GPU K={K} full GAC train step (AIQN actor, twin critic, value)",
-                           "global_batch": B * world, "action_samples": K, "parallelism": f"dp{world}",
-                           "selected_rows_mean": m_mean, "candidate_rows": 2 * P,
-                           "l2": "per-step working set (activations saved for BPTT) is GBs >> 126 MB L2; no flush needed",
-                           "engine": "tcgen05 3xTF32 GEMMs, 3xFP16 GRU step" if args.engine == 0 else "SIMT fp32", "actor": args.actor},
+                "data": "synthetic", "config": cfg,
+                "engine": "tcgen05: 3xFP16 (kind::f16) GRU step / heads / dgrads / large wgrads, 3xTF32 elsewhere" if args.engine == 0 else "SIMT fp32",
+                "actor": args.actor, "selected_rows_mean": m_mean, "candidate_rows": 2 * P, "graph": bool(args.graph),
                 "steps_per_s": 1e3 / ms_per_step,
                 "step_flops": {"algorithmic_gflop_min": f_min / 1e9, "as_written_gflop": f_ref / 1e9,
-                               "achieved_tflops_min": f_min * world / (ms_per_step * 1e-3) / 1e12,
-                               "frac_of_3xtf32_peak": f_min / (ms_per_step * 1e-3) / 1e12 / (pk["bf16_sustained"] / 6.0)},
+                               "achieved_tflops_min": tf,
+                               # the hot kernels issue kind::f16 MMAs (3 passes per fp32 product): that is the honest whole-step ceiling
+                               "frac_of_3xf16_sustained_peak": tf / world / (pk["bf16_sustained"] / 3.0),
+                               "frac_of_3xtf32_sustained_peak": tf / world / (pk["bf16_sustained"] / 6.0),
+                               "note": "3xf16: bf16_sustained / 3 (the issued MMA kind of the dominant kernels); 3xtf32: bf16_sustained / 6 (what a pure kind::tf32 path could reach)"},
                 "clocks": clk, "gpu_launches": int(launches),
                 "e2e": {"value": pairs_per_step / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms,
                         "selected_rows_mean": float(m_e2e.item()) / args.steps / world,
                         "note": "fresh device-side random draws every step (the kernel-only loop replays one fixed draw), so the data-dependent number of selected rows differs"},
                 "roofline": roof, "cpu_baseline": cpu, "hbm_kernels": hbm}
+        if ant is not None:
+            line["ant_strong"] = ant
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ant_strong_probe(dev, rank, world, steps=2, engine=0):
+    """configs[3]: Ant-v2 dims, GLOBAL batch 16384 states x K=256 samples split over the ranks (strong scaling: the job
+    is fixed, each rank takes 16384 / N states), full train steps with the NCCL SUM all-reduce.  Carried in every bench
+    line so that the driver's N = 1, 2, 4, 8 runs give the strong-scaling curve; per-rank selected rows show the load
+    imbalance the data-dependent filter causes."""
+    import torch
+    import torch.distributed as dist
+    from dpo_replication_b200 import GACAgent
+    S, A, BG, K = CONFIGS["ant"]
+    B = BG // world
+    P = B * K
+    nets = _synth_module().agent_state(np.random.default_rng(WEIGHT_SEED), S, A)
+    agent = GACAgent(A, S, action_samples=K, batch_size=B, device=dev, engine=engine)
+    agent.load_state(nets)
+    g = torch.Generator(device=dev).manual_seed(4000 + rank)
+    r = lambda *sh: torch.rand(*sh, device=dev, generator=g)
+    n = lambda *sh: torch.randn(*sh, device=dev, generator=g)
+    batch = dict(s=n(B, S), a=r(B, A) * 2 - 1, r=n(B, 1), sp=n(B, S), it=(r(B, 1) < 0.05).float())
+    noise = dict(critic_u=r(B, A), value_tau=r(P, A), filter_tau=r(P, A), filter_normal=n(P, A), filter_rand=r(P, A) * 2 - 1,
+                 actor_tau=r(2 * P, A))
+    taps = dict(q_out=torch.zeros(2 * P, device=dev), v_out=torch.zeros(2 * P, device=dev))
+    agent.train_on_batch(batch, noise, taps)
+    shift = (taps["q_out"] - taps["v_out"]).median()
+    if world > 1:
+        dist.all_reduce(shift)
+        shift /= world
+    for buf in (agent.arena.target, agent.arena.online):
+        agent.arena.view(buf, "value.b2").add_(shift)
+    del taps
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    m_local = torch.zeros(1, device=dev)
+    agent.train_on_batch(batch, noise)                                   # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    io = agent.engine.step_io(agent.arena, batch, noise)
+    t_grads = 0.0
+    e[0].record()
+    for _ in range(steps):
+        # the two phases timed apart: gradients (rank-local, data dependent) and exchange + update
+        e[2].record()
+        agent.engine.step_grads(io, agent._hp)
+        e[3].record()
+        m_local.add_(agent.arena.stats[5])                               # local M, before the all-reduce sums it
+        if world > 1:
+            dist.all_reduce(agent.arena.grad)
+        agent.engine.step_apply(io, agent._hp)
+        e[3].synchronize()
+        t_grads += e[2].elapsed_time(e[3])
+    e[1].record()
+    torch.cuda.synchronize()
+    per = torch.tensor([e[0].elapsed_time(e[1]) / steps, t_grads / steps, float(m_local.item()) / steps], device=dev)
+    allr = [torch.zeros_like(per) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allr, per)
+    else:
+        allr = [per]
+    ms = max(float(x[0]) for x in allr)
+    _, f_min = step_flops(S, A, B, K, float(per[2]))
+    out = {"workload": f"ant: S={S} A={A} global batch {BG} states x K={K}, {B} states per GPU, full GAC train step",
+           "scaling": "strong", "n_gpus": world, "steps": steps, "ms_per_step": ms, "pairs_per_s": 2 * BG * K / (ms * 1e-3),
+           "grads_phase_ms_per_rank": [float(x[1]) for x in allr], "selected_rows_per_rank": [float(x[2]) for x in allr],
+           "candidate_rows_per_rank": 2 * P, "achieved_tflops_min_rank0": f_min / (float(per[1]) * 1e-3) / 1e12,
+           "note": "ms_per_step = slowest rank (max over ranks, CUDA events); grads phase excludes the all-reduce and the optimiser"}
+    del agent, batch, noise
+    torch.cuda.empty_cache()
+    return out
 
 
 def hbm_kernels(agent, dev, reps=10):
@@ -444,6 +583,8 @@ def main():
     ap.add_argument("--engine", type=int, default=0, help="0 = tcgen05 3xTF32 GEMMs, 1 = SIMT fp32")
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ant", action="store_true", help="skip the Ant strong-scaling probe (ant_strong key)")
+    ap.add_argument("--graph", type=int, default=0, help="1 = replay the train step from a CUDA graph")
     ap.add_argument("--actor", default="AIQN", choices=["AIQN", "IQN"], help="AIQN = BASELINE.json's actor; IQN = the reference CLI default (main.py:78)")
     ap.add_argument("--sweep-chunks", type=int, default=0, help="walker2d sweep: number of 4096-state chunks (0 = all 1M states)")
     args = ap.parse_args()

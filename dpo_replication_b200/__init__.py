@@ -8,9 +8,9 @@ from . import _lib  # noqa: F401  (loads the shared library or raises)
 from .agent import GACAgent
 from .engine import Arena, Engine
 from .helpers import ActionSampler, DeviceReplayBuffer, ReplayBuffer, denormalize, normalize, update
-from .utils import load_checkpoint, load_model, save_checkpoint, save_model
+from .utils import RunningMeanStd, load_checkpoint, load_model, save_checkpoint, save_model
 from .networks import (FNN, AutoRegressiveStochasticActor, CosineBasisLinear, Critic, IQNActor, StochasticActor, Value)
 
 __all__ = ["GACAgent", "Arena", "Engine", "ActionSampler", "ReplayBuffer", "DeviceReplayBuffer", "update", "normalize", "denormalize", "FNN",
            "AutoRegressiveStochasticActor", "CosineBasisLinear", "Critic", "IQNActor", "StochasticActor", "Value", "save_model", "load_model",
-           "save_checkpoint", "load_checkpoint"]
+           "save_checkpoint", "load_checkpoint", "RunningMeanStd"]

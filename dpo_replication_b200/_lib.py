@@ -68,6 +68,7 @@ SIGNATURES = {
     "gac_workspace_bytes": (C.c_size_t, [C.POINTER(Config)]),
     "gac_create": (C.c_int, [C.POINTER(Config), _P, C.c_size_t, _P, C.POINTER(_P)]),
     "gac_destroy": (None, [_P]),
+    "gac_set_stream": (C.c_int, [_P, _P]),
     "gac_last_error": (C.c_char_p, []),
     "gac_abi_version": (C.c_int, []),
     "gac_polyak": (C.c_int, [_P, _P, _L, _F, _P]),

@@ -11,6 +11,7 @@ from . import dist as gdist
 from .engine import Arena, Engine, f32, keras_default_init
 from .helpers import ActionSampler, DeviceReplayBuffer, ReplayBuffer, normalize, update
 from .networks import AutoRegressiveStochasticActor, Critic, StochasticActor, Value
+from .utils import RunningMeanStd
 
 
 class GACAgent:
@@ -26,10 +27,10 @@ class GACAgent:
         if actor not in ('AIQN', 'IQN'):
             raise NotImplementedError("actor must be 'AIQN' or 'IQN' (agent.py:65-70)")
         self.actor_kind = 1 if actor == 'IQN' else 0
-        if normalize_obs or normalize_rewards:
-            raise NotImplementedError("RunningMeanStd normalisation is out of scope (off by default, agent.py:25)")
-        self.obs_rms = None
-        self.ret_rms = None
+        # agent.py:72-80: running statistics of observations / discounted returns (utils/utils.py:41-56)
+        self.obs_rms = RunningMeanStd(shape=state_dim) if normalize_obs else None
+        self.ret_rms = RunningMeanStd(shape=1) if normalize_rewards else None
+        self.ret = 0
         if not torch.cuda.is_available():
             raise RuntimeError("dpo_replication_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -55,6 +56,7 @@ class GACAgent:
         self.replay = DeviceReplayBuffer(S, A, buffer_size, self.device) if replay_on_device else ReplayBuffer(S, A, buffer_size)
         self.action_sampler = ActionSampler(self.actor.action_dim)
         self._hp = self.engine.hparams(gamma, tau, q_normalization, beta, mode)
+        gdist.broadcast_state(self.arena)       # data-parallel replicas must start from identical parameters
 
     # ---- weights in / out (parity harness) ------------------------------------------------
     def load_state(self, nets: Dict[str, Dict[str, np.ndarray]]):
@@ -68,6 +70,7 @@ class GACAgent:
                 ar.load(ar.adam_v, name, nets["v_" + name])
         ts = [int(nets.get("t_" + n, 0)) for n in ("actor", "fnn1", "fnn2", "value")]
         ar.adam_t.copy_(torch.tensor(ts, dtype=torch.int32))
+        gdist.broadcast_state(ar)
 
     def dump_state(self):
         ar = self.arena
@@ -183,5 +186,12 @@ class GACAgent:
         return torch.clamp(action, -1, 1)
 
     def store_transition(self, state, action, reward, next_state, is_done):
-        """agent.py:250-268 (normalisation statistics are out of scope, see __init__)."""
+        """agent.py:250-268."""
         self.replay.store(state, action, reward, next_state, is_done)
+        if self.normalize_observations:
+            self.obs_rms.update(state)
+        if self.normalize_rewards:
+            self.ret = self.ret * self.gamma + reward
+            self.ret_rms.update(np.array([self.ret]))
+            if is_done:
+                self.ret = 0

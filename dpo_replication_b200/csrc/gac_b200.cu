@@ -144,6 +144,8 @@ int derive(gac_ctx* c) {
   if (f.S <= 0 || f.A <= 0 || f.B <= 0 || f.K <= 0) return fail(GAC_ERR_INVALID, "gac_config: S, A, B, K must be positive");
   const int64_t P = (int64_t)f.B * f.K;
   if (3 * P > (int64_t)1 << 30) return fail(GAC_ERR_INVALID, "gac_config: B*K too large");
+  // the per-state gradient reduction keeps one shared-memory counter per unique state (seg_hist_kernel)
+  if (f.B > 50 * 1024) return fail(GAC_ERR_INVALID, "gac_config: B (states per rank) must be <= 51200; shard the batch over more ranks");
   c->P = (int)P;
   int mc = f.chunk_rows > 0 ? f.chunk_rows : (int)(2 * P < 65536 ? 2 * P : 65536);
   c->Mc = round_up(mc, 128);
@@ -862,6 +864,14 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   // rows grouped by state with a stable counting sort (block histograms -> scan -> ranked scatter), then one block
   // per (state, column slab) streams exactly its rows in ascending row order: deterministic, no atomics on floats
   const int nsb = cdiv(Mc, SEG_BLOCK);
+  {
+    // one int of shared memory per unique state: above the 48 KB default the opt-in limit has to be raised (derive() caps B)
+    static size_t hist_attr = 48 * 1024;
+    if (NU * sizeof(int) > hist_attr) {
+      GAC_CUDA(cudaFuncSetAttribute(seg_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NU * sizeof(int))));
+      hist_attr = NU * sizeof(int);
+    }
+  }
   seg_hist_kernel<<<nsb, SEG_BLOCK, NU * sizeof(int), st>>>(c->bwd_sidx, Mc, live, NU, c->seg_hist);
   LAUNCHED(c, "seg_hist");
   seg_scan_kernel<<<1, 1024, 0, st>>>(c->seg_hist, nsb, NU, c->seg_info);
@@ -1056,6 +1066,11 @@ int gac_create(const gac_config_t* cfg, void* workspace, size_t workspace_bytes,
 }
 
 void gac_destroy(gac_ctx_t* ctx) { delete ctx; }
+int gac_set_stream(gac_ctx_t* ctx, void* stream) {
+  if (!ctx) return fail(GAC_ERR_INVALID, "gac_set_stream: null context");
+  ctx->stream = reinterpret_cast<cudaStream_t>(stream);
+  return GAC_OK;
+}
 int64_t gac_launch_count(const gac_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
 
 int gac_polyak(float* target, const float* source, int64_t n, float rho, void* stream) {
@@ -1273,7 +1288,7 @@ int gac_step_grads(gac_ctx_t* c, const gac_step_io_t* io, const gac_hparams_t* h
   LAUNCHED(c, "gather_v");
   GAC_TRY(compact(c, c->q3 + P, c->v2, 2 * P, c->idx_sel, c->pos, c->m_dev, c->sum_adv, c->adv_sel, c->cand + (size_t)P * A, A,
                   c->act_sel, c->sidx3 + P, c->sidx_sel));
-  chunk_rows_kernel<<<1, 1024, 0, st>>>(c->m_dev, Mc, c->nchunks, c->rows_c);
+  chunk_rows_kernel<<<cdiv(c->nchunks, 1024), 1024, 0, st>>>(c->m_dev, Mc, c->nchunks, c->rows_c);
   LAUNCHED(c, "chunk_rows");
   stats_m_kernel<<<1, 32, 0, st>>>(c->m_dev, stats);
   LAUNCHED(c, "stats_m");

@@ -807,8 +807,11 @@ __global__ void replay_gather_kernel(const float* __restrict__ obs1, const float
 // ---- step glue: chunk row counts and the actor gradient normalisation ----
 // rows_c[c] = clamp(M - c*chunk, 0, chunk)
 __global__ void chunk_rows_kernel(const int* __restrict__ m, int chunk, int nchunks, int* __restrict__ rows_c) {
-  const int c = threadIdx.x;
-  if (c < nchunks) rows_c[c] = max(0, min(chunk, *m - c * chunk));
+  const int M = *m;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += gridDim.x * blockDim.x) {
+    const long long left = (long long)M - (long long)c * chunk;      // c * chunk can pass 2^31 with small chunks
+    rows_c[c] = (int)(left < 0 ? 0 : (left > chunk ? chunk : left));
+  }
 }
 // stats (after the cross-rank SUM) -> gscale[4], skip[4].  IQNActor.train: weights = adv/sum(adv)
 // (linear) or 1 (boltzmann, F6); loss = mean over M*A (networks.py:91,93,120); agent.py:158 skip.

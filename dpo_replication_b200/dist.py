@@ -24,6 +24,14 @@ def allreduce_grads(flat: torch.Tensor) -> torch.Tensor:
     return flat
 
 
+def broadcast_state(arena, src: int = 0):
+    """Make every replica start from rank `src`'s parameters, targets, Adam moments and step counters.  Replicas only
+    stay identical if they start identical: the train step exchanges gradients, never parameters."""
+    if world()[1] > 1:
+        for t in (arena.online, arena.target, arena.adam_m, arena.adam_v, arena.adam_t):
+            dist.broadcast(t, src=src)
+
+
 def shard_rows(n: int, rank: int, world_size: int) -> slice:
     """Contiguous shard of `n` replay states for `rank` (n must divide evenly)."""
     if n % world_size:

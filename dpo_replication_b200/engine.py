@@ -107,8 +107,21 @@ def keras_default_init(S: int, A: int, net: str, generator=None) -> Dict[str, to
             "w2": glorot(300, 1), "b2": torch.zeros(1)}
 
 
+def _on_stream(fn):
+    """Entry-point wrapper: make the engine's device current and bind the context to torch's CURRENT stream
+    (so a caller inside `torch.cuda.stream(...)` / a graph capture gets stream-ordered work)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.device):
+            self.bind_current_stream()
+            return fn(self, *a, **k)
+    return wrapped
+
+
 class Engine:
-    """One gac_ctx bound to the current torch CUDA stream."""
+    """One gac_ctx; every call runs on torch's current stream of the engine's device."""
 
     def __init__(self, S: int, A: int, B: int, K: int, device=None, chunk_rows: int = 0, engine: int = 0, actor_kind: int = 0):
         _require_cuda()
@@ -144,6 +157,16 @@ class Engine:
     def launch_count(self) -> int:
         return int(lib.gac_launch_count(self.h))
 
+    def bind_current_stream(self):
+        """Re-bind the context when torch's current stream changed since the last call; the new stream first waits
+        for everything queued on the old one (the workspace is shared)."""
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != self.stream.cuda_stream:
+            if not torch.cuda.is_current_stream_capturing():
+                cur.wait_stream(self.stream)
+            check(lib.gac_set_stream(self.h, C.c_void_p(cur.cuda_stream)))
+            self.stream = cur
+
     def hparams(self, gamma=0.99, rho=5e-3, q_normalization=0.01, beta=1.0, mode="linear", lr=1e-4, beta1=0.9,
                 beta2=0.999, eps=1e-7) -> HParams:
         if mode not in MODES:
@@ -151,20 +174,24 @@ class Engine:
         return HParams(gamma, rho, q_normalization, beta, MODES[mode], lr, beta1, beta2, eps)
 
     # ---- entry points -----------------------------------------------------------------
+    @_on_stream
     def polyak(self, target: torch.Tensor, source: torch.Tensor, rho: float):
         assert target.numel() == source.numel()
         check(lib.gac_polyak(ptr(target), ptr(source), target.numel(), rho, C.c_void_p(self.stream.cuda_stream)))
 
+    @_on_stream
     def adam_polyak(self, online, target, m, v, grad, hp: HParams, adam_t, grad_scale=None, skip=None):
         check(lib.gac_adam_polyak(self.h, ptr(online), ptr(target), ptr(m), ptr(v), ptr(grad), C.byref(hp), ptr(adam_t),
                                   ptr(grad_scale), ptr(skip)))
 
+    @_on_stream
     def aiqn_sample(self, actor, states_u, state_idx, taus):
         rows = taus.shape[0]
         out = self._new(rows, self.A)
         check(lib.gac_aiqn_sample(self.h, ptr(actor), ptr(states_u), states_u.shape[0], ptr(state_idx), ptr(taus), rows, ptr(out)))
         return out
 
+    @_on_stream
     def gru_step(self, actor, states_u, state_idx, action_emb, h_prev=None, reuse=False, actor_inputs=False):
         """One GRU(400) step of the AIQN actor (reference GAC/networks.py:166): h' = GRU([se[state_idx] | action_emb], h_prev).
         actor_inputs: action_emb / h_prev come from the actor itself (bounded by its weights) -> 3xFP16 variant allowed."""
@@ -174,12 +201,14 @@ class Engine:
                                ptr(out), int(reuse) | (2 if actor_inputs else 0)))
         return out
 
+    @_on_stream
     def iqn_forward(self, actor, states_u, state_idx, taus):
         rows = taus.shape[0]
         out = self._new(rows, self.A)
         check(lib.gac_iqn_forward(self.h, ptr(actor), ptr(states_u), states_u.shape[0], ptr(state_idx), ptr(taus), rows, ptr(out)))
         return out
 
+    @_on_stream
     def iqn_train_fwd(self, actor, states_u, state_idx, taus, d_rows=None):
         rows = taus.shape[0]
         pred = self._new(rows, self.A)
@@ -187,21 +216,25 @@ class Engine:
                                     ptr(pred)))
         return pred
 
+    @_on_stream
     def iqn_bwd(self, actor, dpred, grad_actor, accumulate=False):
         check(lib.gac_iqn_bwd(self.h, ptr(actor), ptr(dpred), ptr(grad_actor), int(accumulate)))
 
+    @_on_stream
     def critic_eval(self, fnn1, fnn2, states_u, state_idx, actions):
         rows = actions.shape[0]
         q = self._new(rows, 1)
         check(lib.gac_critic_eval(self.h, ptr(fnn1), ptr(fnn2), ptr(states_u), ptr(state_idx), ptr(actions), rows, ptr(q)))
         return q
 
+    @_on_stream
     def value_eval(self, value, states):
         rows = states.shape[0]
         v = self._new(rows, 1)
         check(lib.gac_value_eval(self.h, ptr(value), ptr(states), rows, ptr(v)))
         return v
 
+    @_on_stream
     def advantage_compact(self, q, v, actions=None, state_idx=None):
         n = q.numel()
         idx = self._new(n, dtype=torch.int64)
@@ -216,6 +249,7 @@ class Engine:
                                         ptr(act_out), ptr(state_idx), ptr(sidx_out)))
         return dict(idx=idx, pos=pos, m=m, sum_adv=sadv, adv=adv, actions=act_out, state_idx=sidx_out)
 
+    @_on_stream
     def aiqn_supervised_fwd(self, actor, states_u, state_idx, taus, teacher, d_rows=None):
         rows = taus.shape[0]
         pred = self._new(rows, self.A)
@@ -223,6 +257,7 @@ class Engine:
                                           rows, ptr(d_rows), ptr(pred)))
         return pred
 
+    @_on_stream
     def qhuber_loss_bwd(self, pred, target, taus, weights, inv_norm: float, d_rows=None):
         rows, A = pred.shape
         dpred = torch.zeros_like(pred)
@@ -231,14 +266,17 @@ class Engine:
                                       ptr(loss)))
         return loss, dpred
 
+    @_on_stream
     def aiqn_bwd(self, actor, dpred, grad_actor, accumulate=False):
         check(lib.gac_aiqn_bwd(self.h, ptr(actor), ptr(dpred), ptr(grad_actor), int(accumulate)))
 
+    @_on_stream
     def td_fwd_bwd(self, fnn, n_in, x, y, grad_fnn):
         loss = self._new(1)
         check(lib.gac_td_fwd_bwd(self.h, ptr(fnn), n_in, ptr(x), ptr(y), x.shape[0], ptr(grad_fnn), ptr(loss)))
         return loss
 
+    @_on_stream
     def gemm(self, a, b, trans_a=False, trans_b=False, engine=0):
         M = a.shape[1] if trans_a else a.shape[0]
         K = a.shape[0] if trans_a else a.shape[1]
@@ -258,8 +296,10 @@ class Engine:
             setattr(io, k, t.data_ptr())
         return io
 
+    @_on_stream
     def step_grads(self, io: StepIO, hp: HParams):
         check(lib.gac_step_grads(self.h, C.byref(io), C.byref(hp)))
 
+    @_on_stream
     def step_apply(self, io: StepIO, hp: HParams):
         check(lib.gac_step_apply(self.h, C.byref(io), C.byref(hp)))

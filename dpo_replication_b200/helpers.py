@@ -122,4 +122,5 @@ def denormalize(x, stats):
     """helpers.py:98-101."""
     if stats is None:
         return x
-    return x * stats.std + stats.mean
+    as_t = lambda v: torch.as_tensor(v, dtype=torch.float32, device=x.device) if isinstance(x, torch.Tensor) else v
+    return x * as_t(stats.std) + as_t(stats.mean)

@@ -22,6 +22,43 @@ import torch
 CHECKPOINT_VERSION = 1
 
 
+class RunningMeanStd(object):
+    """utils/utils.py:41-56 (OpenAI-baselines running mean / variance, parallel-variance merge), host side like the
+    reference's: it is fed one transition per environment step (agent.py:263-268), far from the train step.
+
+    The reference's merge (utils/utils.py:25-38) adds ``sqrt(delta) * count * batch_count / tot_count`` where the
+    parallel-variance formula has ``delta ** 2``: NaN as soon as a batch mean falls below the running mean.
+    ``bug_compatible=True`` (default) reproduces that line as written; ``False`` uses the square."""
+
+    def __init__(self, epsilon=1e-4, shape=(), bug_compatible=True):
+        self.mean = np.zeros(shape, np.float32)
+        self.var = np.ones(shape, np.float32)
+        self.count = epsilon
+        self.bug_compatible = bug_compatible
+
+    @property
+    def std(self):                     # read by helpers.denormalize (helpers.py:98-101); the reference never defines it
+        return np.sqrt(self.var)
+
+    def update(self, x):
+        x = np.asarray(x.detach().cpu() if isinstance(x, torch.Tensor) else x)
+        batch_mean = np.mean(x, axis=0).astype(np.float32)             # tf.reduce_mean(x, axis=0) cast to float32
+        batch_var = np.square(np.std(x, axis=0)).astype(np.float32)    # tf.square(tf.math.reduce_std(x, axis=0))
+        self.update_from_moments(batch_mean, batch_var, x.shape[0])
+
+    def update_from_moments(self, batch_mean, batch_var, batch_count):
+        f = np.float32
+        delta = batch_mean - self.mean
+        tot_count = self.count + batch_count
+        new_mean = self.mean + delta * f(batch_count) / f(tot_count)
+        m_a = self.var * f(self.count)
+        m_b = batch_var * f(batch_count)
+        with np.errstate(invalid="ignore"):
+            cross = np.sqrt(delta) if self.bug_compatible else np.square(delta)
+        M2 = m_a + m_b + cross * f(self.count) * f(batch_count) / f(tot_count)
+        self.mean, self.var, self.count = new_mean.astype(f), (M2 / f(tot_count)).astype(f), tot_count
+
+
 def _actor_kind_name(actor) -> str:
     return "IQN" if getattr(actor, "actor_kind", 0) == 1 else "AIQN"
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GAC_B200_ABI_VERSION 3
+#define GAC_B200_ABI_VERSION 4
 
 enum gac_status {
   GAC_OK = 0,
@@ -97,6 +97,10 @@ size_t gac_workspace_bytes(const gac_config_t* cfg);
 int gac_create(const gac_config_t* cfg, void* workspace, size_t workspace_bytes, void* stream,
                gac_ctx_t** out);
 void gac_destroy(gac_ctx_t* ctx);
+/* Re-bind the context to another stream (a cudaStream_t passed as void*): every later call is ordered on it.  The caller
+ * orders the two streams (an event wait) if work issued on the old one may still touch the workspace.  Needed by callers that
+ * change the current stream after construction, e.g. to capture a whole train step into a CUDA graph. */
+int gac_set_stream(gac_ctx_t* ctx, void* stream);
 const char* gac_last_error(void);
 int gac_abi_version(void);
 

@@ -581,3 +581,24 @@ def train_one_step(nets, batch, noise, K, gamma=0.99, rho=5e-3, q_normalization=
         for k in nets[name]:
             nets["target_" + name][k] = polyak(nets["target_" + name][k], nets[name][k], rho)
     return nets, info
+
+
+# --------------------------------------------------------------------------------------
+# running observation / return statistics (agent.py:72-80, 263-268)
+# --------------------------------------------------------------------------------------
+def running_mean_std_merge(mean, var, count, batch_mean, batch_var, batch_count):
+    """utils/utils.py:25-38, as written: the cross term uses sqrt(delta) where the parallel-variance formula has
+    delta**2 (NaN for a negative delta).  fp32 state, Python-float count."""
+    f = np.float32
+    delta = np.asarray(batch_mean, f) - np.asarray(mean, f)
+    tot = count + batch_count
+    new_mean = np.asarray(mean, f) + delta * f(batch_count) / f(tot)
+    with np.errstate(invalid="ignore"):
+        m2 = np.asarray(var, f) * f(count) + np.asarray(batch_var, f) * f(batch_count) + np.sqrt(delta) * f(count) * f(batch_count) / f(tot)
+    return new_mean.astype(f), (m2 / f(tot)).astype(f), tot
+
+
+def running_mean_std_update(mean, var, count, x):
+    """RunningMeanStd.update, utils/utils.py:48-52: population moments over axis 0, batch_count = x.shape[0]."""
+    x = np.asarray(x)
+    return running_mean_std_merge(mean, var, count, np.mean(x, axis=0).astype(np.float32), np.square(np.std(x, axis=0)).astype(np.float32), x.shape[0])

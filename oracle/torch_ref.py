@@ -21,8 +21,10 @@ import torch.nn.functional as F
 from . import gac_oracle as O
 
 
-def to_t(p, dtype=torch.float32, grad=False):
-    return {k: torch.tensor(np.asarray(v), dtype=dtype, requires_grad=grad) for k, v in p.items()}
+def to_t(p, dtype=torch.float32, grad=False, device="cpu"):
+    """Parameter dict -> tensors.  dtype / device generic: fp32 on the CPU is the timed baseline, fp64 on a GPU is the
+    checker the full-size parity tests use (tests/test_fullsize_oracle_gpu.py)."""
+    return {k: torch.tensor(np.asarray(v), dtype=dtype, device=device).requires_grad_(grad) for k, v in p.items()}
 
 
 class CosineBasisLinearT:
@@ -35,8 +37,11 @@ class CosineBasisLinearT:
     def __call__(self, x):
         rows = x.shape[0]
         col = x.reshape(-1, 1).to(torch.float32)
-        ipi = np.tile(np.arange(1, self.n + 1, dtype=np.float32), (col.shape[0], 1)) * np.float32(np.pi)
-        emb = torch.cos((col * torch.from_numpy(ipi)).to(self.w.dtype))
+        if col.device.type == "cpu":       # the timed CPU path keeps the reference's per-call host-side tile (networks.py:45-46)
+            ipi = torch.from_numpy(np.tile(np.arange(1, self.n + 1, dtype=np.float32), (col.shape[0], 1)) * np.float32(np.pi))
+        else:                              # checker on a device: same fp32 constants fl32(i) * fl32(pi), broadcast
+            ipi = torch.from_numpy(np.arange(1, self.n + 1, dtype=np.float32) * np.float32(np.pi)).to(col.device)
+        emb = torch.cos((col * ipi).to(self.w.dtype))
         out = emb @ self.w + self.b
         if self.act is not None:
             out = F.leaky_relu(out, self.act)
@@ -74,8 +79,8 @@ class AIQNT:
         rows = state.shape[0]
         se = self._state(state)
         ne = self.noise_embedding(taus)
-        a = torch.zeros(rows, dtype=state.dtype)
-        h = torch.zeros(rows, O.E, dtype=state.dtype)
+        a = torch.zeros(rows, dtype=state.dtype, device=state.device)
+        h = torch.zeros(rows, O.E, dtype=state.dtype, device=state.device)
         outs = []
         for d in range(self.action_dim):
             ae = F.leaky_relu(self.action_embedding(a.reshape(rows, 1, 1)), 0.2)[:, 0, :]
@@ -94,7 +99,7 @@ class AIQNT:
         shifted[:, 1:] = acts[:, :-1]
         ae = F.leaky_relu(self.action_embedding(shifted), 0.2)
         ne = self.noise_embedding(taus)
-        h = torch.zeros(rows, O.E, dtype=state.dtype)
+        h = torch.zeros(rows, O.E, dtype=state.dtype, device=state.device)
         hs = []
         for d in range(A):
             h = self._gru(torch.cat([se, ae[:, d]], dim=1), h)
@@ -148,15 +153,15 @@ class TorchGAC:
     NETS = ("actor", "fnn1", "fnn2", "value")
 
     def __init__(self, nets, A, K, gamma=0.99, rho=5e-3, q_normalization=0.01, mode="linear", beta=1.0,
-                 dtype=torch.float32):
+                 dtype=torch.float32, device="cpu"):
         self.A, self.K, self.gamma, self.rho, self.qn, self.mode, self.beta = A, K, gamma, rho, q_normalization, mode, beta
-        self.dtype = dtype
+        self.dtype, self.device = dtype, device
         self.n = {}
         for k in self.NETS:
-            self.n[k] = to_t(nets[k], dtype, grad=True)
-            self.n["target_" + k] = to_t(nets["target_" + k], dtype)
-            self.n["m_" + k] = to_t(nets["m_" + k], dtype)
-            self.n["v_" + k] = to_t(nets["v_" + k], dtype)
+            self.n[k] = to_t(nets[k], dtype, grad=True, device=device)
+            self.n["target_" + k] = to_t(nets["target_" + k], dtype, device=device)
+            self.n["m_" + k] = to_t(nets["m_" + k], dtype, device=device)
+            self.n["v_" + k] = to_t(nets["v_" + k], dtype, device=device)
         self.t = {k: int(nets["t_" + k]) for k in self.NETS}
 
     def _apply(self, name, loss_vec_sum):
@@ -170,7 +175,7 @@ class TorchGAC:
 
     def sample_positive(self, s, noise):
         n, K, dt = self.n, self.K, self.dtype
-        T = lambda a: torch.as_tensor(a, dtype=dt)
+        T = lambda a: torch.as_tensor(a, dtype=dt, device=self.device)
         tiled = s.repeat(K, 1)
         tactor = AIQNT(n["target_actor"], self.A)
         with torch.no_grad():
@@ -190,7 +195,7 @@ class TorchGAC:
 
     def train_one_step(self, batch, noise):
         n, K, dt = self.n, self.K, self.dtype
-        T = lambda a: torch.as_tensor(a, dtype=dt)
+        T = lambda a: torch.as_tensor(a, dtype=dt, device=self.device)
         s, a, r, sp, it = (T(batch[k]) for k in ("s", "a", "r", "sp", "it"))
         B = s.shape[0]
         info = {}

@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported(lib):
     raw = C.CDLL(lib.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.lib.gac_abi_version() == 3
+    assert lib.lib.gac_abi_version() == 4
 
 
 @pytest.mark.parametrize("S,A", [(3, 1), (17, 6), (376, 17), (111, 8)])

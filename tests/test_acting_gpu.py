@@ -1,0 +1,177 @@
+"""Acting path (GACAgent.get_action / select_perturbed_action, agent.py:218-248; main.py:119-121,195-203 call it with one
+state per environment step) against the oracle at batch 1 and small batches, AIQN and IQN, eager and CUDA-graph replay;
+the GRU gate transcendentals at saturating and vanishing arguments; engine calls under a non-default current stream;
+observation / reward normalisation (agent.py:133-138, helpers.py:89-95)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import FWD_RTOL, assert_close
+from oracle import gac_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gb():
+    import __graft_entry__ as ge
+    ge.build()
+    import dpo_replication_b200 as g
+    return g
+
+
+def dev(x, dtype=torch.float32):
+    return torch.as_tensor(np.asarray(x)).to("cuda", dtype).contiguous()
+
+
+@pytest.mark.parametrize("rows", [1, 7])
+@pytest.mark.parametrize("S,A", [(17, 6), (3, 1), (376, 17)])
+def test_get_action_aiqn_vs_oracle(gb, S, A, rows):
+    rng = np.random.default_rng(31 + rows + S)
+    nets = O.make_agent(rng, S, A, bias_scale=0.05)
+    ag = gb.GACAgent(A, S, action_samples=4, batch_size=8, device="cuda")
+    ag.load_state(nets)
+    st = rng.standard_normal((rows, S)).astype(np.float32)
+    tau = rng.uniform(size=(rows, A)).astype(np.float32)
+    eager = ag.action_sampler.get_actions(ag.actor, dev(st), taus=dev(tau)).cpu().numpy()     # what get_action runs, tau injected
+    graphed = ag.get_action_graphed(dev(st), taus=dev(tau)).cpu().numpy()
+    replay = ag.get_action_graphed(dev(st), taus=dev(tau)).cpu().numpy()
+    assert np.array_equal(graphed, replay)
+    ref = O.aiqn_sample(nets["actor"], st, tau, np.float64)
+    for name, got in (("eager", eager), ("graphed", graphed)):
+        assert got.shape == (rows, A) and np.abs(got).max() < 1.0
+        # dimension 0 has no feedback: strict.  Later dimensions: the oracle teacher-forced on the CUDA path's own previous
+        # actions must reproduce them (actor(s, tau, actor(s, tau)) == actor(s, tau); the free-running map is chaotic, F3)
+        assert np.abs(got[:, 0] - ref[:, 0]).max() <= FWD_RTOL, name
+        tf, _ = O.aiqn_supervised(nets["actor"], st, tau, got, np.float64)
+        assert_close(got, tf, FWD_RTOL, f"{name} acting path, every dimension on its own previous actions")
+    if rows == 1:    # rank-1 state, as main.py passes it (helpers.py:22-25)
+        one = ag.get_action_graphed(dev(st[0]), taus=dev(tau)).cpu().numpy()
+        assert np.array_equal(one, graphed)
+
+
+@pytest.mark.parametrize("rows", [1, 5])
+def test_get_action_iqn_vs_oracle(gb, rows):
+    S, A = 17, 6
+    rng = np.random.default_rng(41 + rows)
+    p = O.init_iqn(rng, S, A, bias_scale=0.05)
+    ag = gb.GACAgent(A, S, action_samples=4, batch_size=8, actor='IQN', device="cuda")
+    ag.arena.load(ag.arena.online, "actor", p)
+    st = rng.standard_normal((rows, S)).astype(np.float32)
+    tau = rng.uniform(size=(rows, A)).astype(np.float32)
+    ref = O.iqn_forward(p, st, tau, np.float64)
+    eager = ag.action_sampler.get_actions(ag.actor, dev(st), taus=dev(tau)).cpu().numpy()
+    graphed = ag.get_action_graphed(dev(st), taus=dev(tau)).cpu().numpy()
+    assert_close(eager, ref, FWD_RTOL, "IQN get_action")
+    assert_close(graphed, ref, FWD_RTOL, "IQN get_action_graphed")
+
+
+def test_select_perturbed_action_clips_and_adds_noise(gb):
+    S, A = 11, 3
+    ag = gb.GACAgent(A, S, action_samples=4, batch_size=8, device="cuda")
+    s = torch.randn(S)
+    a = ag.select_perturbed_action(s, action_noise=lambda: np.full(A, 5.0, np.float32))      # agent.py:244-247
+    assert tuple(a.shape) == (1, A) and torch.equal(a.cpu(), torch.ones(1, A))
+    b = ag.select_perturbed_action(s)
+    assert float(b.abs().max()) < 1.0
+
+
+@pytest.mark.parametrize("bounded", [True, False])
+def test_gru_gates_saturating_and_vanishing_arguments(gb, bounded):
+    """sigmoid / tanh in the fused GRU step go through ex2.approx + a fast reciprocal (gru_step_tc.cuh): elementwise
+    |error| must stay below 2e-6 -- far inside the 1e-5 contract -- where the gates saturate (|pre-activation| up to 60,
+    beyond expf's fp32 overflow in the tanh) and where tanh sees arguments near zero."""
+    S, A, rows, nst = 17, 6, 512, 16
+    rng = np.random.default_rng(77)
+    p = {k: np.array(v, copy=True) for k, v in O.init_actor(rng, S, A, bias_scale=0.05).items()}
+    big = np.array([-60, -45, -30, -20, -10, -5, 5, 10, 20, 30, 45, 60, 88, -88, 100, -100], np.float32)
+    p["gb"][1, 0:16] = big                        # z gate saturates both ways on units 0..15
+    p["gb"][1, 400 + 16:400 + 32] = big           # r gate on units 16..31
+    p["gb"][1, 800 + 32:800 + 48] = big           # recurrent part of the candidate (scaled by r) on units 32..47
+    p["gb"][0, 800 + 48:800 + 64] = big           # input part of the candidate: tanh at +-100
+    p["kx"][:, 800 + 64:800 + 128] *= np.float32(1e-4)      # candidate pre-activation ~1e-5 on units 64..127: tanh near zero
+    p["u"][:, 800 + 64:800 + 128] *= np.float32(1e-4)
+    p["gb"][:, 800 + 64:800 + 128] = 0
+    eng = gb.Engine(S, A, 1024, 1, "cuda")
+    ar = gb.Arena(S, A, torch.device("cuda"))
+    ar.load(ar.online, "actor", p)
+    su = rng.standard_normal((nst, S)).astype(np.float32)
+    sidx = rng.integers(0, nst, rows).astype(np.int32)
+    if bounded:
+        ae = O.cosine_basis_linear(rng.uniform(-1, 1, (rows, 1)).astype(np.float32), p["wa"], p["ba"], np.float32, 0.2)[:, 0, :]
+    else:
+        ae = rng.standard_normal((rows, 400)).astype(np.float32)
+    h = np.tanh(rng.standard_normal((rows, 400))).astype(np.float32)
+    p64 = O.cast(p, np.float64)
+    se, _ = O.state_embed(p64, su.astype(np.float64))
+    ref, (z, r, c, _) = O.gru_step(p64, np.concatenate([se[sidx], ae.astype(np.float64)], axis=1), h.astype(np.float64))
+    assert z[:, :16].min() < 1e-20 and z[:, :16].max() > 1 - 1e-12 and np.abs(c[:, 64:128]).max() < 1e-2
+    got = eng.gru_step(ar.net_slice(ar.online, "actor"), dev(su), dev(sidx, torch.int32), dev(ae), dev(h), actor_inputs=bounded).cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - ref)
+    assert err.max() <= 2e-6, (err.max(), np.unravel_index(err.argmax(), err.shape))
+
+
+def test_engine_follows_the_current_stream(gb):
+    """Engine calls run on torch's CURRENT stream (gac_set_stream), so producers / consumers queued on a side stream are
+    ordered with the kernels without any explicit synchronisation."""
+    S, A, rows = 17, 6, 300
+    rng = np.random.default_rng(5)
+    p = O.init_actor(rng, S, A, bias_scale=0.05)
+    eng = gb.Engine(S, A, 512, 1, "cuda")
+    ar = gb.Arena(S, A, torch.device("cuda"))
+    ar.load(ar.online, "actor", p)
+    su, taus = dev(rng.standard_normal((rows, S))), dev(rng.uniform(size=(rows, A)))
+    sidx = torch.arange(rows, dtype=torch.int32, device="cuda")
+    base = ar.net_slice(ar.online, "actor")
+    a0 = eng.aiqn_sample(base, su, sidx, taus)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        big = torch.randn(4096, 4096, device="cuda")
+        for _ in range(20):                         # keep the side stream busy before the inputs are produced on it
+            big = big @ big * 1e-3
+        su2 = su + 0 * big[0, 0]
+        a1 = eng.aiqn_sample(base, su2, sidx, taus)
+        a1c = a1.clone()
+    torch.cuda.current_stream().wait_stream(side)
+    a2 = eng.aiqn_sample(base, su, sidx, taus)      # back on the default stream
+    torch.cuda.synchronize()
+    assert torch.equal(a0, a1c) and torch.equal(a0, a2)
+
+
+def test_normalised_agent_runs_and_matches_manual_normalisation(gb):
+    """normalize_obs / normalize_rewards (agent.py:72-80,133-138,263-268): statistics follow utils.RunningMeanStd, and a
+    train step on the normalised batch equals a step of an un-normalised agent fed the manually normalised batch."""
+    S, A, B, K = 5, 2, 8, 4
+    rng = np.random.default_rng(9)
+    nets = O.make_agent(rng, S, A, bias_scale=0.05)
+    a_n = gb.GACAgent(A, S, action_samples=K, batch_size=B, normalize_obs=True, normalize_rewards=True, device="cuda", replay_on_device=False)
+    a_p = gb.GACAgent(A, S, action_samples=K, batch_size=B, device="cuda", replay_on_device=False)
+    for ag in (a_n, a_p):
+        ag.load_state(nets)
+    # statistics that stay finite under the reference's sqrt(delta) merge: feed them directly
+    a_n.obs_rms.mean[:] = rng.standard_normal(S).astype(np.float32)
+    a_n.obs_rms.var[:] = rng.uniform(0.5, 2.0, S).astype(np.float32)
+    a_n.ret_rms.mean[:] = 0.3
+    a_n.ret_rms.var[:] = 1.7
+    batch, noise = O.make_batch(rng, S, A, B), O.make_noise(rng, A, B, K)
+    norm = lambda x, st: ((x - st.mean) / np.sqrt(st.var)).astype(np.float32)
+    manual = dict(s=norm(batch["s"], a_n.obs_rms), a=batch["a"], r=norm(batch["r"], a_n.ret_rms), sp=norm(batch["sp"], a_n.obs_rms), it=batch["it"])
+    for i in range(B):
+        a_n.replay.store(batch["s"][i], batch["a"][i], batch["r"][i], batch["sp"][i], batch["it"][i])
+    import random
+    random.seed(3)
+    order = random.sample(range(B), B)
+    random.seed(3)
+    torch.manual_seed(11)
+    a_n.train_one_step()
+    torch.manual_seed(11)
+    a_p.train_on_batch({k: v[order] for k, v in manual.items()})
+    torch.cuda.synchronize()
+    for k in ("online", "target"):
+        assert_close(getattr(a_n.arena, k).cpu().numpy(), getattr(a_p.arena, k).cpu().numpy(), 1e-6, f"normalised step, {k} arena")
+    # store_transition feeds the running statistics (agent.py:263-268)
+    b = gb.GACAgent(A, S, action_samples=K, batch_size=B, normalize_obs=True, normalize_rewards=True, device="cuda")
+    b.store_transition(np.ones(S, np.float32), np.zeros(A, np.float32), 2.0, np.ones(S, np.float32), False)
+    assert b.obs_rms.count > 1 and b.ret == 2.0 and b.replay.size == 1

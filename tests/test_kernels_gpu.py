@@ -125,7 +125,9 @@ def test_aiqn_sampler(gb, engine, S, A, rows, nstates):
     # divergence (the free-running sampler is chaotic: cos(i*pi*a) feedback)
     assert np.abs(got[:, 0] - ref64[:, 0]).max() <= FWD_RTOL
     for d in range(1, A):
-        env = max(5.0 * np.abs(ref32[:, d] - ref64[:, d]).max(), 1e-5 * 10 ** d)
+        # envelope = the oracle's own fp32-vs-fp64 divergence on the same inputs; the floor covers rows where that
+        # divergence happens to be tiny and is capped so that it can never become vacuous on values in (-1, 1)
+        env = max(5.0 * np.abs(ref32[:, d] - ref64[:, d]).max(), min(1e-5 * 10 ** d, 1e-2))
         assert np.abs(got[:, d] - ref64[:, d]).max() <= env, (d, env)
     # stage-wise: teacher-force the ORACLE's own actions => every step sees oracle inputs
     sup = eng.aiqn_supervised_fwd(ar.net_slice(ar.online, "actor"), dev(su), dev(sidx, torch.int32), dev(taus),
