@@ -21,7 +21,11 @@ from oracle import gac_oracle as O
 from oracle import torch_ref as T
 
 pytestmark = pytest.mark.gpu
-KINK = 5e-5        # relative distance from a kink below which a row is left out of the strict gradient comparison
+# Relative distance from a kink below which a row is left out of the strict gradient comparison: ~10x the CUDA path's
+# forward rounding error at these sizes (5e-7 of a tensor's largest entry), i.e. rows on which a correct fp32 forward may
+# still take the other branch of a LeakyReLU / of the Huber indicator than the fp64 checker does.
+KINK = 5e-6
+TD_KINK = 3e-6     # the 256-row TD nets: (256 x 700) pre-activations, re-seeded until none lies inside the band
 
 
 @pytest.fixture(scope="module")
@@ -33,18 +37,22 @@ def gb():
 
 
 def _nets(S, A, B, K, seed):
-    """Oracle-initialised agent + batch whose 256 TD rows are clear of the FNN kinks (checked in fp64, re-seeded if not)."""
-    for attempt in range(8):
-        rng = np.random.default_rng(seed + 17 * attempt)
-        nets = O.make_agent(rng, S, A, bias_scale=0.05)
-        batch, noise = O.make_batch(rng, S, A, B), O.make_noise(rng, A, B, K)
-        t = lambda a: torch.as_tensor(a, dtype=torch.float64, device="cuda")
+    """Oracle-initialised agent + batch whose 256 TD rows are clear of the FNN kinks: rows with a pre-activation inside the
+    band (checked in fp64) are re-drawn until none is left."""
+    rng = np.random.default_rng(seed)
+    nets = O.make_agent(rng, S, A, bias_scale=0.05)
+    batch, noise = O.make_batch(rng, S, A, B), O.make_noise(rng, A, B, K)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device="cuda")
+    p64 = {n: CK.params64(nets[n], "cuda") for n in ("fnn1", "fnn2", "value")}
+    for attempt in range(100):
         x = torch.cat([t(batch["s"]), torch.clamp(t(batch["a"]) + (t(noise["critic_u"]) * 2 - 1) * 0.01, -1, 1)], dim=-1)
-        ok = all(float(CK.fnn_margin(CK.params64(nets[n], "cuda"), x).min()) > KINK for n in ("fnn1", "fnn2"))
-        ok = ok and float(CK.fnn_margin(CK.params64(nets["value"], "cuda"), t(batch["s"])).min()) > KINK
-        if ok:
+        margin = torch.minimum(torch.minimum(CK.fnn_margin(p64["fnn1"], x), CK.fnn_margin(p64["fnn2"], x)), CK.fnn_margin(p64["value"], t(batch["s"])))
+        bad = torch.nonzero(margin <= TD_KINK).reshape(-1).cpu().numpy()
+        if bad.size == 0:
             return nets, batch, noise
-    raise AssertionError("no kink-free TD batch in 8 seeds")
+        batch["s"][bad] = rng.standard_normal((bad.size, S)).astype(np.float32)
+        batch["a"][bad] = rng.uniform(-1, 1, (bad.size, A)).astype(np.float32)
+    raise AssertionError("could not clear the TD batch of kink rows")
 
 
 @pytest.mark.parametrize("name,S,A,B,K", [("halfcheetah", 17, 6, 256, 64), ("humanoid", 376, 17, 256, 128)])
