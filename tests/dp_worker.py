@@ -34,6 +34,8 @@ def main():
         nets = {k: ({n: v * 0 for n, v in d.items()} if isinstance(d, dict) else d) for k, d in nets.items()}
     agent.load_state(nets)
     b, n = gdist.shard_step_inputs(batch, noise, K, rank, world)
+    if f"actor_tau_rank{rank}" in z.files:              # the draws this rank's compacted rows have in the one-process run
+        n["actor_tau"] = z[f"actor_tau_rank{rank}"]
     P = Bl * K
     taps = dict(sel_idx=torch.zeros(2 * P, dtype=torch.int64, device=dev), q_out=torch.zeros(2 * P, device=dev), v_out=torch.zeros(2 * P, device=dev))
     agent.train_on_batch(b, n, taps)

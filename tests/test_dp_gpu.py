@@ -59,7 +59,19 @@ def test_two_ranks_equal_one_process(gb, S, A, B, K, strict):
     # two ranks
     with tempfile.TemporaryDirectory() as td:
         inp, out = os.path.join(td, "in.npz"), os.path.join(td, "out")
-        np.savez(inp, nets=np.array(nets, dtype=object), batch=np.array(batch, dtype=object), noise=np.array(noise, dtype=object), S=S, A=A, K=K)
+        # networks.py:134 draws tau per COMPACTED row: one process gives compacted row j the j-th draw.  A rank's compacted
+        # rows are the selected candidates of its own states, in the same relative order, so hand every rank the draws its
+        # rows have in the one-process run (otherwise both runs are valid but use different random numbers)
+        Bl = B // 2
+        b_of = idx1 % B                                           # candidate r = blk*P + k*B + b
+        extra = {}
+        for rk in range(2):
+            mine = np.nonzero((b_of >= rk * Bl) & (b_of < (rk + 1) * Bl))[0]
+            tau = np.zeros((2 * Bl * K, A), np.float32)
+            tau[:mine.size] = noise["actor_tau"][mine]
+            extra[f"actor_tau_rank{rk}"] = tau
+        np.savez(inp, nets=np.array(nets, dtype=object), batch=np.array(batch, dtype=object), noise=np.array(noise, dtype=object), S=S, A=A, K=K,
+                 **extra)
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                             "--master-port", str(29533 + A), os.path.join(ROOT, "tests", "dp_worker.py"), inp, out], cwd=ROOT, capture_output=True, text=True,
                            timeout=600)
