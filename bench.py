@@ -341,11 +341,11 @@ def run_gpu(args):
             h = torch.tanh(torch.randn(rows, 400, device=dev))
             eng.gru_step(actor, states, sidx, ae, h, actor_inputs=True)
             for _ in range(3):
-                eng.gru_step(actor, states, sidx, ae, h, reuse=True, actor_inputs=True)
+                eng.gru_step(actor, states, sidx, ae, h, reuse=True, actor_inputs=True, same_inputs=True)
             torch.cuda.synchronize()
             e0.record()
             for _ in range(n_rep):
-                eng.gru_step(actor, states, sidx, ae, h, reuse=True, actor_inputs=True)
+                eng.gru_step(actor, states, sidx, ae, h, reuse=True, actor_inputs=True, same_inputs=True)
             e1.record()
             torch.cuda.synchronize()
             kms = e0.elapsed_time(e1) / n_rep

@@ -15,7 +15,7 @@
 // accumulate truncation (<= 12 x 2^-24) needs no separate correction accumulator.  Non-finite / absurd weights clear the
 // device flag and the CTA computes its tile with plain fp32 FMAs instead.
 #pragma once
-#include "gemm_tc.cuh"
+#include "gru_step_v2.cuh"
 
 namespace gac {
 namespace tc {
@@ -33,6 +33,8 @@ struct EmbArgs {
   int act; float alpha;          // 1: LeakyReLU(alpha)
   const float* mul; int ldmul;   // optional (rows, 400) Hadamard factor applied last
   float* C; int ldc;             // (rows, 400)
+  // optional a16 image (gru_step_v2.cuh) of the result, scaled by *c16_scale: written INSTEAD of C while *c16_ok != 0
+  unsigned char* C16; const float* c16_scale; const int* c16_ok;
 };
 
 constexpr uint32_t EMB_W_TILE = (uint32_t)GAC_E * 128u;          // 51,200 B per hi / lo
@@ -87,6 +89,8 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
   }
   if (m0 >= m_end) return;
   const bool ok = g.sc->ok != 0;
+  const bool use16 = g.C16 != nullptr && *g.c16_ok != 0;
+  const float s16 = use16 ? *g.c16_scale : 1.f;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sw_hi = smem0, sw_lo = smem0 + EMB_W_TILE, sa_hi = smem0 + 2 * EMB_W_TILE, sa_lo = sa_hi + EMB_A_TILE;
 
@@ -101,7 +105,13 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
       float v = acc + g.bias[n];
       if (g.act) v = v > 0.f ? v : g.alpha * v;
       if (g.mul) v *= g.mul[(size_t)m * g.ldmul + n];
-      g.C[(size_t)m * g.ldc + n] = v;
+      if (use16) {
+        const __half hh = __float2half_rn(v * s16), ll = __float2half_rn(v * s16 - __half2float(hh));
+        unsigned char* dst = g.C16 + a16_off(m, n & ~3) + (n & 3) * 2;
+        *reinterpret_cast<__half*>(dst) = hh; *reinterpret_cast<__half*>(dst + G2_A_TILE) = ll;
+      } else {
+        g.C[(size_t)m * g.ldc + n] = v;
+      }
     }
     return;
   }
@@ -202,7 +212,16 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
           if (!okk[u]) continue;
           float4 x = *reinterpret_cast<const float4*>(stg + (size_t)row[u] * SS + col[u]);
           if (g.mul) { x.x *= ml[u].x; x.y *= ml[u].y; x.z *= ml[u].z; x.w *= ml[u].w; }
-          *reinterpret_cast<float4*>(g.C + (size_t)(m0 + row[u]) * g.ldc + col0 + col[u]) = x;
+          if (use16) {                                             // the GRU step's A operand: split, scaled, swizzled here
+            uint32_t h0, l0, h1, l1;
+            split_f16x2_u(x.x * s16, x.y * s16, h0, l0);
+            split_f16x2_u(x.z * s16, x.w * s16, h1, l1);
+            unsigned char* dst = g.C16 + a16_off(m0 + row[u], col0 + col[u]);
+            *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(dst + G2_A_TILE) = make_uint2(l0, l1);
+          } else {
+            *reinterpret_cast<float4*>(g.C + (size_t)(m0 + row[u]) * g.ldc + col0 + col[u]) = x;
+          }
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");             // the staging area is rewritten by the second half

@@ -8,6 +8,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "gru_step_tc.cuh"
+#include "gru_step_v2.cuh"
 #include "dot_gemm_tc.cuh"
 
 constexpr int FNN_BN = 160, FNN_NT = 2;     // FNN tail: 300 hidden columns in two 160-wide tiles
@@ -125,6 +126,9 @@ struct gac_ctx {
   unsigned char* gru_pack16[2]; tc::GruScales* gru_sc[2];   // 3xFP16 variant: tiles + power-of-two scales (device)
   unsigned char* gru_pack[2];                   // fused GRU-step weights (tc::gru_pack_kernel): target / online actor
   const unsigned char *gru_t, *gru_o;           // valid for the current call; nullptr = unfused path
+  // second-generation GRU step (gru_step_v2.cuh): weight tiles + scales per actor (target / online), a16 images of the
+  // sampler's action embedding and of the two ping-pong GRU states
+  unsigned char* g2_wpk[2]; tc::Gru2Scales* g2_sc[2]; unsigned char *ae_pk, *h_pk[2]; bool g2_on[2];
 };
 
 namespace {
@@ -217,6 +221,9 @@ size_t partition(gac_ctx* c, void* ws) {
   for (int i = 0; i < 2; ++i) c->gru_pack[i] = b.take<unsigned char>(tc::GRU_PACK_BYTES);
   for (int i = 0; i < 2; ++i) c->gru_pack16[i] = b.take<unsigned char>(tc::GRU_PACK16_BYTES);
   for (int i = 0; i < 2; ++i) c->gru_sc[i] = b.take<tc::GruScales>(1);
+  for (int i = 0; i < 2; ++i) { c->g2_wpk[i] = b.take<unsigned char>(tc::G2_WPK_BYTES); c->g2_sc[i] = b.take<tc::Gru2Scales>(1); }
+  c->ae_pk = b.take<unsigned char>(tc::a16_bytes((long long)Rs));
+  for (int i = 0; i < 2; ++i) c->h_pk[i] = b.take<unsigned char>(tc::a16_bytes((long long)Rs));
   c->head_pack32 = b.take<unsigned char>(tc::dot_pack_bytes(GAC_E, HEAD_BN, HEAD_NT, false));
   c->head_pack16 = b.take<unsigned char>(tc::dot_pack_bytes(GAC_E, HEAD_BN, HEAD_NT, true));
   c->head_sc = b.take<tc::DotScales>(1); c->head_part = b.take<float>((size_t)Rs * HEAD_NT);
@@ -277,10 +284,36 @@ const unsigned char* pack_gru(gac_ctx* c, int which, const float* actor, int row
                c->gru_pack[which], c->gru_pack16[which], tf32_only ? nullptr : c->gru_sc[which], c->stream) != cudaSuccess)
     return nullptr;
   c->launches += tf32_only ? 1 : 4;
+  // second-generation kernel (persistent, bulk-copied pre-split A, double-buffered accumulators): sampler only so far;
+  // GAC_GRU_V1=1 keeps round 1's kernel for everything
+  static const bool v1_only = getenv("GAC_GRU_V1") != nullptr;
+  c->g2_on[which] = !v1_only && !tf32_only && which == 0;
+  if (c->g2_on[which]) {
+    if (gru2_pack(var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, var(c, actor, 0, GAC_A_U), var(c, actor, 0, GAC_A_WA), var(c, actor, 0, GAC_A_BA),
+                  c->g2_wpk[which], c->g2_sc[which], c->stream) != cudaSuccess)
+      c->g2_on[which] = false;
+    else
+      c->launches += 3;
+  }
   return c->gru_pack[which];
 }
+// the v2 kernel on a16 operand images; it exits at once when its scales are not usable, and round 1's kernel (launched
+// right after with skip_if = &scales->ok) then does the step from the fp32 operands
+int run_gru_step_v2(gac_ctx* c, int which, const float* actor, const float* sx, const int* sidx, const unsigned char* ae_pk,
+                    const unsigned char* h_pk, const float* hprev, float* hout, unsigned char* hout_pk, int rows, const int* dyn) {
+  static const bool timeline = getenv("GAC_GRU_TIMELINE") != nullptr;
+  tc::Gru2Args a;
+  a.rows = rows; a.dyn_rows = dyn; a.ae_pk = ae_pk; a.h_pk = hprev ? h_pk : nullptr; a.hprev = hprev; a.wpk = c->g2_wpk[which]; a.sc = c->g2_sc[which];
+  a.sx = sx; a.sidx = sidx; a.b1 = var(c, actor, 0, GAC_A_GB) + GAC_G; a.hout = hout; a.hout_pk = hout_pk;
+  a.z = a.r = a.c = a.mhh = nullptr;
+  a.dbg = timeline ? reinterpret_cast<unsigned long long*>(c->spart) : nullptr;
+  GAC_CUDA(launch_gru_step_v2(a, c->stream));
+  c->launches++;
+  return GAC_OK;
+}
 int run_gru_step(gac_ctx* c, int which, const float* actor, const float* sx, const int* sidx, const float* ae,
-                 const float* hprev, float* hout, int rows, const int* dyn, float* z, float* r, float* cc, float* mhh, bool bounded = true) {
+                 const float* hprev, float* hout, int rows, const int* dyn, float* z, float* r, float* cc, float* mhh, bool bounded = true,
+                 const int* skip_if = nullptr) {
   static const bool timeline = getenv("GAC_GRU_TIMELINE") != nullptr;
   static const bool tf32_only = getenv("GAC_GRU_TF32") != nullptr;
   tc::GruStepArgs a;
@@ -289,6 +322,7 @@ int run_gru_step(gac_ctx* c, int which, const float* actor, const float* sx, con
   a.rows = rows; a.dyn_rows = dyn; a.ae = ae; a.hprev = hprev; a.wpk = c->gru_pack[which]; a.sx = sx; a.sidx = sidx;
   a.b1 = var(c, actor, 0, GAC_A_GB) + GAC_G; a.hout = hout; a.z = z; a.r = r; a.c = cc; a.mhh = mhh;
   a.wpk16 = tf32_only ? nullptr : c->gru_pack16[which];
+  a.skip_if = skip_if;
   GAC_CUDA(launch_gru_step(a, c->stream));
   c->launches++;
   return GAC_OK;
@@ -484,6 +518,8 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
   cudaStream_t st = c->stream;
   const RowValid all{nullptr, 1};
   float* hprev = c->hA; float* hcur = c->hB;
+  unsigned char* pk_prev = c->h_pk[0]; unsigned char* pk_cur = c->h_pk[1];
+  const bool v2 = c->gru_t && c->g2_on[0];
   const float* kxa = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
   for (int d = 0; d < A; ++d) {
     GemmArgs g;
@@ -492,6 +528,8 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
       tc::EmbArgs e;
       e.rows = rows; e.dyn_rows = nullptr; e.seg_rows = 0; e.x = x; e.incx = A; e.wpk = c->emb_pack_buf[which]; e.sc = c->emb_sc[which];
       e.W = W; e.bias = bias; e.act = act; e.alpha = alpha; e.mul = mul; e.ldmul = GAC_E; e.C = out; e.ldc = GAC_E;
+      // the action embedding feeds only the GRU step: with the v2 kernel it is written as that kernel's A-operand image
+      e.C16 = (which == 0 && v2) ? c->ae_pk : nullptr; e.c16_scale = &c->g2_sc[0]->s_ae; e.c16_ok = &c->g2_sc[0]->ok;
       GAC_CUDA(launch_emb_gemm(e, st));
       c->launches++;
       return GAC_OK;
@@ -506,10 +544,13 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
       g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->ae, GAC_E);
       g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.Bpacked = c->pk[PK_T_WA]; g.Bpacked_bn = c->pk_bn[PK_T_WA];
       GAC_TRY(run_gemm(c, g));
+      if (v2) { GAC_CUDA(a16_pack(c->ae, GAC_E, rows, nullptr, &c->g2_sc[0]->s_ae, c->ae_pk, st)); c->launches++; }
     }
     if (c->gru_t) {
       // both projections + gates in one kernel: mxa / mh never touch HBM
-      GAC_TRY(run_gru_step(c, 0, actor, c->sx_u, sidx, c->ae, d ? hprev : nullptr, hcur, rows, nullptr, nullptr, nullptr, nullptr, nullptr));
+      if (v2) GAC_TRY(run_gru_step_v2(c, 0, actor, c->sx_u, sidx, c->ae_pk, pk_prev, d ? hprev : nullptr, hcur, pk_cur, rows, nullptr));
+      GAC_TRY(run_gru_step(c, 0, actor, c->sx_u, sidx, c->ae, d ? hprev : nullptr, hcur, rows, nullptr, nullptr, nullptr, nullptr, nullptr, true,
+                           v2 ? &c->g2_sc[0]->ok : nullptr));
     } else {
       g = gemm_args(rows, GAC_G, GAC_E, c->ae, GAC_E, kxa, GAC_G, c->mxa, GAC_G);
       g.Bpacked = c->pk[PK_T_KXA]; g.Bpacked_bn = c->pk_bn[PK_T_KXA];
@@ -554,6 +595,7 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
       LAUNCHED(c, "rowdot_tanh");
     }
     float* t = hprev; hprev = hcur; hcur = t;
+    unsigned char* tp = pk_prev; pk_prev = pk_cur; pk_cur = tp;
   }
   return GAC_OK;
 }
@@ -1127,9 +1169,21 @@ int gac_gru_step(gac_ctx_t* c, const float* actor, const float* states_u, int32_
       c->pk[PK_T_U] = pack_w(c, PK_T_U, var(c, actor, 0, GAC_A_U), GAC_G, GAC_E, GAC_G, 0, rows);
     }
   }
-  if (c->gru_t)
-    return run_gru_step(c, 0, actor, c->sx_u, state_idx, action_emb, h_prev, h_out, rows, nullptr, nullptr, nullptr, nullptr, nullptr,
-                        (flags & GAC_GRU_ACTOR_INPUTS) != 0);
+  if (c->gru_t) {
+    const bool bounded = (flags & GAC_GRU_ACTOR_INPUTS) != 0;
+    const bool v2 = bounded && c->g2_on[0];
+    if (v2) {
+      // external fp32 operands: build the a16 images the v2 kernel consumes (inside the sampler the producing kernels write them)
+      if (!(flags & GAC_GRU_SAME_INPUTS)) {
+        GAC_CUDA(a16_pack(action_emb, GAC_E, rows, nullptr, &c->g2_sc[0]->s_ae, c->ae_pk, st));
+        if (h_prev) GAC_CUDA(a16_pack(h_prev, GAC_E, rows, nullptr, &c->g2_sc[0]->s_h, c->h_pk[0], st));
+        c->launches += h_prev ? 2 : 1;
+      }
+      GAC_TRY(run_gru_step_v2(c, 0, actor, c->sx_u, state_idx, c->ae_pk, c->h_pk[0], h_prev, h_out, c->h_pk[1], rows, nullptr));
+    }
+    return run_gru_step(c, 0, actor, c->sx_u, state_idx, action_emb, h_prev, h_out, rows, nullptr, nullptr, nullptr, nullptr, nullptr, bounded,
+                        v2 ? &c->g2_sc[0]->ok : nullptr);
+  }
   GemmArgs g = gemm_args(rows, GAC_G, GAC_E, action_emb, GAC_E, kxa, GAC_G, c->mxa, GAC_G);
   g.Bpacked = c->pk[PK_T_KXA]; g.Bpacked_bn = c->pk_bn[PK_T_KXA];
   GAC_TRY(run_gemm(c, g));

@@ -52,6 +52,7 @@ struct GruStepArgs {
   float *z, *r, *c, *mhh;      // optional saves (rows, 400)
   unsigned long long* dbg;     // optional per-CTA phase stamps (tools/gru_probe.py --timeline)
   const struct GruScales* sc;  // 3xFP16 scales (nullptr: 3xTF32 only)
+  const int* skip_if;          // optional device flag: non-zero = gru_step_v2_kernel did this step, exit at once
 };
 
 struct GruScales {
@@ -440,6 +441,7 @@ __device__ __forceinline__ void gru_step_body(const GruStepArgs& g) {
 
 // one launch, variant chosen on the device (no host round trip, no second grid)
 __global__ void __launch_bounds__(THREADS, 1) gru_step_tc_kernel(const GruStepArgs g) {
+  if (g.skip_if && *g.skip_if) return;
   if (g.sc && g.sc->ok) gru_step_body<true>(g);
   else gru_step_body<false>(g);
 }

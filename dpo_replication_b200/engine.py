@@ -192,13 +192,13 @@ class Engine:
         return out
 
     @_on_stream
-    def gru_step(self, actor, states_u, state_idx, action_emb, h_prev=None, reuse=False, actor_inputs=False):
+    def gru_step(self, actor, states_u, state_idx, action_emb, h_prev=None, reuse=False, actor_inputs=False, same_inputs=False):
         """One GRU(400) step of the AIQN actor (reference GAC/networks.py:166): h' = GRU([se[state_idx] | action_emb], h_prev).
         actor_inputs: action_emb / h_prev come from the actor itself (bounded by its weights) -> 3xFP16 variant allowed."""
         rows = action_emb.shape[0]
         out = self._new(rows, 400)
         check(lib.gac_gru_step(self.h, ptr(actor), ptr(states_u), states_u.shape[0], ptr(state_idx), ptr(action_emb), ptr(h_prev), rows,
-                               ptr(out), int(reuse) | (2 if actor_inputs else 0)))
+                               ptr(out), int(reuse) | (2 if actor_inputs else 0) | (4 if same_inputs else 0)))
         return out
 
     @_on_stream

@@ -133,8 +133,10 @@ int gac_aiqn_sample(gac_ctx_t* ctx, const float* actor, const float* states_u, i
  *   GAC_GRU_ACTOR_INPUTS   action_emb is the actor's own embedding LeakyReLU(cos(.) wa + ba) and |h_prev| < 1, i.e.
  *                          both are bounded by the weights: allows the 3xFP16 arithmetic variant (same accuracy,
  *                          half the tensor-core instructions).  Without it the 3xTF32 variant runs, which has
- *                          fp32's exponent range. ---- */
-enum { GAC_GRU_REUSE = 1, GAC_GRU_ACTOR_INPUTS = 2 };
+ *                          fp32's exponent range.
+ *   GAC_GRU_SAME_INPUTS    action_emb and h_prev hold the same values as in the previous call on this context (their
+ *                          pre-split fp16 operand images are reused instead of rebuilt; only meaningful with ACTOR_INPUTS). ---- */
+enum { GAC_GRU_REUSE = 1, GAC_GRU_ACTOR_INPUTS = 2, GAC_GRU_SAME_INPUTS = 4 };
 int gac_gru_step(gac_ctx_t* ctx, const float* actor, const float* states_u, int32_t n_states, const int32_t* state_idx,
                  const float* action_emb, const float* h_prev, int32_t rows, float* h_out, int32_t flags);
 
