@@ -19,6 +19,7 @@ constexpr int HEAD_BN = 208, HEAD_NT = 2;   // actor head: 400 hidden columns in
 namespace gac {
 thread_local char g_err[512] = {0};
 }
+constexpr int G2_MAX_GRID = 256;               // upper bound of the persistent GRU kernel's grid (SM count; 148 on B200)
 using namespace gac;
 
 // ------------------------------------------------------------------------------------------
@@ -128,7 +129,7 @@ struct gac_ctx {
   const unsigned char *gru_t, *gru_o;           // valid for the current call; nullptr = unfused path
   // second-generation GRU step (gru_step_v2.cuh): weight tiles + scales per actor (target / online), a16 images of the
   // sampler's action embedding and of the two ping-pong GRU states
-  unsigned char* g2_wpk[2]; tc::Gru2Scales* g2_sc[2]; unsigned char *ae_pk, *h_pk[2]; bool g2_on[2];
+  unsigned char* g2_wpk[2]; tc::Gru2Scales* g2_sc[2]; unsigned char *ae_pk, *h_pk[2]; bool g2_on[2]; float* g2_xh;
 };
 
 namespace {
@@ -224,6 +225,7 @@ size_t partition(gac_ctx* c, void* ws) {
   for (int i = 0; i < 2; ++i) { c->g2_wpk[i] = b.take<unsigned char>(tc::G2_WPK_BYTES); c->g2_sc[i] = b.take<tc::Gru2Scales>(1); }
   c->ae_pk = b.take<unsigned char>(tc::a16_bytes((long long)Rs));
   for (int i = 0; i < 2; ++i) c->h_pk[i] = b.take<unsigned char>(tc::a16_bytes((long long)Rs));
+  c->g2_xh = b.take<float>((size_t)G2_MAX_GRID * (tc::G2_XH_BYTES_PER_CTA / 4));
   c->head_pack32 = b.take<unsigned char>(tc::dot_pack_bytes(GAC_E, HEAD_BN, HEAD_NT, false));
   c->head_pack16 = b.take<unsigned char>(tc::dot_pack_bytes(GAC_E, HEAD_BN, HEAD_NT, true));
   c->head_sc = b.take<tc::DotScales>(1); c->head_part = b.take<float>((size_t)Rs * HEAD_NT);
@@ -305,7 +307,9 @@ int run_gru_step_v2(gac_ctx* c, int which, const float* actor, const float* sx, 
   tc::Gru2Args a;
   a.rows = rows; a.dyn_rows = dyn; a.ae_pk = ae_pk; a.h_pk = hprev ? h_pk : nullptr; a.hprev = hprev; a.wpk = c->g2_wpk[which]; a.sc = c->g2_sc[which];
   a.sx = sx; a.sidx = sidx; a.b1 = var(c, actor, 0, GAC_A_GB) + GAC_G; a.hout = hout; a.hout_pk = hout_pk;
-  a.z = a.r = a.c = a.mhh = nullptr;
+  a.z = a.r = a.c = a.mhh = nullptr; a.xh_scratch = c->g2_xh;
+  static const int probe = getenv("GAC_G2_PROBE") ? atoi(getenv("GAC_G2_PROBE")) : 0;
+  a.probe = probe;
   a.dbg = timeline ? reinterpret_cast<unsigned long long*>(c->spart) : nullptr;
   GAC_CUDA(launch_gru_step_v2(a, c->stream));
   c->launches++;

@@ -1,24 +1,31 @@
 // GRU step of the AIQN actor, second generation (sm_100a): a PERSISTENT, warp-specialised tcgen05 kernel whose
-// epilogue overlaps the next tile's main loop.
+// epilogue overlaps the next tile's main loop and whose MMAs are 240 columns wide.
 //
 //   same arithmetic as gru_step_tc.cuh (Keras GRU cell, reset_after, gate order [z|r|h]; GAC/networks.py:166,217,259)
 //
 // What round 1's kernel left on the table (profiles/r1b_gru_step_summary.txt: 21.1k of a tile's 31.8k cycles in the MMA
-// loop, the rest serial): the A operand (action embedding, h_prev) was staged through registers by the same eight warps that
-// later ran the epilogue, so nothing could overlap, and TMEM was full (main + correction accumulator = 512 columns).  Here:
+// loop, the rest serial; N = 192 of 256 per instruction; a 16-unit remainder tile that costs a full main loop): the A
+// operand (action embedding, h_prev) was staged through registers by the same eight warps that later ran the epilogue, so
+// nothing could overlap, and TMEM was full (main + correction accumulator = 512 columns).  Here:
 //   * BOTH operands arrive by cp.async.bulk.  The producers of the activations -- the embedding kernel for `ae`, this
 //     kernel's own epilogue for `h` -- write, next to (or instead of) their fp32 output, the pre-split, pre-scaled,
 //     pre-swizzled fp16 hi / lo tiles the MMA consumes ("a16" images: [row block][K block][hi | lo], 128 rows x 64 bytes,
 //     K-major SWIZZLE_64B).  One producer lane issues two bulk copies per K block; no thread touches operand data.
 //   * ONE accumulator per gate: hi*hi + lo*hi + hi*lo all add into the same TMEM columns with lo = x' - hi kept UNSCALED
-//     (operands are scaled to ~2^12 so lo stays a normal fp16 for every element within 2^-10 of the largest).  A tile is
-//     128 rows x 64 units x [xh | z | r | hh] = 256 columns, so TMEM holds TWO tiles: the MMA lane fills one while the eight
-//     epilogue warps drain the other.  The cost is three accumulate-truncations per K step instead of one (measured
-//     relative shrink ~1e-8 per add, 150 adds per output: ~1e-6 against the 1e-5 contract; the parity tests are the judge).
-//   * 32-deep K blocks (64-byte rows): a stage is 40 KB, four stages fit beside the epilogue's staging buffer, so three
+//     (operands are scaled to ~2^12 so lo stays a normal fp16 for every element within 2^-10 of the largest).  The cost is
+//     three accumulate-truncations per K step instead of one: measured max |h - fp64| 2.4e-6 against round 1's 0.9e-6
+//     (tools/gru2_probe.py), inside the 1e-5 contract; the parity tests are the judge.
+//   * THREE column groups per unit instead of four: [z | r | g].  z and r accumulate over both operand halves; g holds
+//     ae * kx_h while the action-embedding half runs, is copied out by four drain warps the moment that half retires
+//     (TMEM -> registers -> an L2-resident scratch row), and is then OVERWRITTEN by h_prev * U_h during the recurrent half
+//     (reset_after needs the two parts of the candidate gate apart).  A tile is therefore 80 units x 3 = 240 columns:
+//     every MMA is N = 240 (an M = 128 tcgen05.mma takes ~128 cycles whatever N <= 256 -- one A row per clock), 400 units
+//     are exactly five tiles (no remainder tile), and TMEM holds TWO tiles, so the MMA lane fills one while the eight
+//     epilogue warps drain the other.  7 x 150 -> 5 x 150 MMAs per 128-row block.
+//   * 32-deep K blocks (64-byte rows): a stage is 46 KB, four stages fit beside the epilogue's staging buffer, so three
 //     stages of operand data are in flight while one is consumed -- bulk-copy latency is off the critical path.
 //   * persistent grid (one CTA per SM), static round-robin over (row block, unit tile) items: consecutive CTAs share a row
-//     block (its A tiles are L2-hot), every CTA sees all seven unit tiles including the narrow one.
+//     block (its A tiles are L2-hot).
 #pragma once
 #include "gru_step_tc.cuh"
 
@@ -27,17 +34,24 @@ namespace tc {
 
 constexpr int G2_BK = 32;                                        // fp16 K elements per block = one 64-byte swizzle row
 constexpr int G2_KB = (GAC_E + G2_BK - 1) / G2_BK;               // 13 K blocks per operand half (the last has 16 live columns)
+constexpr int G2_NU = 80;                                        // hidden units per tile
+constexpr int G2_NT = GAC_E / G2_NU;                             // 5 tiles, no remainder
+static_assert(G2_NU * G2_NT == GAC_E && G2_NU % 16 == 0, "unit tiles must cover the 400 hidden units in 16-unit chunks");
 constexpr uint32_t G2_A_TILE = (uint32_t)BM * 64u;               // 8 KB per hi / lo
 constexpr uint32_t G2_A_SLOT = 2u * G2_A_TILE;                   // [hi | lo] of one (row block, K block)
-constexpr uint32_t G2_B_TILE = 3u * GRU_NU * 64u;                // 12 KB per hi / lo of a full 64-unit tile
+constexpr uint32_t G2_B_TILE = 3u * G2_NU * 64u;                 // 15 KB per hi / lo: rows [z | r | h] x 80 units
 constexpr uint32_t G2_B_SLOT = 2u * G2_B_TILE;
-constexpr uint32_t G2_STAGE = G2_A_SLOT + G2_B_SLOT;             // 40 KB
+constexpr uint32_t G2_STAGE = G2_A_SLOT + G2_B_SLOT;             // 46 KB
 constexpr int G2_STAGES = 4;
-constexpr int G2_SS = 68;                                        // staging row stride in floats (68 = 4 mod 32: conflict-free v4 row stores)
-constexpr int G2_SMEM = G2_STAGES * (int)G2_STAGE + BM * G2_SS * 4 + 1024;
+constexpr int G2_SS = 52;                                        // staging row stride in floats: [z16 | r16 | g16] + 4 (conflict-free v4 rows)
+constexpr int G2_DS = 20;                                        // drain transposition row stride in floats (16 + 4)
+constexpr int G2_DRAIN_SMEM = 4 * 32 * G2_DS * 4;                // 10 KB: one 32 x 16 block per drain warp
+constexpr int G2_SMEM = G2_STAGES * (int)G2_STAGE + BM * G2_SS * 4 + G2_DRAIN_SMEM + 3 * G2_NU * 4 + 1024;
 constexpr int G2_EPI_WARPS = 8;
-constexpr int G2_THREADS = (G2_EPI_WARPS + 2) * 32;              // 8 epilogue warps, the MMA warp, the producer warp
-constexpr size_t G2_WPK_BYTES = (size_t)GRU_NT * 2 * G2_KB * G2_B_SLOT;   // 4.4 MB
+constexpr int G2_DRAIN_WARP0 = G2_EPI_WARPS + 2;                 // warps 10..13
+constexpr int G2_THREADS = (G2_EPI_WARPS + 2 + 4) * 32;          // 8 epilogue warps, the MMA warp, the producer warp, 4 drain warps
+constexpr size_t G2_WPK_BYTES = (size_t)G2_NT * 2 * G2_KB * G2_B_SLOT;   // 4.0 MB
+constexpr size_t G2_XH_BYTES_PER_CTA = 2u * BM * G2_NU * 4u;     // two tiles' ae * kx_h (one per accumulator buffer)
 inline size_t a16_bytes(long long rows) { return (size_t)((rows + BM - 1) / BM) * G2_KB * G2_A_SLOT; }
 
 struct Gru2Scales {
@@ -61,7 +75,10 @@ struct Gru2Args {
   float* hout;                   // (rows, 400) fp32
   unsigned char* hout_pk;        // optional a16 image of h_out (the next step's A operand)
   float *z, *r, *c, *mhh;        // optional saves (rows, 400)
-  unsigned long long* dbg;       // optional per-CTA counters: [cycles, MMA-lane wait for operands, wait for a free accumulator, tiles]
+  float* xh_scratch;             // gridDim.x * G2_XH_BYTES_PER_CTA bytes (L2 resident): the candidate gate's input part between the halves
+  int probe;                     // timing experiments (GAC_G2_PROBE bits, results are garbage): 1 no drain stores, 2 no TMEM loads in the
+                                 // epilogue, 4 no global operand loads, 8 no global stores, 16 no gate math
+  unsigned long long* dbg;       // optional per-CTA counters: [cycles, MMA-lane wait for operands, for a free accumulator, for the drain, tiles]
 };
 
 // K-major SWIZZLE_64B shared-memory matrix descriptor (cute: Swizzle<2,4,3> o ((8,n),2):((4,SBO),1) in 16-byte units):
@@ -104,20 +121,17 @@ __global__ void gru2_scales_kernel(Gru2Scales* __restrict__ sc) {
   sc->ok = 1;
 }
 
-// Pre-split, pre-swizzled weights.  Slot (tile j, block kb2): kb2 < KB -> rows k of kx_a, gate order [h z r]; kb2 >= KB ->
-// rows k of U, gate order [z r h].  Tile row r = gate * nu + unit; 64-byte rows (32 k).  One thread per 16-byte chunk.
+// Pre-split, pre-swizzled weights.  Slot (tile j, block kb2): kb2 < KB -> rows k of kx_a, kb2 >= KB -> rows k of U; tile row
+// r = gate * 80 + unit in the natural gate order [z r h] for both; 64-byte rows (32 k).  One thread per 16-byte chunk.
 __global__ void gru2_pack_kernel(const float* __restrict__ kxa, const float* __restrict__ U, unsigned char* __restrict__ out,
                                  const Gru2Scales* __restrict__ sc) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long per_slot = 3 * GRU_NU * 4;
-  if (idx >= (long long)GRU_NT * 2 * G2_KB * per_slot || !sc->ok) return;
-  const int c = idx % 4, r = (idx / 4) % (3 * GRU_NU);
+  const long long per_slot = 3 * G2_NU * 4;
+  if (idx >= (long long)G2_NT * 2 * G2_KB * per_slot || !sc->ok) return;
+  const int c = idx % 4, r = (idx / 4) % (3 * G2_NU);
   const int slot = idx / per_slot, kb2 = slot % (2 * G2_KB), j = slot / (2 * G2_KB);
-  const int nu = min(GRU_NU, GAC_E - j * GRU_NU);
-  if (r >= 3 * nu) return;
   const int half = kb2 >= G2_KB, kb = kb2 - half * G2_KB;
-  const int gi = r / nu, u = j * GRU_NU + r % nu;
-  const int gate = half ? gi : (gi + 2) % 3;                       // [z r h] for U, [h z r] for kx_a (z = 0, r = 1, h = 2)
+  const int gate = r / G2_NU, u = j * G2_NU + r % G2_NU;
   const float* W = half ? U : kxa;
   const float sw = half ? sc->s_u : sc->s_kx;
   uint32_t h[4], l[4];
@@ -131,7 +145,7 @@ __global__ void gru2_pack_kernel(const float* __restrict__ kxa, const float* __r
   unsigned char* base = out + (size_t)slot * G2_B_SLOT;
   const uint32_t off = sw64_off(r, c);
   *reinterpret_cast<uint4*>(base + off) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4*>(base + (size_t)3 * nu * 64 + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  *reinterpret_cast<uint4*>(base + G2_B_TILE + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // fp32 (rows, 400) -> a16 image, for activations whose producer does not write the image itself.  One thread per 16-byte
@@ -167,20 +181,27 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 
 __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Args g) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[G2_STAGES], bar_empty[G2_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ __align__(8) uint64_t bar_full[G2_STAGES], bar_empty[G2_STAGES], bar_tfull[2], bar_tempty[2], bar_xfull[2], bar_xfree[2], bar_xsaved[2];
   __shared__ uint32_t tmem_slot;
 
   if (!g.sc->ok) return;                                           // no valid scaling: gru_step_tc_kernel (launched next) does the step
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m_end = g.dyn_rows ? min(g.rows, *g.dyn_rows) : g.rows;
-  const int n_items = ((m_end + BM - 1) / BM) * GRU_NT;           // (row block, unit tile), row-block major
-  const int nkb = g.h_pk ? 2 * G2_KB : G2_KB;
+  const int n_items = ((m_end + BM - 1) / BM) * G2_NT;            // (row block, unit tile), row-block major
+  const bool has_h = g.h_pk != nullptr;
+  const int nkb = has_h ? 2 * G2_KB : G2_KB;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)) + G2_STAGES * G2_STAGE);
+  float* dstg = stg + BM * G2_SS;                                  // drain warps' transposition blocks
+  float* b1_s = dstg + 4 * 32 * G2_DS;                             // recurrent bias of the current tile: [z | r | h] x 80
+  float* xh_cta = g.xh_scratch + (size_t)blockIdx.x * (G2_XH_BYTES_PER_CTA / 4);
 
   if (tid == 0) {
     for (int s = 0; s < G2_STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_tfull[b]), 1); mbar_init(smem_u32(&bar_tempty[b]), G2_EPI_WARPS); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tfull[b]), 1); mbar_init(smem_u32(&bar_tempty[b]), G2_EPI_WARPS);
+      mbar_init(smem_u32(&bar_xfull[b]), 1); mbar_init(smem_u32(&bar_xfree[b]), 4); mbar_init(smem_u32(&bar_xsaved[b]), 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == G2_EPI_WARPS) {
@@ -197,9 +218,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
     if (lane == 0) {
       int it = 0;
       for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
-        const int rb = i / GRU_NT, jt = i - rb * GRU_NT;
-        const int nu = min(GRU_NU, GAC_E - jt * GRU_NU);
-        const uint32_t b_bytes = 2u * 3u * (uint32_t)nu * 64u;
+        const int rb = i / G2_NT, jt = i - rb * G2_NT;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % G2_STAGES;
           const uint32_t ph = (uint32_t)(it / G2_STAGES) & 1u;
@@ -208,9 +227,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
           const int half = kb >= G2_KB, kbl = kb - half * G2_KB;
           const unsigned char* asrc = (half ? g.h_pk : g.ae_pk) + ((size_t)rb * G2_KB + kbl) * G2_A_SLOT;
           const unsigned char* bsrc = g.wpk + ((size_t)jt * 2 * G2_KB + kb) * G2_B_SLOT;
-          mbar_expect_tx_arrive(bar, G2_A_SLOT + b_bytes);
+          if (g.probe & 64) { mbar_arrive(bar); continue; }            // probe 64: no operand copies (MMAs run on stale smem)
+          mbar_expect_tx_arrive(bar, G2_STAGE);
           bulk_g2s(sa, asrc, G2_A_SLOT, bar);
-          bulk_g2s(sa + G2_A_SLOT, bsrc, b_bytes, bar);
+          bulk_g2s(sa + G2_A_SLOT, bsrc, G2_B_SLOT, bar);
         }
       }
     }
@@ -218,21 +238,22 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
   } else if (warp == G2_EPI_WARPS) {
     // ------------------------------ MMA issuer: one lane ------------------------------
     if (lane == 0) {
-      long long t_wait_full = 0, t_wait_acc = 0;
+      long long t_wait_full = 0, t_wait_acc = 0, t_wait_x = 0;
       const long long t_begin = g.dbg ? clock64() : 0;
+      unsigned long long gt0 = 0;
+      if (g.dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+      constexpr uint32_t id3 = (1u << 4) | ((uint32_t)((3 * G2_NU) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // make_idesc_f16(240)
+      constexpr uint32_t id2 = (1u << 4) | ((uint32_t)((2 * G2_NU) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      constexpr uint32_t id1 = (1u << 4) | ((uint32_t)(G2_NU >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int it = 0, t = 0;
       for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++t) {
-        const int jt = i % GRU_NT;
-        const int nu = min(GRU_NU, GAC_E - jt * GRU_NU);
         const int b = t & 1;
         const uint32_t tph = (uint32_t)(t >> 1) & 1u;
         long long c0 = g.dbg ? clock64() : 0;
-        mbar_wait(smem_u32(&bar_tempty[b]), tph ^ 1u);             // the epilogue has drained this accumulator (two tiles ago)
+        mbar_wait(smem_u32(&bar_tempty[b]), tph ^ 1u);             // the epilogue is done with this accumulator (two tiles ago)
         tc_fence_after();
         if (g.dbg) t_wait_acc += clock64() - c0;
-        const uint32_t d0 = tmem_d + (uint32_t)b * 256u;
-        const uint32_t id3 = make_idesc_f16(3 * nu), id2 = make_idesc_f16(2 * nu), id1 = make_idesc_f16(nu);
-        const uint32_t b_lo_off = 3u * (uint32_t)nu * 64u;
+        const uint32_t d0 = tmem_d + (uint32_t)b * 256u;           // columns [z | r | g], 80 each
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % G2_STAGES;
           const uint32_t ph = (uint32_t)(it / G2_STAGES) & 1u;
@@ -242,136 +263,253 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
           if (g.dbg) t_wait_full += clock64() - c0;
           const uint32_t sa = smem0 + (uint32_t)s * G2_STAGE;
           const uint64_t a_hi = make_desc64(sa), a_lo = make_desc64(sa + G2_A_TILE);
-          const uint64_t b_hi = make_desc64(sa + G2_A_SLOT), b_lo = make_desc64(sa + G2_A_SLOT + b_lo_off);
+          const uint64_t b_hi = make_desc64(sa + G2_A_SLOT), b_lo = make_desc64(sa + G2_A_SLOT + G2_B_TILE);
           const int half = kb >= G2_KB, kbl = kb - half * G2_KB, live = min(G2_BK, GAC_E - kbl * G2_BK);
-          const uint32_t dcol = half ? (uint32_t)nu : 0u;          // ae -> [xh z r], h_prev -> [z r hh]
-          const int ksteps = (live + 15) / 16;
+          const int ksteps = (g.probe & 32) ? 0 : (live + 15) / 16;      // probe 32: no MMAs, the operand stream alone
           for (int j = 0; j < ksteps; ++j) {
             const uint64_t adv = (uint64_t)(j * 2);
             if (half && kbl == 0 && j == 0) {
-              // first touch of the hh columns: z, r keep accumulating, hh starts from zero (stale from two tiles ago)
-              const uint64_t bo = (uint64_t)((2u * (uint32_t)nu * 64u) >> 4);
-              mma_f16(d0 + dcol, a_hi + adv, b_hi + adv, id2, 1u);
-              mma_f16(d0 + dcol, a_lo + adv, b_hi + adv, id2, 1u);
-              mma_f16(d0 + dcol, a_hi + adv, b_lo + adv, id2, 1u);
-              mma_f16(d0 + 3u * nu, a_hi + adv, b_hi + bo + adv, id1, 0u);
-              mma_f16(d0 + 3u * nu, a_lo + adv, b_hi + bo + adv, id1, 1u);
-              mma_f16(d0 + 3u * nu, a_hi + adv, b_lo + bo + adv, id1, 1u);
+              // the recurrent half starts: z, r keep accumulating; g switches from ae * kx_h (copied out by the drain warps)
+              // to h_prev * U_h and starts from zero
+              constexpr uint64_t bo = (uint64_t)((2u * G2_NU * 64u) >> 4);
+              mma_f16(d0, a_hi + adv, b_hi + adv, id2, 1u);        // z, r do not depend on the drain: ~3 MMA times of cover
+              mma_f16(d0, a_lo + adv, b_hi + adv, id2, 1u);
+              mma_f16(d0, a_hi + adv, b_lo + adv, id2, 1u);
+              c0 = g.dbg ? clock64() : 0;
+              mbar_wait(smem_u32(&bar_xfree[b]), tph);
+              tc_fence_after();
+              if (g.dbg) t_wait_x += clock64() - c0;
+              mma_f16(d0 + 2u * G2_NU, a_hi + adv, b_hi + bo + adv, id1, 0u);
+              mma_f16(d0 + 2u * G2_NU, a_lo + adv, b_hi + bo + adv, id1, 1u);
+              mma_f16(d0 + 2u * G2_NU, a_hi + adv, b_lo + bo + adv, id1, 1u);
               continue;
             }
-            mma_f16(d0 + dcol, a_hi + adv, b_hi + adv, id3, (kb | j) ? 1u : 0u);
-            mma_f16(d0 + dcol, a_lo + adv, b_hi + adv, id3, 1u);
-            mma_f16(d0 + dcol, a_hi + adv, b_lo + adv, id3, 1u);
+            mma_f16(d0, a_hi + adv, b_hi + adv, id3, (kb | j) ? 1u : 0u);
+            mma_f16(d0, a_lo + adv, b_hi + adv, id3, 1u);
+            mma_f16(d0, a_hi + adv, b_lo + adv, id3, 1u);
           }
           mma_commit(smem_u32(&bar_empty[s]));
+          if (has_h && kb == G2_KB - 1) mma_commit(smem_u32(&bar_xfull[b]));     // the action-embedding half has retired
         }
         mma_commit(smem_u32(&bar_tfull[b]));
       }
       if (g.dbg) {
-        unsigned long long* d = g.dbg + 8 + (size_t)blockIdx.x * 4;
+        unsigned long long* d = g.dbg + 8 + (size_t)blockIdx.x * 16;
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
         d[0] = (unsigned long long)(clock64() - t_begin); d[1] = (unsigned long long)t_wait_full; d[2] = (unsigned long long)t_wait_acc;
-        d[3] = (unsigned long long)t;
-        if (blockIdx.x == 0) { g.dbg[0] = 0x600DC0DE600DC0E2ull; g.dbg[1] = gridDim.x; }
+        d[3] = (unsigned long long)t_wait_x; d[4] = (unsigned long long)t; d[5] = gt1 - gt0;
+        if (blockIdx.x == 0) { g.dbg[0] = 0x600DC0DE600DC0E4ull; g.dbg[1] = gridDim.x; }
       }
     }
     __syncwarp();
+  } else if (warp >= G2_DRAIN_WARP0) {
+    // ------------------------------ drain warps: g = ae * kx_h out of TMEM between the two halves ------------------------------
+    if (has_h) {
+      const int quarter = warp & 3;                               // the TMEM lane quadrant this warp may read
+      const float inv_unit = g.sc->inv_unit;
+      const bool stamp = g.dbg && tid == G2_DRAIN_WARP0 * 32;
+      long long dw = 0, dk = 0;
+      int t = 0;
+      for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++t) {
+        const int b = t & 1;
+        const uint32_t tph = (uint32_t)(t >> 1) & 1u;
+        long long c0 = stamp ? clock64() : 0;
+        mbar_wait(smem_u32(&bar_xfull[b]), tph);
+        tc_fence_after();
+        long long c1 = stamp ? clock64() : 0;
+        dw += c1 - c0;
+        const uint32_t d0 = tmem_d + (uint32_t)b * 256u + 2u * G2_NU + ((uint32_t)(quarter * 32) << 16);
+        // all 80 columns of this lane's row in one go: five loads in flight, one wait, then the columns are free
+        uint32_t v[G2_NU];
+#pragma unroll
+        for (int ci = 0; ci < G2_NU / 16; ++ci)
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+              : "=r"(v[ci * 16 + 0]), "=r"(v[ci * 16 + 1]), "=r"(v[ci * 16 + 2]), "=r"(v[ci * 16 + 3]), "=r"(v[ci * 16 + 4]), "=r"(v[ci * 16 + 5]),
+                "=r"(v[ci * 16 + 6]), "=r"(v[ci * 16 + 7]), "=r"(v[ci * 16 + 8]), "=r"(v[ci * 16 + 9]), "=r"(v[ci * 16 + 10]), "=r"(v[ci * 16 + 11]),
+                "=r"(v[ci * 16 + 12]), "=r"(v[ci * 16 + 13]), "=r"(v[ci * 16 + 14]), "=r"(v[ci * 16 + 15])
+              : "r"(d0 + (uint32_t)(ci * 16)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_xfree[b]));       // the MMA lane may overwrite g now
+        // registers (lane = row) -> 32 x 16 block in smem -> (row, quad) float4: every global store is 8 rows x 64 contiguous bytes
+        float* blk = dstg + (size_t)(warp - G2_DRAIN_WARP0) * 32 * G2_DS;
+        float* dst = xh_cta + ((size_t)b * BM + quarter * 32) * G2_NU;
+        if (!(g.probe & 1)) {
+#pragma unroll
+          for (int ci = 0; ci < G2_NU / 16; ++ci) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              *reinterpret_cast<float4*>(blk + lane * G2_DS + e) =
+                  make_float4(__uint_as_float(v[ci * 16 + e]) * inv_unit, __uint_as_float(v[ci * 16 + e + 1]) * inv_unit,
+                              __uint_as_float(v[ci * 16 + e + 2]) * inv_unit, __uint_as_float(v[ci * 16 + e + 3]) * inv_unit);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int rr = (lane >> 2) + 8 * k, qd = lane & 3;
+              __stcg(reinterpret_cast<float4*>(dst + (size_t)rr * G2_NU + ci * 16 + 4 * qd), *reinterpret_cast<const float4*>(blk + rr * G2_DS + 4 * qd));
+            }
+            __syncwarp();
+          }
+        }
+        __syncwarp();                                              // orders the lanes' stores before lane 0's releasing arrive
+        if (lane == 0) mbar_arrive(smem_u32(&bar_xsaved[b]));
+        if (stamp) dk += clock64() - c1;
+      }
+      if (stamp) { unsigned long long* d = g.dbg + 8 + (size_t)blockIdx.x * 16; d[12] = (unsigned long long)dw; d[13] = (unsigned long long)dk; }
+    }
   } else {
     // ------------------------------ epilogue: eight warps, overlapped with the next tile's main loop ------------------------------
     const int quarter = warp & 3, hf = warp >> 2;
     const float inv_unit = g.sc->inv_unit, s_h = g.sc->s_h;
-    const bool has_h = g.hprev != nullptr;
-    auto sig = [](float x) { return __fdividef(1.f, 1.f + __expf(-x)); };
     auto tnh = [](float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); };
     // phase-2 ownership: lane -> row (lane & 7) of the warp's 8-row strip (+ 64 in the second pass), unit quad lane >> 3:
     // a quarter warp reads eight consecutive staging rows (every bank once) and a warp touches 8 rows x 64 contiguous bytes
     const int prow = warp * 8 + (lane & 7), pj = lane >> 3;
+    const bool stamp = g.dbg && tid == 0;
+    long long e_wt = 0, e_wx = 0, e_p1 = 0, e_b1 = 0, e_p2 = 0, e_b2 = 0, e_ld = 0, ec = 0;
+#define G2_STAMP(acc) if (stamp) { const long long now = clock64(); acc += now - ec; ec = now; }
     int t = 0;
     for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++t) {
-      const int rb = i / GRU_NT, jt = i - rb * GRU_NT;
-      const int nu = min(GRU_NU, GAC_E - jt * GRU_NU), nq = nu >> 4;
+      const int rb = i / G2_NT, jt = i - rb * G2_NT;
       const int m0 = rb * BM, b = t & 1;
+      if (stamp) ec = clock64();
       const uint32_t tph = (uint32_t)(t >> 1) & 1u;
       int sid[2];
 #pragma unroll
       for (int p = 0; p < 2; ++p) { const int m = m0 + prow + 64 * p; sid[p] = m < m_end ? g.sidx[m] : -1; }
+      if (tid < 3 * G2_NU / 4)                                     // this tile's recurrent bias -> smem (read in every chunk's phase 2)
+        *reinterpret_cast<float4*>(b1_s + 4 * tid) = *reinterpret_cast<const float4*>(g.b1 + (tid / (G2_NU / 4)) * GAC_E + jt * G2_NU + 4 * (tid % (G2_NU / 4)));
+      if (has_h) mbar_wait(smem_u32(&bar_xsaved[b]), tph);         // acquire: the drain warps' scratch rows are visible
+      G2_STAMP(e_wx)
+      // Operands of phase 2 that do not depend on the accumulators (gathered state projection, h_prev, the saved input part).
+      // The SM keeps only a few hundred sectors in flight, so a burst of all of a chunk's loads blocks at issue for ~2.5k
+      // cycles: instead the loads of chunk q + 1 are issued one pass at a time inside phase 2 of chunk q, right after the
+      // registers they overwrite were consumed, and fly during the barrier and the next phase 1.
+      float4 sz[2], sr[2], sh[2], hp[2], xh[2];
+      auto load_ops = [&](int p, int q) {
+        hp[p] = make_float4(0.f, 0.f, 0.f, 0.f); xh[p] = hp[p];
+        if (g.probe & 4) { sz[p] = sr[p] = sh[p] = hp[p]; return; }
+        if (sid[p] < 0) return;
+        const int ul = q * 16 + 4 * pj, u = jt * G2_NU + ul;
+        const float* sx = g.sx + (size_t)sid[p] * GAC_G + u;
+        // .cg: with 227 KB of shared memory only ~28 KB of L1 is left, and a cached load needs a line there for its fill --
+        // a couple of hundred lines in flight capped the epilogue's loads at ~15 B/clk
+        sz[p] = __ldcg(reinterpret_cast<const float4*>(sx)); sr[p] = __ldcg(reinterpret_cast<const float4*>(sx + GAC_E));
+        sh[p] = __ldcg(reinterpret_cast<const float4*>(sx + 2 * GAC_E));
+        if (has_h) {
+          hp[p] = __ldcg(reinterpret_cast<const float4*>(g.hprev + (size_t)(m0 + prow + 64 * p) * GAC_E + u));
+          xh[p] = __ldcg(reinterpret_cast<const float4*>(xh_cta + ((size_t)b * BM + prow + 64 * p) * G2_NU + ul));
+        }
+      };
+      load_ops(0, 0);
+      load_ops(1, 0);
+      G2_STAMP(e_ld)
       mbar_wait(smem_u32(&bar_tfull[b]), tph);
       tc_fence_after();
+      G2_STAMP(e_wt)
       const uint32_t d0 = tmem_d + (uint32_t)b * 256u + ((uint32_t)(quarter * 32) << 16);
-      for (int q = 0; q < nq; ++q) {
-        const int u = jt * GRU_NU + q * 16 + 4 * pj;               // this lane's four hidden units
-        // operands that do not depend on the accumulators: in flight across phase 1 and the barrier
-        float4 sz[2], sr[2], sh[2], hp[2];
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          hp[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (sid[p] < 0) continue;
-          const float* sx = g.sx + (size_t)sid[p] * GAC_G + u;
-          sz[p] = *reinterpret_cast<const float4*>(sx); sr[p] = *reinterpret_cast<const float4*>(sx + GAC_E);
-          sh[p] = *reinterpret_cast<const float4*>(sx + 2 * GAC_E);
-          if (has_h) hp[p] = *reinterpret_cast<const float4*>(g.hprev + (size_t)(m0 + prow + 64 * p) * GAC_E + u);
-        }
-        const float4 bz = *reinterpret_cast<const float4*>(g.b1 + u), br = *reinterpret_cast<const float4*>(g.b1 + GAC_E + u),
-                     bh = *reinterpret_cast<const float4*>(g.b1 + 2 * GAC_E + u);
-        // phase 1: 16 units x [xh z r hh] of 128 rows, TMEM -> staging; warps 0-3 take xh and z, warps 4-7 r and hh
+      for (int q = 0; q < G2_NU / 16; ++q) {
+        const int ul = q * 16 + 4 * pj, u = jt * G2_NU + ul;       // this lane's four hidden units (within the tile / of 400)
+        // phase 1: 16 units x [z r g] of 128 rows, TMEM -> staging; warps 0-3 take z and g, warps 4-7 take r.  Both loads
+        // of a warp are in flight before the one wait.
         {
           float* srow = stg + (size_t)(quarter * 32 + lane) * G2_SS;
+          // column groups: warps 0-3 (hf = 0) take z (0) and g (2), warps 4-7 take r (1)
+          uint32_t v0[16], v1[16];
+#define G2_LD16(v, col)                                                                                                            \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"         \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), \
+                 "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                                        \
+               : "r"(col))
+#define G2_ST16(v, grp)                                                                                                            \
+  _Pragma("unroll") for (int e = 0; e < 16; e += 4)                                                                                \
+      *reinterpret_cast<float4*>(srow + (grp) * 16 + e) = make_float4(__uint_as_float(v[e]) * inv_unit, __uint_as_float(v[e + 1]) * inv_unit, \
+                                                                    __uint_as_float(v[e + 2]) * inv_unit, __uint_as_float(v[e + 3]) * inv_unit)
+          if (g.probe & 2) {
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int gi = 2 * hf + k;
-            float v[16];
-            if (gi == 3 && !has_h) {                               // the hh columns were never written on the first step
-#pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = 0.f;
-            } else {
-              tmem_ld16(d0 + (uint32_t)(gi * nu + q * 16), v);
-            }
-#pragma unroll
-            for (int e = 0; e < 16; e += 4)
-              *reinterpret_cast<float4*>(srow + gi * 16 + e) = make_float4(v[e] * inv_unit, v[e + 1] * inv_unit, v[e + 2] * inv_unit, v[e + 3] * inv_unit);
+            for (int e = 0; e < 16; ++e) v0[e] = v1[e] = 0x3f800000u;
+          } else {
+            G2_LD16(v0, d0 + (uint32_t)(hf * G2_NU + q * 16));
+            if (hf == 0) G2_LD16(v1, d0 + (uint32_t)(2 * G2_NU + q * 16));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           }
+          G2_ST16(v0, hf);
+          if (hf == 0) G2_ST16(v1, 2);
+#undef G2_LD16
+#undef G2_ST16
         }
-        if (q == nq - 1) {                                         // last TMEM read of this tile: hand the accumulator back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[b]));
-        }
+        G2_STAMP(e_p1)
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        G2_STAMP(e_b1)
         // phase 2: gate math and the state update, row-contiguous global traffic
+        // (no branch around the math: the two rows' instruction streams interleave; dead rows only skip their stores)
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-          if (sid[p] < 0) continue;
           const int row = prow + 64 * p;
           const float* srow = stg + (size_t)row * G2_SS + 4 * pj;
-          const float4 axh = *reinterpret_cast<const float4*>(srow), az = *reinterpret_cast<const float4*>(srow + 16),
-                       ar = *reinterpret_cast<const float4*>(srow + 32), ahh = *reinterpret_cast<const float4*>(srow + 48);
+          const float4 az = *reinterpret_cast<const float4*>(srow), ar = *reinterpret_cast<const float4*>(srow + 16),
+                       ag = *reinterpret_cast<const float4*>(srow + 32);
+          const float4 bz = *reinterpret_cast<const float4*>(b1_s + ul), br = *reinterpret_cast<const float4*>(b1_s + G2_NU + ul),
+                       bh = *reinterpret_cast<const float4*>(b1_s + 2 * G2_NU + ul);
+          // with a recurrent half g holds h_prev * U_h and the input part comes from the scratch; on the first step g IS the input part
+          const float4 axh = has_h ? xh[p] : ag;
+          const float4 ahh = has_h ? ag : make_float4(0.f, 0.f, 0.f, 0.f);
           float4 ho, zo, ro, co, mo;
+          if (g.probe & 16) { ho = az; zo = ar; ro = ag; co = axh; mo = ahh; } else {
+          // sigmoid(a), sigmoid(b) share ONE reciprocal: with p = 1 + e^-a, q = 1 + e^-b, R = 1 / (p q): z = q R, r = p R.  The
+          // exponents are clamped to +-30 (sigmoid is 0 or 1 to 1e-13 there), so p q <= 1.2e26 never overflows.
 #define GRU2_LANE(f)                                                                              \
   {                                                                                               \
     const float hh = ahh.f + bh.f;                                                                \
-    const float zz = sig((sz[p].f + az.f) + bz.f), rr = sig((sr[p].f + ar.f) + br.f);             \
+    const float pa = 1.f + __expf(-fminf(fmaxf((sz[p].f + az.f) + bz.f, -30.f), 30.f));           \
+    const float pb = 1.f + __expf(-fminf(fmaxf((sr[p].f + ar.f) + br.f, -30.f), 30.f));           \
+    const float R = __fdividef(1.f, pa * pb);                                                     \
+    const float zz = pb * R, rr = pa * R;                                                         \
     const float cc = tnh((sh[p].f + axh.f) + rr * hh);                                            \
     ho.f = zz * hp[p].f + (1.f - zz) * cc; zo.f = zz; ro.f = rr; co.f = cc; mo.f = hh;            \
   }
           GRU2_LANE(x) GRU2_LANE(y) GRU2_LANE(z) GRU2_LANE(w)
 #undef GRU2_LANE
+          }
+          const bool live = sid[p] >= 0 && !(g.probe & 8);
           const int m = m0 + row;
           const size_t o = (size_t)m * GAC_E + u;
-          *reinterpret_cast<float4*>(g.hout + o) = ho;
-          if (g.z) {
-            *reinterpret_cast<float4*>(g.z + o) = zo; *reinterpret_cast<float4*>(g.r + o) = ro;
-            *reinterpret_cast<float4*>(g.c + o) = co; *reinterpret_cast<float4*>(g.mhh + o) = mo;
+          if (live) {
+            *reinterpret_cast<float4*>(g.hout + o) = ho;
+            if (g.z) {
+              *reinterpret_cast<float4*>(g.z + o) = zo; *reinterpret_cast<float4*>(g.r + o) = ro;
+              *reinterpret_cast<float4*>(g.c + o) = co; *reinterpret_cast<float4*>(g.mhh + o) = mo;
+            }
           }
           if (g.hout_pk) {                                         // the next step's A operand, already split / scaled / swizzled
             uint32_t h0, l0, h1, l1;
             split_f16x2_u(ho.x * s_h, ho.y * s_h, h0, l0);
             split_f16x2_u(ho.z * s_h, ho.w * s_h, h1, l1);
-            unsigned char* dst = g.hout_pk + a16_off(m, u);
-            *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(dst + G2_A_TILE) = make_uint2(l0, l1);
+            if (live) {
+              unsigned char* dst = g.hout_pk + a16_off(m, u);
+              *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2*>(dst + G2_A_TILE) = make_uint2(l0, l1);
+            }
           }
+          if (q + 1 < G2_NU / 16) load_ops(p, q + 1);
         }
+        G2_STAMP(e_p2)
         asm volatile("bar.sync 1, 256;" ::: "memory");             // the staging rows are rewritten by the next chunk / tile
+        G2_STAMP(e_b2)
       }
+      // this tile's accumulator columns and scratch rows are free again (all their reads above have completed)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[b]));
+    }
+#undef G2_STAMP
+    if (stamp) {
+      unsigned long long* d = g.dbg + 8 + (size_t)blockIdx.x * 16;
+      d[6] = (unsigned long long)e_wt; d[7] = (unsigned long long)e_wx; d[8] = (unsigned long long)e_p1; d[9] = (unsigned long long)e_b1;
+      d[10] = (unsigned long long)e_p2; d[11] = (unsigned long long)e_b2; d[14] = (unsigned long long)e_ld;
     }
   }
 
@@ -391,7 +529,7 @@ inline cudaError_t gru2_pack(const float* kxa, const float* U, const float* wa, 
   if (e != cudaSuccess) return e;
   tc::gru_amax_kernel<<<60, 256, 0, st>>>(kxa, U, wa, ba, sc->slots);
   tc::gru2_scales_kernel<<<1, 1, 0, st>>>(sc);
-  const long long total = (long long)tc::GRU_NT * 2 * tc::G2_KB * 3 * tc::GRU_NU * 4;
+  const long long total = (long long)tc::G2_NT * 2 * tc::G2_KB * 3 * tc::G2_NU * 4;
   tc::gru2_pack_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(kxa, U, out, sc);
   return cudaGetLastError();
 }
@@ -406,6 +544,7 @@ inline int gru2_grid() {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    if (sms > 256) sms = 256;                                    // the scratch rows are sized for 256 CTAs (G2_MAX_GRID)
   }
   return sms;
 }
@@ -416,8 +555,10 @@ inline cudaError_t launch_gru_step_v2(const tc::Gru2Args& g, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  const int items = tc::GRU_NT * cdiv(g.rows, tc::BM);
-  const int grid = items < gru2_grid() ? items : gru2_grid();
+  const int items = tc::G2_NT * cdiv(g.rows, tc::BM);
+  static const int grid_env = getenv("GAC_G2_GRID") ? atoi(getenv("GAC_G2_GRID")) : 0;
+  const int cap = grid_env > 0 && grid_env < gru2_grid() ? grid_env : gru2_grid();
+  const int grid = items < cap ? items : cap;
   tc::gru_step_v2_kernel<<<grid, tc::G2_THREADS, tc::G2_SMEM, st>>>(g);
   return cudaGetLastError();
 }

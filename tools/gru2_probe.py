@@ -71,12 +71,17 @@ def main():
     print(f"  {ms * 1e3:8.1f} us per launch = {fl / (ms * 1e-3) / 1e12:6.1f} TFLOP/s algorithmic; repeat is bit-identical: {bool(torch.equal(out, out2))}")
     if os.environ.get("GAC_GRU_TIMELINE"):
         arr = eng.workspace.view(torch.int64).cpu().numpy()
-        hits = np.nonzero(arr == 0x600DC0DE600DC0E2)[0]
+        hits = np.nonzero(arr == 0x600DC0DE600DC0E4)[0]
         if hits.size:
             n = int(arr[hits[0] + 1])
-            rec = arr[hits[0] + 8: hits[0] + 8 + 4 * n].reshape(n, 4)
-            print(f"  MMA lane per CTA ({n} CTAs): cycles {rec[:, 0].mean():.0f}  waiting for operands {rec[:, 1].mean():.0f} ({100 * rec[:, 1].sum() / rec[:, 0].sum():.1f}%)  "
-                  f"waiting for a free accumulator {rec[:, 2].mean():.0f} ({100 * rec[:, 2].sum() / rec[:, 0].sum():.1f}%)  tiles {rec[:, 3].mean():.2f}")
+            rec = arr[hits[0] + 8: hits[0] + 8 + 16 * n].reshape(n, 16)
+            pct = lambda k: 100 * rec[:, k].sum() / rec[:, 0].sum()
+            tl = rec[:, 4].sum()
+            print(f"  SM clock {1e3 * rec[:, 0].sum() / rec[:, 5].sum():.0f} MHz;  per tile (cycles): MMA lane {rec[:, 0].sum() / tl:.0f}"
+                  f" | epilogue: wait drain {rec[:, 7].sum() / tl:.0f} wait accum {rec[:, 6].sum() / tl:.0f} load issue {rec[:, 14].sum() / tl:.0f} phase1 {rec[:, 8].sum() / tl:.0f} bar {rec[:, 9].sum() / tl:.0f}"
+                  f" phase2 {rec[:, 10].sum() / tl:.0f} bar {rec[:, 11].sum() / tl:.0f} | drain warps: wait {rec[:, 12].sum() / tl:.0f} work {rec[:, 13].sum() / tl:.0f}")
+            print(f"  MMA lane per CTA ({n} CTAs): cycles mean {rec[:, 0].mean():.0f} max {rec[:, 0].max()}  waiting for operands {pct(1):.1f}%  "
+                  f"for a free accumulator {pct(2):.1f}%  for the drain warps {pct(3):.1f}%  tiles {rec[:, 4].mean():.2f} (max {rec[:, 4].max()})")
         else:
             print("  no counters found")
 
