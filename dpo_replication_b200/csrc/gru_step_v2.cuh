@@ -44,12 +44,20 @@ constexpr uint32_t G2_B_SLOT = 2u * G2_B_TILE;
 constexpr uint32_t G2_STAGE = G2_A_SLOT + G2_B_SLOT;             // 46 KB
 constexpr int G2_STAGES = 4;
 constexpr int G2_SS = 52;                                        // staging row stride in floats: [z16 | r16 | g16] + 4 (conflict-free v4 rows)
-constexpr int G2_DS = 20;                                        // drain transposition row stride in floats (16 + 4)
-constexpr int G2_DRAIN_SMEM = 4 * 32 * G2_DS * 4;                // 10 KB: one 32 x 16 block per drain warp
+constexpr int G2_DRAIN_WARPS = 8;                                // two per TMEM lane quadrant, 40 columns each
+constexpr int G2_DS = 12;                                        // drain transposition row stride in floats (8 + 4)
+constexpr int G2_DRAIN_SMEM = G2_DRAIN_WARPS * 32 * G2_DS * 4;   // 12 KB: one 32 x 8 block per drain warp
 constexpr int G2_SMEM = G2_STAGES * (int)G2_STAGE + BM * G2_SS * 4 + G2_DRAIN_SMEM + 3 * G2_NU * 4 + 1024;
-constexpr int G2_EPI_WARPS = 8;
-constexpr int G2_DRAIN_WARP0 = G2_EPI_WARPS + 2;                 // warps 10..13
-constexpr int G2_THREADS = (G2_EPI_WARPS + 2 + 4) * 32;          // 8 epilogue warps, the MMA warp, the producer warp, 4 drain warps
+// Warp roles, in warpgroups of four (setmaxnreg works per warpgroup): warps 0-15 epilogue (the gate math is a long dependent
+// chain per thread: with two warps per scheduler its latencies were exposed and a tile's epilogue took ~29k cycles against a
+// 23k-cycle main loop; four warps per scheduler hide them), warp 16 MMA issuer, warp 17 producer, warps 18-19 idle, warps 20-27
+// drain (two per TMEM lane quadrant, so that a row's 80 columns are read in one batch of loads within the register budget).
+constexpr int G2_EPI_WARPS = 16;
+constexpr int G2_MMA_WARP = G2_EPI_WARPS, G2_PROD_WARP = G2_EPI_WARPS + 1;
+constexpr int G2_DRAIN_WARP0 = G2_EPI_WARPS + 4;                 // warps 20..23 (lane quadrant = warp & 3)
+constexpr int G2_THREADS = (G2_EPI_WARPS + 4 + G2_DRAIN_WARPS) * 32;   // 896: every role fits the 72 registers that leaves
+// (ptxas 12.9 does not widen its allocation after setmaxnreg.inc -- tried: the drain region still spilled at the block-wide
+// cap -- so every role is written to fit the 80 registers a 768-thread block gets.)
 constexpr size_t G2_WPK_BYTES = (size_t)G2_NT * 2 * G2_KB * G2_B_SLOT;   // 4.0 MB
 constexpr size_t G2_XH_BYTES_PER_CTA = 2u * BM * G2_NU * 4u;     // two tiles' ae * kx_h (one per accumulator buffer)
 inline size_t a16_bytes(long long rows) { return (size_t)((rows + BM - 1) / BM) * G2_KB * G2_A_SLOT; }
@@ -179,7 +187,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+template <bool DBG>
 __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Args g) {
+  // DBG = false: the counters and the timing-experiment switches are compiled out (they cost registers in every role)
+  unsigned long long* const dbgp = DBG ? g.dbg : nullptr;
+  const int probe = DBG ? g.probe : 0;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[G2_STAGES], bar_empty[G2_STAGES], bar_tfull[2], bar_tempty[2], bar_xfull[2], bar_xfree[2], bar_xsaved[2];
   __shared__ uint32_t tmem_slot;
@@ -193,18 +205,18 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)) + G2_STAGES * G2_STAGE);
   float* dstg = stg + BM * G2_SS;                                  // drain warps' transposition blocks
-  float* b1_s = dstg + 4 * 32 * G2_DS;                             // recurrent bias of the current tile: [z | r | h] x 80
+  float* b1_s = dstg + G2_DRAIN_WARPS * 32 * G2_DS;                             // recurrent bias of the current tile: [z | r | h] x 80
   float* xh_cta = g.xh_scratch + (size_t)blockIdx.x * (G2_XH_BYTES_PER_CTA / 4);
 
   if (tid == 0) {
     for (int s = 0; s < G2_STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_tfull[b]), 1); mbar_init(smem_u32(&bar_tempty[b]), G2_EPI_WARPS);
-      mbar_init(smem_u32(&bar_xfull[b]), 1); mbar_init(smem_u32(&bar_xfree[b]), 4); mbar_init(smem_u32(&bar_xsaved[b]), 4);
+      mbar_init(smem_u32(&bar_xfull[b]), 1); mbar_init(smem_u32(&bar_xfree[b]), G2_DRAIN_WARPS); mbar_init(smem_u32(&bar_xsaved[b]), G2_DRAIN_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == G2_EPI_WARPS) {
+  if (warp == G2_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -213,7 +225,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
 
-  if (warp == G2_EPI_WARPS + 1) {
+  if (warp == G2_PROD_WARP) {
     // ------------------------------ producer: one lane, two bulk copies per K block ------------------------------
     if (lane == 0) {
       int it = 0;
@@ -227,7 +239,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
           const int half = kb >= G2_KB, kbl = kb - half * G2_KB;
           const unsigned char* asrc = (half ? g.h_pk : g.ae_pk) + ((size_t)rb * G2_KB + kbl) * G2_A_SLOT;
           const unsigned char* bsrc = g.wpk + ((size_t)jt * 2 * G2_KB + kb) * G2_B_SLOT;
-          if (g.probe & 64) { mbar_arrive(bar); continue; }            // probe 64: no operand copies (MMAs run on stale smem)
+          if (probe & 64) { mbar_arrive(bar); continue; }            // probe 64: no operand copies (MMAs run on stale smem)
           mbar_expect_tx_arrive(bar, G2_STAGE);
           bulk_g2s(sa, asrc, G2_A_SLOT, bar);
           bulk_g2s(sa + G2_A_SLOT, bsrc, G2_B_SLOT, bar);
@@ -235,13 +247,13 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
       }
     }
     __syncwarp();
-  } else if (warp == G2_EPI_WARPS) {
+  } else if (warp == G2_MMA_WARP) {
     // ------------------------------ MMA issuer: one lane ------------------------------
     if (lane == 0) {
       long long t_wait_full = 0, t_wait_acc = 0, t_wait_x = 0;
-      const long long t_begin = g.dbg ? clock64() : 0;
+      const long long t_begin = dbgp ? clock64() : 0;
       unsigned long long gt0 = 0;
-      if (g.dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
+      if (dbgp) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
       constexpr uint32_t id3 = (1u << 4) | ((uint32_t)((3 * G2_NU) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // make_idesc_f16(240)
       constexpr uint32_t id2 = (1u << 4) | ((uint32_t)((2 * G2_NU) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       constexpr uint32_t id1 = (1u << 4) | ((uint32_t)(G2_NU >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -249,23 +261,23 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
       for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++t) {
         const int b = t & 1;
         const uint32_t tph = (uint32_t)(t >> 1) & 1u;
-        long long c0 = g.dbg ? clock64() : 0;
+        long long c0 = dbgp ? clock64() : 0;
         mbar_wait(smem_u32(&bar_tempty[b]), tph ^ 1u);             // the epilogue is done with this accumulator (two tiles ago)
         tc_fence_after();
-        if (g.dbg) t_wait_acc += clock64() - c0;
+        if (dbgp) t_wait_acc += clock64() - c0;
         const uint32_t d0 = tmem_d + (uint32_t)b * 256u;           // columns [z | r | g], 80 each
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % G2_STAGES;
           const uint32_t ph = (uint32_t)(it / G2_STAGES) & 1u;
-          c0 = g.dbg ? clock64() : 0;
+          c0 = dbgp ? clock64() : 0;
           mbar_wait(smem_u32(&bar_full[s]), ph);
           tc_fence_after();
-          if (g.dbg) t_wait_full += clock64() - c0;
+          if (dbgp) t_wait_full += clock64() - c0;
           const uint32_t sa = smem0 + (uint32_t)s * G2_STAGE;
           const uint64_t a_hi = make_desc64(sa), a_lo = make_desc64(sa + G2_A_TILE);
           const uint64_t b_hi = make_desc64(sa + G2_A_SLOT), b_lo = make_desc64(sa + G2_A_SLOT + G2_B_TILE);
           const int half = kb >= G2_KB, kbl = kb - half * G2_KB, live = min(G2_BK, GAC_E - kbl * G2_BK);
-          const int ksteps = (g.probe & 32) ? 0 : (live + 15) / 16;      // probe 32: no MMAs, the operand stream alone
+          const int ksteps = (probe & 32) ? 0 : (live + 15) / 16;      // probe 32: no MMAs, the operand stream alone
           for (int j = 0; j < ksteps; ++j) {
             const uint64_t adv = (uint64_t)(j * 2);
             if (half && kbl == 0 && j == 0) {
@@ -275,10 +287,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
               mma_f16(d0, a_hi + adv, b_hi + adv, id2, 1u);        // z, r do not depend on the drain: ~3 MMA times of cover
               mma_f16(d0, a_lo + adv, b_hi + adv, id2, 1u);
               mma_f16(d0, a_hi + adv, b_lo + adv, id2, 1u);
-              c0 = g.dbg ? clock64() : 0;
+              c0 = dbgp ? clock64() : 0;
               mbar_wait(smem_u32(&bar_xfree[b]), tph);
               tc_fence_after();
-              if (g.dbg) t_wait_x += clock64() - c0;
+              if (dbgp) t_wait_x += clock64() - c0;
               mma_f16(d0 + 2u * G2_NU, a_hi + adv, b_hi + bo + adv, id1, 0u);
               mma_f16(d0 + 2u * G2_NU, a_lo + adv, b_hi + bo + adv, id1, 1u);
               mma_f16(d0 + 2u * G2_NU, a_hi + adv, b_lo + bo + adv, id1, 1u);
@@ -293,22 +305,24 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
         }
         mma_commit(smem_u32(&bar_tfull[b]));
       }
-      if (g.dbg) {
-        unsigned long long* d = g.dbg + 8 + (size_t)blockIdx.x * 16;
+      if (dbgp) {
+        unsigned long long* d = dbgp + 8 + (size_t)blockIdx.x * 16;
         unsigned long long gt1;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
         d[0] = (unsigned long long)(clock64() - t_begin); d[1] = (unsigned long long)t_wait_full; d[2] = (unsigned long long)t_wait_acc;
         d[3] = (unsigned long long)t_wait_x; d[4] = (unsigned long long)t; d[5] = gt1 - gt0;
-        if (blockIdx.x == 0) { g.dbg[0] = 0x600DC0DE600DC0E4ull; g.dbg[1] = gridDim.x; }
+        if (blockIdx.x == 0) { dbgp[0] = 0x600DC0DE600DC0E4ull; dbgp[1] = gridDim.x; }
       }
     }
     __syncwarp();
+  } else if (warp > G2_PROD_WARP && warp < G2_DRAIN_WARP0) {
+    // idle warps of the control warpgroup
   } else if (warp >= G2_DRAIN_WARP0) {
     // ------------------------------ drain warps: g = ae * kx_h out of TMEM between the two halves ------------------------------
     if (has_h) {
       const int quarter = warp & 3;                               // the TMEM lane quadrant this warp may read
       const float inv_unit = g.sc->inv_unit;
-      const bool stamp = g.dbg && tid == G2_DRAIN_WARP0 * 32;
+      const bool stamp = dbgp && tid == G2_DRAIN_WARP0 * 32;
       long long dw = 0, dk = 0;
       int t = 0;
       for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++t) {
@@ -319,37 +333,41 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
         tc_fence_after();
         long long c1 = stamp ? clock64() : 0;
         dw += c1 - c0;
-        const uint32_t d0 = tmem_d + (uint32_t)b * 256u + 2u * G2_NU + ((uint32_t)(quarter * 32) << 16);
-        // all 80 columns of this lane's row in one go: five loads in flight, one wait, then the columns are free
-        uint32_t v[G2_NU];
-#pragma unroll
-        for (int ci = 0; ci < G2_NU / 16; ++ci)
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-              : "=r"(v[ci * 16 + 0]), "=r"(v[ci * 16 + 1]), "=r"(v[ci * 16 + 2]), "=r"(v[ci * 16 + 3]), "=r"(v[ci * 16 + 4]), "=r"(v[ci * 16 + 5]),
-                "=r"(v[ci * 16 + 6]), "=r"(v[ci * 16 + 7]), "=r"(v[ci * 16 + 8]), "=r"(v[ci * 16 + 9]), "=r"(v[ci * 16 + 10]), "=r"(v[ci * 16 + 11]),
-                "=r"(v[ci * 16 + 12]), "=r"(v[ci * 16 + 13]), "=r"(v[ci * 16 + 14]), "=r"(v[ci * 16 + 15])
-              : "r"(d0 + (uint32_t)(ci * 16)));
+        const int hsel = (warp - G2_DRAIN_WARP0) >> 2;             // which 40 of the 80 g columns
+        const uint32_t d0 = tmem_d + (uint32_t)b * 256u + 2u * G2_NU + (uint32_t)(hsel * 40) + ((uint32_t)(quarter * 32) << 16);
+        // 40 columns of this lane's row: three loads in flight, ONE wait, and the MMA lane is released; only then the values
+        // go through a 32 x 8 block in smem to (row, quad) float4 so that every global store is four rows x 32 contiguous bytes
+        uint32_t v[40];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                       "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                     : "r"(d0));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                     : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                       "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                     : "r"(d0 + 16u));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                     : "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39])
+                     : "r"(d0 + 32u));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_xfree[b]));       // the MMA lane may overwrite g now
-        // registers (lane = row) -> 32 x 16 block in smem -> (row, quad) float4: every global store is 8 rows x 64 contiguous bytes
-        float* blk = dstg + (size_t)(warp - G2_DRAIN_WARP0) * 32 * G2_DS;
-        float* dst = xh_cta + ((size_t)b * BM + quarter * 32) * G2_NU;
-        if (!(g.probe & 1)) {
+        if (!(probe & 1)) {
+          float* blk = dstg + (size_t)(warp - G2_DRAIN_WARP0) * 32 * G2_DS;
+          float* dst = xh_cta + ((size_t)b * BM + quarter * 32) * G2_NU + hsel * 40;
 #pragma unroll
-          for (int ci = 0; ci < G2_NU / 16; ++ci) {
+          for (int ci = 0; ci < 5; ++ci) {
 #pragma unroll
-            for (int e = 0; e < 16; e += 4)
+            for (int e = 0; e < 8; e += 4)
               *reinterpret_cast<float4*>(blk + lane * G2_DS + e) =
-                  make_float4(__uint_as_float(v[ci * 16 + e]) * inv_unit, __uint_as_float(v[ci * 16 + e + 1]) * inv_unit,
-                              __uint_as_float(v[ci * 16 + e + 2]) * inv_unit, __uint_as_float(v[ci * 16 + e + 3]) * inv_unit);
+                  make_float4(__uint_as_float(v[ci * 8 + e]) * inv_unit, __uint_as_float(v[ci * 8 + e + 1]) * inv_unit,
+                              __uint_as_float(v[ci * 8 + e + 2]) * inv_unit, __uint_as_float(v[ci * 8 + e + 3]) * inv_unit);
             __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int rr = (lane >> 2) + 8 * k, qd = lane & 3;
-              __stcg(reinterpret_cast<float4*>(dst + (size_t)rr * G2_NU + ci * 16 + 4 * qd), *reinterpret_cast<const float4*>(blk + rr * G2_DS + 4 * qd));
+            for (int k = 0; k < 2; ++k) {
+              const int rr = (lane >> 1) + 16 * k, qd = lane & 1;
+              __stcg(reinterpret_cast<float4*>(dst + (size_t)rr * G2_NU + ci * 8 + 4 * qd), *reinterpret_cast<const float4*>(blk + rr * G2_DS + 4 * qd));
             }
             __syncwarp();
           }
@@ -358,17 +376,19 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
         if (lane == 0) mbar_arrive(smem_u32(&bar_xsaved[b]));
         if (stamp) dk += clock64() - c1;
       }
-      if (stamp) { unsigned long long* d = g.dbg + 8 + (size_t)blockIdx.x * 16; d[12] = (unsigned long long)dw; d[13] = (unsigned long long)dk; }
+      if (stamp) { unsigned long long* d = dbgp + 8 + (size_t)blockIdx.x * 16; d[12] = (unsigned long long)dw; d[13] = (unsigned long long)dk; }
     }
   } else {
-    // ------------------------------ epilogue: eight warps, overlapped with the next tile's main loop ------------------------------
-    const int quarter = warp & 3, hf = warp >> 2;
+    // ------------------------------ epilogue: sixteen warps, overlapped with the next tile's main loop ------------------------------
+    const int quarter = warp & 3, sub = warp >> 2;                 // TMEM lane quadrant; phase-1 column group (0 z, 1 r, 2 g, 3 none)
     const float inv_unit = g.sc->inv_unit, s_h = g.sc->s_h;
     auto tnh = [](float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); };
-    // phase-2 ownership: lane -> row (lane & 7) of the warp's 8-row strip (+ 64 in the second pass), unit quad lane >> 3:
-    // a quarter warp reads eight consecutive staging rows (every bank once) and a warp touches 8 rows x 64 contiguous bytes
-    const int prow = warp * 8 + (lane & 7), pj = lane >> 3;
-    const bool stamp = g.dbg && tid == 0;
+    // phase-2 ownership: ONE (row, unit quad) item per thread and chunk: row = 8 warp + (lane >> 2), quad = lane & 3.  128-bit
+    // global accesses are coalesced per QUARTER warp: eight consecutive lanes = two rows x 64 contiguous bytes = four full
+    // sectors.  (The first version put eight different rows into a quarter warp to make the staging reads conflict-free: every
+    // global access then touched eight half-used sectors, and the operand loads alone cost 2.5k cycles per chunk.)
+    const int prow = warp * 8 + (lane >> 2), pj = lane & 3;
+    const bool stamp = dbgp && tid == 0;
     long long e_wt = 0, e_wx = 0, e_p1 = 0, e_b1 = 0, e_p2 = 0, e_b2 = 0, e_ld = 0, ec = 0;
 #define G2_STAMP(acc) if (stamp) { const long long now = clock64(); acc += now - ec; ec = now; }
     int t = 0;
@@ -377,35 +397,30 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
       const int m0 = rb * BM, b = t & 1;
       if (stamp) ec = clock64();
       const uint32_t tph = (uint32_t)(t >> 1) & 1u;
-      int sid[2];
-#pragma unroll
-      for (int p = 0; p < 2; ++p) { const int m = m0 + prow + 64 * p; sid[p] = m < m_end ? g.sidx[m] : -1; }
+      const int m = m0 + prow;
+      const int sid = m < m_end ? g.sidx[m] : -1;
       if (tid < 3 * G2_NU / 4)                                     // this tile's recurrent bias -> smem (read in every chunk's phase 2)
         *reinterpret_cast<float4*>(b1_s + 4 * tid) = *reinterpret_cast<const float4*>(g.b1 + (tid / (G2_NU / 4)) * GAC_E + jt * G2_NU + 4 * (tid % (G2_NU / 4)));
       if (has_h) mbar_wait(smem_u32(&bar_xsaved[b]), tph);         // acquire: the drain warps' scratch rows are visible
       G2_STAMP(e_wx)
-      // Operands of phase 2 that do not depend on the accumulators (gathered state projection, h_prev, the saved input part).
-      // The SM keeps only a few hundred sectors in flight, so a burst of all of a chunk's loads blocks at issue for ~2.5k
-      // cycles: instead the loads of chunk q + 1 are issued one pass at a time inside phase 2 of chunk q, right after the
-      // registers they overwrite were consumed, and fly during the barrier and the next phase 1.
-      float4 sz[2], sr[2], sh[2], hp[2], xh[2];
-      auto load_ops = [&](int p, int q) {
-        hp[p] = make_float4(0.f, 0.f, 0.f, 0.f); xh[p] = hp[p];
-        if (g.probe & 4) { sz[p] = sr[p] = sh[p] = hp[p]; return; }
-        if (sid[p] < 0) return;
+      // Operands of phase 2 that do not depend on the accumulators (gathered state projection, h_prev, the saved input part):
+      // those of chunk q + 1 are issued inside phase 2 of chunk q, right after the registers they overwrite were consumed, and
+      // fly during the barrier and the next phase 1.  (.cg: nothing here is reused through L1, which is 28 KB beside the smem.)
+      float4 sz, sr, sh, hp, xh;
+      auto load_ops = [&](int q) {
+        hp = make_float4(0.f, 0.f, 0.f, 0.f); xh = hp;
+        if (probe & 4) { sz = sr = sh = hp; return; }
+        if (sid < 0) return;
         const int ul = q * 16 + 4 * pj, u = jt * G2_NU + ul;
-        const float* sx = g.sx + (size_t)sid[p] * GAC_G + u;
-        // .cg: with 227 KB of shared memory only ~28 KB of L1 is left, and a cached load needs a line there for its fill --
-        // a couple of hundred lines in flight capped the epilogue's loads at ~15 B/clk
-        sz[p] = __ldcg(reinterpret_cast<const float4*>(sx)); sr[p] = __ldcg(reinterpret_cast<const float4*>(sx + GAC_E));
-        sh[p] = __ldcg(reinterpret_cast<const float4*>(sx + 2 * GAC_E));
+        const float* sx = g.sx + (size_t)sid * GAC_G + u;
+        sz = __ldcg(reinterpret_cast<const float4*>(sx)); sr = __ldcg(reinterpret_cast<const float4*>(sx + GAC_E));
+        sh = __ldcg(reinterpret_cast<const float4*>(sx + 2 * GAC_E));
         if (has_h) {
-          hp[p] = __ldcg(reinterpret_cast<const float4*>(g.hprev + (size_t)(m0 + prow + 64 * p) * GAC_E + u));
-          xh[p] = __ldcg(reinterpret_cast<const float4*>(xh_cta + ((size_t)b * BM + prow + 64 * p) * G2_NU + ul));
+          hp = __ldcg(reinterpret_cast<const float4*>(g.hprev + (size_t)m * GAC_E + u));
+          xh = __ldcg(reinterpret_cast<const float4*>(xh_cta + ((size_t)b * BM + prow) * G2_NU + ul));
         }
       };
-      load_ops(0, 0);
-      load_ops(1, 0);
+      load_ops(0);
       G2_STAMP(e_ld)
       mbar_wait(smem_u32(&bar_tfull[b]), tph);
       tc_fence_after();
@@ -413,69 +428,57 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
       const uint32_t d0 = tmem_d + (uint32_t)b * 256u + ((uint32_t)(quarter * 32) << 16);
       for (int q = 0; q < G2_NU / 16; ++q) {
         const int ul = q * 16 + 4 * pj, u = jt * G2_NU + ul;       // this lane's four hidden units (within the tile / of 400)
-        // phase 1: 16 units x [z r g] of 128 rows, TMEM -> staging; warps 0-3 take z and g, warps 4-7 take r.  Both loads
-        // of a warp are in flight before the one wait.
-        {
-          float* srow = stg + (size_t)(quarter * 32 + lane) * G2_SS;
-          // column groups: warps 0-3 (hf = 0) take z (0) and g (2), warps 4-7 take r (1)
-          uint32_t v0[16], v1[16];
-#define G2_LD16(v, col)                                                                                                            \
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"         \
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), \
-                 "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                                        \
-               : "r"(col))
-#define G2_ST16(v, grp)                                                                                                            \
-  _Pragma("unroll") for (int e = 0; e < 16; e += 4)                                                                                \
-      *reinterpret_cast<float4*>(srow + (grp) * 16 + e) = make_float4(__uint_as_float(v[e]) * inv_unit, __uint_as_float(v[e + 1]) * inv_unit, \
-                                                                    __uint_as_float(v[e + 2]) * inv_unit, __uint_as_float(v[e + 3]) * inv_unit)
-          if (g.probe & 2) {
+        // phase 1: 16 units x [z r g] of 128 rows, TMEM -> staging: warp (quadrant, sub) moves 32 rows of column group `sub`
+        if (sub < 3) {
+          float* srow = stg + (size_t)(quarter * 32 + lane) * G2_SS + sub * 16;
+          uint32_t v[16];
+          if (probe & 2) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v0[e] = v1[e] = 0x3f800000u;
+            for (int e = 0; e < 16; ++e) v[e] = 0x3f800000u;
           } else {
-            G2_LD16(v0, d0 + (uint32_t)(hf * G2_NU + q * 16));
-            if (hf == 0) G2_LD16(v1, d0 + (uint32_t)(2 * G2_NU + q * 16));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(d0 + (uint32_t)(sub * G2_NU + q * 16)));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           }
-          G2_ST16(v0, hf);
-          if (hf == 0) G2_ST16(v1, 2);
-#undef G2_LD16
-#undef G2_ST16
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            *reinterpret_cast<float4*>(srow + e) = make_float4(__uint_as_float(v[e]) * inv_unit, __uint_as_float(v[e + 1]) * inv_unit,
+                                                               __uint_as_float(v[e + 2]) * inv_unit, __uint_as_float(v[e + 3]) * inv_unit);
         }
         G2_STAMP(e_p1)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");
         G2_STAMP(e_b1)
-        // phase 2: gate math and the state update, row-contiguous global traffic
-        // (no branch around the math: the two rows' instruction streams interleave; dead rows only skip their stores)
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          const int row = prow + 64 * p;
-          const float* srow = stg + (size_t)row * G2_SS + 4 * pj;
+        // phase 2: gate math and the state update, row-contiguous global traffic (no branch around the math: dead rows only
+        // skip their stores)
+        {
+          const float* srow = stg + (size_t)prow * G2_SS + 4 * pj;
           const float4 az = *reinterpret_cast<const float4*>(srow), ar = *reinterpret_cast<const float4*>(srow + 16),
                        ag = *reinterpret_cast<const float4*>(srow + 32);
           const float4 bz = *reinterpret_cast<const float4*>(b1_s + ul), br = *reinterpret_cast<const float4*>(b1_s + G2_NU + ul),
                        bh = *reinterpret_cast<const float4*>(b1_s + 2 * G2_NU + ul);
           // with a recurrent half g holds h_prev * U_h and the input part comes from the scratch; on the first step g IS the input part
-          const float4 axh = has_h ? xh[p] : ag;
+          const float4 axh = has_h ? xh : ag;
           const float4 ahh = has_h ? ag : make_float4(0.f, 0.f, 0.f, 0.f);
           float4 ho, zo, ro, co, mo;
-          if (g.probe & 16) { ho = az; zo = ar; ro = ag; co = axh; mo = ahh; } else {
+          if (probe & 16) { ho = az; zo = ar; ro = ag; co = axh; mo = ahh; } else {
           // sigmoid(a), sigmoid(b) share ONE reciprocal: with p = 1 + e^-a, q = 1 + e^-b, R = 1 / (p q): z = q R, r = p R.  The
           // exponents are clamped to +-30 (sigmoid is 0 or 1 to 1e-13 there), so p q <= 1.2e26 never overflows.
 #define GRU2_LANE(f)                                                                              \
   {                                                                                               \
     const float hh = ahh.f + bh.f;                                                                \
-    const float pa = 1.f + __expf(-fminf(fmaxf((sz[p].f + az.f) + bz.f, -30.f), 30.f));           \
-    const float pb = 1.f + __expf(-fminf(fmaxf((sr[p].f + ar.f) + br.f, -30.f), 30.f));           \
+    const float pa = 1.f + __expf(-fminf(fmaxf((sz.f + az.f) + bz.f, -30.f), 30.f));              \
+    const float pb = 1.f + __expf(-fminf(fmaxf((sr.f + ar.f) + br.f, -30.f), 30.f));              \
     const float R = __fdividef(1.f, pa * pb);                                                     \
     const float zz = pb * R, rr = pa * R;                                                         \
-    const float cc = tnh((sh[p].f + axh.f) + rr * hh);                                            \
-    ho.f = zz * hp[p].f + (1.f - zz) * cc; zo.f = zz; ro.f = rr; co.f = cc; mo.f = hh;            \
+    const float cc = tnh((sh.f + axh.f) + rr * hh);                                               \
+    ho.f = zz * hp.f + (1.f - zz) * cc; zo.f = zz; ro.f = rr; co.f = cc; mo.f = hh;               \
   }
           GRU2_LANE(x) GRU2_LANE(y) GRU2_LANE(z) GRU2_LANE(w)
 #undef GRU2_LANE
           }
-          const bool live = sid[p] >= 0 && !(g.probe & 8);
-          const int m = m0 + row;
+          const bool live = sid >= 0 && !(probe & 8);
           const size_t o = (size_t)m * GAC_E + u;
           if (live) {
             *reinterpret_cast<float4*>(g.hout + o) = ho;
@@ -494,10 +497,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
               *reinterpret_cast<uint2*>(dst + G2_A_TILE) = make_uint2(l0, l1);
             }
           }
-          if (q + 1 < G2_NU / 16) load_ops(p, q + 1);
+          if (q + 1 < G2_NU / 16) load_ops(q + 1);
         }
         G2_STAMP(e_p2)
-        asm volatile("bar.sync 1, 256;" ::: "memory");             // the staging rows are rewritten by the next chunk / tile
+        asm volatile("bar.sync 1, 512;" ::: "memory");             // the staging rows are rewritten by the next chunk / tile
         G2_STAMP(e_b2)
       }
       // this tile's accumulator columns and scratch rows are free again (all their reads above have completed)
@@ -507,7 +510,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
     }
 #undef G2_STAMP
     if (stamp) {
-      unsigned long long* d = g.dbg + 8 + (size_t)blockIdx.x * 16;
+      unsigned long long* d = dbgp + 8 + (size_t)blockIdx.x * 16;
       d[6] = (unsigned long long)e_wt; d[7] = (unsigned long long)e_wx; d[8] = (unsigned long long)e_p1; d[9] = (unsigned long long)e_b1;
       d[10] = (unsigned long long)e_p2; d[11] = (unsigned long long)e_b2; d[14] = (unsigned long long)e_ld;
     }
@@ -515,7 +518,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
 
   tc_fence_before();
   __syncthreads();
-  if (warp == G2_EPI_WARPS) {
+  if (warp == G2_MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512) : "memory");
   }
 }
@@ -551,7 +554,8 @@ inline int gru2_grid() {
 inline cudaError_t launch_gru_step_v2(const tc::Gru2Args& g, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc::gru_step_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::G2_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(tc::gru_step_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::G2_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gru_step_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::G2_SMEM);
     if (e != cudaSuccess) return e;
     attr = true;
   }
@@ -559,7 +563,8 @@ inline cudaError_t launch_gru_step_v2(const tc::Gru2Args& g, cudaStream_t st) {
   static const int grid_env = getenv("GAC_G2_GRID") ? atoi(getenv("GAC_G2_GRID")) : 0;
   const int cap = grid_env > 0 && grid_env < gru2_grid() ? grid_env : gru2_grid();
   const int grid = items < cap ? items : cap;
-  tc::gru_step_v2_kernel<<<grid, tc::G2_THREADS, tc::G2_SMEM, st>>>(g);
+  if (g.dbg || g.probe) tc::gru_step_v2_kernel<true><<<grid, tc::G2_THREADS, tc::G2_SMEM, st>>>(g);
+  else tc::gru_step_v2_kernel<false><<<grid, tc::G2_THREADS, tc::G2_SMEM, st>>>(g);
   return cudaGetLastError();
 }
 
