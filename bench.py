@@ -261,8 +261,16 @@ def run_gpu(args):
 
     m_log = torch.zeros(args.steps + args.warmup + 1, device=dev)
 
-    def step(i):
+    use_graph = bool(args.graph) and world == 1
+    step_fn = agent.train_on_batch_graphed if use_graph else agent.train_on_batch
+    launches_per_step = None
+    if use_graph:                          # the context's launch counter only sees eager launches: count one eager step
+        l0 = agent.engine.launch_count()
         agent.train_on_batch(batch, noise)
+        launches_per_step = agent.engine.launch_count() - l0
+
+    def step(i):
+        step_fn(batch, noise)
         m_log[i].copy_(agent.arena.stats[5])
 
     for i in range(args.warmup):
@@ -288,6 +296,8 @@ def run_gpu(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item()) / args.steps
     launches = agent.engine.launch_count() - launches0
+    if launches_per_step is not None:
+        launches = launches_per_step * args.steps      # kernels executed by the graph replays
     clk = clocks.stop() if clocks else None
     m_mean = float(m_log[args.warmup:args.warmup + args.steps].mean().item()) / world   # stats hold the all-reduced (global) M
 
@@ -300,7 +310,7 @@ def run_gpu(args):
 
     def e2e_step():
         b = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-        agent.train_on_batch(b)                              # RNG drawn on device, as the reference's tf.random does
+        (agent.train_on_batch_graphed if use_graph else agent.train_on_batch)(b)   # RNG drawn on device, as the reference's tf.random does
         stats_host.copy_(agent.arena.stats, non_blocking=True)
         m_e2e.add_(agent.arena.stats[5])                     # fresh random draws every step => its own selected-row count
 
@@ -584,7 +594,7 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ant", action="store_true", help="skip the Ant strong-scaling probe (ant_strong key)")
-    ap.add_argument("--graph", type=int, default=0, help="1 = replay the train step from a CUDA graph")
+    ap.add_argument("--graph", type=int, default=1, help="1 = replay the train step from one CUDA graph (single process; ranks > 1 run eagerly), 0 = eager launches")
     ap.add_argument("--actor", default="AIQN", choices=["AIQN", "IQN"], help="AIQN = BASELINE.json's actor; IQN = the reference CLI default (main.py:78)")
     ap.add_argument("--sweep-chunks", type=int, default=0, help="walker2d sweep: number of 4096-state chunks (0 = all 1M states)")
     args = ap.parse_args()

@@ -106,6 +106,46 @@ class GACAgent:
         gdist.allreduce_grads(self.arena.grad)
         self.engine.step_apply(io, self._hp)
 
+    def train_on_batch_graphed(self, batch: Dict, noise: Optional[Dict] = None):
+        """`train_on_batch` replayed from ONE CUDA graph (single process only; with a process group the eager path runs).
+        The step is ~280 kernel launches with no host synchronisation and nothing data-dependent on the host (the number of
+        selected rows stays on the device), so it captures as is: inputs are copied into static buffers, the reference's
+        seven tf.random draws are made in place outside the graph, and one cudaGraphLaunch replaces the launches -- what
+        matters for the small configs (Pendulum: the eager step is launch bound) and for the host thread's time."""
+        if gdist.world()[1] > 1:
+            return self.train_on_batch(batch, noise)
+        dev = self.device
+        if not hasattr(self, "_step_graph"):
+            b0 = {k: torch.zeros_like(f32(batch[k], dev)) for k in ("s", "a", "r", "sp", "it")}
+            n0 = self.draw_noise()
+            io = self.engine.step_io(self.arena, b0, n0)
+            cap = torch.cuda.Stream(device=dev)
+            cap.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(cap):      # warm up on the capture stream: lazy module loading and one-time attribute calls
+                state = [t.clone() for t in (self.arena.online, self.arena.target, self.arena.adam_m, self.arena.adam_v, self.arena.adam_t)]
+                self.engine.step_grads(io, self._hp)
+                self.engine.step_apply(io, self._hp)
+                for t, sv in zip((self.arena.online, self.arena.target, self.arena.adam_m, self.arena.adam_v, self.arena.adam_t), state):
+                    t.copy_(sv)               # the warm-up step must not count as a train step
+            cap.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=cap):
+                self.engine.step_grads(io, self._hp)
+                self.engine.step_apply(io, self._hp)
+            self._step_graph = (graph, b0, n0, io)
+        graph, b0, n0, _ = self._step_graph
+        for k, t in b0.items():
+            t.copy_(f32(batch[k], dev).reshape(t.shape), non_blocking=True)
+        if noise is None:                     # the reference's tf.random sites (SURVEY.md 8a), drawn in place
+            for k in ("critic_u", "value_tau", "filter_tau", "actor_tau"):
+                n0[k].uniform_()
+            n0["filter_normal"].normal_()
+            n0["filter_rand"].uniform_(-1, 1)
+        else:
+            for k, t in n0.items():
+                t.copy_(f32(noise[k], dev).reshape(t.shape), non_blocking=True)
+        graph.replay()
+
     def train_one_step(self):
         """agent.py:121-168."""
         t = self.replay.sample_batch(self.batch_size, device=self.device)

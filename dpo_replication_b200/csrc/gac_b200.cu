@@ -130,6 +130,7 @@ struct gac_ctx {
   // second-generation GRU step (gru_step_v2.cuh): weight tiles + scales per actor (target / online), a16 images of the
   // sampler's action embedding and of the two ping-pong GRU states
   unsigned char* g2_wpk[2]; tc::Gru2Scales* g2_sc[2]; unsigned char *ae_pk, *h_pk[2]; bool g2_on[2]; float* g2_xh;
+  unsigned char *a_ae_pk, *a_h_pk[2];           // training forward: a16 images of the (A * Mc)-row action embedding and of two ping-pong states
 };
 
 namespace {
@@ -226,6 +227,8 @@ size_t partition(gac_ctx* c, void* ws) {
   c->ae_pk = b.take<unsigned char>(tc::a16_bytes((long long)Rs));
   for (int i = 0; i < 2; ++i) c->h_pk[i] = b.take<unsigned char>(tc::a16_bytes((long long)Rs));
   c->g2_xh = b.take<float>((size_t)G2_MAX_GRID * (tc::G2_XH_BYTES_PER_CTA / 4));
+  c->a_ae_pk = b.take<unsigned char>(tc::a16_bytes((long long)AM));
+  for (int i = 0; i < 2; ++i) c->a_h_pk[i] = b.take<unsigned char>(tc::a16_bytes((long long)Mc));
   c->head_pack32 = b.take<unsigned char>(tc::dot_pack_bytes(GAC_E, HEAD_BN, HEAD_NT, false));
   c->head_pack16 = b.take<unsigned char>(tc::dot_pack_bytes(GAC_E, HEAD_BN, HEAD_NT, true));
   c->head_sc = b.take<tc::DotScales>(1); c->head_part = b.take<float>((size_t)Rs * HEAD_NT);
@@ -286,10 +289,10 @@ const unsigned char* pack_gru(gac_ctx* c, int which, const float* actor, int row
                c->gru_pack[which], c->gru_pack16[which], tf32_only ? nullptr : c->gru_sc[which], c->stream) != cudaSuccess)
     return nullptr;
   c->launches += tf32_only ? 1 : 4;
-  // second-generation kernel (persistent, bulk-copied pre-split A, double-buffered accumulators): sampler only so far;
-  // GAC_GRU_V1=1 keeps round 1's kernel for everything
+  // second-generation kernel (persistent, bulk-copied pre-split A, double-buffered accumulators); GAC_GRU_V1=1 keeps round
+  // 1's kernel for everything
   static const bool v1_only = getenv("GAC_GRU_V1") != nullptr;
-  c->g2_on[which] = !v1_only && !tf32_only && which == 0;
+  c->g2_on[which] = !v1_only && !tf32_only;
   if (c->g2_on[which]) {
     if (gru2_pack(var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, var(c, actor, 0, GAC_A_U), var(c, actor, 0, GAC_A_WA), var(c, actor, 0, GAC_A_BA),
                   c->g2_wpk[which], c->g2_sc[which], c->stream) != cudaSuccess)
@@ -302,12 +305,13 @@ const unsigned char* pack_gru(gac_ctx* c, int which, const float* actor, int row
 // the v2 kernel on a16 operand images; it exits at once when its scales are not usable, and round 1's kernel (launched
 // right after with skip_if = &scales->ok) then does the step from the fp32 operands
 int run_gru_step_v2(gac_ctx* c, int which, const float* actor, const float* sx, const int* sidx, const unsigned char* ae_pk,
-                    const unsigned char* h_pk, const float* hprev, float* hout, unsigned char* hout_pk, int rows, const int* dyn) {
+                    const unsigned char* h_pk, const float* hprev, float* hout, unsigned char* hout_pk, int rows, const int* dyn,
+                    float* z = nullptr, float* r = nullptr, float* cc = nullptr, float* mhh = nullptr) {
   static const bool timeline = getenv("GAC_GRU_TIMELINE") != nullptr;
   tc::Gru2Args a;
   a.rows = rows; a.dyn_rows = dyn; a.ae_pk = ae_pk; a.h_pk = hprev ? h_pk : nullptr; a.hprev = hprev; a.wpk = c->g2_wpk[which]; a.sc = c->g2_sc[which];
   a.sx = sx; a.sidx = sidx; a.b1 = var(c, actor, 0, GAC_A_GB) + GAC_G; a.hout = hout; a.hout_pk = hout_pk;
-  a.z = a.r = a.c = a.mhh = nullptr; a.xh_scratch = c->g2_xh;
+  a.z = z; a.r = r; a.c = cc; a.mhh = mhh; a.xh_scratch = c->g2_xh;
   static const int probe = getenv("GAC_G2_PROBE") ? atoi(getenv("GAC_G2_PROBE")) : 0;
   a.probe = probe;
   a.dbg = timeline ? reinterpret_cast<unsigned long long*>(c->spart) : nullptr;
@@ -548,7 +552,7 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
       g = gemm_args(rows, GAC_E, GAC_NB, c->cosb, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->ae, GAC_E);
       g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.Bpacked = c->pk[PK_T_WA]; g.Bpacked_bn = c->pk_bn[PK_T_WA];
       GAC_TRY(run_gemm(c, g));
-      if (v2) { GAC_CUDA(a16_pack(c->ae, GAC_E, rows, nullptr, &c->g2_sc[0]->s_ae, c->ae_pk, st)); c->launches++; }
+      if (v2) { GAC_CUDA(a16_pack(c->ae, GAC_E, rows, nullptr, 0, &c->g2_sc[0]->s_ae, c->ae_pk, st)); c->launches++; }
     }
     if (c->gru_t) {
       // both projections + gates in one kernel: mxa / mh never touch HBM
@@ -755,8 +759,18 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
   for (int d = 0; d < A; ++d) {
     const size_t o4 = (size_t)d * Mc * GAC_E, o12 = (size_t)d * Mc * GAC_G;
     if (c->gru_o) {
+      const bool v2 = c->g2_on[1];
+      if (v2) {
+        if (d == 0) {   // every step's action embedding -> a16 images in one pass (row blocks never straddle a step: Mc is a multiple of 128)
+          GAC_CUDA(a16_pack(c->a_ae, GAC_E, AM, live, Mc, &c->g2_sc[1]->s_ae, c->a_ae_pk, st));
+          c->launches++;
+        }
+        GAC_TRY(run_gru_step_v2(c, 1, actor, c->a_sx_u, sidx, c->a_ae_pk + tc::a16_bytes((long long)d * Mc), c->a_h_pk[d & 1],
+                                d ? c->hall + o4 : nullptr, c->hall + o4 + (size_t)Mc * GAC_E, c->a_h_pk[(d + 1) & 1], Mc, live, c->zs + o4,
+                                c->rs + o4, c->cs + o4, c->mhh + o4));
+      }
       GAC_TRY(run_gru_step(c, 1, actor, c->a_sx_u, sidx, c->a_ae + o4, d ? c->hall + o4 : nullptr, c->hall + o4 + (size_t)Mc * GAC_E, Mc,
-                           live, c->zs + o4, c->rs + o4, c->cs + o4, c->mhh + o4));
+                           live, c->zs + o4, c->rs + o4, c->cs + o4, c->mhh + o4, true, v2 ? &c->g2_sc[1]->ok : nullptr));
       continue;
     }
     if (d) {
@@ -1179,8 +1193,8 @@ int gac_gru_step(gac_ctx_t* c, const float* actor, const float* states_u, int32_
     if (v2) {
       // external fp32 operands: build the a16 images the v2 kernel consumes (inside the sampler the producing kernels write them)
       if (!(flags & GAC_GRU_SAME_INPUTS)) {
-        GAC_CUDA(a16_pack(action_emb, GAC_E, rows, nullptr, &c->g2_sc[0]->s_ae, c->ae_pk, st));
-        if (h_prev) GAC_CUDA(a16_pack(h_prev, GAC_E, rows, nullptr, &c->g2_sc[0]->s_h, c->h_pk[0], st));
+        GAC_CUDA(a16_pack(action_emb, GAC_E, rows, nullptr, 0, &c->g2_sc[0]->s_ae, c->ae_pk, st));
+        if (h_prev) GAC_CUDA(a16_pack(h_prev, GAC_E, rows, nullptr, 0, &c->g2_sc[0]->s_h, c->h_pk[0], st));
         c->launches += h_prev ? 2 : 1;
       }
       GAC_TRY(run_gru_step_v2(c, 0, actor, c->sx_u, state_idx, c->ae_pk, c->h_pk[0], h_prev, h_out, c->h_pk[1], rows, nullptr));

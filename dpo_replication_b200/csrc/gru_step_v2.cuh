@@ -158,18 +158,21 @@ __global__ void gru2_pack_kernel(const float* __restrict__ kxa, const float* __r
 
 // fp32 (rows, 400) -> a16 image, for activations whose producer does not write the image itself.  One thread per 16-byte
 // chunk, ordered (K block, row, chunk) so that a warp writes 512 contiguous bytes and reads eight 128-byte row segments.
-__global__ void a16_pack_kernel(const float* __restrict__ X, int ldx, int rows, const int* __restrict__ dyn_rows, const float* __restrict__ scale,
-                                unsigned char* __restrict__ out) {
-  const int m_end = dyn_rows ? min(rows, *dyn_rows) : rows;
-  const int n_rb = (m_end + BM - 1) / BM;
+__global__ void a16_pack_kernel(const float* __restrict__ X, int ldx, int rows, const int* __restrict__ dyn_rows, int seg_rows,
+                                const float* __restrict__ scale, unsigned char* __restrict__ out) {
+  // rows come in segments of seg_rows (a multiple of 128; 0 = one segment) of which the first *dyn_rows are live
+  const int nvalid = dyn_rows ? *dyn_rows : 0x7fffffff;
+  const int n_rb = (rows + BM - 1) / BM;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)n_rb * G2_KB * BM * 4) return;
   const int c = idx & 3, r = (idx >> 2) & 127;
   const int t = idx >> 9, kb = t % G2_KB, rb = t / G2_KB;
   const int m = rb * BM + r, k0 = kb * G2_BK + 8 * c;
+  const int in_seg = seg_rows > 0 ? m % seg_rows : m;
+  if (seg_rows > 0 ? (rb * BM) % seg_rows >= nvalid : rb * BM >= nvalid) return;      // dead row block: never read
   const float s = *scale;
   uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
-  if (m < m_end && k0 < GAC_E) {                                    // 400 = 50 x 8: a chunk is entirely inside or outside
+  if (m < rows && in_seg < nvalid && k0 < GAC_E) {                  // 400 = 50 x 8: a chunk is entirely inside or outside
     const float4 a = *reinterpret_cast<const float4*>(X + (size_t)m * ldx + k0), b = *reinterpret_cast<const float4*>(X + (size_t)m * ldx + k0 + 4);
     split_f16x2_u(a.x * s, a.y * s, h[0], l[0]); split_f16x2_u(a.z * s, a.w * s, h[1], l[1]);
     split_f16x2_u(b.x * s, b.y * s, h[2], l[2]); split_f16x2_u(b.z * s, b.w * s, h[3], l[3]);
@@ -536,9 +539,10 @@ inline cudaError_t gru2_pack(const float* kxa, const float* U, const float* wa, 
   tc::gru2_pack_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(kxa, U, out, sc);
   return cudaGetLastError();
 }
-inline cudaError_t a16_pack(const float* X, int ldx, int rows, const int* dyn_rows, const float* scale, unsigned char* out, cudaStream_t st) {
-  const long long total = (long long)cdiv(rows, tc::BM) * tc::G2_KB * tc::BM * 4;
-  tc::a16_pack_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(X, ldx, rows, dyn_rows, scale, out);
+inline cudaError_t a16_pack(const float* X, int ldx, long long rows, const int* dyn_rows, int seg_rows, const float* scale, unsigned char* out,
+                            cudaStream_t st) {
+  const long long total = cdiv64(rows, tc::BM) * tc::G2_KB * tc::BM * 4;
+  tc::a16_pack_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(X, ldx, (int)rows, dyn_rows, seg_rows, scale, out);
   return cudaGetLastError();
 }
 inline int gru2_grid() {

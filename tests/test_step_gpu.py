@@ -222,3 +222,27 @@ def test_graphed_acting_path_matches_eager(gb, actor):
     g2 = ag.get_action_graphed(st, taus=tau)
     assert torch.equal(eager2, g2) and not torch.equal(g1, g2)
     assert tuple(ag.get_action_graphed(torch.randn(11)).shape) == (1, 3)
+
+
+def test_graphed_step_is_bit_identical_to_eager(gb):
+    """GACAgent.train_on_batch_graphed (one cudaGraphLaunch per step) against the eager path: same inputs, same draws =>
+    bit-identical parameters, targets, Adam moments and counters over several steps."""
+    S, A, B, K = 17, 6, 32, 16
+    nets, batch, noise = setup(S, A, B, K, 400)
+    a1 = gb.GACAgent(A, S, action_samples=K, batch_size=B, device="cuda")
+    a2 = gb.GACAgent(A, S, action_samples=K, batch_size=B, device="cuda")
+    rng = np.random.default_rng(5)
+    for ag in (a1, a2):
+        ag.load_state(nets)
+    for step in range(3):
+        b, n = O.make_batch(rng, S, A, B), O.make_noise(rng, A, B, K)
+        a1.train_on_batch(b, n)
+        a2.train_on_batch_graphed(b, n)
+    torch.cuda.synchronize()
+    for k in ("online", "target", "adam_m", "adam_v", "adam_t"):
+        assert torch.equal(getattr(a1.arena, k), getattr(a2.arena, k)), k
+    assert a1.arena.adam_t.cpu().tolist() == [8, 8, 8, 8]
+    # device-side draws: the graphed step runs and keeps advancing
+    a2.train_on_batch_graphed(b)
+    torch.cuda.synchronize()
+    assert a2.arena.adam_t.cpu().tolist() == [9, 9, 9, 9] and bool(torch.isfinite(a2.arena.online).all())
