@@ -545,8 +545,12 @@ def hbm_kernels(agent, dev, reps=10):
 
 
 def run_sweep(args):
-    """configs[4]: forward-only AIQN sampling over 1,000,000 states x 32 samples (Walker2d dims), streamed
-    in state chunks, + the Polyak / delayed-actor update bandwidth."""
+    """configs[4]: forward-only AIQN sampling over 1,000,000 DISTINCT states x 32 samples (Walker2d dims), streamed in
+    chunks of 4096 states (+ one 576-state tail), + the Polyak / delayed-actor update bandwidth.  Two legs:
+    `value`: all states resident in HBM, every chunk reads its own slice, draws fresh taus on the device (the reference draws
+    them inside the actor, networks.py:202) and writes its own slice of the (32M, A) action array;
+    `e2e`: the states start in pinned HOST memory and the actions end there -- chunk c + 1's H2D copy and chunk c - 1's D2H
+    copy run on a second stream under chunk c's kernels."""
     import torch
     import __graft_entry__ as ge
     ge.build()
@@ -555,30 +559,87 @@ def run_sweep(args):
     dev = torch.device("cuda:0")
     S, A, NS, K = CONFIGS["walker2d"]
     chunk_states = 4096
+    if args.sweep_chunks:
+        NS = min(NS, args.sweep_chunks * chunk_states)
     agent = GACAgent(A, S, action_samples=K, batch_size=chunk_states, device=dev, engine=args.engine, chunk_rows=128)
     eng, ar = agent.engine, agent.arena
-    rows = chunk_states * K
-    sidx = torch.arange(chunk_states, dtype=torch.int32, device=dev).repeat_interleave(K)
-    n_chunks = NS // chunk_states if not args.sweep_chunks else args.sweep_chunks
-    states = torch.randn(chunk_states, S, device=dev)
-    taus = torch.rand(rows, A, device=dev)
     base = ar.net_slice(ar.target, "actor")
-    for _ in range(2):
-        eng.aiqn_sample(base, states, sidx, taus)
+    gen = torch.Generator().manual_seed(11)
+    states_host = torch.randn(NS, S, generator=gen).pin_memory()
+    out_host = torch.empty(NS * K, A).pin_memory()
+    states_dev = states_host.to(dev)
+    out_dev = torch.empty(NS * K, A, device=dev)
+    dgen = torch.Generator(device=dev).manual_seed(12)
+    bounds = [(c0, min(c0 + chunk_states, NS)) for c0 in range(0, NS, chunk_states)]
+    sidx_full = torch.arange(chunk_states, dtype=torch.int32, device=dev).repeat_interleave(K)
+
+    def sample(st, c0, c1, dst):
+        n = c1 - c0
+        taus = torch.rand(n * K, A, device=dev, generator=dgen)
+        eng.aiqn_sample(base, st, sidx_full[:n * K], taus, out=dst)
+
+    for c0, c1 in bounds[:2]:
+        sample(states_dev[c0:c1], c0, c1, out_dev[c0 * K:c1 * K])
     torch.cuda.synchronize()
+    l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n_chunks):
-        out = eng.aiqn_sample(base, states, sidx, taus)
+    for c0, c1 in bounds:
+        sample(states_dev[c0:c1], c0, c1, out_dev[c0 * K:c1 * K])
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    pairs = n_chunks * rows
+    launches = eng.launch_count() - l0
+    # every chunk produced its own actions (distinct states, distinct draws): no two chunk slices are equal, all are in (-1, 1)
+    chk = out_dev.view(-1, chunk_states * K * A)[:min(8, len(bounds) - 1)] if len(bounds) > 1 else out_dev.view(1, -1)
+    distinct = bool(len(bounds) < 2 or not torch.equal(chk[0], chk[1]))
+    finite = bool(torch.isfinite(out_dev).all().item() and out_dev.abs().max().item() <= 1.0)
+
+    # e2e: host -> device -> host, double buffered on a copy stream
+    main_s, copy_s = torch.cuda.current_stream(), torch.cuda.Stream()
+    st_buf = [torch.empty(chunk_states, S, device=dev) for _ in range(2)]
+    act_buf = [torch.empty(chunk_states * K, A, device=dev) for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    torch.cuda.synchronize()
+    e0.record()
+    with torch.cuda.stream(copy_s):
+        c0, c1 = bounds[0]
+        st_buf[0][:c1 - c0].copy_(states_host[c0:c1], non_blocking=True)
+        ev_in[0].record(copy_s)
+    for i, (c0, c1) in enumerate(bounds):
+        b = i & 1
+        if i + 1 < len(bounds):                                          # prefetch the next chunk's states
+            n0, n1 = bounds[i + 1]
+            with torch.cuda.stream(copy_s):
+                if i >= 1:
+                    copy_s.wait_event(ev_done[1 - b])                    # chunk i - 1 has finished reading st_buf[1 - b]
+                st_buf[1 - b][:n1 - n0].copy_(states_host[n0:n1], non_blocking=True)
+                ev_in[1 - b].record(copy_s)
+        main_s.wait_event(ev_in[b])
+        if i >= 2:
+            main_s.wait_event(ev_out[b])                                 # act_buf[b] has been copied out (chunk i - 2)
+        sample(st_buf[b][:c1 - c0], c0, c1, act_buf[b][:(c1 - c0) * K])
+        ev_done[b].record(main_s)
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(ev_done[b])
+            out_host[c0 * K:c1 * K].copy_(act_buf[b][:(c1 - c0) * K], non_blocking=True)
+            ev_out[b].record(copy_s)
+    main_s.wait_stream(copy_s)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    pairs = NS * K
     f_min = 2 * ((400 * S + 480000) / K + 1171600 * A - 480000)
     line = {"metric": "AIQN forward-only sampled (s,a) pairs/s (Walker2d dims, 1M states x 32, streamed)", "value": pairs / (ms * 1e-3),
             "unit": "pairs/s", "n_gpus": 1, "ms_total": ms, "pairs": pairs, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"walker2d sweep: S={S} A={A} states={n_chunks * chunk_states} K={K} chunk={chunk_states} states"},
-            "achieved_tflops_min": pairs * f_min / (ms * 1e-3) / 1e12, "hbm_kernels": hbm_kernels(agent, dev)}
+            "config": {"workload": f"walker2d sweep: S={S} A={A} states={NS} (all distinct) K={K} chunk={chunk_states} states, {len(bounds)} chunks, fresh taus per chunk"},
+            "achieved_tflops_min": pairs * f_min / (ms * 1e-3) / 1e12, "gpu_launches": int(launches),
+            "checks": {"chunks_distinct": distinct, "actions_finite_in_unit_box": finite},
+            "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_total": e2e_ms, "h2d_bytes_total": NS * S * 4, "d2h_bytes_total": NS * K * A * 4,
+                    "note": "states from pinned host memory, actions back to pinned host memory, copies double-buffered on a second stream"},
+            "hbm_kernels": hbm_kernels(agent, dev)}
     print(json.dumps(line))
     return 0
 

@@ -185,9 +185,12 @@ class Engine:
                                   ptr(grad_scale), ptr(skip)))
 
     @_on_stream
-    def aiqn_sample(self, actor, states_u, state_idx, taus):
+    def aiqn_sample(self, actor, states_u, state_idx, taus, out=None):
         rows = taus.shape[0]
-        out = self._new(rows, self.A)
+        if out is None:
+            out = self._new(rows, self.A)
+        elif out.shape != (rows, self.A) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != taus.device:
+            raise ValueError("aiqn_sample: out must be a contiguous float32 (rows, A) tensor on the engine's device")
         check(lib.gac_aiqn_sample(self.h, ptr(actor), ptr(states_u), states_u.shape[0], ptr(state_idx), ptr(taus), rows, ptr(out)))
         return out
 
