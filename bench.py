@@ -331,9 +331,10 @@ def run_gpu(args):
     e2e_ms = float(ms2.item()) / args.steps
 
     # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream.
-    # AIQN actor on the tcgen05 engine: gru_step_tc_kernel (one GRU step of the sampler on its 2P candidate rows: both
-    # input projections + gates, 3xFP16 arithmetic; profiles/r1c_launches_summary.txt: the largest single kernel of
-    # the step).  Algorithmic flops per launch = 2 * rows * (400 + 400) * 1200 (the GRU's two
+    # AIQN actor on the tcgen05 engine: gru_step_v2_kernel (one GRU step of the sampler on its 2P candidate rows: both
+    # input projections + gates, 3xFP16 arithmetic; profiles/r2*_launches_summary.txt: the largest single kernel of
+    # the step; the loop below goes through the C-ABI entry gac_gru_step, so each iteration also pays the ~3 us stand-by
+    # launch of round 1's kernel that takes over when the weights admit no fp16 scaling).  Algorithmic flops per launch = 2 * rows * (400 + 400) * 1200 (the GRU's two
     # projections).  Otherwise: the packed-weight GEMM (rows x 400) * (400 x 1200). ----
     roof = None
     if rank == 0:
@@ -361,11 +362,13 @@ def run_gpu(args):
             kms = e0.elapsed_time(e1) / n_rep
             ach = 2.0 * rows * 800 * 1200 / (kms * 1e-3) / 1e12
             peak = pk["bf16_burst"] / 3.0
-            roof = {"bound": "tensor", "kernel": "gru_step_tc_kernel (3xFP16: kind::f16 MMAs, 3 passes per product)",
+            roof = {"bound": "tensor", "kernel": "gru_step_v2_kernel (persistent, bulk-copied pre-split operands, 3xFP16: kind::f16 MMAs, 3 passes per product)",
                     "shape": f"rows={rows}: [ae | h_prev] ({rows}x800) * [kx_a ; U] (800x1200) + gates", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": measured_traffic("gru_step_tc_kernel", rows)[0],
-                    "traffic_source": measured_traffic("gru_step_tc_kernel", rows)[1], "ms_per_launch": kms,
+                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": measured_traffic("gru_step_v2_kernel", rows)[0],
+                    "traffic_source": measured_traffic("gru_step_v2_kernel", rows)[1], "ms_per_launch": kms,
                     "algorithmic_bytes": rows * 400 * 4 * 3,
+                    "mma_issue_bound": {"cycles_per_mma": 168, "source": "profiles/r2b_mma_rate.txt (tools/mma_rate.cu): an M = 128 kind::f16 tcgen05.mma takes ~168 SM cycles whatever N <= 256 and cta_group",
+                                        "mmas_per_launch_per_sm_max": 9 * 150, "note": "N = 240 of 256 columns per instruction and 9 tiles on the busiest SM bound this formulation at ~0.86 of the peak below"},
                     "peak_source": f"{pk['source']} bf16 burst {pk['bf16_burst']} TF/s / 3 (three fp16 passes per fp32 product)"}
         else:
             a = torch.randn(rows, 400, device=dev)

@@ -9,6 +9,7 @@
 #include "gemm_tc.cuh"
 #include "gru_step_tc.cuh"
 #include "gru_step_v2.cuh"
+#include "gru_step_v3.cuh"
 #include "dot_gemm_tc.cuh"
 
 constexpr int FNN_BN = 160, FNN_NT = 2;     // FNN tail: 300 hidden columns in two 160-wide tiles
@@ -130,6 +131,10 @@ struct gac_ctx {
   // second-generation GRU step (gru_step_v2.cuh): weight tiles + scales per actor (target / online), a16 images of the
   // sampler's action embedding and of the two ping-pong GRU states
   unsigned char* g2_wpk[2]; tc::Gru2Scales* g2_sc[2]; unsigned char *ae_pk, *h_pk[2]; bool g2_on[2]; float* g2_xh;
+  unsigned char* g3_wpk[2];                     // the same weights split per CTA of a pair (gru_step_v3.cuh, cta_group::2)
+  // second lane of gac_step_grads: the three TD updates (B-row problems, ~65 small launches) run on a side stream beside the
+  // sampler / critic evaluation / actor update; they touch only the td_* buffers and their own split-K / column-sum scratch
+  cudaStream_t side; cudaEvent_t ev_fork, ev_q, ev_join; float *spart2, *cpart2;
   unsigned char *a_ae_pk, *a_h_pk[2];           // training forward: a16 images of the (A * Mc)-row action embedding and of two ping-pong states
 };
 
@@ -203,6 +208,8 @@ size_t partition(gac_ctx* c, void* ws) {
   c->dhu = b.take<float>(AM * GAC_E); c->dhc0 = b.take<float>(Mc * GAC_E); c->dhc1 = b.take<float>(Mc * GAC_E);
   c->dop = b.take<float>(AM); c->pred_c = b.take<float>(Mc * A); c->dpred_c = b.take<float>(Mc * A);
   c->spart = b.take<float>((size_t)c->max_splits * GAC_E * GAC_G);
+  c->spart2 = b.take<float>((size_t)c->max_splits * GAC_H1 * GAC_E);     // side lane: no product larger than B x 400 / 400 x 300 is split there
+  c->cpart2 = b.take<float>(((B + 15) / 16 + 8192 / 16 + 1) * GAC_G);
   const size_t maxrows = AM > Rs ? AM : Rs;
   c->cpart = b.take<float>(((maxrows + COLSUM_ROWS - 1) / COLSUM_ROWS + 8192 / 16 + 1) * GAC_G);
   if (f.actor_kind == GAC_ACTOR_IQN) {
@@ -224,6 +231,7 @@ size_t partition(gac_ctx* c, void* ws) {
   for (int i = 0; i < 2; ++i) c->gru_pack16[i] = b.take<unsigned char>(tc::GRU_PACK16_BYTES);
   for (int i = 0; i < 2; ++i) c->gru_sc[i] = b.take<tc::GruScales>(1);
   for (int i = 0; i < 2; ++i) { c->g2_wpk[i] = b.take<unsigned char>(tc::G2_WPK_BYTES); c->g2_sc[i] = b.take<tc::Gru2Scales>(1); }
+  for (int i = 0; i < 2; ++i) c->g3_wpk[i] = b.take<unsigned char>(tc::G2_WPK_BYTES);
   c->ae_pk = b.take<unsigned char>(tc::a16_bytes((long long)Rs));
   for (int i = 0; i < 2; ++i) c->h_pk[i] = b.take<unsigned char>(tc::a16_bytes((long long)Rs));
   c->g2_xh = b.take<float>((size_t)G2_MAX_GRID * (tc::G2_XH_BYTES_PER_CTA / 4));
@@ -280,6 +288,13 @@ const unsigned char* pack_w(gac_ctx* c, int slot, const float* W, int ld, int K,
   return c->pack[slot];
 }
 
+// cta_group::2 variant of the GRU step kernel: opt-in (GAC_GRU_PAIR=1).  Measured SLOWER than the single-CTA v2 kernel
+// (205 vs 179 us per 32768-row step, profiles/r2d_gru_pair_probe.txt): a tcgen05.mma takes the same ~168 cycles per SM in
+// both modes (tools/mma_rate.cu), so the pair only adds the stage relay and the drain stall to the critical path.
+inline bool gru3_enabled() {
+  static const bool pair = getenv("GAC_GRU_PAIR") != nullptr;
+  return pair;
+}
 // weights of the fused GRU step (gru_step_tc.cuh); nullptr = not applicable, use the GEMM + gates kernels
 const unsigned char* pack_gru(gac_ctx* c, int which, const float* actor, int rows) {
   static const bool off = getenv("GAC_NO_FUSED_GRU") != nullptr;
@@ -299,6 +314,12 @@ const unsigned char* pack_gru(gac_ctx* c, int which, const float* actor, int row
       c->g2_on[which] = false;
     else
       c->launches += 3;
+    if (c->g2_on[which] && gru3_enabled()) {
+      if (gru3_pack(var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, var(c, actor, 0, GAC_A_U), c->g3_wpk[which], c->g2_sc[which], c->stream) != cudaSuccess)
+        c->g2_on[which] = false;
+      else
+        c->launches++;
+    }
   }
   return c->gru_pack[which];
 }
@@ -309,13 +330,14 @@ int run_gru_step_v2(gac_ctx* c, int which, const float* actor, const float* sx, 
                     float* z = nullptr, float* r = nullptr, float* cc = nullptr, float* mhh = nullptr) {
   static const bool timeline = getenv("GAC_GRU_TIMELINE") != nullptr;
   tc::Gru2Args a;
-  a.rows = rows; a.dyn_rows = dyn; a.ae_pk = ae_pk; a.h_pk = hprev ? h_pk : nullptr; a.hprev = hprev; a.wpk = c->g2_wpk[which]; a.sc = c->g2_sc[which];
+  const bool pair = gru3_enabled();
+  a.rows = rows; a.dyn_rows = dyn; a.ae_pk = ae_pk; a.h_pk = hprev ? h_pk : nullptr; a.hprev = hprev; a.wpk = pair ? c->g3_wpk[which] : c->g2_wpk[which]; a.sc = c->g2_sc[which];
   a.sx = sx; a.sidx = sidx; a.b1 = var(c, actor, 0, GAC_A_GB) + GAC_G; a.hout = hout; a.hout_pk = hout_pk;
   a.z = z; a.r = r; a.c = cc; a.mhh = mhh; a.xh_scratch = c->g2_xh;
   static const int probe = getenv("GAC_G2_PROBE") ? atoi(getenv("GAC_G2_PROBE")) : 0;
   a.probe = probe;
   a.dbg = timeline ? reinterpret_cast<unsigned long long*>(c->spart) : nullptr;
-  GAC_CUDA(launch_gru_step_v2(a, c->stream));
+  GAC_CUDA(pair ? launch_gru_step_v3(a, c->stream) : launch_gru_step_v2(a, c->stream));
   c->launches++;
   return GAC_OK;
 }
@@ -431,14 +453,15 @@ int fnn_forward(gac_ctx* c, const float* fnn, int n_in, const float* x, int rows
   return GAC_OK;
 }
 
-int value_eval(gac_ctx* c, const float* value, const float* states, int rows, float* v) {
+int value_eval(gac_ctx* c, const float* value, const float* states, int rows, float* v, float* h0 = nullptr, float* h1 = nullptr) {
   const int S = c->cfg.S;
+  if (!h0) { h0 = c->ch0a; h1 = c->ch1a; }                        // hidden-layer scratch (Rs rows); the side lane passes its own
   int64_t off[7];
   fnn_offsets(S, off);
   for (int r0 = 0; r0 < rows; r0 += c->Rs) {
     const int n = rows - r0 < c->Rs ? rows - r0 : c->Rs;
-    GAC_TRY(fnn_forward(c, value, S, states + (size_t)r0 * S, n, c->ch0a, c->ch1a));
-    rowdot_kernel<<<cdiv(n * 32, 256), 256, 0, c->stream>>>(c->ch1a, GAC_H2, value + off[4], value + off[5], nullptr, nullptr,
+    GAC_TRY(fnn_forward(c, value, S, states + (size_t)r0 * S, n, h0, h1));
+    rowdot_kernel<<<cdiv(n * 32, 256), 256, 0, c->stream>>>(h1, GAC_H2, value + off[4], value + off[5], nullptr, nullptr,
                                                            nullptr, GAC_H2, n, 0, v + r0, 1, nullptr, 0, RowValid{nullptr, 1});
     LAUNCHED(c, "rowdot");
   }
@@ -1120,12 +1143,23 @@ int gac_create(const gac_config_t* cfg, void* workspace, size_t workspace_bytes,
   if (e == cudaSuccess) e = cudaMemsetAsync(c->hall, 0, (size_t)c->Mc * GAC_E * sizeof(float), c->stream);  // h_{-1} = 0
   if (e == cudaSuccess) e = tc_gemm_init();
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  if (e != cudaSuccess) { delete c; return fail(GAC_ERR_CUDA, "gac_create: %s", cudaGetErrorString(e)); }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_q, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+  if (e != cudaSuccess) { gac_destroy(c); return fail(GAC_ERR_CUDA, "gac_create: %s", cudaGetErrorString(e)); }
   *out = c;
   return GAC_OK;
 }
 
-void gac_destroy(gac_ctx_t* ctx) { delete ctx; }
+void gac_destroy(gac_ctx_t* ctx) {
+  if (!ctx) return;
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_q) cudaEventDestroy(ctx->ev_q);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  delete ctx;
+}
 int gac_set_stream(gac_ctx_t* ctx, void* stream) {
   if (!ctx) return fail(GAC_ERR_INVALID, "gac_set_stream: null context");
   ctx->stream = reinterpret_cast<cudaStream_t>(stream);
@@ -1327,14 +1361,34 @@ int gac_step_grads(gac_ctx_t* c, const gac_step_io_t* io, const gac_hparams_t* h
   sidx3_kernel<<<cdiv(3 * P, 256), 256, 0, st>>>(c->sidx3, P, B, K);
   LAUNCHED(c, "sidx3");
 
+  // Two lanes.  The three TD updates are B-row problems (~65 launches of a few microseconds each) whose results nobody reads
+  // before gac_step_apply: they run on the side stream, with their own split-K / column-sum scratch, in the gaps the big
+  // kernels of the main lane leave (launch tails, partial waves).  Fork / join by events, so a CUDA-graph capture of the
+  // caller's stream takes the side lane along.  GAC_NO_SIDE_STREAM=1: everything on the caller's stream, in program order.
+  static const bool no_side = getenv("GAC_NO_SIDE_STREAM") != nullptr;
+  const bool two_lanes = !no_side && c->side != nullptr;
+  float* const spart_main = c->spart; float* const cpart_main = c->cpart;
+  struct LaneGuard {                                              // whatever path leaves this function, the context is back on the main lane
+    gac_ctx* c; cudaStream_t st; float *sp, *cp;
+    ~LaneGuard() { c->stream = st; c->spart = sp; c->cpart = cp; }
+  } lane_guard{c, st, spart_main, cpart_main};
+  auto side_lane = [&]() { if (two_lanes) { c->stream = c->side; c->spart = c->spart2; c->cpart = c->cpart2; } };
+  auto main_lane = [&]() { c->stream = st; c->spart = spart_main; c->cpart = cpart_main; };
+  if (two_lanes) {
+    GAC_CUDA(cudaEventRecord(c->ev_fork, st));                    // the batch and the parameters are ready at this point of the caller's stream
+    GAC_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+  }
+
   // ---- Critic.train (networks.py:410-426) ----
-  critic_train_x_kernel<<<cdiv(B * (S + A), 256), 256, 0, st>>>(io->s, io->a, io->critic_u, hp->q_normalization, S, A, B, c->td_x);
+  side_lane();
+  critic_train_x_kernel<<<cdiv(B * (S + A), 256), 256, 0, c->stream>>>(io->s, io->a, io->critic_u, hp->q_normalization, S, A, B, c->td_x);
   LAUNCHED(c, "critic_train_x");
-  GAC_TRY(value_eval(c, t_v, io->sp, B, c->td_vnext));
-  td_target_kernel<<<cdiv(B, 256), 256, 0, st>>>(io->r, c->td_vnext, io->done, hp->gamma, B, c->td_y);
+  GAC_TRY(value_eval(c, t_v, io->sp, B, c->td_vnext, c->td_h0, c->td_h1));
+  td_target_kernel<<<cdiv(B, 256), 256, 0, c->stream>>>(io->r, c->td_vnext, io->done, hp->gamma, B, c->td_y);
   LAUNCHED(c, "td_target");
   GAC_TRY(td_fwd_bwd(c, io->online + L.net_begin[GAC_NET_FNN1], S + A, c->td_x, c->td_y, B, io->grad + L.net_begin[GAC_NET_FNN1], stats + 0));
   GAC_TRY(td_fwd_bwd(c, io->online + L.net_begin[GAC_NET_FNN2], S + A, c->td_x, c->td_y, B, io->grad + L.net_begin[GAC_NET_FNN2], stats + 1));
+  main_lane();
 
   // ---- both target-actor sampling passes in one 2P-row batch (F9) ----
   GAC_CUDA(cudaMemcpyAsync(c->taus2, io->value_tau, (size_t)P * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1349,10 +1403,17 @@ int gac_step_grads(gac_ctx_t* c, const gac_step_io_t* io, const gac_hparams_t* h
   GAC_CUDA(cudaMemcpyAsync(c->cand + (size_t)2 * P * A, io->filter_rand, (size_t)P * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
   GAC_TRY(critic_eval(c, t_f1, t_f2, io->s, c->sidx3, c->cand, 3 * P, c->q3, B));
 
-  // ---- Value.train (networks.py:483-496) ----
-  mean_k_kernel<<<cdiv(B * 32, 256), 256, 0, st>>>(c->q3, K, B, c->td_vcrit);
+  // ---- Value.train (networks.py:483-496): needs the critics' values of the first P candidates ----
+  if (two_lanes) {
+    GAC_CUDA(cudaEventRecord(c->ev_q, st));
+    GAC_CUDA(cudaStreamWaitEvent(c->side, c->ev_q, 0));
+  }
+  side_lane();
+  mean_k_kernel<<<cdiv(B * 32, 256), 256, 0, c->stream>>>(c->q3, K, B, c->td_vcrit);
   LAUNCHED(c, "mean_k");
   GAC_TRY(td_fwd_bwd(c, io->online + L.net_begin[GAC_NET_VALUE], S, io->s, c->td_vcrit, B, io->grad + L.net_begin[GAC_NET_VALUE], stats + 2));
+  if (two_lanes) GAC_CUDA(cudaEventRecord(c->ev_join, c->side));
+  main_lane();
 
   // ---- advantage filter (agent.py:198-215) ----
   GAC_TRY(value_eval(c, t_v, io->s, B, c->vt));
@@ -1383,6 +1444,7 @@ int gac_step_grads(gac_ctx_t* c, const gac_step_io_t* io, const gac_hparams_t* h
     else GAC_TRY(aiqn_bwd(c, o_actor, c->dpred_c, g_actor, ch > 0));
   }
 
+  if (two_lanes) GAC_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));   // join: gac_step_apply (and the caller's all-reduce) read the TD gradients
   // optional taps for the parity tests
   if (io->sel_idx) GAC_CUDA(cudaMemcpyAsync(io->sel_idx, c->idx_sel, (size_t)2 * P * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   if (io->q_out) GAC_CUDA(cudaMemcpyAsync(io->q_out, c->q3 + P, (size_t)2 * P * sizeof(float), cudaMemcpyDeviceToDevice, st));

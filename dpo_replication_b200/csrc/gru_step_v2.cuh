@@ -25,7 +25,11 @@
 //   * 32-deep K blocks (64-byte rows): a stage is 46 KB, four stages fit beside the epilogue's staging buffer, so three
 //     stages of operand data are in flight while one is consumed -- bulk-copy latency is off the critical path.
 //   * persistent grid (one CTA per SM), static round-robin over (row block, unit tile) items: consecutive CTAs share a row
-//     block (its A tiles are L2-hot).
+//     block (its A tiles are L2-hot).  (Tried and dropped: cp.async.bulk.prefetch.L2 of the next item's row block one tile
+//     ahead -- 180.5 vs 176.8 us, profiles/r2e_gru2_prefetch_ab.txt: the operand stream is not waiting on HBM latency.)
+//   * what bounds it now: tcgen05.mma issue.  An M = 128 kind::f16 instruction takes ~168 SM cycles whatever N <= 256 and
+//     whatever the cta_group (tools/mma_rate.cu, profiles/r2b_mma_rate.txt), a tile is 150 of them = 25.2k cycles, and the
+//     MMA lane's timeline shows 28-29k per tile (profiles/r2b_gru2_timeline.txt): ~88 % of its life is instruction issue.
 #pragma once
 #include "gru_step_tc.cuh"
 
@@ -43,10 +47,11 @@ constexpr uint32_t G2_B_TILE = 3u * G2_NU * 64u;                 // 15 KB per hi
 constexpr uint32_t G2_B_SLOT = 2u * G2_B_TILE;
 constexpr uint32_t G2_STAGE = G2_A_SLOT + G2_B_SLOT;             // 46 KB
 constexpr int G2_STAGES = 4;
-constexpr int G2_SS = 52;                                        // staging row stride in floats: [z16 | r16 | g16] + 4 (conflict-free v4 rows)
+constexpr int G2_SS = 48;                                        // staging row stride in floats: [z16 | r16 | g16], quads XOR-rotated by (row >> 1) & 3:
+                                                                 // conflict-free for phase 1 (8 consecutive rows, one quad) and phase 2 (2 rows x 4 quads)
 constexpr int G2_DRAIN_WARPS = 8;                                // two per TMEM lane quadrant, 40 columns each
-constexpr int G2_DS = 12;                                        // drain transposition row stride in floats (8 + 4)
-constexpr int G2_DRAIN_SMEM = G2_DRAIN_WARPS * 32 * G2_DS * 4;   // 12 KB: one 32 x 8 block per drain warp
+constexpr int G2_DS = 8;                                         // drain transposition row stride in floats; quad slot XOR (row >> 2) & 1
+constexpr int G2_DRAIN_SMEM = G2_DRAIN_WARPS * 32 * G2_DS * 4;   // 8 KB: one 32 x 8 block per drain warp
 constexpr int G2_SMEM = G2_STAGES * (int)G2_STAGE + BM * G2_SS * 4 + G2_DRAIN_SMEM + 3 * G2_NU * 4 + 1024;
 // Warp roles, in warpgroups of four (setmaxnreg works per warpgroup): warps 0-15 epilogue (the gate math is a long dependent
 // chain per thread: with two warps per scheduler its latencies were exposed and a tile's epilogue took ~29k cycles against a
@@ -363,14 +368,15 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
           for (int ci = 0; ci < 5; ++ci) {
 #pragma unroll
             for (int e = 0; e < 8; e += 4)
-              *reinterpret_cast<float4*>(blk + lane * G2_DS + e) =
+              *reinterpret_cast<float4*>(blk + lane * G2_DS + 4 * ((e >> 2) ^ ((lane >> 2) & 1))) =
                   make_float4(__uint_as_float(v[ci * 8 + e]) * inv_unit, __uint_as_float(v[ci * 8 + e + 1]) * inv_unit,
                               __uint_as_float(v[ci * 8 + e + 2]) * inv_unit, __uint_as_float(v[ci * 8 + e + 3]) * inv_unit);
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               const int rr = (lane >> 1) + 16 * k, qd = lane & 1;
-              __stcg(reinterpret_cast<float4*>(dst + (size_t)rr * G2_NU + ci * 8 + 4 * qd), *reinterpret_cast<const float4*>(blk + rr * G2_DS + 4 * qd));
+              __stcg(reinterpret_cast<float4*>(dst + (size_t)rr * G2_NU + ci * 8 + 4 * qd),
+                     *reinterpret_cast<const float4*>(blk + rr * G2_DS + 4 * (qd ^ ((rr >> 2) & 1))));
             }
             __syncwarp();
           }
@@ -425,6 +431,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
       };
       load_ops(0);
       G2_STAMP(e_ld)
+      asm volatile("bar.sync 1, 512;" ::: "memory");               // this tile's bias rows are in smem (phase 1 reads them)
       mbar_wait(smem_u32(&bar_tfull[b]), tph);
       tc_fence_after();
       G2_STAMP(e_wt)
@@ -434,6 +441,11 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
         // phase 1: 16 units x [z r g] of 128 rows, TMEM -> staging: warp (quadrant, sub) moves 32 rows of column group `sub`
         if (sub < 3) {
           float* srow = stg + (size_t)(quarter * 32 + lane) * G2_SS + sub * 16;
+          const int rot = (lane >> 1) & 3;                           // == (row >> 1) & 3: the row's quad rotation
+          // recurrent bias of this column group, added here (one broadcast read per warp) instead of per item in phase 2;
+          // on the first step g holds the INPUT part of the candidate gate, whose bias is already in sx
+          const float* bsub = b1_s + sub * G2_NU + q * 16;
+          const bool add_b = sub < 2 || has_h;
           uint32_t v[16];
           if (probe & 2) {
 #pragma unroll
@@ -446,9 +458,13 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           }
 #pragma unroll
-          for (int e = 0; e < 16; e += 4)
-            *reinterpret_cast<float4*>(srow + e) = make_float4(__uint_as_float(v[e]) * inv_unit, __uint_as_float(v[e + 1]) * inv_unit,
-                                                               __uint_as_float(v[e + 2]) * inv_unit, __uint_as_float(v[e + 3]) * inv_unit);
+          for (int e = 0; e < 16; e += 4) {
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (add_b) bb = *reinterpret_cast<const float4*>(bsub + e);
+            *reinterpret_cast<float4*>(srow + 4 * (((e >> 2) + rot) & 3)) =
+                make_float4(fmaf(__uint_as_float(v[e]), inv_unit, bb.x), fmaf(__uint_as_float(v[e + 1]), inv_unit, bb.y),
+                            fmaf(__uint_as_float(v[e + 2]), inv_unit, bb.z), fmaf(__uint_as_float(v[e + 3]), inv_unit, bb.w));
+          }
         }
         G2_STAMP(e_p1)
         asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -456,11 +472,11 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
         // phase 2: gate math and the state update, row-contiguous global traffic (no branch around the math: dead rows only
         // skip their stores)
         {
-          const float* srow = stg + (size_t)prow * G2_SS + 4 * pj;
+          const float* srow = stg + (size_t)prow * G2_SS + 4 * ((pj + (prow >> 1)) & 3);
           const float4 az = *reinterpret_cast<const float4*>(srow), ar = *reinterpret_cast<const float4*>(srow + 16),
-                       ag = *reinterpret_cast<const float4*>(srow + 32);
-          const float4 bz = *reinterpret_cast<const float4*>(b1_s + ul), br = *reinterpret_cast<const float4*>(b1_s + G2_NU + ul),
-                       bh = *reinterpret_cast<const float4*>(b1_s + 2 * G2_NU + ul);
+                       ag = *reinterpret_cast<const float4*>(srow + 32);     // z, r (and g with a recurrent half) include the recurrent bias
+          float4 bh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!has_h) bh = *reinterpret_cast<const float4*>(b1_s + 2 * G2_NU + ul);   // first step: h_prev * U_h = 0, the bias alone
           // with a recurrent half g holds h_prev * U_h and the input part comes from the scratch; on the first step g IS the input part
           const float4 axh = has_h ? xh : ag;
           const float4 ahh = has_h ? ag : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -471,8 +487,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
 #define GRU2_LANE(f)                                                                              \
   {                                                                                               \
     const float hh = ahh.f + bh.f;                                                                \
-    const float pa = 1.f + __expf(-fminf(fmaxf((sz.f + az.f) + bz.f, -30.f), 30.f));              \
-    const float pb = 1.f + __expf(-fminf(fmaxf((sr.f + ar.f) + br.f, -30.f), 30.f));              \
+    const float pa = 1.f + __expf(-fminf(fmaxf(sz.f + az.f, -30.f), 30.f));                       \
+    const float pb = 1.f + __expf(-fminf(fmaxf(sr.f + ar.f, -30.f), 30.f));                       \
     const float R = __fdividef(1.f, pa * pb);                                                     \
     const float zz = pb * R, rr = pa * R;                                                         \
     const float cc = tnh((sh.f + axh.f) + rr * hh);                                               \

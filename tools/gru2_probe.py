@@ -55,7 +55,7 @@ def main():
     c = torch.tanh(mx[:, 800:] + r * mh[:, 800:])
     ref = z * hh + (1 - z) * c
     err = (out.double() - ref).abs()
-    print(f"rows={rows} first={a.first} v1={bool(os.environ.get('GAC_GRU_V1'))}: max |h - fp64| = {err.max().item():.3e}  mean = {err.mean().item():.3e}  "
+    print(f"rows={rows} first={a.first} kernel={'v1' if os.environ.get('GAC_GRU_V1') else 'v3 (cta_group::2)' if os.environ.get('GAC_GRU_PAIR') else 'v2'}: max |h - fp64| = {err.max().item():.3e}  mean = {err.mean().item():.3e}  "
           f"(max |h| = {ref.abs().max().item():.3f}); worst column {int(err.max(0).values.argmax())}, worst row {int(err.max(1).values.argmax())}")
     for _ in range(3):
         eng.gru_step(actor, states, sidx, ae, h, reuse=True, actor_inputs=True, same_inputs=True)
@@ -75,13 +75,16 @@ def main():
         if hits.size:
             n = int(arr[hits[0] + 1])
             rec = arr[hits[0] + 8: hits[0] + 8 + 16 * n].reshape(n, 16)
-            pct = lambda k: 100 * rec[:, k].sum() / rec[:, 0].sum()
-            tl = rec[:, 4].sum()
-            print(f"  SM clock {1e3 * rec[:, 0].sum() / rec[:, 5].sum():.0f} MHz;  per tile (cycles): MMA lane {rec[:, 0].sum() / tl:.0f}"
-                  f" | epilogue: wait drain {rec[:, 7].sum() / tl:.0f} wait accum {rec[:, 6].sum() / tl:.0f} load issue {rec[:, 14].sum() / tl:.0f} phase1 {rec[:, 8].sum() / tl:.0f} bar {rec[:, 9].sum() / tl:.0f}"
-                  f" phase2 {rec[:, 10].sum() / tl:.0f} bar {rec[:, 11].sum() / tl:.0f} | drain warps: wait {rec[:, 12].sum() / tl:.0f} work {rec[:, 13].sum() / tl:.0f}")
-            print(f"  MMA lane per CTA ({n} CTAs): cycles mean {rec[:, 0].mean():.0f} max {rec[:, 0].max()}  waiting for operands {pct(1):.1f}%  "
-                  f"for a free accumulator {pct(2):.1f}%  for the drain warps {pct(3):.1f}%  tiles {rec[:, 4].mean():.2f} (max {rec[:, 4].max()})")
+            lead = rec[:, 0] > 0                      # the pair kernel's peer CTAs issue no MMAs (their lane counters are zero)
+            L = rec[lead]
+            pct = lambda k: 100 * L[:, k].sum() / L[:, 0].sum()
+            tl = L[:, 4].sum()
+            tl_all = tl * n / max(int(lead.sum()), 1)  # (128 rows x 80 units) tiles over all CTAs
+            print(f"  SM clock {1e3 * L[:, 0].sum() / L[:, 5].sum():.0f} MHz;  per tile (cycles): MMA lane {L[:, 0].sum() / tl:.0f}"
+                  f" | epilogue: wait drain {rec[:, 7].sum() / tl_all:.0f} wait accum {rec[:, 6].sum() / tl_all:.0f} load issue {rec[:, 14].sum() / tl_all:.0f} phase1 {rec[:, 8].sum() / tl_all:.0f} bar {rec[:, 9].sum() / tl_all:.0f}"
+                  f" phase2 {rec[:, 10].sum() / tl_all:.0f} bar {rec[:, 11].sum() / tl_all:.0f} | drain warps: wait {rec[:, 12].sum() / tl_all:.0f} work {rec[:, 13].sum() / tl_all:.0f}")
+            print(f"  MMA lane per issuing CTA ({int(lead.sum())} of {n} CTAs): cycles mean {L[:, 0].mean():.0f} max {L[:, 0].max()}  waiting for operands {pct(1):.1f}%  "
+                  f"for a free accumulator {pct(2):.1f}%  for the drain warps {pct(3):.1f}%  tiles {L[:, 4].mean():.2f} (max {L[:, 4].max()})")
         else:
             print("  no counters found")
 
