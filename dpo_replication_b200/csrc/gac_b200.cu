@@ -134,7 +134,8 @@ struct gac_ctx {
   unsigned char* g3_wpk[2];                     // the same weights split per CTA of a pair (gru_step_v3.cuh, cta_group::2)
   // second lane of gac_step_grads: the three TD updates (B-row problems, ~65 small launches) run on a side stream beside the
   // sampler / critic evaluation / actor update; they touch only the td_* buffers and their own split-K / column-sum scratch
-  cudaStream_t side; cudaEvent_t ev_fork, ev_q, ev_join; float *spart2, *cpart2;
+  cudaStream_t side; cudaEvent_t ev_fork, ev_q, ev_join, ev_cprep, ev_aprep; float *spart2, *cpart2;
+  bool critic_prepped; const float* actor_prep_token;   // weight preparation already issued by gac_step_grads (on its side lane)
   unsigned char *a_ae_pk, *a_h_pk[2];           // training forward: a16 images of the (A * Mc)-row action embedding and of two ping-pong states
 };
 
@@ -468,32 +469,47 @@ int value_eval(gac_ctx* c, const float* value, const float* states, int rows, fl
   return GAC_OK;
 }
 
+// Fused critic tail (dot_gemm_tc.cuh): layer 2 + LeakyReLU + output dot in one kernel, 3xFP16 with the bound of the first
+// hidden layer derived from the weights and the batch's states (|action| <= 1).  Needs the number of unique states.
+inline bool critic_fused(const gac_ctx* c, int rows, int n_states, const int* sidx) {
+  static const bool off_env = getenv("GAC_NO_FUSED_CRITIC") != nullptr;
+  return !off_env && c->cfg.engine == 0 && rows >= 1024 && n_states > 0 && n_states <= c->NUs && sidx != nullptr;
+}
+// everything of the fused critic evaluation that depends on the weights and the unique states only (on c->stream)
+int critic_prep(gac_ctx* c, const float* f1, const float* f2, const float* states_u, int n_states) {
+  const int S = c->cfg.S, A = c->cfg.A, W = S + A;
+  cudaStream_t st = c->stream;
+  int64_t off[7];
+  fnn_offsets(W, off);
+  const float* fn[2] = {f1, f2};
+  GAC_CUDA(cudaMemsetAsync(c->cr_bound, 0, 4 * sizeof(unsigned int), st));
+  for (int i = 0; i < 2; ++i) {
+    fnn_bound_kernel<<<1, 512, W * sizeof(float), st>>>(states_u, n_states, S, W, fn[i] + off[0], fn[i] + off[1], GAC_H1, c->cr_bound + i);
+    LAUNCHED(c, "fnn_bound");
+    GAC_CUDA(dot_pack(fn[i] + off[2], GAC_H2, 0, GAC_H1, GAC_H2, FNN_BN, FNN_NT, nullptr, nullptr, 0, 0, c->cr_pack32[i], c->cr_pack16[i],
+                      c->cr_sc[i], st));
+    GAC_CUDA(dot_ascale(c->cr_sc[i], c->cr_bound + i, st));
+    c->launches += 5;
+    // state half of layer 1, once per unique state: sx0 = s_u W0[:S] + b0
+    GemmArgs g0 = gemm_args(n_states, GAC_H1, S, states_u, S, fn[i] + off[0], GAC_H1, c->cr_sx0[i], GAC_H1);
+    g0.bias = fn[i] + off[1];
+    GAC_TRY(run_gemm(c, g0));
+  }
+  return GAC_OK;
+}
+
 int critic_eval(gac_ctx* c, const float* f1, const float* f2, const float* states_u, const int* sidx, const float* actions,
                 int rows, float* q, int n_states = 0) {
   const int S = c->cfg.S, A = c->cfg.A, W = S + A;
   cudaStream_t st = c->stream;
   int64_t off[7];
   fnn_offsets(W, off);
-  // Fused tail (dot_gemm_tc.cuh): layer 2 + LeakyReLU + output dot in one kernel, 3xFP16 with the bound of the first
-  // hidden layer derived from the weights and the batch's states (|action| <= 1).  Needs the number of unique states.
-  static const bool off_env = getenv("GAC_NO_FUSED_CRITIC") != nullptr;
-  const bool fused = !off_env && c->cfg.engine == 0 && rows >= 1024 && n_states > 0 && n_states <= c->NUs && sidx != nullptr;
+  const bool fused = critic_fused(c, rows, n_states, sidx);
   const float* fn[2] = {f1, f2};
   const unsigned char *pk1 = nullptr, *pk2 = nullptr;
   if (fused) {
-    GAC_CUDA(cudaMemsetAsync(c->cr_bound, 0, 4 * sizeof(unsigned int), st));
-    for (int i = 0; i < 2; ++i) {
-      fnn_bound_kernel<<<1, 512, W * sizeof(float), st>>>(states_u, n_states, S, W, fn[i] + off[0], fn[i] + off[1], GAC_H1, c->cr_bound + i);
-      LAUNCHED(c, "fnn_bound");
-      GAC_CUDA(dot_pack(fn[i] + off[2], GAC_H2, 0, GAC_H1, GAC_H2, FNN_BN, FNN_NT, nullptr, nullptr, 0, 0, c->cr_pack32[i], c->cr_pack16[i],
-                        c->cr_sc[i], st));
-      GAC_CUDA(dot_ascale(c->cr_sc[i], c->cr_bound + i, st));
-      c->launches += 5;
-      // state half of layer 1, once per unique state: sx0 = s_u W0[:S] + b0
-      GemmArgs g0 = gemm_args(n_states, GAC_H1, S, states_u, S, fn[i] + off[0], GAC_H1, c->cr_sx0[i], GAC_H1);
-      g0.bias = fn[i] + off[1];
-      GAC_TRY(run_gemm(c, g0));
-    }
+    if (c->critic_prepped) c->critic_prepped = false;             // gac_step_grads issued it on its side lane
+    else GAC_TRY(critic_prep(c, f1, f2, states_u, n_states));
   } else if (rows >= 1024) {
     const int prow = rows < c->Rs ? rows : (rows % c->Rs ? rows % c->Rs : c->Rs);
     pk1 = pack_w(c, PK_C_F1, f1 + off[2], GAC_H2, GAC_H1, GAC_H2, 0, prow);
@@ -709,24 +725,11 @@ int td_fwd_bwd(gac_ctx* c, const float* fnn, int n_in, const float* x, const flo
   return GAC_OK;
 }
 
-int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_states, const int* sidx, const float* taus,
-                   const float* teacher, int max_rows, const int* d_rows, float* pred) {
-  const int A = c->cfg.A, Mc = c->Mc;
-  if (max_rows > Mc) return fail(GAC_ERR_WORKSPACE, "gac_aiqn_supervised_fwd: max_rows exceeds chunk_rows");
-  if (n_states > c->NUa) return fail(GAC_ERR_WORKSPACE, "gac_aiqn_supervised_fwd: n_states exceeds the workspace capacity");
+// Weight-only preparation of the actor's training pass: packed / pre-split tiles of every weight matrix its forward and
+// backward GEMMs read, and the scales / bounds of the 3xFP16 variants.  Depends on the online actor alone, so one call serves
+// every row chunk of a step (on c->stream).
+int actor_train_prep(gac_ctx* c, const float* actor) {
   cudaStream_t st = c->stream;
-  // rows beyond max_rows inside the chunk are dead too: clamp through a device counter
-  int* live = c->rows_c + c->nchunks;  // scratch slot
-  if (d_rows) GAC_CUDA(cudaMemcpyAsync(live, d_rows, sizeof(int), cudaMemcpyDeviceToDevice, st));
-  else GAC_CUDA(cudaMemcpyAsync(live, &max_rows, sizeof(int), cudaMemcpyHostToDevice, st));
-  const RowValid rv{live, Mc};
-  const long long AM = (long long)A * Mc;
-  // the backward needs the row->state map and the unique states: keep private copies (the
-  // caller's buffers may be gone by then)
-  GAC_CUDA(cudaMemcpyAsync(c->a_sidx, sidx, (size_t)max_rows * sizeof(int), cudaMemcpyDeviceToDevice, st));
-  GAC_CUDA(cudaMemcpyAsync(c->a_states, states_u, (size_t)n_states * c->cfg.S * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  c->bwd_sidx = c->a_sidx; c->bwd_states = c->a_states; c->bwd_nstates = n_states; c->bwd_drows = live;
-  GAC_TRY(state_prep(c, actor, states_u, n_states, c->a_se_u, c->a_sx_u));
   const float* kxa_w = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
   c->pk[PK_O_WA] = pack_w(c, PK_O_WA, var(c, actor, 0, GAC_A_WA), GAC_E, GAC_NB, GAC_E, 0, c->Mc);
   c->gru_o = pack_gru(c, 1, actor, c->Mc);
@@ -769,6 +772,29 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
       c->pk[PK_O_KXAT] = pack_w(c, PK_O_KXAT, kxa_w, GAC_G, GAC_G, GAC_E, 1, c->Mc);
     }
   }
+  return GAC_OK;
+}
+
+int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_states, const int* sidx, const float* taus,
+                   const float* teacher, int max_rows, const int* d_rows, float* pred) {
+  const int A = c->cfg.A, Mc = c->Mc;
+  if (max_rows > Mc) return fail(GAC_ERR_WORKSPACE, "gac_aiqn_supervised_fwd: max_rows exceeds chunk_rows");
+  if (n_states > c->NUa) return fail(GAC_ERR_WORKSPACE, "gac_aiqn_supervised_fwd: n_states exceeds the workspace capacity");
+  cudaStream_t st = c->stream;
+  // rows beyond max_rows inside the chunk are dead too: clamp through a device counter
+  int* live = c->rows_c + c->nchunks;  // scratch slot
+  if (d_rows) GAC_CUDA(cudaMemcpyAsync(live, d_rows, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  else GAC_CUDA(cudaMemcpyAsync(live, &max_rows, sizeof(int), cudaMemcpyHostToDevice, st));
+  const RowValid rv{live, Mc};
+  const long long AM = (long long)A * Mc;
+  // the backward needs the row->state map and the unique states: keep private copies (the
+  // caller's buffers may be gone by then)
+  GAC_CUDA(cudaMemcpyAsync(c->a_sidx, sidx, (size_t)max_rows * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  GAC_CUDA(cudaMemcpyAsync(c->a_states, states_u, (size_t)n_states * c->cfg.S * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  c->bwd_sidx = c->a_sidx; c->bwd_states = c->a_states; c->bwd_nstates = n_states; c->bwd_drows = live;
+  GAC_TRY(state_prep(c, actor, states_u, n_states, c->a_se_u, c->a_sx_u));
+  const float* kxa_w = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
+  if (c->actor_prep_token != actor) GAC_TRY(actor_train_prep(c, actor));   // else: gac_step_grads issued it once for all chunks, on its side lane
   cos_basis_seq_kernel<<<(unsigned)cdiv64(AM * (GAC_NB / 4), 256), 256, 0, st>>>(teacher, taus, A, Mc, c->ca, c->cn, live);
   LAUNCHED(c, "cos_basis_seq");
   GemmArgs g = gemm_args((int)AM, GAC_E, GAC_NB, c->ca, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->a_ae, GAC_E);
@@ -1147,6 +1173,8 @@ int gac_create(const gac_config_t* cfg, void* workspace, size_t workspace_bytes,
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_q, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_cprep, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_aprep, cudaEventDisableTiming);
   if (e != cudaSuccess) { gac_destroy(c); return fail(GAC_ERR_CUDA, "gac_create: %s", cudaGetErrorString(e)); }
   *out = c;
   return GAC_OK;
@@ -1157,6 +1185,8 @@ void gac_destroy(gac_ctx_t* ctx) {
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_q) cudaEventDestroy(ctx->ev_q);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_cprep) cudaEventDestroy(ctx->ev_cprep);
+  if (ctx->ev_aprep) cudaEventDestroy(ctx->ev_aprep);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   delete ctx;
 }
@@ -1370,13 +1400,30 @@ int gac_step_grads(gac_ctx_t* c, const gac_step_io_t* io, const gac_hparams_t* h
   float* const spart_main = c->spart; float* const cpart_main = c->cpart;
   struct LaneGuard {                                              // whatever path leaves this function, the context is back on the main lane
     gac_ctx* c; cudaStream_t st; float *sp, *cp;
-    ~LaneGuard() { c->stream = st; c->spart = sp; c->cpart = cp; }
+    ~LaneGuard() { c->stream = st; c->spart = sp; c->cpart = cp; c->critic_prepped = false; c->actor_prep_token = nullptr; }
   } lane_guard{c, st, spart_main, cpart_main};
   auto side_lane = [&]() { if (two_lanes) { c->stream = c->side; c->spart = c->spart2; c->cpart = c->cpart2; } };
   auto main_lane = [&]() { c->stream = st; c->spart = spart_main; c->cpart = cpart_main; };
   if (two_lanes) {
     GAC_CUDA(cudaEventRecord(c->ev_fork, st));                    // the batch and the parameters are ready at this point of the caller's stream
     GAC_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+  }
+
+  // weight-only preparation of the critic evaluation and of the actor's training pass: first on the side lane, so that it is
+  // long done when the main lane gets there (and done ONCE for all row chunks of the actor update)
+  if (two_lanes) {
+    side_lane();
+    if (critic_fused(c, 3 * P, B, c->sidx3)) {
+      GAC_TRY(critic_prep(c, t_f1, t_f2, io->s, B));
+      c->critic_prepped = true;
+    }
+    GAC_CUDA(cudaEventRecord(c->ev_cprep, c->side));
+    if (c->cfg.actor_kind == GAC_ACTOR_AIQN) {
+      GAC_TRY(actor_train_prep(c, io->online + L.net_begin[GAC_NET_ACTOR]));
+      c->actor_prep_token = io->online + L.net_begin[GAC_NET_ACTOR];
+    }
+    GAC_CUDA(cudaEventRecord(c->ev_aprep, c->side));
+    main_lane();
   }
 
   // ---- Critic.train (networks.py:410-426) ----
@@ -1401,6 +1448,7 @@ int gac_step_grads(gac_ctx_t* c, const gac_step_io_t* io, const gac_hparams_t* h
                                                                            (long long)P * A, c->cand + (size_t)P * A);
   LAUNCHED(c, "noise_clip");
   GAC_CUDA(cudaMemcpyAsync(c->cand + (size_t)2 * P * A, io->filter_rand, (size_t)P * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (two_lanes) GAC_CUDA(cudaStreamWaitEvent(st, c->ev_cprep, 0));
   GAC_TRY(critic_eval(c, t_f1, t_f2, io->s, c->sidx3, c->cand, 3 * P, c->q3, B));
 
   // ---- Value.train (networks.py:483-496): needs the critics' values of the first P candidates ----
@@ -1431,6 +1479,7 @@ int gac_step_grads(gac_ctx_t* c, const gac_step_io_t* io, const gac_hparams_t* h
   // ---- IQNActor.train (networks.py:122-141) in row chunks; un-normalised weights ----
   float* g_actor = io->grad + L.net_begin[GAC_NET_ACTOR];
   const float* o_actor = io->online + L.net_begin[GAC_NET_ACTOR];
+  if (two_lanes) GAC_CUDA(cudaStreamWaitEvent(st, c->ev_aprep, 0));
   for (int ch = 0; ch < c->nchunks; ++ch) {
     const size_t r0 = (size_t)ch * Mc;
     const int maxr = (int)((size_t)2 * P - r0 < (size_t)Mc ? (size_t)2 * P - r0 : (size_t)Mc);
