@@ -135,6 +135,7 @@ struct gac_ctx {
   // second lane of gac_step_grads: the three TD updates (B-row problems, ~65 small launches) run on a side stream beside the
   // sampler / critic evaluation / actor update; they touch only the td_* buffers and their own split-K / column-sum scratch
   cudaStream_t side; cudaEvent_t ev_fork, ev_q, ev_join, ev_cprep, ev_aprep; float *spart2, *cpart2;
+  bool lanes_on; cudaStream_t main_stream; float *spart_main, *cpart_main; cudaEvent_t ev_w, ev_wjoin;   // lane state while gac_step_grads runs
   bool critic_prepped; const float* actor_prep_token;   // weight preparation already issued by gac_step_grads (on its side lane)
   unsigned char *a_ae_pk, *a_h_pk[2];           // training forward: a16 images of the (A * Mc)-row action embedding and of two ping-pong states
 };
@@ -209,10 +210,10 @@ size_t partition(gac_ctx* c, void* ws) {
   c->dhu = b.take<float>(AM * GAC_E); c->dhc0 = b.take<float>(Mc * GAC_E); c->dhc1 = b.take<float>(Mc * GAC_E);
   c->dop = b.take<float>(AM); c->pred_c = b.take<float>(Mc * A); c->dpred_c = b.take<float>(Mc * A);
   c->spart = b.take<float>((size_t)c->max_splits * GAC_E * GAC_G);
-  c->spart2 = b.take<float>((size_t)c->max_splits * GAC_H1 * GAC_E);     // side lane: no product larger than B x 400 / 400 x 300 is split there
-  c->cpart2 = b.take<float>(((B + 15) / 16 + 8192 / 16 + 1) * GAC_G);
+  c->spart2 = b.take<float>((size_t)c->max_splits * GAC_E * GAC_G);      // side lane: TD updates, then the actor's large weight gradients
   const size_t maxrows = AM > Rs ? AM : Rs;
   c->cpart = b.take<float>(((maxrows + COLSUM_ROWS - 1) / COLSUM_ROWS + 8192 / 16 + 1) * GAC_G);
+  c->cpart2 = b.take<float>(((maxrows + COLSUM_ROWS - 1) / COLSUM_ROWS + 8192 / 16 + 1) * GAC_G);
   if (f.actor_kind == GAC_ACTOR_IQN) {
     const size_t D = c->iq_D;
     c->iq_se_u = b.take<float>((size_t)c->NUs * D); c->iq_cos = b.take<float>(Rs * A * GAC_NB); c->iq_ne = b.take<float>(Rs * D);
@@ -859,6 +860,22 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
   return GAC_OK;
 }
 
+// Lanes of gac_step_grads (lanes_on): work that nothing on the critical chain waits for goes to the side stream with its own
+// split-K / column-sum scratch.  Outside gac_step_grads (the single-op C-ABI entries) these are no-ops.
+inline void lane_side(gac_ctx* c) { if (c->lanes_on) { c->stream = c->side; c->spart = c->spart2; c->cpart = c->cpart2; } }
+inline void lane_main(gac_ctx* c) { if (c->lanes_on) { c->stream = c->main_stream; c->spart = c->spart_main; c->cpart = c->cpart_main; } }
+// side lane continues only after everything issued on the main lane so far
+inline cudaError_t lane_side_after_main(gac_ctx* c) {
+  if (!c->lanes_on) return cudaSuccess;
+  cudaError_t e = cudaEventRecord(c->ev_w, c->main_stream);
+  return e != cudaSuccess ? e : cudaStreamWaitEvent(c->side, c->ev_w, 0);
+}
+inline cudaError_t lane_main_after_side(gac_ctx* c) {
+  if (!c->lanes_on) return cudaSuccess;
+  cudaError_t e = cudaEventRecord(c->ev_wjoin, c->side);
+  return e != cudaSuccess ? e : cudaStreamWaitEvent(c->main_stream, c->ev_wjoin, 0);
+}
+
 int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, int acc) {
   const int A = c->cfg.A, Mc = c->Mc, S = c->cfg.S;
   if (!c->bwd_drows) return fail(GAC_ERR_INVALID, "gac_aiqn_bwd: no saved forward");
@@ -874,11 +891,11 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
     GemmArgs g = gemm_args(M, N, (int)rows, X, ldx, dY, ldy, dst, N);
     g.transA = 1; g.accumulate = acc;
     if (site >= 0 && c->wg_f16) {
-      wg_scale_kernel<<<1, 1, 0, st>>>(c->wg_sc + site, amax_dy, bound_x, bound_const);
+      wg_scale_kernel<<<1, 1, 0, c->stream>>>(c->wg_sc + site, amax_dy, bound_x, bound_const);
       LAUNCHED(c, "wg_scale");
       g.f16 = c->wg_sc + site;
       if (dyn && M == GAC_E && ldx == GAC_E && rows == AM && c->cfg.engine == 0) {
-        GAC_CUDA(wg_pack_x(X, ldx, M, Mc, A, live, c->wg_sc + site, c->wg_xpack, st));
+        GAC_CUDA(wg_pack_x(X, ldx, M, Mc, A, live, c->wg_sc + site, c->wg_xpack, c->stream));
         c->launches++;
         g.Bpk16 = c->wg_xpack;
       }
@@ -887,6 +904,17 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
     if (timeline && site == 2) g.dbg = c->dbg_buf;           // the kx_a weight gradient: (2, 10, splits) CTAs
     if (dyn) { g.dyn_rows = live; g.seg_rows = Mc; g.valid_on_k = 1; }
     return run_gemm(c, g);
+  };
+  // The five time-parallel weight gradients feed nothing downstream: each is issued on the side lane as soon as its operands
+  // exist (an event orders it after the main lane's producers) and runs beside the serial chain head -> Hadamard ->
+  // recurrence -> input gradients, much of which is HBM-bound.  Joined at the end of this function: the next chunk's forward
+  // overwrites their operands.
+  auto side_wgrad = [&](auto&& fn) -> int {
+    GAC_CUDA(lane_side_after_main(c));
+    lane_side(c);
+    const int rc = fn();
+    lane_main(c);
+    return rc;
   };
   // C (rows, 400) = X (rows, K) * W^T through dot_gemm_tc.cuh (store mode); which: 0 = W1, 1 = U, 2 = kx_a
   auto dgrad = [&](int which, const float* X, int ldx, int K, long long rows, float* Cdst, const float* gate, float gate_alpha, int accumulate,
@@ -918,7 +946,7 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   LAUNCHED(c, "reduce_cols");
   reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart1, nrb_all, GAC_E, G(GAC_A_W2), acc);
   LAUNCHED(c, "reduce_cols");
-  GAC_TRY(wgrad(GAC_E, GAC_E, c->au, GAC_E, c->dy1p, GAC_E, AM, G(GAC_A_W1), true, 0, c->dg_amax + 2, c->wg_bound + 1));
+  GAC_TRY(side_wgrad([&] { return wgrad(GAC_E, GAC_E, c->au, GAC_E, c->dy1p, GAC_E, AM, G(GAC_A_W1), true, 0, c->dg_amax + 2, c->wg_bound + 1); }));
   GemmArgs g = gemm_args((int)AM, GAC_E, GAC_E, c->dy1p, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->du, GAC_E);
   if (c->dg_fused) {
     GAC_TRY(dgrad(0, c->dy1p, GAC_E, GAC_E, AM, c->du, nullptr, 0.f, 0, amax_g + 2));
@@ -931,7 +959,7 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   LAUNCHED(c, "hadamard_bwd");
   reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart0, nrb_all, GAC_E, G(GAC_A_BN), acc);
   LAUNCHED(c, "reduce_cols");
-  GAC_TRY(wgrad(GAC_NB, GAC_E, c->cn, GAC_NB, c->dne, GAC_E, AM, G(GAC_A_WN), true));
+  GAC_TRY(side_wgrad([&] { return wgrad(GAC_NB, GAC_E, c->cn, GAC_NB, c->dne, GAC_E, AM, G(GAC_A_WN), true); }));
   // recurrence, reverse time.  mx is overwritten with dmx step by step (it is dead after the forward gates)
   float* dh_next = nullptr; float* carry = c->dhc0;
   const int nrb_step = Mc / FB_ROWS;
@@ -953,12 +981,12 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
     carry = carry == c->dhc0 ? c->dhc1 : c->dhc0;
   }
   // time-parallel weight gradients of the GRU
-  GAC_TRY(wgrad(GAC_E, GAC_G, c->hall, GAC_E, c->dmh, GAC_G, AM, G(GAC_A_U), true, 1, c->dg_amax, nullptr, 1.f));
+  GAC_TRY(side_wgrad([&] { return wgrad(GAC_E, GAC_G, c->hall, GAC_E, c->dmh, GAC_G, AM, G(GAC_A_U), true, 1, c->dg_amax, nullptr, 1.f); }));
   reduce_cols_kernel<<<cdiv(GAC_G, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart1, A * nrb_step, GAC_G, G(GAC_A_GB) + GAC_G, acc);
   LAUNCHED(c, "reduce_cols");
   reduce_cols_kernel<<<cdiv(GAC_G, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart0, A * nrb_step, GAC_G, G(GAC_A_GB), acc);
   LAUNCHED(c, "reduce_cols");
-  GAC_TRY(wgrad(GAC_E, GAC_G, c->a_ae, GAC_E, c->mx, GAC_G, AM, G(GAC_A_KX) + (size_t)GAC_E * GAC_G, true, 2, c->dg_amax, c->wg_bound + 3));
+  GAC_TRY(side_wgrad([&] { return wgrad(GAC_E, GAC_G, c->a_ae, GAC_E, c->mx, GAC_G, AM, G(GAC_A_KX) + (size_t)GAC_E * GAC_G, true, 2, c->dg_amax, c->wg_bound + 3); }));
   if (c->dg_fused) {
     GAC_TRY(dgrad(2, c->mx, GAC_G, GAC_G, AM, c->du, c->a_ae, 0.2f, 0, amax_g));
   } else {
@@ -966,8 +994,10 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
     g.transB = 1; g.gate = c->a_ae; g.ldgate = GAC_E; g.gate_alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_KXAT]; g.Bpacked_bn = c->pk_bn[PK_O_KXAT];
     GAC_TRY(run_gemm(c, g));
   }
-  GAC_TRY(wgrad(GAC_NB, GAC_E, c->ca, GAC_NB, c->du, GAC_E, AM, G(GAC_A_WA), true));
-  GAC_TRY(run_colsum(c, c->du, GAC_E, nullptr, GAC_E, AM, rv, G(GAC_A_BA), acc));
+  GAC_TRY(side_wgrad([&] {
+    GAC_TRY(wgrad(GAC_NB, GAC_E, c->ca, GAC_NB, c->du, GAC_E, AM, G(GAC_A_WA), true));
+    return run_colsum(c, c->du, GAC_E, nullptr, GAC_E, AM, rv, G(GAC_A_BA), acc);
+  }));
   // state half: reduce d(sx) per unique state, then B-row GEMMs
   const int NU = c->bwd_nstates;
   // rows grouped by state with a stable counting sort (block histograms -> scan -> ranked scatter), then one block
@@ -995,6 +1025,7 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   GAC_TRY(run_gemm(c, g));
   GAC_TRY(wgrad(S, GAC_E, c->bwd_states, S, c->a_dse_u, GAC_E, NU, G(GAC_A_WS), false));
   GAC_TRY(run_colsum(c, c->a_dse_u, GAC_E, nullptr, GAC_E, NU, RowValid{nullptr, 1}, G(GAC_A_BS), acc));
+  GAC_CUDA(lane_main_after_side(c));
   return GAC_OK;
 }
 
@@ -1175,6 +1206,8 @@ int gac_create(const gac_config_t* cfg, void* workspace, size_t workspace_bytes,
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_cprep, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_aprep, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_w, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_wjoin, cudaEventDisableTiming);
   if (e != cudaSuccess) { gac_destroy(c); return fail(GAC_ERR_CUDA, "gac_create: %s", cudaGetErrorString(e)); }
   *out = c;
   return GAC_OK;
@@ -1187,6 +1220,8 @@ void gac_destroy(gac_ctx_t* ctx) {
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->ev_cprep) cudaEventDestroy(ctx->ev_cprep);
   if (ctx->ev_aprep) cudaEventDestroy(ctx->ev_aprep);
+  if (ctx->ev_w) cudaEventDestroy(ctx->ev_w);
+  if (ctx->ev_wjoin) cudaEventDestroy(ctx->ev_wjoin);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   delete ctx;
 }
@@ -1400,10 +1435,11 @@ int gac_step_grads(gac_ctx_t* c, const gac_step_io_t* io, const gac_hparams_t* h
   float* const spart_main = c->spart; float* const cpart_main = c->cpart;
   struct LaneGuard {                                              // whatever path leaves this function, the context is back on the main lane
     gac_ctx* c; cudaStream_t st; float *sp, *cp;
-    ~LaneGuard() { c->stream = st; c->spart = sp; c->cpart = cp; c->critic_prepped = false; c->actor_prep_token = nullptr; }
+    ~LaneGuard() { c->stream = st; c->spart = sp; c->cpart = cp; c->lanes_on = false; c->critic_prepped = false; c->actor_prep_token = nullptr; }
   } lane_guard{c, st, spart_main, cpart_main};
-  auto side_lane = [&]() { if (two_lanes) { c->stream = c->side; c->spart = c->spart2; c->cpart = c->cpart2; } };
-  auto main_lane = [&]() { c->stream = st; c->spart = spart_main; c->cpart = cpart_main; };
+  c->lanes_on = two_lanes; c->main_stream = st; c->spart_main = spart_main; c->cpart_main = cpart_main;
+  auto side_lane = [&]() { lane_side(c); };
+  auto main_lane = [&]() { lane_main(c); };
   if (two_lanes) {
     GAC_CUDA(cudaEventRecord(c->ev_fork, st));                    // the batch and the parameters are ready at this point of the caller's stream
     GAC_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
