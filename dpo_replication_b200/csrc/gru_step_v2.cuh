@@ -52,7 +52,7 @@ constexpr int G2_SS = 48;                                        // staging row 
 constexpr int G2_DRAIN_WARPS = 8;                                // two per TMEM lane quadrant, 40 columns each
 constexpr int G2_DS = 8;                                         // drain transposition row stride in floats; quad slot XOR (row >> 2) & 1
 constexpr int G2_DRAIN_SMEM = G2_DRAIN_WARPS * 32 * G2_DS * 4;   // 8 KB: one 32 x 8 block per drain warp
-constexpr int G2_SMEM = G2_STAGES * (int)G2_STAGE + BM * G2_SS * 4 + G2_DRAIN_SMEM + 3 * G2_NU * 4 + 1024;
+constexpr int G2_SMEM = G2_STAGES * (int)G2_STAGE + BM * G2_SS * 4 + G2_DRAIN_SMEM + 2 * 3 * G2_NU * 4 + 1024;
 // Warp roles, in warpgroups of four (setmaxnreg works per warpgroup): warps 0-15 epilogue (the gate math is a long dependent
 // chain per thread: with two warps per scheduler its latencies were exposed and a tile's epilogue took ~29k cycles against a
 // 23k-cycle main loop; four warps per scheduler hide them), warp 16 MMA issuer, warp 17 producer, warps 18-19 idle, warps 20-27
@@ -195,6 +195,55 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+// One K block of the 3-pass product as ONE instruction group: hi*hi, lo*hi, hi*lo for both 16-element K steps.  The tensor
+// core needs N / 2 cycles per M = 128 kind::f16 instruction (120 at N = 240), but the single issuing lane used to spend ~168:
+// a predicate set-up and four 64-bit descriptor computations per instruction, interleaved with seven other warps of its
+// scheduler (tools/mma_issue.cu, profiles/r2k_mma_issue.txt: the same loop stripped to this form runs at 120.1 cycles).
+// Here the lane passes ONE descriptor (A hi of the stage); the other three differ from it by compile-time constants, the
+// second K step by +32 bytes, and six MMAs share one predicate.  acc0: accumulate flag of the first instruction.
+template <uint32_t A_LO, uint32_t B_HI, uint32_t B_LO>
+__device__ __forceinline__ void mma_f16_kblock(uint32_t d, uint64_t a_hi, uint32_t idesc, uint32_t acc0) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 al, bh, bl, ah2, al2, bh2, bl2;\n"
+      "setp.ne.b32 q, %3, 0;\n"
+      "setp.eq.b32 p, 1, 1;\n"
+      "add.u64 al, %1, %4;\n"
+      "add.u64 bh, %1, %5;\n"
+      "add.u64 bl, %1, %6;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, bh, %2, q;\n"
+      "add.u64 ah2, %1, 2;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], al, bh, %2, p;\n"
+      "add.u64 bh2, bh, 2;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, bl, %2, p;\n"
+      "add.u64 al2, al, 2;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ah2, bh2, %2, p;\n"
+      "add.u64 bl2, bl, 2;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], al2, bh2, %2, p;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ah2, bl2, %2, p;\n"
+      "}\n" ::"r"(d), "l"(a_hi), "r"(idesc), "r"(acc0), "n"(A_LO), "n"(B_HI), "n"(B_LO)
+      : "memory");
+}
+// the last K block of an operand half has 16 live columns: one K step
+template <uint32_t A_LO, uint32_t B_HI, uint32_t B_LO>
+__device__ __forceinline__ void mma_f16_kstep(uint32_t d, uint64_t a_hi, uint32_t idesc, uint32_t acc0) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 al, bh, bl;\n"
+      "setp.ne.b32 q, %3, 0;\n"
+      "setp.eq.b32 p, 1, 1;\n"
+      "add.u64 al, %1, %4;\n"
+      "add.u64 bh, %1, %5;\n"
+      "add.u64 bl, %1, %6;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, bh, %2, q;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], al, bh, %2, p;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, bl, %2, p;\n"
+      "}\n" ::"r"(d), "l"(a_hi), "r"(idesc), "r"(acc0), "n"(A_LO), "n"(B_HI), "n"(B_LO)
+      : "memory");
+}
+
 template <bool DBG>
 __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Args g) {
   // DBG = false: the counters and the timing-experiment switches are compiled out (they cost registers in every role)
@@ -213,7 +262,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)) + G2_STAGES * G2_STAGE);
   float* dstg = stg + BM * G2_SS;                                  // drain warps' transposition blocks
-  float* b1_s = dstg + G2_DRAIN_WARPS * 32 * G2_DS;                             // recurrent bias of the current tile: [z | r | h] x 80
+  float* b1_base = dstg + G2_DRAIN_WARPS * 32 * G2_DS;                          // recurrent bias of the current tile, [z | r | h] x 80, one copy per epilogue group
   float* xh_cta = g.xh_scratch + (size_t)blockIdx.x * (G2_XH_BYTES_PER_CTA / 4);
 
   if (tid == 0) {
@@ -265,6 +314,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
       constexpr uint32_t id3 = (1u << 4) | ((uint32_t)((3 * G2_NU) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // make_idesc_f16(240)
       constexpr uint32_t id2 = (1u << 4) | ((uint32_t)((2 * G2_NU) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       constexpr uint32_t id1 = (1u << 4) | ((uint32_t)(G2_NU >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint64_t desc0 = make_desc64(smem0);                   // A hi of stage 0
       int it = 0, t = 0;
       for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++t) {
         const int b = t & 1;
@@ -281,32 +331,32 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
           mbar_wait(smem_u32(&bar_full[s]), ph);
           tc_fence_after();
           if (dbgp) t_wait_full += clock64() - c0;
-          const uint32_t sa = smem0 + (uint32_t)s * G2_STAGE;
-          const uint64_t a_hi = make_desc64(sa), a_lo = make_desc64(sa + G2_A_TILE);
-          const uint64_t b_hi = make_desc64(sa + G2_A_SLOT), b_lo = make_desc64(sa + G2_A_SLOT + G2_B_TILE);
-          const int half = kb >= G2_KB, kbl = kb - half * G2_KB, live = min(G2_BK, GAC_E - kbl * G2_BK);
-          const int ksteps = (probe & 32) ? 0 : (live + 15) / 16;      // probe 32: no MMAs, the operand stream alone
-          for (int j = 0; j < ksteps; ++j) {
-            const uint64_t adv = (uint64_t)(j * 2);
-            if (half && kbl == 0 && j == 0) {
-              // the recurrent half starts: z, r keep accumulating; g switches from ae * kx_h (copied out by the drain warps)
-              // to h_prev * U_h and starts from zero
-              constexpr uint64_t bo = (uint64_t)((2u * G2_NU * 64u) >> 4);
-              mma_f16(d0, a_hi + adv, b_hi + adv, id2, 1u);        // z, r do not depend on the drain: ~3 MMA times of cover
-              mma_f16(d0, a_lo + adv, b_hi + adv, id2, 1u);
-              mma_f16(d0, a_hi + adv, b_lo + adv, id2, 1u);
-              c0 = dbgp ? clock64() : 0;
-              mbar_wait(smem_u32(&bar_xfree[b]), tph);
-              tc_fence_after();
-              if (dbgp) t_wait_x += clock64() - c0;
-              mma_f16(d0 + 2u * G2_NU, a_hi + adv, b_hi + bo + adv, id1, 0u);
-              mma_f16(d0 + 2u * G2_NU, a_lo + adv, b_hi + bo + adv, id1, 1u);
-              mma_f16(d0 + 2u * G2_NU, a_hi + adv, b_lo + bo + adv, id1, 1u);
-              continue;
-            }
-            mma_f16(d0, a_hi + adv, b_hi + adv, id3, (kb | j) ? 1u : 0u);
-            mma_f16(d0, a_lo + adv, b_hi + adv, id3, 1u);
-            mma_f16(d0, a_hi + adv, b_lo + adv, id3, 1u);
+          // stages are contiguous: the descriptors of stage s are those of stage 0 plus s * (G2_STAGE >> 4) in the address field
+          const uint64_t a_hi = desc0 + (uint64_t)((uint32_t)s * (G2_STAGE >> 4));
+          constexpr uint32_t C_ALO = G2_A_TILE >> 4, C_BHI = G2_A_SLOT >> 4, C_BLO = (G2_A_SLOT + G2_B_TILE) >> 4;
+          const bool last_of_half = kb == G2_KB - 1 || kb == 2 * G2_KB - 1;       // 400 = 12 x 32 + 16: one K step
+          if (DBG && (probe & 32)) {
+            // probe 32: no MMAs, the operand stream alone
+          } else if (kb == G2_KB) {
+            // the recurrent half starts: z, r keep accumulating; g switches from ae * kx_h (copied out by the drain warps)
+            // to h_prev * U_h and starts from zero
+            const uint64_t a_lo = a_hi + C_ALO, b_hi = a_hi + C_BHI, b_lo = a_hi + C_BLO;
+            constexpr uint64_t bo = (uint64_t)((2u * G2_NU * 64u) >> 4);
+            mma_f16(d0, a_hi, b_hi, id2, 1u);                      // z, r do not depend on the drain: ~3 MMA times of cover
+            mma_f16(d0, a_lo, b_hi, id2, 1u);
+            mma_f16(d0, a_hi, b_lo, id2, 1u);
+            c0 = dbgp ? clock64() : 0;
+            mbar_wait(smem_u32(&bar_xfree[b]), tph);
+            tc_fence_after();
+            if (dbgp) t_wait_x += clock64() - c0;
+            mma_f16(d0 + 2u * G2_NU, a_hi, b_hi + bo, id1, 0u);
+            mma_f16(d0 + 2u * G2_NU, a_lo, b_hi + bo, id1, 1u);
+            mma_f16(d0 + 2u * G2_NU, a_hi, b_lo + bo, id1, 1u);
+            mma_f16_kstep<C_ALO, C_BHI, C_BLO>(d0, a_hi + 2, id3, 1u);   // second K step of this block
+          } else if (last_of_half) {
+            mma_f16_kstep<C_ALO, C_BHI, C_BLO>(d0, a_hi, id3, 1u);
+          } else {
+            mma_f16_kblock<C_ALO, C_BHI, C_BLO>(d0, a_hi, id3, kb ? 1u : 0u);
           }
           mma_commit(smem_u32(&bar_empty[s]));
           if (has_h && kb == G2_KB - 1) mma_commit(smem_u32(&bar_xfull[b]));     // the action-embedding half has retired
@@ -390,13 +440,22 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
   } else {
     // ------------------------------ epilogue: sixteen warps, overlapped with the next tile's main loop ------------------------------
     const int quarter = warp & 3, sub = warp >> 2;                 // TMEM lane quadrant; phase-1 column group (0 z, 1 r, 2 g, 3 none)
+    // Two independent half-tile groups: the eight warps of TMEM lane quadrants {0, 1} own rows 0..63, those of {2, 3} rows
+    // 64..127.  Each group runs its own phase 1 -> barrier -> phase 2 -> barrier cycle on its own staging rows and named
+    // barrier, so one group's TMEM reads overlap the other's gate math and global traffic instead of all sixteen warps
+    // idling at the same barrier.
+    const int grp = quarter >> 1, gw = sub * 2 + (warp & 1);       // group; warp index within the group (0..7)
+    const int gtid = gw * 32 + lane;                                // thread index within the group (0..255)
+    const uint32_t gbar = 1u + (uint32_t)grp;
+    float* b1_s = b1_base + grp * (3 * G2_NU);
+#define G2_GROUP_SYNC() asm volatile("bar.sync %0, 256;" ::"r"(gbar) : "memory")
     const float inv_unit = g.sc->inv_unit, s_h = g.sc->s_h;
     auto tnh = [](float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); };
     // phase-2 ownership: ONE (row, unit quad) item per thread and chunk: row = 8 warp + (lane >> 2), quad = lane & 3.  128-bit
     // global accesses are coalesced per QUARTER warp: eight consecutive lanes = two rows x 64 contiguous bytes = four full
     // sectors.  (The first version put eight different rows into a quarter warp to make the staging reads conflict-free: every
     // global access then touched eight half-used sectors, and the operand loads alone cost 2.5k cycles per chunk.)
-    const int prow = warp * 8 + (lane >> 2), pj = lane & 3;
+    const int prow = 64 * grp + gw * 8 + (lane >> 2), pj = lane & 3;
     const bool stamp = dbgp && tid == 0;
     long long e_wt = 0, e_wx = 0, e_p1 = 0, e_b1 = 0, e_p2 = 0, e_b2 = 0, e_ld = 0, ec = 0;
 #define G2_STAMP(acc) if (stamp) { const long long now = clock64(); acc += now - ec; ec = now; }
@@ -408,8 +467,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
       const uint32_t tph = (uint32_t)(t >> 1) & 1u;
       const int m = m0 + prow;
       const int sid = m < m_end ? g.sidx[m] : -1;
-      if (tid < 3 * G2_NU / 4)                                     // this tile's recurrent bias -> smem (read in every chunk's phase 2)
-        *reinterpret_cast<float4*>(b1_s + 4 * tid) = *reinterpret_cast<const float4*>(g.b1 + (tid / (G2_NU / 4)) * GAC_E + jt * G2_NU + 4 * (tid % (G2_NU / 4)));
+      if (gtid < 3 * G2_NU / 4)                                    // this tile's recurrent bias -> the group's smem copy
+        *reinterpret_cast<float4*>(b1_s + 4 * gtid) = *reinterpret_cast<const float4*>(g.b1 + (gtid / (G2_NU / 4)) * GAC_E + jt * G2_NU + 4 * (gtid % (G2_NU / 4)));
       if (has_h) mbar_wait(smem_u32(&bar_xsaved[b]), tph);         // acquire: the drain warps' scratch rows are visible
       G2_STAMP(e_wx)
       // Operands of phase 2 that do not depend on the accumulators (gathered state projection, h_prev, the saved input part):
@@ -431,7 +490,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
       };
       load_ops(0);
       G2_STAMP(e_ld)
-      asm volatile("bar.sync 1, 512;" ::: "memory");               // this tile's bias rows are in smem (phase 1 reads them)
+      G2_GROUP_SYNC();                                             // this tile's bias rows are in smem (phase 1 reads them)
       mbar_wait(smem_u32(&bar_tfull[b]), tph);
       tc_fence_after();
       G2_STAMP(e_wt)
@@ -467,7 +526,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
           }
         }
         G2_STAMP(e_p1)
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+        G2_GROUP_SYNC();
         G2_STAMP(e_b1)
         // phase 2: gate math and the state update, row-contiguous global traffic (no branch around the math: dead rows only
         // skip their stores)
@@ -519,7 +578,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
           if (q + 1 < G2_NU / 16) load_ops(q + 1);
         }
         G2_STAMP(e_p2)
-        asm volatile("bar.sync 1, 512;" ::: "memory");             // the staging rows are rewritten by the next chunk / tile
+        G2_GROUP_SYNC();                                           // the staging rows are rewritten by the next chunk / tile
         G2_STAMP(e_b2)
       }
       // this tile's accumulator columns and scratch rows are free again (all their reads above have completed)
@@ -528,6 +587,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
       if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[b]));
     }
 #undef G2_STAMP
+#undef G2_GROUP_SYNC
     if (stamp) {
       unsigned long long* d = dbgp + 8 + (size_t)blockIdx.x * 16;
       d[6] = (unsigned long long)e_wt; d[7] = (unsigned long long)e_wx; d[8] = (unsigned long long)e_p1; d[9] = (unsigned long long)e_b1;

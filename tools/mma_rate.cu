@@ -17,7 +17,7 @@ using namespace gac;
 using namespace gac::tc;
 
 struct RateArgs {
-  int N, sw, tiles, copies, epi;
+  int N, sw, tiles, copies, epi, mn;   // mn: both operands MN-major (the weight-gradient layout: 64-element groups x 32 k-rows x 128 bytes)
   const unsigned char* src;        // >= 64 KB of global memory per CTA for the bulk copies
   unsigned long long* out;         // per CTA: [cycles, mmas, ns]
 };
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(384, 1) mma_rate_kernel(const RateArgs a) {
   uint8_t* sm = smem_raw + (smem0 - smem_u32(smem_raw));
   const int rowb = a.sw;                                        // bytes per operand row in a K block
   const int ncta = CG == 2 ? a.N / 2 : a.N;
-  const uint32_t a_tile = 128u * rowb, b_tile = (uint32_t)ncta * rowb;
+  const uint32_t a_tile = a.mn ? 2u * 4096u : 128u * rowb, b_tile = a.mn ? (uint32_t)((ncta + 63) / 64) * 4096u : (uint32_t)ncta * rowb;
   const uint32_t stage = 2 * a_tile + 2 * b_tile;
   const int nstages = a.sw == 64 ? 4 : 1;
   const uint32_t cp_bytes = stage < 32768u ? stage : 32768u;
@@ -79,11 +79,11 @@ __global__ void __launch_bounds__(384, 1) mma_rate_kernel(const RateArgs a) {
   }
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
-  const int ksteps_per_stage = rowb / 32, ksteps = 50;          // one GRU tile: 2 x 25 K steps of 16 elements
+  const int ksteps_per_stage = a.mn ? 2 : rowb / 32, ksteps = 50;   // one GRU tile: 2 x 25 K steps of 16 elements
 
   if (warp == 0) {
     if (lane == 0 && crank == 0) {
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(a.N >> 3) << 17) | ((uint32_t)((CG == 2 ? 256 : 128) >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(a.N >> 3) << 17) | ((uint32_t)((CG == 2 ? 256 : 128) >> 4) << 24) | (a.mn ? (1u << 15) | (1u << 16) : 0u);
       unsigned long long g0, g1;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g0));
       const long long t0 = clock64();
@@ -93,10 +93,10 @@ __global__ void __launch_bounds__(384, 1) mma_rate_kernel(const RateArgs a) {
         for (int k = 0; k < ksteps; ++k) {
           const int s = (k / ksteps_per_stage) % nstages, j = k % ksteps_per_stage;
           const uint32_t sa = smem0 + (uint32_t)s * stage;
-          const uint64_t adv = (uint64_t)(j * 2);
-          const uint64_t ah = (a.sw == 64 ? make_desc64(sa) : make_desc(sa)) + adv, al = (a.sw == 64 ? make_desc64(sa + a_tile) : make_desc(sa + a_tile)) + adv;
-          const uint64_t bh = (a.sw == 64 ? make_desc64(sa + 2 * a_tile) : make_desc(sa + 2 * a_tile)) + adv,
-                         bl = (a.sw == 64 ? make_desc64(sa + 2 * a_tile + b_tile) : make_desc(sa + 2 * a_tile + b_tile)) + adv;
+          const uint64_t adv = a.mn ? (uint64_t)(j * 128) : (uint64_t)(j * 2);
+          auto mk = [&](uint32_t addr) { return a.mn ? make_desc_mn16(addr) : (a.sw == 64 ? make_desc64(addr) : make_desc(addr)); };
+          const uint64_t ah = mk(sa) + adv, al = mk(sa + a_tile) + adv;
+          const uint64_t bh = mk(sa + 2 * a_tile) + adv, bl = mk(sa + 2 * a_tile + b_tile) + adv;
           if (CG == 2) {
             mma_f16_cg2(d0, ah, bh, idesc, k ? 1u : 0u); mma_f16_cg2(d0, al, bh, idesc, 1u); mma_f16_cg2(d0, ah, bl, idesc, 1u);
           } else {
@@ -163,13 +163,13 @@ __global__ void __launch_bounds__(384, 1) mma_rate_kernel(const RateArgs a) {
   }
 }
 
-static void run(int cg, int N, int sw, int copies, int epi, const unsigned char* src, unsigned long long* out_d) {
-  RateArgs a{N, sw, 40, copies, epi, src, out_d};
+static void run(int cg, int N, int sw, int copies, int epi, const unsigned char* src, unsigned long long* out_d, int mn = 0) {
+  RateArgs a{N, sw, 40, copies, epi, mn, src, out_d};
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   sms &= ~1;
   const int ncta = cg == 2 ? N / 2 : N;
-  const int stage = 2 * 128 * sw + 2 * ncta * sw, nstages = sw == 64 ? 4 : 1;
+  const int stage = mn ? 2 * 8192 + 2 * ((ncta + 63) / 64) * 4096 : 2 * 128 * sw + 2 * ncta * sw, nstages = sw == 64 ? 4 : 1;
   const int smem = nstages * stage + 2 * (stage < 32768 ? stage : 32768) + 12 * 32 * 36 * 4 + 2048;
   if (smem > 227 * 1024) { printf("cg=%d N=%3d sw=%3d: needs %d bytes of smem, skipped\n", cg, N, sw, smem); return; }
   cudaMemset(out_d, 0, sms * 4 * sizeof(unsigned long long));
@@ -202,7 +202,7 @@ static void run(int cg, int N, int sw, int copies, int epi, const unsigned char*
   const double per = cyc / n, mhz = 1e3 * cyc / ns;
   const double macs = (cg == 2 ? 256.0 : 128.0) * N * 16;                 // per instruction
   const double tf = 2.0 * macs * n / (ms * 1e-3) / 1e12;
-  printf("cg=%d N=%3d sw=%3d copies=%d epi=%d: %6.1f cycles per MMA (%d issuing CTAs), SM clock %4.0f MHz, %7.1f TFLOP/s fp16 chip-wide (%.0f MAC/clk/SM)\n", cg, N, sw,
+  printf("%s cg=%d N=%3d sw=%3d copies=%d epi=%d: %6.1f cycles per MMA (%d issuing CTAs), SM clock %4.0f MHz, %7.1f TFLOP/s fp16 chip-wide (%.0f MAC/clk/SM)\n", mn ? "MN-major" : " K-major", cg, N, sw,
          copies, epi, per, cnt, mhz, tf, macs / per / (cg == 2 ? 2 : 1));
 }
 
@@ -212,6 +212,11 @@ int main() {
   cudaMemset(src, 0x14, (size_t)160 * 65536 + (1 << 20));
   cudaMalloc(&out, 256 * 4 * sizeof(unsigned long long));
   const int Ns[] = {64, 128, 192, 240, 256};
+  if (getenv("MMA_RATE_MN")) {                                      // the weight-gradient operand layout against the K-major one
+    for (int N : {64, 128, 208, 256}) { run(1, N, 64, 0, 0, src, out, 1); run(1, N, 128, 0, 0, src, out, 0); }
+    run(1, 208, 64, 1, 0, src, out, 1);
+    return 0;
+  }
   for (int cg = 1; cg <= 2; ++cg)
     for (int sw : {64, 128})
       for (int N : Ns) run(cg, N, sw, 0, 0, src, out);
