@@ -373,8 +373,30 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
       }
     }
     __syncwarp();
+  } else if (warp == G2_PROD_WARP + 1) {
+    // ------------------------------ h_prev prefetcher ------------------------------
+    // The gate math reads h_prev (fp32, from HBM: the previous step wrote 52 MB of it) one 16-unit chunk ahead -- about one
+    // barrier and one TMEM read of lead, far less than an HBM round trip under load, so every chunk of every tile used to
+    // wait for it.  This warp pulls the NEXT tile's 128 x 80 block (three 128-byte lines per row) into L2 while the current
+    // tile's MMAs run; it paces itself on the accumulator barriers (waiting on a phase consumes nothing).
+    if (has_h) {
+      int t = 0;
+      for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++t) {
+        if (t > 0) mbar_wait(smem_u32(&bar_tfull[(t - 1) & 1]), (uint32_t)((t - 1) >> 1) & 1u);   // tile t - 1 has left the tensor core
+        const int rb = i / G2_NT, jt = i - rb * G2_NT;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {                            // 128 rows x 3 lines = 384 = 12 per lane
+          const int idx = k * 32 + lane, row = idx / 3, part = idx - row * 3;
+          const int m = rb * BM + row;
+          if (m < m_end) {
+            const float* p = g.hprev + (size_t)m * GAC_E + jt * G2_NU + part * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+          }
+        }
+      }
+    }
   } else if (warp > G2_PROD_WARP && warp < G2_DRAIN_WARP0) {
-    // idle warps of the control warpgroup
+    // idle warp of the control warpgroup
   } else if (warp >= G2_DRAIN_WARP0) {
     // ------------------------------ drain warps: g = ae * kx_h out of TMEM between the two halves ------------------------------
     if (has_h) {
