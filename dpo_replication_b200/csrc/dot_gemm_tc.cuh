@@ -405,13 +405,18 @@ __device__ __forceinline__ void dot_gemm_body(const DotGemmArgs& g) {
         const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
         const uint64_t b_hi = make_desc(sa + 2 * A_TILE_BYTES), b_lo = make_desc(sa + 2 * A_TILE_BYTES + (uint32_t)bn * 128u);
         const int ksteps = F16 ? (live + 15) / 16 : (live + 7) / 8;
-        for (int j = 0; j < ksteps; ++j) {
+        if constexpr (F16) {
+          // one instruction group per K block (gemm_tc.cuh, mma_f16_dual_k)
+          const uint32_t acc0 = kb ? 1u : 0u;
+          if (ksteps == 4) mma_f16_dual_k<4>(tmem_d, corr, a_hi, a_lo, b_hi, b_lo, idesc, acc0);
+          else if (ksteps == 3) mma_f16_dual_k<3>(tmem_d, corr, a_hi, a_lo, b_hi, b_lo, idesc, acc0);
+          else if (ksteps == 2) mma_f16_dual_k<2>(tmem_d, corr, a_hi, a_lo, b_hi, b_lo, idesc, acc0);
+          else mma_f16_dual_k<1>(tmem_d, corr, a_hi, a_lo, b_hi, b_lo, idesc, acc0);
+        }
+        for (int j = 0; j < (F16 ? 0 : ksteps); ++j) {
           const uint64_t adv = (uint64_t)(j * 2);
           const uint32_t acc = (kb | j) ? 1u : 0u;
           if constexpr (F16) {
-            mma_f16(corr, a_lo + adv, b_hi + adv, idesc, acc);
-            mma_f16(corr, a_hi + adv, b_lo + adv, idesc, 1u);
-            mma_f16(tmem_d, a_hi + adv, b_hi + adv, idesc, acc);
           } else {
             mma_tf32(corr, a_lo + adv, b_hi + adv, idesc, acc);
             mma_tf32(corr, a_hi + adv, b_lo + adv, idesc, 1u);

@@ -103,6 +103,36 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Consecutive K steps of the dual-accumulator 3-pass product as ONE instruction group (see gru_step_v2.cuh, mma_f16_kblock:
+// the issuing lane, not the tensor core, limits a loop that rebuilds a predicate and the descriptor advances per
+// instruction).  Per K step: corr (+)= lo * hi, corr += hi * lo, main (+)= hi * hi.  acc0: accumulate flag of the first step's
+// first write to each accumulator.  K-major SWIZZLE_128B tiles advance by 32 bytes (2 >> 4 units) per 16-element step,
+// the MN-major weight-gradient tiles by 16 k-rows x 128 bytes (128 units).
+#define GAC_MMA_F16 "tcgen05.mma.cta_group::1.kind::f16 "
+#define GAC_DUAL_FIRST GAC_MMA_F16 "[%1], %3, %4, %6, q;\n" GAC_MMA_F16 "[%1], %2, %5, %6, p;\n" GAC_MMA_F16 "[%0], %2, %4, %6, q;\n"
+#define GAC_DUAL_NEXT(adv)                                                                                          \
+  "add.u64 ah, %2, " adv ";\n add.u64 al, %3, " adv ";\n add.u64 bh, %4, " adv ";\n add.u64 bl, %5, " adv ";\n" \
+  GAC_MMA_F16 "[%1], al, bh, %6, p;\n" GAC_MMA_F16 "[%1], ah, bl, %6, p;\n" GAC_MMA_F16 "[%0], ah, bh, %6, p;\n"
+#define GAC_DUAL_ASM(body)                                                                                                         \
+  asm volatile("{\n.reg .pred p, q;\n.reg .b64 ah, al, bh, bl;\nsetp.ne.b32 q, %7, 0;\nsetp.eq.b32 p, 1, 1;\n" body "}\n" ::"r"(d_main), \
+               "r"(d_corr), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc0)                                       \
+               : "memory")
+template <int KSTEPS>
+__device__ __forceinline__ void mma_f16_dual_k(uint32_t d_main, uint32_t d_corr, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                               uint32_t idesc, uint32_t acc0) {
+  static_assert(KSTEPS >= 1 && KSTEPS <= 4, "one to four K steps per group");
+  if constexpr (KSTEPS == 1) GAC_DUAL_ASM(GAC_DUAL_FIRST);
+  else if constexpr (KSTEPS == 2) GAC_DUAL_ASM(GAC_DUAL_FIRST GAC_DUAL_NEXT("2"));
+  else if constexpr (KSTEPS == 3) GAC_DUAL_ASM(GAC_DUAL_FIRST GAC_DUAL_NEXT("2") GAC_DUAL_NEXT("4"));
+  else GAC_DUAL_ASM(GAC_DUAL_FIRST GAC_DUAL_NEXT("2") GAC_DUAL_NEXT("4") GAC_DUAL_NEXT("6"));
+}
+template <int KSTEPS>
+__device__ __forceinline__ void mma_f16_dual_mn(uint32_t d_main, uint32_t d_corr, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                                uint32_t idesc, uint32_t acc0) {
+  static_assert(KSTEPS >= 1 && KSTEPS <= 2, "one or two K steps per 32-deep block");
+  if constexpr (KSTEPS == 1) GAC_DUAL_ASM(GAC_DUAL_FIRST);
+  else GAC_DUAL_ASM(GAC_DUAL_FIRST GAC_DUAL_NEXT("128"));
+}
 // x (already scaled) -> fp16 hi and fp16 lo' = (x - hi) * 2^11, two values per 32-bit word
 __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x0, x1);                   // one cvt.rn.f16x2.f32
@@ -587,14 +617,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const GemmArgs g, i
         const uint32_t sa = smem0 + (uint32_t)s * stage16, sb = sa + 2 * a_tile16;
         const uint64_t a_hi = make_desc_mn16(sa), a_lo = make_desc_mn16(sa + a_tile16);
         const uint64_t b_hi = make_desc_mn16(sb), b_lo = make_desc_mn16(sb + b_tile16);
-        const int ksteps = (live + 15) / 16;
-        for (int j = 0; j < ksteps; ++j) {
-          const uint64_t adv = (uint64_t)(j * 128);              // 16 k-rows x 128 bytes, >> 4
-          const uint32_t acc = (kb | j) ? 1u : 0u;
-          mma_f16(tmem_d + (uint32_t)bn, a_lo + adv, b_hi + adv, idesc, acc);
-          mma_f16(tmem_d + (uint32_t)bn, a_hi + adv, b_lo + adv, idesc, 1u);
-          mma_f16(tmem_d, a_hi + adv, b_hi + adv, idesc, acc);
-        }
+        // two K steps of 16 k-rows (one when at most 16 rows of the block are live); corr accumulator at +bn
+        if (live > 16) mma_f16_dual_mn<2>(tmem_d, tmem_d + (uint32_t)bn, a_hi, a_lo, b_hi, b_lo, idesc, kb ? 1u : 0u);
+        else mma_f16_dual_mn<1>(tmem_d, tmem_d + (uint32_t)bn, a_hi, a_lo, b_hi, b_lo, idesc, kb ? 1u : 0u);
         mma_commit(smem_u32(&bar_empty[s]));
       }
       mma_commit(smem_u32(&bar_accum));
