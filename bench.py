@@ -346,7 +346,10 @@ def run_gpu(args):
             ar = agent.arena
             actor = ar.net_slice(ar.target, "actor")
             states = torch.randn(B, S, device=dev)
-            sidx = torch.arange(B, device=dev, dtype=torch.int32).repeat_interleave(2 * K)
+            # the sampler's own row -> state map (sidx3_kernel): rows [0, P) state-major b * K + k (networks.py:464-467), rows
+            # [P, 2P) sample-major k * B + b (agent.py:186) -- the gather pattern of the per-state projection matters to the kernel
+            r_ = torch.arange(P, device=dev, dtype=torch.int32)
+            sidx = torch.cat([r_ // K, r_ % B]).contiguous()
             wa, ba = ar.view(ar.target, "actor.wa"), ar.view(ar.target, "actor.ba")
             ae = torch.nn.functional.leaky_relu(torch.cos(torch.rand(rows, 1, device=dev) * 2 - 1) @ wa[:1] + ba, 0.2)   # inside the actor's bound
             h = torch.tanh(torch.randn(rows, 400, device=dev))

@@ -503,8 +503,9 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
         if (sid < 0) return;
         const int ul = q * 16 + 4 * pj, u = jt * G2_NU + ul;
         const float* sx = g.sx + (size_t)sid * GAC_G + u;
-        sz = __ldcg(reinterpret_cast<const float4*>(sx)); sr = __ldcg(reinterpret_cast<const float4*>(sx + GAC_E));
-        sh = __ldcg(reinterpret_cast<const float4*>(sx + 2 * GAC_E));
+        // the per-state projection goes through L1: in the state-major half of the rows 64 consecutive rows share a state
+        sz = __ldg(reinterpret_cast<const float4*>(sx)); sr = __ldg(reinterpret_cast<const float4*>(sx + GAC_E));
+        sh = __ldg(reinterpret_cast<const float4*>(sx + 2 * GAC_E));
         if (has_h) {
           hp = __ldcg(reinterpret_cast<const float4*>(g.hprev + (size_t)m * GAC_E + u));
           xh = __ldcg(reinterpret_cast<const float4*>(xh_cta + ((size_t)b * BM + prow) * G2_NU + ul));
