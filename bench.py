@@ -261,7 +261,7 @@ def run_gpu(args):
 
     m_log = torch.zeros(args.steps + args.warmup + 1, device=dev)
 
-    use_graph = bool(args.graph) and world == 1
+    use_graph = bool(args.graph)             # world > 1: two graphs (grads, apply) around the NCCL all-reduce
     step_fn = agent.train_on_batch_graphed if use_graph else agent.train_on_batch
     launches_per_step = None
     if use_graph:                          # the context's launch counter only sees eager launches: count one eager step
@@ -420,7 +420,7 @@ def run_gpu(args):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": cfg,
                 "engine": "tcgen05: 3xFP16 (kind::f16) GRU step / heads / dgrads / large wgrads, 3xTF32 elsewhere" if args.engine == 0 else "SIMT fp32",
-                "actor": args.actor, "selected_rows_mean": m_mean, "candidate_rows": 2 * P, "graph": bool(args.graph),
+                "actor": args.actor, "selected_rows_mean": m_mean, "candidate_rows": 2 * P, "graph": use_graph,
                 "steps_per_s": 1e3 / ms_per_step,
                 "step_flops": {"algorithmic_gflop_min": f_min / 1e9, "as_written_gflop": f_ref / 1e9,
                                "achieved_tflops_min": tf,
@@ -661,7 +661,7 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ant", action="store_true", help="skip the Ant strong-scaling probe (ant_strong key)")
-    ap.add_argument("--graph", type=int, default=1, help="1 = replay the train step from one CUDA graph (single process; ranks > 1 run eagerly), 0 = eager launches")
+    ap.add_argument("--graph", type=int, default=1, help="1 = replay the train step from CUDA graphs (one graph; with ranks > 1 two graphs around the NCCL all-reduce), 0 = eager launches")
     ap.add_argument("--actor", default="AIQN", choices=["AIQN", "IQN"], help="AIQN = BASELINE.json's actor; IQN = the reference CLI default (main.py:78)")
     ap.add_argument("--sweep-chunks", type=int, default=0, help="walker2d sweep: number of 4096-state chunks (0 = all 1M states)")
     args = ap.parse_args()

@@ -107,13 +107,13 @@ class GACAgent:
         self.engine.step_apply(io, self._hp)
 
     def train_on_batch_graphed(self, batch: Dict, noise: Optional[Dict] = None):
-        """`train_on_batch` replayed from ONE CUDA graph (single process only; with a process group the eager path runs).
-        The step is ~280 kernel launches with no host synchronisation and nothing data-dependent on the host (the number of
-        selected rows stays on the device), so it captures as is: inputs are copied into static buffers, the reference's
-        seven tf.random draws are made in place outside the graph, and one cudaGraphLaunch replaces the launches -- what
-        matters for the small configs (Pendulum: the eager step is launch bound) and for the host thread's time."""
-        if gdist.world()[1] > 1:
-            return self.train_on_batch(batch, noise)
+        """`train_on_batch` replayed from CUDA graphs.  The step is ~290 kernel launches on two streams with no host
+        synchronisation and nothing data-dependent on the host (the number of selected rows stays on the device), so it
+        captures as is: inputs are copied into static buffers, the reference's seven tf.random draws are made in place
+        outside the graph, and one cudaGraphLaunch replaces the launches -- what matters for the small configs (Pendulum: the
+        eager step is launch bound) and for the host thread's time.  With a process group the step is TWO graphs,
+        `gac_step_grads` and `gac_step_apply`, with the NCCL all-reduce of the gradient arena between them."""
+        multi = gdist.world()[1] > 1
         dev = self.device
         if not hasattr(self, "_step_graph"):
             b0 = {k: torch.zeros_like(f32(batch[k], dev)) for k in ("s", "a", "r", "sp", "it")}
@@ -128,12 +128,17 @@ class GACAgent:
                 for t, sv in zip((self.arena.online, self.arena.target, self.arena.adam_m, self.arena.adam_v, self.arena.adam_t), state):
                     t.copy_(sv)               # the warm-up step must not count as a train step
             cap.synchronize()
-            graph = torch.cuda.CUDAGraph()
+            graph, graph2 = torch.cuda.CUDAGraph(), None
             with torch.cuda.graph(graph, stream=cap):
                 self.engine.step_grads(io, self._hp)
-                self.engine.step_apply(io, self._hp)
-            self._step_graph = (graph, b0, n0, io)
-        graph, b0, n0, _ = self._step_graph
+                if not multi:
+                    self.engine.step_apply(io, self._hp)
+            if multi:
+                graph2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph2, stream=cap):
+                    self.engine.step_apply(io, self._hp)
+            self._step_graph = (graph, graph2, b0, n0, io)
+        graph, graph2, b0, n0, _ = self._step_graph
         for k, t in b0.items():
             t.copy_(f32(batch[k], dev).reshape(t.shape), non_blocking=True)
         if noise is None:                     # the reference's tf.random sites, drawn in place
@@ -145,6 +150,9 @@ class GACAgent:
             for k, t in n0.items():
                 t.copy_(f32(noise[k], dev).reshape(t.shape), non_blocking=True)
         graph.replay()
+        if graph2 is not None:
+            gdist.allreduce_grads(self.arena.grad)
+            graph2.replay()
 
     def train_one_step(self):
         """agent.py:121-168."""

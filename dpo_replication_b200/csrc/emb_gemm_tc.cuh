@@ -26,6 +26,9 @@ struct EmbArgs {
   int rows;                      // M
   const int* dyn_rows; int seg_rows;   // optional device row count (rows come in segments of seg_rows, the first *dyn_rows live)
   const float* x; int incx;      // x_r = x[r * incx]; nullptr = 0 (first action dimension)
+  // step-major rows of the training pass (xseg > 0): row r = d * xseg + i reads x[i * incx + d + xoff], 0 when d + xoff < 0
+  // (the action embedding of step d sees the teacher's dimension d - 1, the noise embedding tau's dimension d)
+  int xseg, xoff;
   const unsigned char* wpk;      // emb_pack_kernel output: [hi | lo], 400 rows (n) x 128 bytes (64 k), K-major SWIZZLE_128B
   const EmbScales* sc;
   const float* W;                // (64, 400) fp32, for the fallback
@@ -34,7 +37,8 @@ struct EmbArgs {
   const float* mul; int ldmul;   // optional (rows, 400) Hadamard factor applied last
   float* C; int ldc;             // (rows, 400)
   // optional a16 image (gru_step_v2.cuh) of the result, scaled by *c16_scale: written INSTEAD of C while *c16_ok != 0
-  unsigned char* C16; const float* c16_scale; const int* c16_ok;
+  // (c16_also: next to C -- the training pass needs the fp32 embedding for its backward)
+  unsigned char* C16; const float* c16_scale; const int* c16_ok; int c16_also;
 };
 
 constexpr uint32_t EMB_W_TILE = (uint32_t)GAC_E * 128u;          // 51,200 B per hi / lo
@@ -70,10 +74,19 @@ __global__ void emb_pack_kernel(const float* __restrict__ W, const EmbScales* __
   *reinterpret_cast<uint4*>(out + EMB_W_TILE + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+__device__ __forceinline__ float emb_x(const EmbArgs& g, int m) {
+  if (!g.x) return 0.f;
+  if (g.xseg <= 0) return g.x[(size_t)m * g.incx];
+  const int d = m / g.xseg, i = m - d * g.xseg;
+  return d + g.xoff < 0 ? 0.f : g.x[(size_t)i * g.incx + d + g.xoff];
+}
+
 __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_w, bar_a, bar_acc;
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float bias_s[GAC_E];                  // the epilogue used to fetch its bias from L2 once per 16-column chunk, in the
+                                                                 // middle of a TMEM-read -> add -> store chain (profiles/r1c_dot_emb_summary.txt)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM;
   int m_end = g.rows;
@@ -99,7 +112,7 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
     for (int i = tid; i < BM * GAC_E; i += THREADS) {
       const int r = i / GAC_E, n = i - r * GAC_E, m = m0 + r;
       if (m >= m_end) continue;
-      const float xv = g.x ? g.x[(size_t)m * g.incx] : 0.f;
+      const float xv = emb_x(g, m);
       float acc = 0.f;
       for (int k = 0; k < GAC_NB; ++k) acc = fmaf(cosf(__fmul_rn(xv, c_ipi[k])), g.W[(size_t)k * GAC_E + n], acc);
       float v = acc + g.bias[n];
@@ -109,13 +122,13 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
         const __half hh = __float2half_rn(v * s16), ll = __float2half_rn(v * s16 - __half2float(hh));
         unsigned char* dst = g.C16 + a16_off(m, n & ~3) + (n & 3) * 2;
         *reinterpret_cast<__half*>(dst) = hh; *reinterpret_cast<__half*>(dst + G2_A_TILE) = ll;
-      } else {
-        g.C[(size_t)m * g.ldc + n] = v;
       }
+      if (!use16 || g.c16_also) g.C[(size_t)m * g.ldc + n] = v;
     }
     return;
   }
 
+  for (int i = tid; i < GAC_E; i += THREADS) bias_s[i] = g.bias[i];
   if (tid == 0) {
     mbar_init(smem_u32(&bar_w), 1); mbar_init(smem_u32(&bar_a), LOADER_WARPS); mbar_init(smem_u32(&bar_acc), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -141,7 +154,7 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
     // ---- the 128 x 64 cosine basis, straight into the A operand: thread = (row, half of the 64 k) ----
     {
       const int r = tid >> 1, kh = tid & 1, m = m0 + r;
-      const float xv = (m < m_end && g.x) ? g.x[(size_t)m * g.incx] : 0.f;
+      const float xv = m < m_end ? emb_x(g, m) : 0.f;
       const bool live = m < m_end;
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {            // 16-byte chunks (8 k each) of this thread's half row
@@ -183,7 +196,7 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
         const int ci = cbeg + hf + 2 * j;
         float v[16];
         tmem_ld16(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ci * 16), v);
-        const float4* b4 = reinterpret_cast<const float4*>(g.bias + ci * 16);
+        const float4* b4 = reinterpret_cast<const float4*>(bias_s + ci * 16);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 bb = b4[q];
@@ -219,9 +232,8 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
             unsigned char* dst = g.C16 + a16_off(m0 + row[u], col0 + col[u]);
             *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
             *reinterpret_cast<uint2*>(dst + G2_A_TILE) = make_uint2(l0, l1);
-          } else {
-            *reinterpret_cast<float4*>(g.C + (size_t)(m0 + row[u]) * g.ldc + col0 + col[u]) = x;
           }
+          if (!use16 || g.c16_also) *reinterpret_cast<float4*>(g.C + (size_t)(m0 + row[u]) * g.ldc + col0 + col[u]) = x;
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");             // the staging area is rewritten by the second half

@@ -119,7 +119,7 @@ struct gac_ctx {
   // 3xFP16 weight-gradient GEMMs of the actor (dW1, dU, dkx_a): scales per site, embedding bounds ([1] noise, [3] action)
   WgScales* wg_sc; unsigned int* wg_bound; bool wg_f16; unsigned char* wg_xpack; unsigned long long* dbg_buf;
   // cosine embeddings of the sampler as one kernel each (emb_gemm_tc.cuh): [0] action embedding, [1] noise embedding
-  unsigned char* emb_pack_buf[2]; tc::EmbScales* emb_sc[2]; bool emb_fused;
+  unsigned char* emb_pack_buf[4]; tc::EmbScales* emb_sc[4]; bool emb_fused, emb_train;   // [0], [1]: target actor (sampler); [2], [3]: online actor (training forward)
   // fused tails (400 -> 300 -> 1) of the twin critics in critic_eval
   unsigned char *cr_pack32[2], *cr_pack16[2]; tc::DotScales* cr_sc[2]; float* cr_part[2]; unsigned int* cr_bound;
   float* cr_sx0[2];                             // state half of the critics' first layer per unique state (n_states, 400)
@@ -259,7 +259,7 @@ size_t partition(gac_ctx* c, void* ws) {
     c->cr_sx0[i] = b.take<float>((size_t)c->NUs * GAC_H1);
   }
   c->cr_bound = b.take<unsigned int>(4);
-  for (int i = 0; i < 2; ++i) { c->emb_pack_buf[i] = b.take<unsigned char>(2 * tc::EMB_W_TILE); c->emb_sc[i] = b.take<tc::EmbScales>(1); }
+  for (int i = 0; i < 4; ++i) { c->emb_pack_buf[i] = b.take<unsigned char>(2 * tc::EMB_W_TILE); c->emb_sc[i] = b.take<tc::EmbScales>(1); }
   c->wg_sc = b.take<WgScales>(4); c->wg_bound = b.take<unsigned int>(4);
   c->wg_xpack = b.take<unsigned char>(wg_pack_x_bytes((long long)AM, GAC_E));
   c->dbg_buf = b.take<unsigned long long>(8 + 8 * 4096);   // per-CTA phase stamps of one GEMM launch (GAC_WGRAD_TIMELINE)
@@ -574,10 +574,10 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
     // cosine embedding (basis + Dense + activation [+ Hadamard]) as one kernel; x_r = x[r * A]
     auto embed = [&](int which, const float* x, const float* W, const float* bias, int act, float alpha, const float* mul, float* out) -> int {
       tc::EmbArgs e;
-      e.rows = rows; e.dyn_rows = nullptr; e.seg_rows = 0; e.x = x; e.incx = A; e.wpk = c->emb_pack_buf[which]; e.sc = c->emb_sc[which];
+      e.rows = rows; e.dyn_rows = nullptr; e.seg_rows = 0; e.x = x; e.incx = A; e.xseg = 0; e.xoff = 0; e.wpk = c->emb_pack_buf[which]; e.sc = c->emb_sc[which];
       e.W = W; e.bias = bias; e.act = act; e.alpha = alpha; e.mul = mul; e.ldmul = GAC_E; e.C = out; e.ldc = GAC_E;
       // the action embedding feeds only the GRU step: with the v2 kernel it is written as that kernel's A-operand image
-      e.C16 = (which == 0 && v2) ? c->ae_pk : nullptr; e.c16_scale = &c->g2_sc[0]->s_ae; e.c16_ok = &c->g2_sc[0]->ok;
+      e.C16 = (which == 0 && v2) ? c->ae_pk : nullptr; e.c16_scale = &c->g2_sc[0]->s_ae; e.c16_ok = &c->g2_sc[0]->ok; e.c16_also = 0;
       GAC_CUDA(launch_emb_gemm(e, st));
       c->launches++;
       return GAC_OK;
@@ -732,6 +732,16 @@ int td_fwd_bwd(gac_ctx* c, const float* fnn, int n_in, const float* x, const flo
 int actor_train_prep(gac_ctx* c, const float* actor) {
   cudaStream_t st = c->stream;
   const float* kxa_w = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
+  {
+    // both cosine embeddings of the training forward on the one-kernel path of the sampler (emb_gemm_tc.cuh)
+    static const bool emb_off = getenv("GAC_NO_FUSED_EMB") != nullptr;
+    c->emb_train = !emb_off && c->cfg.engine == 0 && c->Mc >= 128;
+    if (c->emb_train) {
+      GAC_CUDA(emb_pack(var(c, actor, 0, GAC_A_WA), c->emb_sc[2], c->emb_pack_buf[2], st));
+      GAC_CUDA(emb_pack(var(c, actor, 0, GAC_A_WN), c->emb_sc[3], c->emb_pack_buf[3], st));
+      c->launches += 6;
+    }
+  }
   c->pk[PK_O_WA] = pack_w(c, PK_O_WA, var(c, actor, 0, GAC_A_WA), GAC_E, GAC_NB, GAC_E, 0, c->Mc);
   c->gru_o = pack_gru(c, 1, actor, c->Mc);
   if (!c->gru_o) {
@@ -798,9 +808,26 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
   if (c->actor_prep_token != actor) GAC_TRY(actor_train_prep(c, actor));   // else: gac_step_grads issued it once for all chunks, on its side lane
   cos_basis_seq_kernel<<<(unsigned)cdiv64(AM * (GAC_NB / 4), 256), 256, 0, st>>>(teacher, taus, A, Mc, c->ca, c->cn, live);
   LAUNCHED(c, "cos_basis_seq");
-  GemmArgs g = gemm_args((int)AM, GAC_E, GAC_NB, c->ca, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->a_ae, GAC_E);
-  g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_WA]; g.Bpacked_bn = c->pk_bn[PK_O_WA];
-  GAC_TRY(run_gemm(c, g));
+  // cosine embedding of the step-major training rows as one kernel (basis in registers); the bases ca / cn above are kept for
+  // the embeddings' weight gradients only
+  auto embed_train = [&](int which, const float* x, int xoff, const float* W, const float* bias, int act, float alpha, float* out, unsigned char* out16) -> int {
+    tc::EmbArgs e;
+    e.rows = (int)AM; e.dyn_rows = live; e.seg_rows = Mc; e.x = x; e.incx = A; e.xseg = Mc; e.xoff = xoff; e.wpk = c->emb_pack_buf[which]; e.sc = c->emb_sc[which];
+    e.W = W; e.bias = bias; e.act = act; e.alpha = alpha; e.mul = nullptr; e.ldmul = 0; e.C = out; e.ldc = GAC_E;
+    e.C16 = out16; e.c16_scale = &c->g2_sc[1]->s_ae; e.c16_ok = &c->g2_sc[1]->ok; e.c16_also = 1;
+    GAC_CUDA(launch_emb_gemm(e, st));
+    c->launches++;
+    return GAC_OK;
+  };
+  const bool ae_image_by_emb = c->emb_train && c->gru_o && c->g2_on[1];
+  GemmArgs g;
+  if (c->emb_train) {
+    GAC_TRY(embed_train(2, teacher, -1, var(c, actor, 0, GAC_A_WA), var(c, actor, 0, GAC_A_BA), 1, 0.2f, c->a_ae, ae_image_by_emb ? c->a_ae_pk : nullptr));
+  } else {
+    g = gemm_args((int)AM, GAC_E, GAC_NB, c->ca, GAC_NB, var(c, actor, 0, GAC_A_WA), GAC_E, c->a_ae, GAC_E);
+    g.bias = var(c, actor, 0, GAC_A_BA); g.act = ACT_LRELU; g.alpha = 0.2f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_WA]; g.Bpacked_bn = c->pk_bn[PK_O_WA];
+    GAC_TRY(run_gemm(c, g));
+  }
   if (!c->gru_o) {
     g = gemm_args((int)AM, GAC_G, GAC_E, c->a_ae, GAC_E, kxa_w, GAC_G, c->mx, GAC_G);
     g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_KXA]; g.Bpacked_bn = c->pk_bn[PK_O_KXA];
@@ -811,7 +838,7 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
     if (c->gru_o) {
       const bool v2 = c->g2_on[1];
       if (v2) {
-        if (d == 0) {   // every step's action embedding -> a16 images in one pass (row blocks never straddle a step: Mc is a multiple of 128)
+        if (d == 0 && !ae_image_by_emb) {   // every step's action embedding -> a16 images in one pass (row blocks never straddle a step: Mc is a multiple of 128)
           GAC_CUDA(a16_pack(c->a_ae, GAC_E, AM, live, Mc, &c->g2_sc[1]->s_ae, c->a_ae_pk, st));
           c->launches++;
         }
@@ -833,9 +860,13 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
         c->hall + o4 + (size_t)Mc * GAC_E, c->zs + o4, c->rs + o4, c->cs + o4, c->mhh + o4, Mc, rv);
     LAUNCHED(c, "gru_gates_fwd");
   }
-  g = gemm_args((int)AM, GAC_E, GAC_NB, c->cn, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->ne, GAC_E);
-  g.bias = var(c, actor, 0, GAC_A_BN); g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_WN]; g.Bpacked_bn = c->pk_bn[PK_O_WN];
-  GAC_TRY(run_gemm(c, g));
+  if (c->emb_train) {
+    GAC_TRY(embed_train(3, taus, 0, var(c, actor, 0, GAC_A_WN), var(c, actor, 0, GAC_A_BN), 0, 0.f, c->ne, nullptr));
+  } else {
+    g = gemm_args((int)AM, GAC_E, GAC_NB, c->cn, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->ne, GAC_E);
+    g.bias = var(c, actor, 0, GAC_A_BN); g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_WN]; g.Bpacked_bn = c->pk_bn[PK_O_WN];
+    GAC_TRY(run_gemm(c, g));
+  }
   mul_kernel<<<(unsigned)cdiv64(AM * GAC_E / 4, 256), 256, 0, st>>>(c->ne, c->hall + (size_t)Mc * GAC_E, AM * GAC_E, Mc, live, c->au);
   LAUNCHED(c, "hadamard");
   if (c->dg_fused) {
