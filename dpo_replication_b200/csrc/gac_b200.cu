@@ -103,7 +103,7 @@ struct gac_ctx {
   float *ca, *cn, *a_ae, *mx, *dmh, *zs, *rs, *cs, *mhh, *hall, *ne, *au, *ay1, *dy1p, *du, *dne, *dhu, *dhc0, *dhc1, *dop;
   float *pred_c, *dpred_c;
   const int* bwd_sidx; const float* bwd_states; int bwd_nstates; const int* bwd_drows;  // saved by supervised_fwd
-  float *spart, *cpart, *fpart0, *fpart1;
+  float *spart, *cpart, *fpart0, *fpart1, *rc_tmp;
   // IQN actor scratch (actor_kind == GAC_ACTOR_IQN): sampling (Rs rows) and training (Mc rows)
   int iq_d, iq_D;
   float *iq_se_u, *iq_cos, *iq_ne, *iq_me;
@@ -224,7 +224,7 @@ size_t partition(gac_ctx* c, void* ws) {
     c->it_dne = b.take<float>(Mc * D); c->it_dse = b.take<float>(Mc * D); c->it_live = b.take<int>(4);
   }
   const size_t nrb = (AM + FB_ROWS - 1) / FB_ROWS + 1;
-  c->fpart0 = b.take<float>(nrb * GAC_G); c->fpart1 = b.take<float>(nrb * GAC_G);
+  c->fpart0 = b.take<float>(nrb * GAC_G); c->fpart1 = b.take<float>(nrb * GAC_G); c->rc_tmp = b.take<float>(64 * GAC_G);
   c->pack_bytes = tc_packed_bytes(GAC_E, GAC_G);
   if (tc_packed_bytes(GAC_G, GAC_E) > c->pack_bytes) c->pack_bytes = tc_packed_bytes(GAC_G, GAC_E);
   c->pack_bytes = (c->pack_bytes + 1023) & ~(size_t)1023;
@@ -428,6 +428,22 @@ int run_gemm(gac_ctx* c, GemmArgs g) {
   }
   if (tc) GAC_CUDA(launch_gemm_tc(g, st)); else GAC_CUDA(launch_gemm_simt(g, st));
   c->launches++;
+  return GAC_OK;
+}
+
+// dst[n] (+)= sum of nsplit partial rows of N columns, fixed order; many partial rows are folded in two stages (main lane only:
+// one scratch buffer)
+int run_reduce_cols(gac_ctx* c, const float* part, int nsplit, int N, float* dst, int accumulate) {
+  if (nsplit >= 512) {
+    const int slices = nsplit >= 2048 ? 32 : 16;
+    reduce_cols_kernel<<<dim3(cdiv(N, 32), slices), dim3(32, RC_LANES), 0, c->stream>>>(part, nsplit, N, c->rc_tmp, 0);
+    LAUNCHED(c, "reduce_cols_slices");
+    reduce_cols_kernel<<<cdiv(N, 32), dim3(32, RC_LANES), 0, c->stream>>>(c->rc_tmp, slices, N, dst, accumulate);
+    LAUNCHED(c, "reduce_cols");
+    return GAC_OK;
+  }
+  reduce_cols_kernel<<<cdiv(N, 32), dim3(32, RC_LANES), 0, c->stream>>>(part, nsplit, N, dst, accumulate);
+  LAUNCHED(c, "reduce_cols");
   return GAC_OK;
 }
 
@@ -973,10 +989,8 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   head_bwd_kernel<<<dim3(GAC_E / FB_COLS, nrb_all), FB_COLS, 0, st>>>(c->dop, var(c, actor, 0, GAC_A_W2), c->ay1, AM, rv, c->dy1p,
                                                                       c->fpart0, c->fpart1, amax_g ? amax_g + 2 : nullptr);
   LAUNCHED(c, "head_bwd");
-  reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart0, nrb_all, GAC_E, G(GAC_A_B1), acc);
-  LAUNCHED(c, "reduce_cols");
-  reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart1, nrb_all, GAC_E, G(GAC_A_W2), acc);
-  LAUNCHED(c, "reduce_cols");
+  GAC_TRY(run_reduce_cols(c, c->fpart0, nrb_all, GAC_E, G(GAC_A_B1), acc));
+  GAC_TRY(run_reduce_cols(c, c->fpart1, nrb_all, GAC_E, G(GAC_A_W2), acc));
   GAC_TRY(side_wgrad([&] { return wgrad(GAC_E, GAC_E, c->au, GAC_E, c->dy1p, GAC_E, AM, G(GAC_A_W1), true, 0, c->dg_amax + 2, c->wg_bound + 1); }));
   GemmArgs g = gemm_args((int)AM, GAC_E, GAC_E, c->dy1p, GAC_E, var(c, actor, 0, GAC_A_W1), GAC_E, c->du, GAC_E);
   if (c->dg_fused) {
@@ -988,8 +1002,7 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   hadamard_bwd_kernel<<<dim3(GAC_E / FB_COLS, nrb_all), FB_COLS, 0, st>>>(c->du, c->hall + (size_t)Mc * GAC_E, c->ne, AM, rv, c->dne,
                                                                           c->dhu, c->fpart0);
   LAUNCHED(c, "hadamard_bwd");
-  reduce_cols_kernel<<<cdiv(GAC_E, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart0, nrb_all, GAC_E, G(GAC_A_BN), acc);
-  LAUNCHED(c, "reduce_cols");
+  GAC_TRY(run_reduce_cols(c, c->fpart0, nrb_all, GAC_E, G(GAC_A_BN), acc));
   GAC_TRY(side_wgrad([&] { return wgrad(GAC_NB, GAC_E, c->cn, GAC_NB, c->dne, GAC_E, AM, G(GAC_A_WN), true); }));
   // recurrence, reverse time.  mx is overwritten with dmx step by step (it is dead after the forward gates)
   float* dh_next = nullptr; float* carry = c->dhc0;
@@ -1013,10 +1026,8 @@ int aiqn_bwd(gac_ctx* c, const float* actor, const float* dpred, float* grad, in
   }
   // time-parallel weight gradients of the GRU
   GAC_TRY(side_wgrad([&] { return wgrad(GAC_E, GAC_G, c->hall, GAC_E, c->dmh, GAC_G, AM, G(GAC_A_U), true, 1, c->dg_amax, nullptr, 1.f); }));
-  reduce_cols_kernel<<<cdiv(GAC_G, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart1, A * nrb_step, GAC_G, G(GAC_A_GB) + GAC_G, acc);
-  LAUNCHED(c, "reduce_cols");
-  reduce_cols_kernel<<<cdiv(GAC_G, 32), dim3(32, RC_LANES), 0, st>>>(c->fpart0, A * nrb_step, GAC_G, G(GAC_A_GB), acc);
-  LAUNCHED(c, "reduce_cols");
+  GAC_TRY(run_reduce_cols(c, c->fpart1, A * nrb_step, GAC_G, G(GAC_A_GB) + GAC_G, acc));
+  GAC_TRY(run_reduce_cols(c, c->fpart0, A * nrb_step, GAC_G, G(GAC_A_GB), acc));
   GAC_TRY(side_wgrad([&] { return wgrad(GAC_E, GAC_G, c->a_ae, GAC_E, c->mx, GAC_G, AM, G(GAC_A_KX) + (size_t)GAC_E * GAC_G, true, 2, c->dg_amax, c->wg_bound + 3); }));
   if (c->dg_fused) {
     GAC_TRY(dgrad(2, c->mx, GAC_G, GAC_G, AM, c->du, c->a_ae, 0.2f, 0, amax_g));

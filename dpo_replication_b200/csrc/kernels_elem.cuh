@@ -236,11 +236,18 @@ __global__ void __launch_bounds__(FB_COLS) hadamard_bwd_kernel(const float* __re
 
 // dst[n] = (accumulate ? dst[n] : 0) + sum_{s < nsplit} part[s*N + n], fixed order.
 // block (32, 32): 32 row lanes each sum every 32nd partial with 4-way ILP, then a fixed-order smem fold.
+// gridDim.y > 1: slice y sums the partials [y * per, (y + 1) * per) into dst + y * N (a scratch row per slice; a second launch
+// with gridDim.y == 1 folds the slices) -- with thousands of partial rows a one-slice launch keeps 13 SMs busy for 50 us.
 constexpr int RC_LANES = 32;
 __global__ void __launch_bounds__(32 * RC_LANES) reduce_cols_kernel(const float* __restrict__ part, int nsplit, int N,
                                                                    float* __restrict__ dst, int accumulate) {
   __shared__ float sh[RC_LANES][33];
   const int n = blockIdx.x * 32 + threadIdx.x, ly = threadIdx.y;
+  if (gridDim.y > 1) {
+    const int per = (nsplit + (int)gridDim.y - 1) / (int)gridDim.y, lo = (int)blockIdx.y * per;
+    part += (size_t)lo * N; dst += (size_t)blockIdx.y * N;
+    nsplit = max(0, min(per, nsplit - lo));
+  }
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (n < N) {
     int s = ly;
