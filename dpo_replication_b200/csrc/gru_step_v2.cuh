@@ -52,7 +52,7 @@ constexpr int G2_SS = 48;                                        // staging row 
 constexpr int G2_DRAIN_WARPS = 8;                                // two per TMEM lane quadrant, 40 columns each
 constexpr int G2_DS = 8;                                         // drain transposition row stride in floats; quad slot XOR (row >> 2) & 1
 constexpr int G2_DRAIN_SMEM = G2_DRAIN_WARPS * 32 * G2_DS * 4;   // 8 KB: one 32 x 8 block per drain warp
-constexpr int G2_SMEM = G2_STAGES * (int)G2_STAGE + BM * G2_SS * 4 + G2_DRAIN_SMEM + 2 * 3 * G2_NU * 4 + 1024;
+constexpr int G2_SMEM = G2_STAGES * (int)G2_STAGE + BM * G2_SS * 4 + G2_DRAIN_SMEM + 4 * 3 * G2_NU * 4 + 1024;
 // Warp roles, in warpgroups of four (setmaxnreg works per warpgroup): warps 0-15 epilogue (the gate math is a long dependent
 // chain per thread: with two warps per scheduler its latencies were exposed and a tile's epilogue took ~29k cycles against a
 // 23k-cycle main loop; four warps per scheduler hide them), warp 16 MMA issuer, warp 17 producer, warps 18-19 idle, warps 20-27
@@ -462,22 +462,22 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
   } else {
     // ------------------------------ epilogue: sixteen warps, overlapped with the next tile's main loop ------------------------------
     const int quarter = warp & 3, sub = warp >> 2;                 // TMEM lane quadrant; phase-1 column group (0 z, 1 r, 2 g, 3 none)
-    // Two independent half-tile groups: the eight warps of TMEM lane quadrants {0, 1} own rows 0..63, those of {2, 3} rows
-    // 64..127.  Each group runs its own phase 1 -> barrier -> phase 2 -> barrier cycle on its own staging rows and named
-    // barrier, so one group's TMEM reads overlap the other's gate math and global traffic instead of all sixteen warps
-    // idling at the same barrier.
-    const int grp = quarter >> 1, gw = sub * 2 + (warp & 1);       // group; warp index within the group (0..7)
-    const int gtid = gw * 32 + lane;                                // thread index within the group (0..255)
+    // Four independent quarter-tile groups: the four warps of a TMEM lane quadrant own its 32 rows.  Each group runs its own
+    // phase 1 -> barrier -> phase 2 -> barrier cycle on its own staging rows and named barrier, so while one group waits for
+    // its operand loads (the exposed latency of this epilogue: profiles/r2v_gru2_probe_bounds.txt) the others read TMEM or do
+    // gate math, instead of all sixteen warps stalling in step.
+    const int grp = quarter, gw = sub;                              // group; warp index within the group (0..3)
+    const int gtid = gw * 32 + lane;                                // thread index within the group (0..127)
     const uint32_t gbar = 1u + (uint32_t)grp;
     float* b1_s = b1_base + grp * (3 * G2_NU);
-#define G2_GROUP_SYNC() asm volatile("bar.sync %0, 256;" ::"r"(gbar) : "memory")
+#define G2_GROUP_SYNC() asm volatile("bar.sync %0, 128;" ::"r"(gbar) : "memory")
     const float inv_unit = g.sc->inv_unit, s_h = g.sc->s_h;
     auto tnh = [](float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); };
     // phase-2 ownership: ONE (row, unit quad) item per thread and chunk: row = 8 warp + (lane >> 2), quad = lane & 3.  128-bit
     // global accesses are coalesced per QUARTER warp: eight consecutive lanes = two rows x 64 contiguous bytes = four full
     // sectors.  (The first version put eight different rows into a quarter warp to make the staging reads conflict-free: every
     // global access then touched eight half-used sectors, and the operand loads alone cost 2.5k cycles per chunk.)
-    const int prow = 64 * grp + gw * 8 + (lane >> 2), pj = lane & 3;
+    const int prow = 32 * grp + gw * 8 + (lane >> 2), pj = lane & 3;
     const bool stamp = dbgp && tid == 0;
     long long e_wt = 0, e_wx = 0, e_p1 = 0, e_b1 = 0, e_p2 = 0, e_b2 = 0, e_ld = 0, ec = 0;
 #define G2_STAMP(acc) if (stamp) { const long long now = clock64(); acc += now - ec; ec = now; }
