@@ -597,8 +597,8 @@ def run_sweep(args):
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
     # every chunk produced its own actions (distinct states, distinct draws): no two chunk slices are equal, all are in (-1, 1)
-    chk = out_dev.view(-1, chunk_states * K * A)[:min(8, len(bounds) - 1)] if len(bounds) > 1 else out_dev.view(1, -1)
-    distinct = bool(len(bounds) < 2 or not torch.equal(chk[0], chk[1]))
+    n0 = chunk_states * K
+    distinct = bool(len(bounds) < 2 or not torch.equal(out_dev[:n0], out_dev[n0:2 * n0]))
     finite = bool(torch.isfinite(out_dev).all().item() and out_dev.abs().max().item() <= 1.0)
 
     # e2e: host -> device -> host, double buffered on a copy stream
