@@ -5,9 +5,11 @@
 // As two kernels (cosine basis, then a K = 64 GEMM with 208-wide tiles) this path spent 50-65 us per 32768 rows on 6 us of
 // tensor-core work: every row block was visited twice (two N tiles), the basis went through HBM, and the stores dominate.
 // Here a CTA owns 128 complete rows: the 128 x 64 basis is computed in registers (never stored), W (64 x 400, pre-split fp16
-// hi / lo, 100 KB) arrives by one bulk copy, 24 MMAs (4 K steps x 3 passes x 2 column halves) accumulate all 400 columns in
-// TMEM, and the epilogue applies bias / LeakyReLU / the Hadamard factor and writes the rows: the kernel runs at the speed
-// of its output stream.
+// hi / lo) arrives by bulk copy, 12 MMAs (4 K steps x 3 passes, one instruction group) accumulate the columns in TMEM, and the
+// epilogue applies bias / LeakyReLU / the Hadamard factor and writes the rows.
+// Round 2: a CTA owns 128 rows x ONE column half (208 or 192 of the 400): 87 KB of smem and 256 TMEM columns instead of 136 KB
+// and 512, so TWO CTAs share an SM and one's serial chain (weight copy -> basis -> MMAs -> TMEM reads -> stores) runs under the
+// other's; the basis is computed twice per row block, which costs less than an SM idling through every latency of the chain.
 //
 // Arithmetic: 3xFP16 with ONE accumulator.  |cos| <= 1 is scaled by 2^13 and W by a power of two from its scanned maximum
 // (emb_scale_kernel); lo = x' - hi is kept UNSCALED so that all three passes share a unit -- its absolute precision
@@ -43,7 +45,9 @@ struct EmbArgs {
 
 constexpr uint32_t EMB_W_TILE = (uint32_t)GAC_E * 128u;          // 51,200 B per hi / lo
 constexpr uint32_t EMB_A_TILE = (uint32_t)BM * 128u;             // 16 KB per hi / lo
-constexpr int EMB_SMEM = 2 * EMB_W_TILE + 2 * EMB_A_TILE + 1024;
+constexpr int EMB_N0 = 208, EMB_N1 = GAC_E - EMB_N0;              // the two column halves (multiples of 16)
+constexpr uint32_t EMB_WH_TILE = (uint32_t)EMB_N0 * 128u;        // smem of one half's hi (or lo) weight rows
+constexpr int EMB_SMEM = 2 * EMB_WH_TILE + 2 * EMB_A_TILE + 1024;   // 87,040 B: two CTAs per SM
 
 __global__ void emb_scale_kernel(EmbScales* __restrict__ sc) {
   const float mw = __uint_as_float(sc->amax[0]);
@@ -81,14 +85,15 @@ __device__ __forceinline__ float emb_x(const EmbArgs& g, int m) {
   return d + g.xoff < 0 ? 0.f : g.x[(size_t)i * g.incx + d + g.xoff];
 }
 
-__global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g) {
+__global__ void __launch_bounds__(THREADS, 2) emb_gemm_tc_kernel(const EmbArgs g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_w, bar_a, bar_acc;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_s[GAC_E];                  // the epilogue used to fetch its bias from L2 once per 16-column chunk, in the
                                                                  // middle of a TMEM-read -> add -> store chain (profiles/r1c_dot_emb_summary.txt)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * BM;
+  const int chalf = (int)blockIdx.x & 1, m0 = ((int)blockIdx.x >> 1) * BM;   // this CTA's column half and row block
+  const int n0 = chalf ? EMB_N0 : 0, ncols = chalf ? EMB_N1 : EMB_N0;
   int m_end = g.rows;
   if (g.dyn_rows) {
     const int nvalid = *g.dyn_rows;
@@ -105,12 +110,12 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
   const bool use16 = g.C16 != nullptr && *g.c16_ok != 0;
   const float s16 = use16 ? *g.c16_scale : 1.f;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sw_hi = smem0, sw_lo = smem0 + EMB_W_TILE, sa_hi = smem0 + 2 * EMB_W_TILE, sa_lo = sa_hi + EMB_A_TILE;
+  const uint32_t sw_hi = smem0, sw_lo = smem0 + EMB_WH_TILE, sa_hi = smem0 + 2 * EMB_WH_TILE, sa_lo = sa_hi + EMB_A_TILE;
 
   if (!ok) {
     // fallback: plain fp32 (one thread per (row, column) pair, strided); correct for any finite weights
-    for (int i = tid; i < BM * GAC_E; i += THREADS) {
-      const int r = i / GAC_E, n = i - r * GAC_E, m = m0 + r;
+    for (int i = tid; i < BM * ncols; i += THREADS) {
+      const int r = i / ncols, n = n0 + (i - r * ncols), m = m0 + r;
       if (m >= m_end) continue;
       const float xv = emb_x(g, m);
       float acc = 0.f;
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == LOADER_WARPS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -143,12 +148,15 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
   const uint32_t tmem_d = tmem_slot;
 
   if (warp < LOADER_WARPS) {
-    if (tid == 0) {   // the whole pre-split weight matrix: one bulk copy
-      const uint32_t bar = smem_u32(&bar_w), bytes = 2 * EMB_W_TILE;
+    if (tid == 0) {   // this half's rows of the pre-split weight image: hi rows and lo rows, one bulk copy each
+      const uint32_t bar = smem_u32(&bar_w), bytes = (uint32_t)ncols * 128u;
       // the barrier has one pending arrival: this thread's arrive carries the expected byte count
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sw_hi), "l"(g.wpk), "r"(bytes),
-                   "r"(bar)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sw_hi),
+                   "l"(g.wpk + (size_t)n0 * 128), "r"(bytes), "r"(bar)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sw_lo),
+                   "l"(g.wpk + EMB_W_TILE + (size_t)n0 * 128), "r"(bytes), "r"(bar)
                    : "memory");
     }
     // ---- the 128 x 64 cosine basis, straight into the A operand: thread = (row, half of the 64 k) ----
@@ -186,9 +194,10 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
     const int quarter = warp & 3, hf = warp >> 2;
     const float inv = g.sc->inv_unit, alpha = g.alpha;
     float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)));
+    const int nchunks = ncols / 16;                               // 13 or 12 sixteen-column chunks in this CTA's half
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      const int cbeg = half ? 13 : 0, cend = half ? 25 : 13;      // 16-column chunks of this half: 208 / 192 columns
+    for (int cbeg = 0; cbeg < nchunks; cbeg += 7) {               // staged through the idle operand smem at most 7 chunks (59 KB) at a time
+      const int cend = min(cbeg + 7, nchunks);
       const int wcols = (cend - cbeg) * 16, SS = wcols + 4;       // (wcols + 4) / 4 is odd: conflict-free 128-bit row stores
       const int nmine = (cend - cbeg + 1 - hf) / 2;               // chunks cbeg + hf, cbeg + hf + 2, ...
       float* srow = stg + (size_t)(quarter * 32 + lane) * SS;
@@ -196,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
         const int ci = cbeg + hf + 2 * j;
         float v[16];
         tmem_ld16(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ci * 16), v);
-        const float4* b4 = reinterpret_cast<const float4*>(bias_s + ci * 16);
+        const float4* b4 = reinterpret_cast<const float4*>(bias_s + n0 + ci * 16);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 bb = b4[q];
@@ -206,7 +215,7 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int n4 = wcols >> 2, total = BM * n4, col0 = cbeg * 16;
+      const int n4 = wcols >> 2, total = BM * n4, col0 = n0 + cbeg * 16;
       constexpr int IB = 4;
       for (int i0 = tid; i0 < total; i0 += IB * LOADER_WARPS * 32) {
         float4 ml[IB];
@@ -236,28 +245,15 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
           if (!use16 || g.c16_also) *reinterpret_cast<float4*>(g.C + (size_t)(m0 + row[u]) * g.ldc + col0 + col[u]) = x;
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");             // the staging area is rewritten by the second half
+      asm volatile("bar.sync 1, 256;" ::: "memory");             // the staging area is rewritten by the next sub-range
     }
   } else {
     if (lane == 0) {
       mbar_wait(smem_u32(&bar_w), 0);
       mbar_wait(smem_u32(&bar_a), 0);
       tc_fence_after();
-      const uint32_t id256 = make_idesc_f16(256), id144 = make_idesc_f16(GAC_E - 256);
-      const uint64_t a_hi = make_desc(sa_hi), a_lo = make_desc(sa_lo);
-      const uint64_t b_hi = make_desc(sw_hi), b_lo = make_desc(sw_lo);
-      const uint64_t nb2 = (uint64_t)((256u * 128u) >> 4);       // second column part: B rows 256..399
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {                              // K = 64 = 4 steps of 16
-        const uint64_t adv = (uint64_t)(j * 2);
-        const uint32_t acc = j ? 1u : 0u;
-        mma_f16(tmem_d, a_hi + adv, b_hi + adv, id256, acc);
-        mma_f16(tmem_d, a_lo + adv, b_hi + adv, id256, 1u);
-        mma_f16(tmem_d, a_hi + adv, b_lo + adv, id256, 1u);
-        mma_f16(tmem_d + 256u, a_hi + adv, b_hi + nb2 + adv, id144, acc);
-        mma_f16(tmem_d + 256u, a_lo + adv, b_hi + nb2 + adv, id144, 1u);
-        mma_f16(tmem_d + 256u, a_hi + adv, b_lo + nb2 + adv, id144, 1u);
-      }
+      // K = 64 = 4 steps of 16, three passes each, as one instruction group (gemm_tc.cuh)
+      mma_f16_single_k4(tmem_d, make_desc(sa_hi), make_desc(sa_lo), make_desc(sw_hi), make_desc(sw_lo), make_idesc_f16(ncols), 0u);
       mma_commit(smem_u32(&bar_acc));
     }
     __syncwarp();
@@ -265,7 +261,7 @@ __global__ void __launch_bounds__(THREADS, 1) emb_gemm_tc_kernel(const EmbArgs g
   tc_fence_before();
   __syncthreads();
   if (warp == LOADER_WARPS) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256) : "memory");
   }
 }
 
@@ -286,7 +282,7 @@ inline cudaError_t launch_emb_gemm(const tc::EmbArgs& g, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  tc::emb_gemm_tc_kernel<<<cdiv(g.rows, tc::BM), tc::THREADS, tc::EMB_SMEM, st>>>(g);
+  tc::emb_gemm_tc_kernel<<<2 * cdiv(g.rows, tc::BM), tc::THREADS, tc::EMB_SMEM, st>>>(g);
   return cudaGetLastError();
 }
 

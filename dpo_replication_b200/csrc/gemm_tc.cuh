@@ -126,6 +126,18 @@ __device__ __forceinline__ void mma_f16_dual_k(uint32_t d_main, uint32_t d_corr,
   else if constexpr (KSTEPS == 3) GAC_DUAL_ASM(GAC_DUAL_FIRST GAC_DUAL_NEXT("2") GAC_DUAL_NEXT("4"));
   else GAC_DUAL_ASM(GAC_DUAL_FIRST GAC_DUAL_NEXT("2") GAC_DUAL_NEXT("4") GAC_DUAL_NEXT("6"));
 }
+// single accumulator, unscaled lo (emb_gemm_tc.cuh): d (+)= hi * hi, d += lo * hi, d += hi * lo for four K steps of a K-major
+// SWIZZLE_128B block (K = 64)
+#define GAC_SGL_FIRST GAC_MMA_F16 "[%0], %1, %3, %5, q;\n" GAC_MMA_F16 "[%0], %2, %3, %5, p;\n" GAC_MMA_F16 "[%0], %1, %4, %5, p;\n"
+#define GAC_SGL_NEXT(adv)                                                                                          \
+  "add.u64 ah, %1, " adv ";\n add.u64 al, %2, " adv ";\n add.u64 bh, %3, " adv ";\n add.u64 bl, %4, " adv ";\n" \
+  GAC_MMA_F16 "[%0], ah, bh, %5, p;\n" GAC_MMA_F16 "[%0], al, bh, %5, p;\n" GAC_MMA_F16 "[%0], ah, bl, %5, p;\n"
+__device__ __forceinline__ void mma_f16_single_k4(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc, uint32_t acc0) {
+  asm volatile("{\n.reg .pred p, q;\n.reg .b64 ah, al, bh, bl;\nsetp.ne.b32 q, %6, 0;\nsetp.eq.b32 p, 1, 1;\n" GAC_SGL_FIRST GAC_SGL_NEXT("2")
+                   GAC_SGL_NEXT("4") GAC_SGL_NEXT("6") "}\n" ::"r"(d),
+               "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc0)
+               : "memory");
+}
 template <int KSTEPS>
 __device__ __forceinline__ void mma_f16_dual_mn(uint32_t d_main, uint32_t d_corr, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
                                                 uint32_t idesc, uint32_t acc0) {
