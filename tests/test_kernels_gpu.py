@@ -189,7 +189,7 @@ def test_gru_step_operand_scales(gb, s_kx, s_u, s_wa):
 
 # the arithmetic variant is chosen once per process from the environment: re-run the actor tests in a child process
 @pytest.mark.parametrize("env", ["GAC_GRU_V1", "GAC_GRU_TF32", "GAC_NO_FUSED_GRU", "GAC_NO_FUSED_HEAD", "GAC_HEAD_TF32", "GAC_NO_F16_DGRAD", "GAC_NO_F16_WGRAD", "GAC_NO_FUSED_EMB", "GAC_NO_FUSED_CRITIC", "GAC_DGRAD_TF32",
-                                 "GAC_NO_SMALL_SPLITK"])
+                                 "GAC_NO_SMALL_SPLITK", "GAC_GRU_PAIR", "GAC_NO_SIDE_STREAM"])
 def test_actor_paths_other_variants(env):
     import os
     import subprocess
