@@ -38,6 +38,8 @@ struct EmbArgs {
   int act; float alpha;          // 1: LeakyReLU(alpha)
   const float* mul; int ldmul;   // optional (rows, 400) Hadamard factor applied last
   float* C; int ldc;             // (rows, 400)
+  float* C2;                     // optional (with mul): C keeps the embedding itself and C2 (same ldc) takes the Hadamard product
+                                 // (the training pass needs both: networks.py:219-221 and its backward)
   // optional a16 image (gru_step_v2.cuh) of the result, scaled by *c16_scale: written INSTEAD of C while *c16_ok != 0
   // (c16_also: next to C -- the training pass needs the fp32 embedding for its backward)
   unsigned char* C16; const float* c16_scale; const int* c16_ok; int c16_also;
@@ -122,7 +124,10 @@ __global__ void __launch_bounds__(THREADS, 2) emb_gemm_tc_kernel(const EmbArgs g
       for (int k = 0; k < GAC_NB; ++k) acc = fmaf(cosf(__fmul_rn(xv, c_ipi[k])), g.W[(size_t)k * GAC_E + n], acc);
       float v = acc + g.bias[n];
       if (g.act) v = v > 0.f ? v : g.alpha * v;
-      if (g.mul) v *= g.mul[(size_t)m * g.ldmul + n];
+      if (g.mul) {
+        const float v2 = v * g.mul[(size_t)m * g.ldmul + n];
+        if (g.C2) g.C2[(size_t)m * g.ldc + n] = v2; else v = v2;
+      }
       if (use16) {
         const __half hh = __float2half_rn(v * s16), ll = __float2half_rn(v * s16 - __half2float(hh));
         unsigned char* dst = g.C16 + a16_off(m, n & ~3) + (n & 3) * 2;
@@ -233,7 +238,10 @@ __global__ void __launch_bounds__(THREADS, 2) emb_gemm_tc_kernel(const EmbArgs g
         for (int u = 0; u < IB; ++u) {
           if (!okk[u]) continue;
           float4 x = *reinterpret_cast<const float4*>(stg + (size_t)row[u] * SS + col[u]);
-          if (g.mul) { x.x *= ml[u].x; x.y *= ml[u].y; x.z *= ml[u].z; x.w *= ml[u].w; }
+          if (g.mul) {
+            const float4 x2 = make_float4(x.x * ml[u].x, x.y * ml[u].y, x.z * ml[u].z, x.w * ml[u].w);
+            if (g.C2) *reinterpret_cast<float4*>(g.C2 + (size_t)(m0 + row[u]) * g.ldc + col0 + col[u]) = x2; else x = x2;
+          }
           if (use16) {                                             // the GRU step's A operand: split, scaled, swizzled here
             uint32_t h0, l0, h1, l1;
             split_f16x2_u(x.x * s16, x.y * s16, h0, l0);

@@ -591,7 +591,7 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
     auto embed = [&](int which, const float* x, const float* W, const float* bias, int act, float alpha, const float* mul, float* out) -> int {
       tc::EmbArgs e;
       e.rows = rows; e.dyn_rows = nullptr; e.seg_rows = 0; e.x = x; e.incx = A; e.xseg = 0; e.xoff = 0; e.wpk = c->emb_pack_buf[which]; e.sc = c->emb_sc[which];
-      e.W = W; e.bias = bias; e.act = act; e.alpha = alpha; e.mul = mul; e.ldmul = GAC_E; e.C = out; e.ldc = GAC_E;
+      e.W = W; e.bias = bias; e.act = act; e.alpha = alpha; e.mul = mul; e.ldmul = GAC_E; e.C = out; e.ldc = GAC_E; e.C2 = nullptr;
       // the action embedding feeds only the GRU step: with the v2 kernel it is written as that kernel's A-operand image
       e.C16 = (which == 0 && v2) ? c->ae_pk : nullptr; e.c16_scale = &c->g2_sc[0]->s_ae; e.c16_ok = &c->g2_sc[0]->ok; e.c16_also = 0;
       GAC_CUDA(launch_emb_gemm(e, st));
@@ -826,10 +826,11 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
   LAUNCHED(c, "cos_basis_seq");
   // cosine embedding of the step-major training rows as one kernel (basis in registers); the bases ca / cn above are kept for
   // the embeddings' weight gradients only
-  auto embed_train = [&](int which, const float* x, int xoff, const float* W, const float* bias, int act, float alpha, float* out, unsigned char* out16) -> int {
+  auto embed_train = [&](int which, const float* x, int xoff, const float* W, const float* bias, int act, float alpha, float* out, unsigned char* out16,
+                         const float* mul = nullptr, float* out2 = nullptr) -> int {
     tc::EmbArgs e;
     e.rows = (int)AM; e.dyn_rows = live; e.seg_rows = Mc; e.x = x; e.incx = A; e.xseg = Mc; e.xoff = xoff; e.wpk = c->emb_pack_buf[which]; e.sc = c->emb_sc[which];
-    e.W = W; e.bias = bias; e.act = act; e.alpha = alpha; e.mul = nullptr; e.ldmul = 0; e.C = out; e.ldc = GAC_E;
+    e.W = W; e.bias = bias; e.act = act; e.alpha = alpha; e.mul = mul; e.ldmul = GAC_E; e.C = out; e.ldc = GAC_E; e.C2 = out2;
     e.C16 = out16; e.c16_scale = &c->g2_sc[1]->s_ae; e.c16_ok = &c->g2_sc[1]->ok; e.c16_also = 1;
     GAC_CUDA(launch_emb_gemm(e, st));
     c->launches++;
@@ -877,14 +878,17 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
     LAUNCHED(c, "gru_gates_fwd");
   }
   if (c->emb_train) {
-    GAC_TRY(embed_train(3, taus, 0, var(c, actor, 0, GAC_A_WN), var(c, actor, 0, GAC_A_BN), 0, 0.f, c->ne, nullptr));
+    // noise embedding and its Hadamard product with the GRU states of every step in one pass (ne is kept for the backward)
+    GAC_TRY(embed_train(3, taus, 0, var(c, actor, 0, GAC_A_WN), var(c, actor, 0, GAC_A_BN), 0, 0.f, c->ne, nullptr, c->hall + (size_t)Mc * GAC_E, c->au));
   } else {
     g = gemm_args((int)AM, GAC_E, GAC_NB, c->cn, GAC_NB, var(c, actor, 0, GAC_A_WN), GAC_E, c->ne, GAC_E);
     g.bias = var(c, actor, 0, GAC_A_BN); g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_WN]; g.Bpacked_bn = c->pk_bn[PK_O_WN];
     GAC_TRY(run_gemm(c, g));
   }
-  mul_kernel<<<(unsigned)cdiv64(AM * GAC_E / 4, 256), 256, 0, st>>>(c->ne, c->hall + (size_t)Mc * GAC_E, AM * GAC_E, Mc, live, c->au);
-  LAUNCHED(c, "hadamard");
+  if (!c->emb_train) {
+    mul_kernel<<<(unsigned)cdiv64(AM * GAC_E / 4, 256), 256, 0, st>>>(c->ne, c->hall + (size_t)Mc * GAC_E, AM * GAC_E, Mc, live, c->au);
+    LAUNCHED(c, "hadamard");
+  }
   if (c->dg_fused) {
     tc::DotGemmArgs q;
     q.rows = (int)AM; q.dyn_rows = live; q.seg_rows = Mc; q.A = c->au; q.lda = GAC_E; q.K = GAC_E; q.N = GAC_E; q.bn = HEAD_BN; q.ntiles = HEAD_NT;
@@ -898,12 +902,9 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
     g.bias = var(c, actor, 0, GAC_A_B1); g.act = ACT_LRELU; g.alpha = 0.01f; g.dyn_rows = live; g.seg_rows = Mc; g.Bpacked = c->pk[PK_O_W1]; g.Bpacked_bn = c->pk_bn[PK_O_W1];
     GAC_TRY(run_gemm(c, g));
   }
-  for (int d = 0; d < A; ++d) {
-    rowdot_kernel<<<cdiv(Mc * 32, 256), 256, 0, st>>>(c->ay1 + (size_t)d * Mc * GAC_E, GAC_E, var(c, actor, 0, GAC_A_W2),
-                                                     var(c, actor, 0, GAC_A_B2), nullptr, nullptr, nullptr, GAC_E, Mc, 1,
-                                                     c->pred_c + d, A, pred ? pred + d : nullptr, A, rv);
-    LAUNCHED(c, "rowdot_tanh");
-  }
+  rowdot_steps_kernel<<<dim3(cdiv(Mc * 32, 256), A), 256, 0, st>>>(c->ay1, GAC_E, var(c, actor, 0, GAC_A_W2), var(c, actor, 0, GAC_A_B2), GAC_E, Mc, A,
+                                                                  c->pred_c, pred, rv);
+  LAUNCHED(c, "rowdot_tanh");
   return GAC_OK;
 }
 

@@ -291,6 +291,22 @@ __global__ void rowdot_kernel(const float* __restrict__ x, int ldx, const float*
   }
 }
 
+// the training pass's head output for every step in one launch: blockIdx.y = step d, rows step-major (d * seg + i);
+// out[i * A + d] = tanh(dot(x[d * seg + i], w) + b) (and the same to out2 when given)
+__global__ void rowdot_steps_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b, int n, int seg,
+                                    int A, float* __restrict__ out, float* __restrict__ out2, RowValid rv) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, d = blockIdx.y;
+  if (row >= seg || !rv(row)) return;
+  const float* xr = x + ((size_t)d * seg + row) * ldx;
+  float s = 0.f;
+  for (int j = lane; j < n; j += 32) s = fmaf(xr[j], w[j], s);
+  s = tanhf(warp_sum(s) + b[0]);
+  if (lane == 0) {
+    out[(size_t)row * A + d] = s;
+    if (out2) out2[(size_t)row * A + d] = s;
+  }
+}
+
 // ---- consumer of dot_gemm_tc_kernel's tile partials for the actor head (networks.py:221): a = tanh(sum_t part[r][t] + b2),
 // written to actions[r*inc_out]; when cosb != nullptr also the cosine basis of a (the next dimension's action
 // embedding input, networks.py:44-47 / 208-210), 64 threads per row. ----
