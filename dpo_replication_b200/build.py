@@ -24,16 +24,31 @@ def up_to_date() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile when the library is missing or older than a source.  Safe under concurrent callers (one process per GPU all
+    call this first): an exclusive file lock serialises them, the late ones find the library up to date, and the compiler
+    writes to a temporary name that is renamed into place, so no process ever dlopens a half-written file."""
     if not force and up_to_date():
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", OUT]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libgac_b200.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
-    return OUT
+    import fcntl
+    with open(OUT + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and up_to_date():
+                return OUT
+            tmp = f"{OUT}.tmp.{os.getpid()}"
+            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", tmp]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building libgac_b200.so")
+            if verbose:
+                sys.stderr.write(r.stderr)
+            os.replace(tmp, OUT)
+            return OUT
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":

@@ -612,7 +612,8 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
     }
     if (c->gru_t) {
       // both projections + gates in one kernel: mxa / mh never touch HBM
-      if (v2) GAC_TRY(run_gru_step_v2(c, 0, actor, c->sx_u, sidx, c->ae_pk, pk_prev, d ? hprev : nullptr, hcur, pk_cur, rows, nullptr));
+      // (the last dimension's state feeds no further GRU step: no operand image of it)
+      if (v2) GAC_TRY(run_gru_step_v2(c, 0, actor, c->sx_u, sidx, c->ae_pk, pk_prev, d ? hprev : nullptr, hcur, d + 1 < A ? pk_cur : nullptr, rows, nullptr));
       GAC_TRY(run_gru_step(c, 0, actor, c->sx_u, sidx, c->ae, d ? hprev : nullptr, hcur, rows, nullptr, nullptr, nullptr, nullptr, nullptr, true,
                            v2 ? &c->g2_sc[0]->ok : nullptr));
     } else {
