@@ -388,6 +388,16 @@ int run_gemm(gac_ctx* c, GemmArgs g) {
     // shrink ~2.0e-9 per reduction element, tools/gemm_accuracy.py), so bound the chain that one
     // TMEM accumulator sees to 4096 reduction rows (<= 8e-6); the partials are summed in fp32 (round to nearest)
     if (tc && splits < cdiv(g.K, 4096)) splits = cdiv(g.K, 4096);
+    static const bool old_splits = getenv("GAC_WG_OLD_SPLITS") != nullptr;   // A/B switch
+    if (tc && g.valid_on_k && !old_splits) {
+      // Whole waves: tiles x splits a multiple of the SM count (the kernel keeps one CTA per SM), e.g. 20 tiles x 37 splits =
+      // 5 x 148 instead of 20 x 48 = 6.49 waves, with fewer partial tiles to write and fold.  Dead rows are skipped, so a split
+      // rarely sees the 4096 rows the rule above allows; when every row is live the chain grows to <= 6144 rows (bias <= 1.2e-5).
+      static int nsm = 0;
+      if (!nsm) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148; }
+      for (int s2 = cdiv(g.K, 6144); s2 <= c->max_splits && s2 <= splits; ++s2)
+        if (s2 >= 2 && (tiles * s2) % nsm == 0) { splits = s2; break; }
+    }
     if (splits > c->max_splits) splits = c->max_splits;
     if (splits > g.K / 512) splits = g.K / 512;
     if ((size_t)g.M * g.N > (size_t)GAC_E * GAC_G) splits = 1;
