@@ -97,7 +97,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
