@@ -194,7 +194,10 @@ int gac_td_fwd_bwd(gac_ctx_t* ctx, const float* fnn, int32_t n_in, const float* 
 /* ---- The whole GACAgent.train_one_step (agent.py:121-168), split at the data-parallel
  * exchange point: gac_step_grads fills `grad` (all four nets; the actor slice un-normalised)
  * and stats; the caller all-reduces (SUM) grad[0 .. n_total+GAC_STEP_NSTATS) across ranks when
- * world_size > 1; gac_step_apply normalises the actor gradient, runs Adam x4 and Polyak x3. */
+ * world_size > 1; gac_step_apply normalises the actor gradient, runs Adam x4 and Polyak x3.
+ * gac_step_grads runs part of its work (weight preparation, the TD updates, the actor's weight gradients) on a side stream
+ * owned by the context, forked from and joined back into the context's stream by events: for the caller it stays one
+ * stream-ordered call, and a stream capture of the context's stream captures both lanes (env GAC_NO_SIDE_STREAM=1: one lane). */
 #define GAC_STEP_NSTATS 8
 /* stats[] layout (floats appended to the grad arena at offset n_total):
  * 0 loss_fnn1, 1 loss_fnn2, 2 loss_value, 3 actor loss (un-normalised sum), 4 sum_adv, 5 M,
