@@ -961,8 +961,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pair_kernel(const GemmAr
       // leader: one lane issues the pair's MMAs (M = 256 across the two CTAs)
       // each K step = 2 instructions of N = 2*bn against the CTA pair's contiguous [B_hi | B_lo] rows:
       //   A_hi x [B_hi | B_lo] -> [main | corr],   A_lo x [B_hi | B_lo] -> [main += lo*hi | corr += lo*lo (2^-24, harmless)]
-      // the per-instruction cost of tcgen05.mma is ~145 cycles almost independent of N (measured), so two wide
-      // instructions beat three narrow ones by 1.46x; main sees 2 truncating adds per K step instead of 1.
+      // (round 1 measured ~145 cycles per instruction "almost independent of N" here and chose two wide instructions over
+      // three narrow ones; round 2's tools/mma_issue.cu shows that figure was this lane's own per-instruction overhead --
+      // the tensor core needs N / 2 cycles -- see mma_f16_dual_k for the grouped form the default kernels now use.)
+      // main sees 2 truncating adds per K step instead of 1.
       const uint32_t idesc = make_idesc2(2 * bn);
       int gk = 0, ti = 0;
       for (int item = cluster_id; item < nitems; item += nclusters) {

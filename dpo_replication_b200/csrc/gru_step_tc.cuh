@@ -22,8 +22,9 @@
 //   3xTF32 (F16 = false): hi = rna_tf32(x), lo = x - hi, kind::tf32, 8 K-elements per MMA.
 //   3xFP16 (F16 = true) : x' = x * 2^e, hi = rn_fp16(x'), lo' = rn_fp16((x' - hi) * 2^11), kind::f16, 16 K-elements
 //       per MMA -- the same 11 + 11 significand bits and the same three passes, but HALF the tcgen05.mma
-//       instructions, and the kernel is bound by MMA issue (measured ~128 cycles per M = 128 instruction whatever
-//       N and kind: 26 K-blocks x 12 MMAs = 40k of a tile's 52k cycles).  fp16 has 5 exponent bits, so every
+//       instructions, and this kernel's loop is bound by MMA issue (round 1 measured ~128 cycles per M = 128 instruction
+//       "whatever N and kind": 26 K-blocks x 12 MMAs = 40k of a tile's 52k cycles; round 2 found that to be the issuing
+//       lane's per-instruction overhead, not the tensor core's N / 2 cycles -- gru_step_v2.cuh).  fp16 has 5 exponent bits, so every
 //       operand needs a known magnitude bound; this kernel is the one place where all four have one WITHOUT any
 //       activation statistics: |h_prev| < 1 (GRU state), |ae| <= max_j (sum_i |wa_ij| + |ba_j|) (LeakyReLU of a
 //       cosine embedding, |cos| <= 1), and the two weight matrices are scanned when they are packed.

@@ -19,17 +19,23 @@
 //     ae * kx_h while the action-embedding half runs, is copied out by four drain warps the moment that half retires
 //     (TMEM -> registers -> an L2-resident scratch row), and is then OVERWRITTEN by h_prev * U_h during the recurrent half
 //     (reset_after needs the two parts of the candidate gate apart).  A tile is therefore 80 units x 3 = 240 columns:
-//     every MMA is N = 240 (an M = 128 tcgen05.mma takes ~128 cycles whatever N <= 256 -- one A row per clock), 400 units
-//     are exactly five tiles (no remainder tile), and TMEM holds TWO tiles, so the MMA lane fills one while the eight
-//     epilogue warps drain the other.  7 x 150 -> 5 x 150 MMAs per 128-row block.
+//     every MMA is N = 240 (the tensor core needs N / 2 cycles per M = 128 kind::f16 instruction: 240 of the 256 columns it
+//     could take), 400 units are exactly five tiles (no remainder tile), and TMEM holds TWO tiles, so the MMA lane fills one
+//     while the epilogue warps work on the other.  7 x 150 -> 5 x 150 MMAs per 128-row block.
 //   * 32-deep K blocks (64-byte rows): a stage is 46 KB, four stages fit beside the epilogue's staging buffer, so three
 //     stages of operand data are in flight while one is consumed -- bulk-copy latency is off the critical path.
 //   * persistent grid (one CTA per SM), static round-robin over (row block, unit tile) items: consecutive CTAs share a row
 //     block (its A tiles are L2-hot).  (Tried and dropped: cp.async.bulk.prefetch.L2 of the next item's row block one tile
 //     ahead -- 180.5 vs 176.8 us, profiles/r2e_gru2_prefetch_ab.txt: the operand stream is not waiting on HBM latency.)
-//   * what bounds it now: tcgen05.mma issue.  An M = 128 kind::f16 instruction takes ~168 SM cycles whatever N <= 256 and
-//     whatever the cta_group (tools/mma_rate.cu, profiles/r2b_mma_rate.txt), a tile is 150 of them = 25.2k cycles, and the
-//     MMA lane's timeline shows 28-29k per tile (profiles/r2b_gru2_timeline.txt): ~88 % of its life is instruction issue.
+//   * MMA issue: ONE instruction group per K block (mma_f16_kblock below).  Written instruction by instruction -- a predicate
+//     and four 64-bit descriptor computations each -- the issuing lane needed ~168 cycles per MMA whatever N <= 256 and
+//     whatever the cta_group (tools/mma_rate.cu, profiles/r2b_mma_rate.txt); the tensor core itself needs 120 at N = 240
+//     (tools/mma_issue.cu, profiles/r2k_mma_issue.txt).
+//   * what bounds it now (profiles/r2_final_gru2_timeline.txt, r2v_gru2_probe_bounds.txt): 18k of a tile's ~25k cycles are
+//     MMA issue; the rest is the lane waiting for the epilogue to free an accumulator (its prefetched operand loads land
+//     late behind the operand stream: 46 KB per 720 cycles = 64 B/clk per SM from L2) and for operands.  Removing those
+//     stalls with dedicated TMEM reader warps cut the cycles and LOST time: the pool's B200s are power capped and the SM clock
+//     fell with the stalls (profiles/r2z_gru2_reader_warps_probe.txt).
 #pragma once
 #include "gru_step_tc.cuh"
 
@@ -55,8 +61,9 @@ constexpr int G2_DRAIN_SMEM = G2_DRAIN_WARPS * 32 * G2_DS * 4;   // 8 KB: one 32
 constexpr int G2_SMEM = G2_STAGES * (int)G2_STAGE + BM * G2_SS * 4 + G2_DRAIN_SMEM + 4 * 3 * G2_NU * 4 + 1024;
 // Warp roles, in warpgroups of four (setmaxnreg works per warpgroup): warps 0-15 epilogue (the gate math is a long dependent
 // chain per thread: with two warps per scheduler its latencies were exposed and a tile's epilogue took ~29k cycles against a
-// 23k-cycle main loop; four warps per scheduler hide them), warp 16 MMA issuer, warp 17 producer, warps 18-19 idle, warps 20-27
-// drain (two per TMEM lane quadrant, so that a row's 80 columns are read in one batch of loads within the register budget).
+// 23k-cycle main loop; four warps per scheduler hide them), warp 16 MMA issuer, warp 17 producer, warp 18 h_prev prefetcher,
+// warp 19 idle, warps 20-27 drain (two per TMEM lane quadrant, so that a row's 80 columns are read in one batch of loads within
+// the register budget).
 constexpr int G2_EPI_WARPS = 16;
 constexpr int G2_MMA_WARP = G2_EPI_WARPS, G2_PROD_WARP = G2_EPI_WARPS + 1;
 constexpr int G2_DRAIN_WARP0 = G2_EPI_WARPS + 4;                 // warps 20..23 (lane quadrant = warp & 3)
