@@ -298,10 +298,28 @@ inline bool gru3_enabled() {
   return pair;
 }
 // weights of the fused GRU step (gru_step_tc.cuh); nullptr = not applicable, use the GEMM + gates kernels
-const unsigned char* pack_gru(gac_ctx* c, int which, const float* actor, int rows) {
+// need_v1: the caller also runs round 1's kernel on these weights (gac_gru_step with operands it cannot bound); the sampler
+// and the training forward only need it when the v2 kernel is switched off
+const unsigned char* pack_gru(gac_ctx* c, int which, const float* actor, int rows, bool need_v1 = false) {
   static const bool off = getenv("GAC_NO_FUSED_GRU") != nullptr;
   static const bool tf32_only = getenv("GAC_GRU_TF32") != nullptr;   // A/B switch: skip the 3xFP16 variant
+  static const bool v1_env = getenv("GAC_GRU_V1") != nullptr;
   if (off || c->cfg.engine != 0 || rows < 64) return nullptr;
+  if (!v1_env && !tf32_only && !need_v1) {
+    // the v2 kernel alone (it has its own fp32 path for weights that admit no fp16 scaling)
+    c->g2_on[which] = gru2_pack(var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, var(c, actor, 0, GAC_A_U), var(c, actor, 0, GAC_A_WA),
+                                var(c, actor, 0, GAC_A_BA), c->g2_wpk[which], c->g2_sc[which], c->stream) == cudaSuccess;
+    if (c->g2_on[which]) {
+      c->launches += 3;
+      if (gru3_enabled()) {
+        if (gru3_pack(var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, var(c, actor, 0, GAC_A_U), c->g3_wpk[which], c->g2_sc[which], c->stream) != cudaSuccess)
+          c->g2_on[which] = false;
+        else
+          c->launches++;
+      }
+    }
+    if (c->g2_on[which]) return c->g2_wpk[which];
+  }
   if (gru_pack(var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G, var(c, actor, 0, GAC_A_U), var(c, actor, 0, GAC_A_WA), var(c, actor, 0, GAC_A_BA),
                c->gru_pack[which], c->gru_pack16[which], tf32_only ? nullptr : c->gru_sc[which], c->stream) != cudaSuccess)
     return nullptr;
@@ -327,7 +345,7 @@ const unsigned char* pack_gru(gac_ctx* c, int which, const float* actor, int row
 }
 // the v2 kernel on a16 operand images; it exits at once when its scales are not usable, and round 1's kernel (launched
 // right after with skip_if = &scales->ok) then does the step from the fp32 operands
-int run_gru_step_v2(gac_ctx* c, int which, const float* actor, const float* sx, const int* sidx, const unsigned char* ae_pk,
+int run_gru_step_v2(gac_ctx* c, int which, const float* actor, const float* sx, const int* sidx, const unsigned char* ae_pk, const float* ae32,
                     const unsigned char* h_pk, const float* hprev, float* hout, unsigned char* hout_pk, int rows, const int* dyn,
                     float* z = nullptr, float* r = nullptr, float* cc = nullptr, float* mhh = nullptr) {
   static const bool timeline = getenv("GAC_GRU_TIMELINE") != nullptr;
@@ -336,6 +354,7 @@ int run_gru_step_v2(gac_ctx* c, int which, const float* actor, const float* sx, 
   a.rows = rows; a.dyn_rows = dyn; a.ae_pk = ae_pk; a.h_pk = hprev ? h_pk : nullptr; a.hprev = hprev; a.wpk = pair ? c->g3_wpk[which] : c->g2_wpk[which]; a.sc = c->g2_sc[which];
   a.sx = sx; a.sidx = sidx; a.b1 = var(c, actor, 0, GAC_A_GB) + GAC_G; a.hout = hout; a.hout_pk = hout_pk;
   a.z = z; a.r = r; a.c = cc; a.mhh = mhh; a.xh_scratch = c->g2_xh;
+  a.ae32 = ae32; a.kxa32 = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G; a.U32 = var(c, actor, 0, GAC_A_U);
   static const int probe = getenv("GAC_G2_PROBE") ? atoi(getenv("GAC_G2_PROBE")) : 0;
   a.probe = probe;
   a.dbg = timeline ? reinterpret_cast<unsigned long long*>(c->spart) : nullptr;
@@ -623,9 +642,8 @@ int aiqn_sample_rows(gac_ctx* c, const float* actor, const int* sidx, const floa
     if (c->gru_t) {
       // both projections + gates in one kernel: mxa / mh never touch HBM
       // (the last dimension's state feeds no further GRU step: no operand image of it)
-      if (v2) GAC_TRY(run_gru_step_v2(c, 0, actor, c->sx_u, sidx, c->ae_pk, pk_prev, d ? hprev : nullptr, hcur, d + 1 < A ? pk_cur : nullptr, rows, nullptr));
-      GAC_TRY(run_gru_step(c, 0, actor, c->sx_u, sidx, c->ae, d ? hprev : nullptr, hcur, rows, nullptr, nullptr, nullptr, nullptr, nullptr, true,
-                           v2 ? &c->g2_sc[0]->ok : nullptr));
+      if (v2) GAC_TRY(run_gru_step_v2(c, 0, actor, c->sx_u, sidx, c->ae_pk, c->ae, pk_prev, d ? hprev : nullptr, hcur, d + 1 < A ? pk_cur : nullptr, rows, nullptr));
+      else GAC_TRY(run_gru_step(c, 0, actor, c->sx_u, sidx, c->ae, d ? hprev : nullptr, hcur, rows, nullptr, nullptr, nullptr, nullptr, nullptr, true, nullptr));
     } else {
       g = gemm_args(rows, GAC_G, GAC_E, c->ae, GAC_E, kxa, GAC_G, c->mxa, GAC_G);
       g.Bpacked = c->pk[PK_T_KXA]; g.Bpacked_bn = c->pk_bn[PK_T_KXA];
@@ -870,12 +888,13 @@ int supervised_fwd(gac_ctx* c, const float* actor, const float* states_u, int n_
           GAC_CUDA(a16_pack(c->a_ae, GAC_E, AM, live, Mc, &c->g2_sc[1]->s_ae, c->a_ae_pk, st));
           c->launches++;
         }
-        GAC_TRY(run_gru_step_v2(c, 1, actor, c->a_sx_u, sidx, c->a_ae_pk + tc::a16_bytes((long long)d * Mc), c->a_h_pk[d & 1],
+        GAC_TRY(run_gru_step_v2(c, 1, actor, c->a_sx_u, sidx, c->a_ae_pk + tc::a16_bytes((long long)d * Mc), c->a_ae + o4, c->a_h_pk[d & 1],
                                 d ? c->hall + o4 : nullptr, c->hall + o4 + (size_t)Mc * GAC_E, c->a_h_pk[(d + 1) & 1], Mc, live, c->zs + o4,
                                 c->rs + o4, c->cs + o4, c->mhh + o4));
+      } else {
+        GAC_TRY(run_gru_step(c, 1, actor, c->a_sx_u, sidx, c->a_ae + o4, d ? c->hall + o4 : nullptr, c->hall + o4 + (size_t)Mc * GAC_E, Mc,
+                             live, c->zs + o4, c->rs + o4, c->cs + o4, c->mhh + o4, true, nullptr));
       }
-      GAC_TRY(run_gru_step(c, 1, actor, c->a_sx_u, sidx, c->a_ae + o4, d ? c->hall + o4 : nullptr, c->hall + o4 + (size_t)Mc * GAC_E, Mc,
-                           live, c->zs + o4, c->rs + o4, c->cs + o4, c->mhh + o4, true, v2 ? &c->g2_sc[1]->ok : nullptr));
       continue;
     }
     if (d) {
@@ -1334,7 +1353,7 @@ int gac_gru_step(gac_ctx_t* c, const float* actor, const float* states_u, int32_
   const float* kxa = var(c, actor, 0, GAC_A_KX) + (size_t)GAC_E * GAC_G;
   if (!reuse) {
     GAC_TRY(state_prep(c, actor, states_u, n_states, c->se_u, c->sx_u));
-    c->gru_t = pack_gru(c, 0, actor, rows);
+    c->gru_t = pack_gru(c, 0, actor, rows, /*need_v1=*/true);   // callers may pass operands this library cannot bound: round 1's kernel too
     if (!c->gru_t) {
       c->pk[PK_T_KXA] = pack_w(c, PK_T_KXA, kxa, GAC_G, GAC_E, GAC_G, 0, rows);
       c->pk[PK_T_U] = pack_w(c, PK_T_U, var(c, actor, 0, GAC_A_U), GAC_G, GAC_E, GAC_G, 0, rows);
@@ -1350,10 +1369,9 @@ int gac_gru_step(gac_ctx_t* c, const float* actor, const float* states_u, int32_
         if (h_prev) GAC_CUDA(a16_pack(h_prev, GAC_E, rows, nullptr, 0, &c->g2_sc[0]->s_h, c->h_pk[0], st));
         c->launches += h_prev ? 2 : 1;
       }
-      GAC_TRY(run_gru_step_v2(c, 0, actor, c->sx_u, state_idx, c->ae_pk, c->h_pk[0], h_prev, h_out, c->h_pk[1], rows, nullptr));
+      return run_gru_step_v2(c, 0, actor, c->sx_u, state_idx, c->ae_pk, action_emb, c->h_pk[0], h_prev, h_out, c->h_pk[1], rows, nullptr);
     }
-    return run_gru_step(c, 0, actor, c->sx_u, state_idx, action_emb, h_prev, h_out, rows, nullptr, nullptr, nullptr, nullptr, nullptr, bounded,
-                        v2 ? &c->g2_sc[0]->ok : nullptr);
+    return run_gru_step(c, 0, actor, c->sx_u, state_idx, action_emb, h_prev, h_out, rows, nullptr, nullptr, nullptr, nullptr, nullptr, bounded, nullptr);
   }
   GemmArgs g = gemm_args(rows, GAC_G, GAC_E, action_emb, GAC_E, kxa, GAC_G, c->mxa, GAC_G);
   g.Bpacked = c->pk[PK_T_KXA]; g.Bpacked_bn = c->pk_bn[PK_T_KXA];

@@ -95,6 +95,8 @@ struct Gru2Args {
   float* hout;                   // (rows, 400) fp32
   unsigned char* hout_pk;        // optional a16 image of h_out (the next step's A operand)
   float *z, *r, *c, *mhh;        // optional saves (rows, 400)
+  // fp32 operands and weights for the in-kernel fallback (taken when the weights admit no fp16 scaling: sc->ok == 0)
+  const float *ae32, *kxa32, *U32;
   float* xh_scratch;             // gridDim.x * G2_XH_BYTES_PER_CTA bytes (L2 resident): the candidate gate's input part between the halves
   int probe;                     // timing experiments (GAC_G2_PROBE bits, results are garbage): 1 no drain stores, 2 no TMEM loads in the
                                  // epilogue, 4 no global operand loads, 8 no global stores, 16 no gate math
@@ -202,6 +204,41 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+// The step in plain fp32 for weights that admit no fp16 scaling (non-finite or absurd magnitudes, an all-zero action embedding):
+// one (row, unit) per thread, 2 x 3 dot products of 400, accurate expf / tanhf.  Correct for any finite weights and slow by
+// design (~6x the tensor path); it replaces a second kernel that used to be launched behind EVERY step just to find the flag
+// clear and exit (12 launches and 8 weight-packing launches per train step).
+__device__ __noinline__ void gru2_fallback(const Gru2Args& g, int m_end, bool has_h) {
+  const long long total = (long long)m_end * GAC_E;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(e / GAC_E), u = (int)(e - (long long)m * GAC_E);
+    const float* a = g.ae32 + (size_t)m * GAC_E;
+    float xz = 0.f, xr = 0.f, xh = 0.f, hz = 0.f, hr = 0.f, hh = 0.f, hp = 0.f;
+    for (int k = 0; k < GAC_E; ++k) {
+      const float av = a[k];
+      const float* w = g.kxa32 + (size_t)k * GAC_G + u;
+      xz = fmaf(av, w[0], xz); xr = fmaf(av, w[GAC_E], xr); xh = fmaf(av, w[2 * GAC_E], xh);
+    }
+    if (has_h) {
+      const float* h = g.hprev + (size_t)m * GAC_E;
+      for (int k = 0; k < GAC_E; ++k) {
+        const float hv = h[k];
+        const float* w = g.U32 + (size_t)k * GAC_G + u;
+        hz = fmaf(hv, w[0], hz); hr = fmaf(hv, w[GAC_E], hr); hh = fmaf(hv, w[2 * GAC_E], hh);
+      }
+      hp = h[u];
+    }
+    const float* sx = g.sx + (size_t)g.sidx[m] * GAC_G + u;
+    const float z = 1.f / (1.f + expf(-((sx[0] + xz) + (hz + g.b1[u]))));
+    const float r = 1.f / (1.f + expf(-((sx[GAC_E] + xr) + (hr + g.b1[GAC_E + u]))));
+    const float hhb = hh + g.b1[2 * GAC_E + u];
+    const float c = tanhf((sx[2 * GAC_E] + xh) + r * hhb);
+    const size_t o = (size_t)m * GAC_E + u;
+    g.hout[o] = z * hp + (1.f - z) * c;
+    if (g.z) { g.z[o] = z; g.r[o] = r; g.c[o] = c; g.mhh[o] = hhb; }
+  }
+}
+
 // One K block of the 3-pass product as ONE instruction group: hi*hi, lo*hi, hi*lo for both 16-element K steps.  The tensor
 // core needs N / 2 cycles per M = 128 kind::f16 instruction (120 at N = 240), but the single issuing lane used to spend ~168:
 // a predicate set-up and four 64-bit descriptor computations per instruction, interleaved with seven other warps of its
@@ -260,9 +297,12 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v2_kernel(const Gru2Ar
   __shared__ __align__(8) uint64_t bar_full[G2_STAGES], bar_empty[G2_STAGES], bar_tfull[2], bar_tempty[2], bar_xfull[2], bar_xfree[2], bar_xsaved[2];
   __shared__ uint32_t tmem_slot;
 
-  if (!g.sc->ok) return;                                           // no valid scaling: gru_step_tc_kernel (launched next) does the step
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m_end = g.dyn_rows ? min(g.rows, *g.dyn_rows) : g.rows;
+  if (!g.sc->ok) {                                                 // no valid fp16 scaling of these weights: plain fp32, no tensor core
+    gru2_fallback(g, m_end, g.hprev != nullptr);
+    return;
+  }
   const int n_items = ((m_end + BM - 1) / BM) * G2_NT;            // (row block, unit tile), row-block major
   const bool has_h = g.h_pk != nullptr;
   const int nkb = has_h ? 2 * G2_KB : G2_KB;

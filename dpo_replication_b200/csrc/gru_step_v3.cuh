@@ -2,11 +2,11 @@
 //
 //   same arithmetic as gru_step_v2.cuh (Keras GRU cell, reset_after, gate order [z|r|h]; GAC/networks.py:166,217,259)
 //
-// What bounds v2 (profiles/r2b_gru2_full_raw.csv, profiles/r2b_gru2_timeline.txt): the SM's L1 / shared-memory DATA PIPE.  It
-// carries one 128-byte wavefront per cycle, and a tile puts 13.9k wavefronts of tcgen05 operand fetch (per instruction: 128 A
-// rows + 240 B rows of 32 bytes = 92 wavefronts) and 14.7k wavefronts of epilogue loads / stores on it: 28.6k against a tile
-// time of ~30k cycles (l1tex__data_pipe_tc_wavefronts 43 % + lsu_wavefronts 46 % of peak), while the 150 MMAs alone would
-// need 19.2k.  Neither L2 (37 %) nor the tensor pipe (56 %) nor HBM is the limit.
+// OPT-IN EXPERIMENT (GAC_GRU_PAIR=1), numerically validated, slower than v2 (205 vs 179 us when it was measured,
+// profiles/r2d_gru_pair_probe.txt).  It was written on the hypothesis that the SM's shared-memory data pipe bounds v2 (operand
+// fetch of the MMAs + epilogue traffic = 28.6k wavefronts against a ~30k-cycle tile in profiles/r2b_gru2_full_raw.csv); the
+// microbenchmarks that followed (tools/mma_rate.cu, tools/mma_issue.cu) showed the tile time was the issuing lane's
+// per-instruction overhead instead, identical for cta_group 1 and 2.  What the pair does buy is operand traffic:
 //   * cta_group::2: the two CTAs of a cluster form one M = 256 x N = 240 instruction.  Each SM keeps its own 128 rows of A
 //     and only HALF of the weight tile (120 of the 240 rows), so an instruction fetches 32 + 30 instead of 32 + 60
 //     wavefronts per SM, a stage is 31 KB instead of 46 KB (5 stages fit), and the weight tile crosses L2 -> SM once per
@@ -79,7 +79,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v3_kernel(const Gru2Ar
       bar_xsaved[2];
   __shared__ uint32_t tmem_slot;
 
-  if (!g.sc->ok) return;                                           // no valid scaling (both CTAs decide alike): gru_step_tc_kernel does the step
+  if (!g.sc->ok) {                                                 // no valid scaling (both CTAs decide alike): plain fp32 (gru_step_v2.cuh)
+    gru2_fallback(g, g.dyn_rows ? min(g.rows, *g.dyn_rows) : g.rows, g.hprev != nullptr);
+    return;
+  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint32_t crank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
