@@ -290,9 +290,11 @@ const unsigned char* pack_w(gac_ctx* c, int slot, const float* W, int ld, int K,
   return c->pack[slot];
 }
 
-// cta_group::2 variant of the GRU step kernel: opt-in (GAC_GRU_PAIR=1).  Measured SLOWER than the single-CTA v2 kernel
-// (205 vs 179 us per 32768-row step, profiles/r2d_gru_pair_probe.txt): a tcgen05.mma takes the same ~168 cycles per SM in
-// both modes (tools/mma_rate.cu), so the pair only adds the stage relay and the drain stall to the critical path.
+// cta_group::2 variant of the GRU step kernel: opt-in (GAC_GRU_PAIR=1).  First measured 205 vs 179 us per 32768-row step
+// (profiles/r2d_gru_pair_probe.txt): every relayed stage paid a MEMBAR.ALL.GPU in front of its remote mbarrier arrive.  With
+// default-semantics arrives, the instruction-group MMA issue and six stages it is level with the v2 kernel (163.5 vs 166.3 us
+// in tools/gru2_probe.py, 162.1 vs 162.0 us in bench.py's loop, profiles/r2_pair_relay_probe.txt) -- both sit at the same
+// power-capped wall -- so the single-CTA kernel, which every parity test of the round ran on, stays the default.
 inline bool gru3_enabled() {
   static const bool pair = getenv("GAC_GRU_PAIR") != nullptr;
   return pair;

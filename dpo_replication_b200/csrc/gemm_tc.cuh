@@ -783,7 +783,11 @@ __device__ __forceinline__ void mma_commit2_mc(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(bar));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+  // default semantics (as CUTLASS's ClusterBarrier::arrive(cta_id)): with an explicit .release.cluster ptxas puts
+  // MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of every arrive -- ~1.4k cycles per relayed stage, which is what starved the
+  // pair kernels of operands (profiles/r2_pair_relay_probe.txt).  What the waiter consumes was written by bulk copies /
+  // tcgen05 and is ordered by their own completion mechanisms, not by this thread's generic-proxy writes.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
 }
 
 __global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_pair_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmapA, int bn,

@@ -2,11 +2,12 @@
 //
 //   same arithmetic as gru_step_v2.cuh (Keras GRU cell, reset_after, gate order [z|r|h]; GAC/networks.py:166,217,259)
 //
-// OPT-IN EXPERIMENT (GAC_GRU_PAIR=1), numerically validated, slower than v2 (205 vs 179 us when it was measured,
-// profiles/r2d_gru_pair_probe.txt).  It was written on the hypothesis that the SM's shared-memory data pipe bounds v2 (operand
-// fetch of the MMAs + epilogue traffic = 28.6k wavefronts against a ~30k-cycle tile in profiles/r2b_gru2_full_raw.csv); the
-// microbenchmarks that followed (tools/mma_rate.cu, tools/mma_issue.cu) showed the tile time was the issuing lane's
-// per-instruction overhead instead, identical for cta_group 1 and 2.  What the pair does buy is operand traffic:
+// OPT-IN (GAC_GRU_PAIR=1), numerically validated, level with v2 (163.5 vs 166.3 us per 32768-row step in tools/gru2_probe.py,
+// equal in bench.py's loop: profiles/r2_pair_relay_probe.txt).  History: written on the hypothesis that the SM's shared-memory
+// data pipe bounds v2; the microbenchmarks that followed (tools/mma_rate.cu, tools/mma_issue.cu) showed v2's tile time was the
+// issuing lane's per-instruction overhead instead, identical for cta_group 1 and 2.  Its first version lost 20 % to the
+// stage relay: an explicit .release.cluster on the remote mbarrier arrive costs a MEMBAR.ALL.GPU per stage (gemm_tc.cuh,
+// mbar_arrive_leader).  What the pair buys is operand traffic:
 //   * cta_group::2: the two CTAs of a cluster form one M = 256 x N = 240 instruction.  Each SM keeps its own 128 rows of A
 //     and only HALF of the weight tile (120 of the 240 rows), so an instruction fetches 32 + 30 instead of 32 + 60
 //     wavefronts per SM, a stage is 31 KB instead of 46 KB (5 stages fit), and the weight tile crosses L2 -> SM once per
@@ -27,8 +28,8 @@ namespace tc {
 constexpr uint32_t G3_B_HALF = (uint32_t)(3 * G2_NU / 2) * 64u;     // 120 weight rows x 64 bytes: this CTA's half of hi (or lo)
 constexpr uint32_t G3_B_SLOT = 2u * G3_B_HALF;                      // [hi | lo] of this CTA's half: 15 KB
 constexpr uint32_t G3_STAGE = G2_A_SLOT + G3_B_SLOT;                // 31 KB
-constexpr int G3_STAGES = 5;
-constexpr int G3_SMEM = G3_STAGES * (int)G3_STAGE + BM * G2_SS * 4 + G2_DRAIN_SMEM + 3 * G2_NU * 4 + 1024;
+constexpr int G3_STAGES = 6;
+constexpr int G3_SMEM = G3_STAGES * (int)G3_STAGE + BM * G2_SS * 4 + G2_DRAIN_SMEM + 4 * 3 * G2_NU * 4 + 1024;
 static_assert((3 * G2_NU / 2) % 8 == 0 && (3 * G2_NU) % 16 == 0, "cta_group::2: N multiple of 16, each CTA's half in whole 8-row swizzle groups");
 static_assert(G3_STAGE % 512 == 0 && G3_B_HALF % 512 == 0, "SWIZZLE_64B tiles start on 512-byte boundaries");
 
@@ -70,6 +71,49 @@ __device__ __forceinline__ void mma_f16_2(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
+// one K block (two K steps x three passes) / one K step as ONE instruction group, cta_group::2 (see mma_f16_kblock in v2)
+template <uint32_t A_LO, uint32_t B_HI, uint32_t B_LO>
+__device__ __forceinline__ void mma_f16_kblock_2(uint32_t d, uint64_t a_hi, uint32_t idesc, uint32_t acc0) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 al, bh, bl, ah2, al2, bh2, bl2;\n"
+      "setp.ne.b32 q, %3, 0;\n"
+      "setp.eq.b32 p, 1, 1;\n"
+      "add.u64 al, %1, %4;\n"
+      "add.u64 bh, %1, %5;\n"
+      "add.u64 bl, %1, %6;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, bh, %2, q;\n"
+      "add.u64 ah2, %1, 2;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], al, bh, %2, p;\n"
+      "add.u64 bh2, bh, 2;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, bl, %2, p;\n"
+      "add.u64 al2, al, 2;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], ah2, bh2, %2, p;\n"
+      "add.u64 bl2, bl, 2;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], al2, bh2, %2, p;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], ah2, bl2, %2, p;\n"
+      "}\n" ::"r"(d), "l"(a_hi), "r"(idesc), "r"(acc0), "n"(A_LO), "n"(B_HI), "n"(B_LO)
+      : "memory");
+}
+template <uint32_t A_LO, uint32_t B_HI, uint32_t B_LO>
+__device__ __forceinline__ void mma_f16_kstep_2(uint32_t d, uint64_t a_hi, uint32_t idesc, uint32_t acc0) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 al, bh, bl;\n"
+      "setp.ne.b32 q, %3, 0;\n"
+      "setp.eq.b32 p, 1, 1;\n"
+      "add.u64 al, %1, %4;\n"
+      "add.u64 bh, %1, %5;\n"
+      "add.u64 bl, %1, %6;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, bh, %2, q;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], al, bh, %2, p;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, bl, %2, p;\n"
+      "}\n" ::"r"(d), "l"(a_hi), "r"(idesc), "r"(acc0), "n"(A_LO), "n"(B_HI), "n"(B_LO)
+      : "memory");
+}
+
 template <bool DBG>
 __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v3_kernel(const Gru2Args g) {
   unsigned long long* const dbgp = DBG ? g.dbg : nullptr;
@@ -95,7 +139,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v3_kernel(const Gru2Ar
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   float* stg = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)) + G3_STAGES * G3_STAGE);
   float* dstg = stg + BM * G2_SS;
-  float* b1_s = dstg + G2_DRAIN_WARPS * 32 * G2_DS;
+  float* b1_base = dstg + G2_DRAIN_WARPS * 32 * G2_DS;
   float* xh_cta = g.xh_scratch + (size_t)blockIdx.x * (G2_XH_BYTES_PER_CTA / 4);
 
   if (tid == 0) {
@@ -154,6 +198,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v3_kernel(const Gru2Ar
       unsigned long long gt0 = 0;
       if (dbgp) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
       constexpr uint32_t id3 = (1u << 4) | ((uint32_t)((3 * G2_NU) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // kind::f16, M = 256, N = 240
+      const uint64_t desc0 = make_desc64(smem0);                   // A hi of stage 0
       int it = 0, t = 0;
       for (int i = cluster_id; i < n_items; i += nclusters, ++t) {
         const int b = t & 1;
@@ -178,16 +223,14 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v3_kernel(const Gru2Ar
             tc_fence_after();
             if (dbgp) t_wait_x += clock64() - c0;
           }
-          const uint32_t sa = smem0 + (uint32_t)s * G3_STAGE;
-          const uint64_t a_hi = make_desc64(sa), a_lo = make_desc64(sa + G2_A_TILE);
-          const uint64_t b_hi = make_desc64(sa + G2_A_SLOT), b_lo = make_desc64(sa + G2_A_SLOT + G3_B_HALF);
-          const int kbl = kb >= G2_KB ? kb - G2_KB : kb, live = min(G2_BK, GAC_E - kbl * G2_BK);
-          const int ksteps = (probe & 32) ? 0 : (live + 15) / 16;
-          for (int j = 0; j < ksteps; ++j) {
-            const uint64_t adv = (uint64_t)(j * 2);
-            mma_f16_2(d0, a_hi + adv, b_hi + adv, id3, (kb | j) ? 1u : 0u);
-            mma_f16_2(d0, a_lo + adv, b_hi + adv, id3, 1u);
-            mma_f16_2(d0, a_hi + adv, b_lo + adv, id3, 1u);
+          const uint64_t a_hi = desc0 + (uint64_t)((uint32_t)s * (G3_STAGE >> 4));
+          constexpr uint32_t C_ALO = G2_A_TILE >> 4, C_BHI = G2_A_SLOT >> 4, C_BLO = (G2_A_SLOT + G3_B_HALF) >> 4;
+          const bool last_of_half = kb == G2_KB - 1 || kb == 2 * G2_KB - 1;       // 400 = 12 x 32 + 16: one K step
+          if (DBG && (probe & 32)) {
+          } else if (last_of_half) {
+            mma_f16_kstep_2<C_ALO, C_BHI, C_BLO>(d0, a_hi, id3, 1u);
+          } else {
+            mma_f16_kblock_2<C_ALO, C_BHI, C_BLO>(d0, a_hi, id3, kb ? 1u : 0u);
           }
           mma_commit2_mc(smem_u32(&bar_empty[s]));                 // frees the stage in both CTAs
           if (has_h && kb == G2_KB - 1) mma_commit2_mc(smem_u32(&bar_xfull[b]));   // the action-embedding half has retired
@@ -214,8 +257,26 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v3_kernel(const Gru2Ar
       if (dbgp) { unsigned long long* d = dbgp + 8 + (size_t)blockIdx.x * 16; d[0] = d[1] = d[2] = d[3] = d[4] = d[5] = 0; }
     }
     __syncwarp();
+  } else if (warp == G2_PROD_WARP + 1) {
+    // h_prev prefetcher (see v2): the NEXT tile's 128 x 80 block of this CTA towards L2 while the current tile's MMAs run
+    if (has_h) {
+      int t = 0;
+      for (int i = cluster_id; i < n_items; i += nclusters, ++t) {
+        if (t > 0) mbar_wait(smem_u32(&bar_tfull[(t - 1) & 1]), (uint32_t)((t - 1) >> 1) & 1u);
+        const int rbp = i / G2_NT, jt = i - rbp * G2_NT, rb = 2 * rbp + (int)crank;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+          const int idx = k * 32 + lane, row = idx / 3, part = idx - row * 3;
+          const int m = rb * BM + row;
+          if (m < m_end) {
+            const float* p = g.hprev + (size_t)m * GAC_E + jt * G2_NU + part * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+          }
+        }
+      }
+    }
   } else if (warp > G2_PROD_WARP && warp < G2_DRAIN_WARP0) {
-    // idle warps of the control warpgroup
+    // idle warp of the control warpgroup
   } else if (warp >= G2_DRAIN_WARP0) {
     // ------------------------------ drain warps: g = ae * kx_h out of TMEM between the two halves, zeros back in ------------------------------
     if (has_h) {
@@ -289,7 +350,13 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v3_kernel(const Gru2Ar
     const int quarter = warp & 3, sub = warp >> 2;
     const float inv_unit = g.sc->inv_unit, s_h = g.sc->s_h;
     auto tnh = [](float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); };
-    const int prow = warp * 8 + (lane >> 2), pj = lane & 3;
+    // four independent quadrant groups with their own named barrier, staging rows and bias copy (see v2)
+    const int grp = quarter, gw = sub;
+    const int gtid = gw * 32 + lane;
+    const uint32_t gbar = 1u + (uint32_t)grp;
+    float* b1_s = b1_base + grp * (3 * G2_NU);
+#define G3_GROUP_SYNC() asm volatile("bar.sync %0, 128;" ::"r"(gbar) : "memory")
+    const int prow = 32 * grp + gw * 8 + (lane >> 2), pj = lane & 3;
     const bool stamp = dbgp && tid == 0;
     long long e_wt = 0, e_wx = 0, e_p1 = 0, e_b1 = 0, e_p2 = 0, e_b2 = 0, e_ld = 0, ec = 0;
 #define G3_STAMP(acc) if (stamp) { const long long now = clock64(); acc += now - ec; ec = now; }
@@ -301,8 +368,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v3_kernel(const Gru2Ar
       const uint32_t tph = (uint32_t)(t >> 1) & 1u;
       const int m = m0 + prow;
       const int sid = m < m_end ? g.sidx[m] : -1;
-      if (tid < 3 * G2_NU / 4)
-        *reinterpret_cast<float4*>(b1_s + 4 * tid) = *reinterpret_cast<const float4*>(g.b1 + (tid / (G2_NU / 4)) * GAC_E + jt * G2_NU + 4 * (tid % (G2_NU / 4)));
+      if (gtid < 3 * G2_NU / 4)
+        *reinterpret_cast<float4*>(b1_s + 4 * gtid) = *reinterpret_cast<const float4*>(g.b1 + (gtid / (G2_NU / 4)) * GAC_E + jt * G2_NU + 4 * (gtid % (G2_NU / 4)));
       if (has_h) mbar_wait(smem_u32(&bar_xsaved[b]), tph);
       G3_STAMP(e_wx)
       float4 sz, sr, sh, hp, xh;
@@ -312,8 +379,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v3_kernel(const Gru2Ar
         if (sid < 0) return;
         const int ul = q * 16 + 4 * pj, u = jt * G2_NU + ul;
         const float* sx = g.sx + (size_t)sid * GAC_G + u;
-        sz = __ldcg(reinterpret_cast<const float4*>(sx)); sr = __ldcg(reinterpret_cast<const float4*>(sx + GAC_E));
-        sh = __ldcg(reinterpret_cast<const float4*>(sx + 2 * GAC_E));
+        sz = __ldg(reinterpret_cast<const float4*>(sx)); sr = __ldg(reinterpret_cast<const float4*>(sx + GAC_E));
+        sh = __ldg(reinterpret_cast<const float4*>(sx + 2 * GAC_E));
         if (has_h) {
           hp = __ldcg(reinterpret_cast<const float4*>(g.hprev + (size_t)m * GAC_E + u));
           xh = __ldcg(reinterpret_cast<const float4*>(xh_cta + ((size_t)b * BM + prow) * G2_NU + ul));
@@ -321,7 +388,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v3_kernel(const Gru2Ar
       };
       load_ops(0);
       G3_STAMP(e_ld)
-      asm volatile("bar.sync 1, 512;" ::: "memory");               // this tile's bias rows are in smem
+      G3_GROUP_SYNC();                                             // this tile's bias rows are in smem
       mbar_wait(smem_u32(&bar_tfull[b]), tph);
       tc_fence_after();
       G3_STAMP(e_wt)
@@ -354,7 +421,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v3_kernel(const Gru2Ar
           }
         }
         G3_STAMP(e_p1)
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+        G3_GROUP_SYNC();
         G3_STAMP(e_b1)
         {
           const float* srow = stg + (size_t)prow * G2_SS + 4 * ((pj + (prow >> 1)) & 3);
@@ -401,7 +468,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v3_kernel(const Gru2Ar
           if (q + 1 < G2_NU / 16) load_ops(q + 1);
         }
         G3_STAMP(e_p2)
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+        G3_GROUP_SYNC();
         G3_STAMP(e_b2)
       }
       tc_fence_before();
@@ -409,6 +476,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gru_step_v3_kernel(const Gru2Ar
       if (lane == 0) mbar_arrive_leader(smem_u32(&bar_tempty[b]));
     }
 #undef G3_STAMP
+#undef G3_GROUP_SYNC
     if (stamp) {
       unsigned long long* d = dbgp + 8 + (size_t)blockIdx.x * 16;
       d[6] = (unsigned long long)e_wt; d[7] = (unsigned long long)e_wx; d[8] = (unsigned long long)e_p1; d[9] = (unsigned long long)e_b1;
